@@ -1,0 +1,158 @@
+/* nmrfit_b200 - C ABI of the B200-native objective-evaluation hot path of pnnl/nmrfit.
+ *
+ * The reference (pure Python, /root/reference/nmrfit) has no FFI layer of its own;
+ * its boundary for this path is the Python call surface
+ *     nmrfit.fit(data, lower, upper, ...)                   core.py:64-95
+ *     FitUtility.fit / generate_result                      utils.py:164-189, 226-295
+ *     pyswarm.pso(objective, lb, ub, args=..., ...)         utils.py:176-182
+ *     equations.objective / voigt / kk_relation*            equations.py:152-212, 115-149, 52-112, 242
+ *     proc_autophase.ps2                                    proc_autophase.py:9-36
+ * Each entry point below names the reference interface it stands in for.  The
+ * Python mirror of that surface (nmrfit_b200/*.py) binds these symbols with ctypes;
+ * INTEGRATION.md shows the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C: pointers and sizes only; no exceptions cross the boundary.
+ *   - every function returns NMRFIT_OK (0) or a negative error code; the message
+ *     is available from nmrfit_last_error() (thread-local).
+ *   - all arrays are float64, C-contiguous.  "dev" = CUDA device memory on the
+ *     context's device, "host" = ordinary host memory (pinned or pageable).
+ *   - functions taking a `stream` (a cudaStream_t passed as void*, NULL = default
+ *     stream) are asynchronous; the caller synchronises.  *_host functions are
+ *     synchronous and do their own staging copies.
+ *   - the caller owns every buffer it passes; the context owns spectra, swarm
+ *     state and scratch.  A context is bound to one device and is not thread-safe.
+ *   - D = 4 + 3*n_peaks; a parameter vector is [p0, p1, r, yoff, (width, loc, area) * n_peaks]
+ *     (equations.py:177, 188-192).
+ */
+#ifndef NMRFIT_B200_H
+#define NMRFIT_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NMRFIT_ABI_VERSION 1
+
+#define NMRFIT_OK 0
+#define NMRFIT_ERR_ARG (-1)    /* bad argument */
+#define NMRFIT_ERR_CUDA (-2)   /* a CUDA call failed */
+#define NMRFIT_ERR_STATE (-3)  /* call sequence violated (e.g. spectrum not set) */
+#define NMRFIT_ERR_NOMEM (-4)
+
+#define NMRFIT_FP64 0
+#define NMRFIT_FP32 1          /* opt-in: FP32 lineshape math, FP64 residual accumulation */
+
+/* fit_im argument of the objective entry points */
+#define NMRFIT_REAL_ONLY 0     /* fit_im is not True: equations.py:202 only */
+#define NMRFIT_IM_REFERENCE 1  /* fit_im is True, reference semantics: equations.py:199 overwrites I_fit,
+                                  so only the LAST peak's Kramers-Kronig curve enters :206 */
+#define NMRFIT_IM_SUM 2        /* imaginary fit accumulated over all peaks (what generate_result does) */
+
+/* stop reasons reported by the swarm (pyswarm's three exits) */
+#define NMRFIT_RUNNING 0
+#define NMRFIT_STOP_MINFUNC 1
+#define NMRFIT_STOP_MINSTEP 2
+#define NMRFIT_STOP_MAXITER 3
+
+typedef struct nmrfit_ctx nmrfit_ctx;
+
+int nmrfit_abi_version(void);
+const char* nmrfit_last_error(void);
+int nmrfit_device_count(int* count);
+
+/* ---- context: one batch of n_spectra spectra of n_points points, n_peaks peaks each ------------- */
+int nmrfit_ctx_create(nmrfit_ctx** out, int device, int n_spectra, int n_points, int n_peaks, int precision);
+void nmrfit_ctx_destroy(nmrfit_ctx* ctx);
+
+/* Upload spectrum b: the `args=(data.w, data.u, data.v, weights, ...)` tuple of utils.py:176.
+ * Host or device pointers (UVA); synchronous. */
+int nmrfit_ctx_set_spectrum(nmrfit_ctx* ctx, int b, const double* w, const double* u, const double* v,
+                            const double* weights);
+
+/* Launch geometry of the objective kernel; 0 keeps the automatic choice for that field.
+ * threads in {128, 256}; points_per_thread in {2, 4, 8}; exp_table_bits in {0, 6, 8, 10}. */
+int nmrfit_ctx_set_tuning(nmrfit_ctx* ctx, int threads, int points_per_thread, int exp_table_bits,
+                          int particles_per_cta);
+int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* points_per_thread, int* exp_table_bits,
+                          int* particles_per_cta, int* n_point_tiles);
+
+/* ---- objective: equations.objective (equations.py:152-212) for a whole swarm generation -------
+ * x [n_spectra][n_particles][D] -> f [n_spectra][n_particles].  One call replaces the
+ * n_particles Python callbacks pyswarm makes per generation (utils.py:176-182). */
+int nmrfit_objective_batch(nmrfit_ctx* ctx, const double* x_dev, int n_particles, int fit_im, double* f_dev,
+                           void* stream);
+int nmrfit_objective_batch_host(nmrfit_ctx* ctx, const double* x_host, int n_particles, int fit_im, double* f_host);
+
+/* ---- swarm: pyswarm.pso as called at utils.py:176-182, state resident on the device -----------
+ * Generation g (g = 0 is the initial swarm) is   begin|advance -> [exchange records] -> commit.
+ * With one rank the exchange is skipped (commit with recs_dev = NULL). */
+typedef struct nmrfit_pso_opts {
+    int swarmsize;               /* particles held by THIS context (local shard) */
+    int maxiter;
+    double omega, phip, phig;    /* utils.py:179-181 defaults -0.2134, -0.3344, 2.3259 */
+    double minstep, minfunc;     /* pyswarm defaults 1e-8, never overridden by the reference */
+    int fit_im;                  /* NMRFIT_REAL_ONLY | NMRFIT_IM_REFERENCE | NMRFIT_IM_SUM */
+    int bounds_per_spectrum;     /* 0: lb/ub are [D] shared by all spectra; 1: [n_spectra][D] */
+    unsigned long long seed;     /* device Philox stream, used wherever a random array is NULL */
+    long long particle_offset;   /* global index of local particle 0 (particle sharding; else 0) */
+} nmrfit_pso_opts;
+
+/* Initial swarm: x = lb + r_pos*(ub-lb), v = vlow + r_vel*(vhigh-vlow), evaluate, personal bests,
+ * local best record.  lb/ub: host.  r_pos/r_vel: [n_spectra][swarmsize][D] uniforms in [0,1), host or
+ * device, or NULL for device Philox. */
+int nmrfit_pso_begin(nmrfit_ctx* ctx, const double* lb, const double* ub, const nmrfit_pso_opts* opts,
+                     const double* r_pos, const double* r_vel, void* stream);
+/* One generation: velocity/position update with rp, rg (host, device, or NULL = Philox), clamp to the
+ * box, evaluate, personal bests, local best record. */
+int nmrfit_pso_advance(nmrfit_ctx* ctx, const double* rp, const double* rg, void* stream);
+/* Device pointer and length (doubles) of the local best record, [n_spectra][D+2] = (f, global index, x[D]). */
+int nmrfit_pso_record(nmrfit_ctx* ctx, double** rec_dev, int* n_doubles);
+/* Swarm-best update and the minfunc/minstep/maxiter tests.  recs_dev = [n_ranks][n_spectra][D+2]
+ * gathered records (rank order), or NULL to commit this context's own record (n_ranks ignored). */
+int nmrfit_pso_commit(nmrfit_ctx* ctx, const double* recs_dev, int n_ranks, void* stream);
+/* Run up to n_generations generations on one rank (advance+commit each).  rp_all/rg_all:
+ * [n_generations][n_spectra][swarmsize][D] host or device arrays, or NULL for Philox.  Synchronises and
+ * returns in *n_running how many spectra have not stopped. */
+int nmrfit_pso_run(nmrfit_ctx* ctx, int n_generations, const double* rp_all, const double* rg_all, int* n_running,
+                   void* stream);
+/* Result (synchronises): x_best [n_spectra][D], f_best [n_spectra], generations done, stop reason.
+ * On a minfunc/minstep stop this is (p_min, fp[i_min]) exactly as pyswarm returns it. Any pointer may be NULL. */
+int nmrfit_pso_get_best(nmrfit_ctx* ctx, double* x_best, double* f_best, int* generations, int* stop_reason);
+/* Copy swarm arrays to the host for inspection; any pointer may be NULL. x,v,p: [n_spectra][swarmsize][D]; fx,fp: [..][swarmsize] */
+int nmrfit_pso_get_state(nmrfit_ctx* ctx, double* x, double* v, double* p, double* fx, double* fp);
+
+/* ---- curves ----------------------------------------------------------------------------------- */
+/* proc_autophase.ps2 (proc_autophase.py:9-36) */
+int nmrfit_ps2(const double* u_dev, const double* v_dev, int n, double p0, double p1, int inv, double* re_dev,
+               double* im_dev, void* stream);
+int nmrfit_ps2_host(int device, const double* u, const double* v, int n, double p0, double p1, int inv, double* re,
+                    double* im);
+/* equations.voigt (equations.py:115-149) */
+int nmrfit_voigt(const double* w_dev, int n, double r, double yoff, double width, double loc, double a,
+                 double* out_dev, void* stream);
+int nmrfit_voigt_host(int device, const double* w, int n, double r, double yoff, double width, double loc, double a,
+                      double* out);
+/* equations.kk_relation_vectorized / kk_relation_parallel (equations.py:52-112, 242), closed form */
+int nmrfit_kk(const double* w_dev, int n, double r, double yoff, double width, double loc, double a, double* out_dev,
+              void* stream);
+int nmrfit_kk_host(int device, const double* w, int n, double r, double yoff, double width, double loc, double a,
+                   double* out);
+/* FitUtility.generate_result (utils.py:243-295) on the grid w[n]: real/imag [n_peaks][n], V/I/u/v [n].
+ * params: host, D doubles. */
+int nmrfit_generate_result(const double* params, int n_peaks, const double* w_dev, int n, double* real_dev,
+                           double* imag_dev, double* V_dev, double* I_dev, double* u_dev, double* v_dev,
+                           void* stream);
+int nmrfit_generate_result_host(int device, const double* params, int n_peaks, const double* w, int n, double* real,
+                                double* imag, double* V, double* I, double* u, double* v);
+
+/* ---- measurement ------------------------------------------------------------------------------ */
+/* DFMA throughput of the device (TFLOP/s): best single launch and back-to-back average. */
+int nmrfit_fp64_peak(int device, int iters, int repeats, double* burst_tflops, double* sustained_tflops);
+/* Kernels launched by this library in this process since load (for bench.py's gpu_launches). */
+long long nmrfit_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,260 @@
+"""ctypes binding of libnmrfit_b200.so (include/nmrfit_b200.h).
+
+There is no CPU fallback: if the shared library has not been built
+(``python -c 'import __graft_entry__ as g; g.build()'``) or no CUDA device is
+usable, the first call raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'csrc', 'libnmrfit_b200.so')
+
+OK = 0
+FP64, FP32 = 0, 1
+REAL_ONLY, IM_REFERENCE, IM_SUM = 0, 1, 2
+RUNNING, STOP_MINFUNC, STOP_MINSTEP, STOP_MAXITER = 0, 1, 2, 3
+
+c_double_p = ctypes.POINTER(ctypes.c_double)
+c_int_p = ctypes.POINTER(ctypes.c_int)
+
+
+class NmrfitError(RuntimeError):
+    """A libnmrfit_b200 call returned a non-zero status."""
+
+    def __init__(self, code, message):
+        super().__init__('libnmrfit_b200 error %d: %s' % (code, message))
+        self.code = code
+
+
+class PsoOpts(ctypes.Structure):
+    _fields_ = [('swarmsize', ctypes.c_int), ('maxiter', ctypes.c_int),
+                ('omega', ctypes.c_double), ('phip', ctypes.c_double), ('phig', ctypes.c_double),
+                ('minstep', ctypes.c_double), ('minfunc', ctypes.c_double),
+                ('fit_im', ctypes.c_int), ('bounds_per_spectrum', ctypes.c_int),
+                ('seed', ctypes.c_ulonglong), ('particle_offset', ctypes.c_longlong)]
+
+
+# name -> (restype, argtypes); every symbol include/nmrfit_b200.h declares
+_vp, _i, _d = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+SIGNATURES = {
+    'nmrfit_abi_version': (_i, []),
+    'nmrfit_last_error': (ctypes.c_char_p, []),
+    'nmrfit_device_count': (_i, [c_int_p]),
+    'nmrfit_ctx_create': (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i]),
+    'nmrfit_ctx_destroy': (None, [_vp]),
+    'nmrfit_ctx_set_spectrum': (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    'nmrfit_ctx_set_tuning': (_i, [_vp, _i, _i, _i, _i]),
+    'nmrfit_ctx_get_tuning': (_i, [_vp, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    'nmrfit_objective_batch': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
+    'nmrfit_objective_batch_host': (_i, [_vp, _vp, _i, _i, _vp]),
+    'nmrfit_pso_begin': (_i, [_vp, _vp, _vp, ctypes.POINTER(PsoOpts), _vp, _vp, _vp]),
+    'nmrfit_pso_advance': (_i, [_vp, _vp, _vp, _vp]),
+    'nmrfit_pso_record': (_i, [_vp, ctypes.POINTER(_vp), c_int_p]),
+    'nmrfit_pso_commit': (_i, [_vp, _vp, _i, _vp]),
+    'nmrfit_pso_run': (_i, [_vp, _i, _vp, _vp, c_int_p, _vp]),
+    'nmrfit_pso_get_best': (_i, [_vp, _vp, _vp, _vp, _vp]),
+    'nmrfit_pso_get_state': (_i, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    'nmrfit_ps2': (_i, [_vp, _vp, _i, _d, _d, _i, _vp, _vp, _vp]),
+    'nmrfit_ps2_host': (_i, [_i, _vp, _vp, _i, _d, _d, _i, _vp, _vp]),
+    'nmrfit_voigt': (_i, [_vp, _i, _d, _d, _d, _d, _d, _vp, _vp]),
+    'nmrfit_voigt_host': (_i, [_i, _vp, _i, _d, _d, _d, _d, _d, _vp]),
+    'nmrfit_kk': (_i, [_vp, _i, _d, _d, _d, _d, _d, _vp, _vp]),
+    'nmrfit_kk_host': (_i, [_i, _vp, _i, _d, _d, _d, _d, _d, _vp]),
+    'nmrfit_generate_result': (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'nmrfit_generate_result_host': (_i, [_i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'nmrfit_fp64_peak': (_i, [_i, _i, _i, c_double_p, c_double_p]),
+    'nmrfit_launch_count': (ctypes.c_longlong, []),
+}
+
+_lib = None
+
+
+def lib():
+    """The loaded library (loads on first use; raises if it is not built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                'libnmrfit_b200.so is not built (%s). Build it with '
+                '`python -c "import __graft_entry__ as g; g.build()"` from the repo root. '
+                'nmrfit_b200 has no CPU fallback.' % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)       # AttributeError here = header and library disagree
+            fn.restype = res
+            fn.argtypes = args
+        if handle.nmrfit_abi_version() != 1:
+            raise ImportError('libnmrfit_b200.so ABI version mismatch')
+        _lib = handle
+    return _lib
+
+
+def check(status):
+    if status != OK:
+        raise NmrfitError(status, lib().nmrfit_last_error().decode('utf-8', 'replace'))
+
+
+def as_f64(a):
+    """C-contiguous float64 view/copy of ``a``."""
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def ptr(a):
+    """void* of a numpy array, a torch tensor (``data_ptr``), an int address, or None."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return ctypes.c_void_p(a.ctypes.data)
+    if hasattr(a, 'data_ptr'):
+        return ctypes.c_void_p(a.data_ptr())
+    return ctypes.c_void_p(int(a))
+
+
+def device_count():
+    n = ctypes.c_int(0)
+    check(lib().nmrfit_device_count(ctypes.byref(n)))
+    return n.value
+
+
+def default_device():
+    """LOCAL_RANK under torchrun, else NMRFIT_DEVICE, else 0."""
+    for key in ('NMRFIT_DEVICE', 'LOCAL_RANK'):
+        if os.environ.get(key):
+            return int(os.environ[key])
+    return 0
+
+
+class Context:
+    """Owner of one ``nmrfit_ctx``: a batch of spectra resident on one GPU."""
+
+    def __init__(self, n_spectra, n_points, n_peaks, device=None, precision=FP64):
+        self._h = ctypes.c_void_p()
+        self.device = default_device() if device is None else int(device)
+        self.B, self.N, self.P = int(n_spectra), int(n_points), int(n_peaks)
+        self.D = 4 + 3 * self.P
+        self.precision = precision
+        check(lib().nmrfit_ctx_create(ctypes.byref(self._h), self.device, self.B, self.N, self.P, precision))
+        self._keep = []
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            lib().nmrfit_ctx_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- spectra
+    def set_spectrum(self, b, w, u, v, weights):
+        arrs = [as_f64(a) for a in (w, u, v, weights)]
+        for a in arrs:
+            if a.shape != (self.N,):
+                raise ValueError('spectrum arrays must have shape (%d,), got %s' % (self.N, a.shape))
+        check(lib().nmrfit_ctx_set_spectrum(self._h, int(b), *[ptr(a) for a in arrs]))
+
+    def set_tuning(self, threads=0, points_per_thread=0, exp_table_bits=0, particles_per_cta=0):
+        check(lib().nmrfit_ctx_set_tuning(self._h, threads, points_per_thread, exp_table_bits, particles_per_cta))
+
+    def get_tuning(self, n_particles):
+        vals = [ctypes.c_int(0) for _ in range(5)]
+        check(lib().nmrfit_ctx_get_tuning(self._h, int(n_particles), *[ctypes.byref(v) for v in vals]))
+        keys = ('threads', 'points_per_thread', 'exp_table_bits', 'particles_per_cta', 'n_point_tiles')
+        return dict(zip(keys, (v.value for v in vals)))
+
+    # -- objective
+    def objective_host(self, x, fit_im=REAL_ONLY):
+        """x: [B, S, D] (or [S, D] when B == 1) host array -> f [B, S] (or [S])."""
+        x = as_f64(x)
+        squeeze = x.ndim == 2
+        if squeeze:
+            if self.B != 1:
+                raise ValueError('x must be [n_spectra, n_particles, D]')
+            x = x[None]
+        if x.ndim != 3 or x.shape[0] != self.B or x.shape[2] != self.D:
+            raise ValueError('x must have shape [%d, S, %d], got %s' % (self.B, self.D, x.shape))
+        f = np.empty((self.B, x.shape[1]), dtype=np.float64)
+        check(lib().nmrfit_objective_batch_host(self._h, ptr(x), x.shape[1], int(fit_im), ptr(f)))
+        return f[0] if squeeze else f
+
+    def objective_device(self, x_dev, n_particles, f_dev, fit_im=REAL_ONLY, stream=None):
+        """Asynchronous: x_dev/f_dev are device pointers (ints) or torch CUDA tensors."""
+        check(lib().nmrfit_objective_batch(self._h, ptr(x_dev), int(n_particles), int(fit_im), ptr(f_dev),
+                                           ptr(stream)))
+
+    # -- swarm
+    def pso_begin(self, lb, ub, opts, r_pos=None, r_vel=None, stream=None):
+        lb, ub = as_f64(lb), as_f64(ub)
+        per = 1 if lb.ndim == 2 else 0
+        want = (self.B, self.D) if per else (self.D,)
+        if lb.shape != want or ub.shape != want:
+            raise ValueError('lb/ub must have shape %s' % (want,))
+        opts.bounds_per_spectrum = per
+        r_pos = self._rand(r_pos, opts.swarmsize)
+        r_vel = self._rand(r_vel, opts.swarmsize)
+        check(lib().nmrfit_pso_begin(self._h, ptr(lb), ptr(ub), ctypes.byref(opts), ptr(r_pos), ptr(r_vel),
+                                     ptr(stream)))
+        self._swarmsize = opts.swarmsize
+
+    def _rand(self, r, S, gens=None):
+        if r is None or not isinstance(r, np.ndarray):
+            return r
+        r = as_f64(r)
+        n = self.B * S * self.D * (1 if gens is None else gens)
+        if r.size != n:
+            raise ValueError('random array has %d elements, expected %d' % (r.size, n))
+        return r
+
+    def pso_advance(self, rp=None, rg=None, stream=None):
+        rp, rg = self._rand(rp, self._swarmsize), self._rand(rg, self._swarmsize)
+        check(lib().nmrfit_pso_advance(self._h, ptr(rp), ptr(rg), ptr(stream)))
+
+    def pso_record(self):
+        p, n = ctypes.c_void_p(), ctypes.c_int(0)
+        check(lib().nmrfit_pso_record(self._h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def pso_commit(self, recs_dev=None, n_ranks=1, stream=None):
+        check(lib().nmrfit_pso_commit(self._h, ptr(recs_dev), int(n_ranks), ptr(stream)))
+
+    def pso_run(self, n_generations, rp_all=None, rg_all=None, stream=None):
+        rp_all = self._rand(rp_all, self._swarmsize, n_generations)
+        rg_all = self._rand(rg_all, self._swarmsize, n_generations)
+        running = ctypes.c_int(0)
+        check(lib().nmrfit_pso_run(self._h, int(n_generations), ptr(rp_all), ptr(rg_all), ctypes.byref(running),
+                                   ptr(stream)))
+        return running.value
+
+    def pso_best(self):
+        x = np.empty((self.B, self.D))
+        f = np.empty(self.B)
+        it = np.empty(self.B, dtype=np.int32)
+        stop = np.empty(self.B, dtype=np.int32)
+        check(lib().nmrfit_pso_get_best(self._h, ptr(x), ptr(f), ptr(it), ptr(stop)))
+        return x, f, it, stop
+
+    def pso_state(self):
+        S = self._swarmsize
+        out = dict(x=np.empty((self.B, S, self.D)), v=np.empty((self.B, S, self.D)), p=np.empty((self.B, S, self.D)),
+                   fx=np.empty((self.B, S)), fp=np.empty((self.B, S)))
+        check(lib().nmrfit_pso_get_state(self._h, *[ptr(out[k]) for k in ('x', 'v', 'p', 'fx', 'fp')]))
+        return out
+
+
+def fp64_peak(device=None, iters=4096, repeats=10):
+    """(burst, sustained) DFMA TFLOP/s of the device."""
+    burst, sus = ctypes.c_double(0), ctypes.c_double(0)
+    dev = default_device() if device is None else int(device)
+    check(lib().nmrfit_fp64_peak(dev, iters, repeats, ctypes.byref(burst), ctypes.byref(sus)))
+    return burst.value, sus.value
+
+
+def launch_count():
+    return int(lib().nmrfit_launch_count())

@@ -1,0 +1,555 @@
+// extern "C" surface of libnmrfit_b200.so (declared in include/nmrfit_b200.h).
+#include <cuda_runtime.h>
+#include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#include "../../include/nmrfit_b200.h"
+#include "nmrfit_internal.h"
+
+namespace nmrfit {
+std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+}
+
+using namespace nmrfit;
+
+namespace {
+
+thread_local std::string t_error;
+
+int fail(int code, const std::string& msg) {
+    t_error = msg;
+    return code;
+}
+
+int fail_cuda(cudaError_t e, const char* where) {
+    t_error = std::string(where) + ": " + cudaGetErrorName(e) + " (" + cudaGetErrorString(e) + ")";
+    return NMRFIT_ERR_CUDA;
+}
+
+#define CK(call)                                              \
+    do {                                                      \
+        cudaError_t _e = (call);                              \
+        if (_e != cudaSuccess) return fail_cuda(_e, #call);   \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* ptr = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMalloc(&ptr, n * sizeof(T));
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() {
+        if (ptr) cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+};
+
+bool is_device_pointer(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+}  // namespace
+
+struct nmrfit_ctx {
+    int device = 0, B = 0, N = 0, P = 0, D = 0, precision = 0;
+    DevBuf<double> spec;               // [B][4][N]
+    std::vector<char> spec_set;
+    DevBuf<double> partials, x_stage, f_stage;
+    ObjTune user_tune{0, 0, 0, 0};
+    // swarm
+    bool swarm = false;
+    SwarmState sw{};
+    int maxiter = 0, kk = 0, generation = 0;
+    DevBuf<double> sx, sv, sp, sfx, sfp, sg, sfg, sbx, sbf, slb, sub, srec, rnd_a, rnd_b;
+    DevBuf<int> sstop, sit;
+    int* h_flags = nullptr;            // pinned [2*B]
+};
+
+namespace {
+
+ObjTune pick_tune(const nmrfit_ctx* c, int S) {
+    ObjTune t;
+    // The point tiling fixes the summation order of the residual, so it may depend on
+    // N alone (never on how many particles or spectra a rank happens to hold).
+    if (c->N >= 8192) { t.threads = 256; t.r = 4; }
+    else if (c->N >= 1024) { t.threads = 128; t.r = 4; }
+    else { t.threads = 128; t.r = 2; }
+    t.tb = 6;
+    if (c->user_tune.threads) t.threads = c->user_tune.threads;
+    if (c->user_tune.r) t.r = c->user_tune.r;
+    if (c->user_tune.tb == -1) t.tb = 0;            // -1: polynomial-only exp
+    else if (c->user_tune.tb > 0) t.tb = c->user_tune.tb;
+    // particles per CTA: amortise the spectrum/coefficients over as many particles as
+    // still leaves >= ~4 CTAs per SM
+    int n_tiles = (c->N + t.threads * t.r - 1) / (t.threads * t.r);
+    long long ctas1 = (long long)n_tiles * S * c->B;
+    int sp = (int)std::max<long long>(1, std::min<long long>(16, ctas1 / (148 * 4)));
+    sp = std::min(sp, std::max(1, S));
+    if (c->user_tune.sp > 0) sp = std::min(c->user_tune.sp, std::max(1, S));
+    t.sp = sp;
+    return t;
+}
+
+int check_ctx(const nmrfit_ctx* c) {
+    if (!c) return fail(NMRFIT_ERR_ARG, "ctx is NULL");
+    return NMRFIT_OK;
+}
+
+int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double* f_dev, const int* frozen,
+                  cudaStream_t st) {
+    for (int b = 0; b < c->B; ++b)
+        if (!c->spec_set[b]) return fail(NMRFIT_ERR_STATE, "spectrum " + std::to_string(b) + " was never set");
+    if (fit_im < 0 || fit_im > 2) return fail(NMRFIT_ERR_ARG, "fit_im must be 0, 1 or 2");
+    ObjTune t = pick_tune(c, S);
+    int n_tiles = objective_tiles(c->N, t);
+    CK(c->partials.reserve((size_t)c->B * S * n_tiles * 2));
+    ObjArgs a;
+    a.spec = c->spec.ptr;
+    a.x = x_dev;
+    a.partials = c->partials.ptr;
+    a.frozen = frozen;
+    a.N = c->N; a.P = c->P; a.S = S; a.kk = fit_im; a.sp = t.sp;
+    cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, st)
+                                                : launch_objective(a, t, c->B, f_dev, st);
+    if (e != cudaSuccess) return fail_cuda(e, "objective launch");
+    return NMRFIT_OK;
+}
+
+// stage a [n] double array that may live on the host into `buf`; returns the device pointer to use
+int stage(const double* src, size_t n, DevBuf<double>& buf, cudaStream_t st, const double** out) {
+    if (!src) { *out = nullptr; return NMRFIT_OK; }
+    if (is_device_pointer(src)) { *out = src; return NMRFIT_OK; }
+    CK(buf.reserve(n));
+    CK(cudaMemcpyAsync(buf.ptr, src, n * sizeof(double), cudaMemcpyHostToDevice, st));
+    *out = buf.ptr;
+    return NMRFIT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nmrfit_abi_version(void) { return NMRFIT_ABI_VERSION; }
+
+const char* nmrfit_last_error(void) { return t_error.c_str(); }
+
+int nmrfit_device_count(int* count) {
+    if (!count) return fail(NMRFIT_ERR_ARG, "count is NULL");
+    CK(cudaGetDeviceCount(count));
+    return NMRFIT_OK;
+}
+
+long long nmrfit_launch_count(void) { return g_launches.load(); }
+
+int nmrfit_ctx_create(nmrfit_ctx** out, int device, int n_spectra, int n_points, int n_peaks, int precision) {
+    if (!out) return fail(NMRFIT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_spectra < 1 || n_points < 1 || n_peaks < 1) return fail(NMRFIT_ERR_ARG, "n_spectra, n_points, n_peaks must be >= 1");
+    if (n_peaks > 256) return fail(NMRFIT_ERR_ARG, "n_peaks > 256 is not supported");
+    if (precision != NMRFIT_FP64 && precision != NMRFIT_FP32) return fail(NMRFIT_ERR_ARG, "unknown precision");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(NMRFIT_ERR_ARG, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    nmrfit_ctx* c = new (std::nothrow) nmrfit_ctx();
+    if (!c) return fail(NMRFIT_ERR_NOMEM, "out of host memory");
+    c->device = device; c->B = n_spectra; c->N = n_points; c->P = n_peaks; c->D = 4 + 3 * n_peaks;
+    c->precision = precision;
+    c->spec_set.assign(n_spectra, 0);
+    cudaError_t e = c->spec.reserve((size_t)n_spectra * 4 * n_points);
+    if (e == cudaSuccess) e = cudaMallocHost(&c->h_flags, sizeof(int) * 2 * n_spectra);
+    if (e != cudaSuccess) {
+        nmrfit_ctx_destroy(c);
+        return fail_cuda(e, "ctx allocation");
+    }
+    *out = c;
+    return NMRFIT_OK;
+}
+
+void nmrfit_ctx_destroy(nmrfit_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    for (DevBuf<double>* b : {&c->spec, &c->partials, &c->x_stage, &c->f_stage, &c->sx, &c->sv, &c->sp, &c->sfx,
+                              &c->sfp, &c->sg, &c->sfg, &c->sbx, &c->sbf, &c->slb, &c->sub, &c->srec, &c->rnd_a,
+                              &c->rnd_b})
+        b->release();
+    c->sstop.release();
+    c->sit.release();
+    if (c->h_flags) cudaFreeHost(c->h_flags);
+    delete c;
+}
+
+int nmrfit_ctx_set_spectrum(nmrfit_ctx* c, int b, const double* w, const double* u, const double* v,
+                            const double* weights) {
+    if (int r = check_ctx(c)) return r;
+    if (b < 0 || b >= c->B) return fail(NMRFIT_ERR_ARG, "spectrum index out of range");
+    if (!w || !u || !v || !weights) return fail(NMRFIT_ERR_ARG, "w, u, v, weights must be non-NULL");
+    CK(cudaSetDevice(c->device));
+    double* dst = c->spec.ptr + (size_t)b * 4 * c->N;
+    const double* src[4] = {w, u, v, weights};
+    for (int k = 0; k < 4; ++k)
+        CK(cudaMemcpy(dst + (size_t)k * c->N, src[k], sizeof(double) * c->N, cudaMemcpyDefault));
+    c->spec_set[b] = 1;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_set_tuning(nmrfit_ctx* c, int threads, int r, int tb, int sp) {
+    if (int rc = check_ctx(c)) return rc;
+    if (threads != 0 && threads != 128 && threads != 256) return fail(NMRFIT_ERR_ARG, "threads must be 0, 128 or 256");
+    if (r != 0 && r != 2 && r != 4 && r != 8) return fail(NMRFIT_ERR_ARG, "points_per_thread must be 0, 2, 4 or 8");
+    if (tb != 0 && tb != 6 && tb != 8 && tb != 10 && tb != -1)
+        return fail(NMRFIT_ERR_ARG, "exp_table_bits must be 0 (auto), -1 (no table), 6, 8 or 10");
+    if (sp < 0 || sp > 64) return fail(NMRFIT_ERR_ARG, "particles_per_cta must be 0..64");
+    c->user_tune = ObjTune{threads, r, tb, sp};
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_get_tuning(nmrfit_ctx* c, int S, int* threads, int* r, int* tb, int* sp, int* n_tiles) {
+    if (int rc = check_ctx(c)) return rc;
+    ObjTune t = pick_tune(c, S < 1 ? 1 : S);
+    if (threads) *threads = t.threads;
+    if (r) *r = t.r;
+    if (tb) *tb = t.tb;
+    if (sp) *sp = t.sp;
+    if (n_tiles) *n_tiles = objective_tiles(c->N, t);
+    return NMRFIT_OK;
+}
+
+int nmrfit_objective_batch(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double* f_dev, void* stream) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!x_dev || !f_dev) return fail(NMRFIT_ERR_ARG, "x_dev and f_dev must be non-NULL");
+    if (S < 1) return fail(NMRFIT_ERR_ARG, "n_particles must be >= 1");
+    CK(cudaSetDevice(c->device));
+    return run_objective(c, x_dev, S, fit_im, f_dev, nullptr, (cudaStream_t)stream);
+}
+
+int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int fit_im, double* f_host) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!x_host || !f_host) return fail(NMRFIT_ERR_ARG, "x_host and f_host must be non-NULL");
+    if (S < 1) return fail(NMRFIT_ERR_ARG, "n_particles must be >= 1");
+    CK(cudaSetDevice(c->device));
+    size_t nx = (size_t)c->B * S * c->D, nf = (size_t)c->B * S;
+    CK(c->x_stage.reserve(nx));
+    CK(c->f_stage.reserve(nf));
+    cudaStream_t st = 0;
+    CK(cudaMemcpyAsync(c->x_stage.ptr, x_host, nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (int rc = run_objective(c, c->x_stage.ptr, S, fit_im, c->f_stage.ptr, nullptr, st)) return rc;
+    CK(cudaMemcpyAsync(f_host, c->f_stage.ptr, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return NMRFIT_OK;
+}
+
+// ---- swarm ---------------------------------------------------------------------------------------
+
+int nmrfit_pso_begin(nmrfit_ctx* c, const double* lb, const double* ub, const nmrfit_pso_opts* o, const double* r_pos,
+                     const double* r_vel, void* stream) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!lb || !ub || !o) return fail(NMRFIT_ERR_ARG, "lb, ub and opts must be non-NULL");
+    if (o->swarmsize < 1) return fail(NMRFIT_ERR_ARG, "swarmsize must be >= 1");
+    if (o->maxiter < 0) return fail(NMRFIT_ERR_ARG, "maxiter must be >= 0");
+    if (o->fit_im < 0 || o->fit_im > 2) return fail(NMRFIT_ERR_ARG, "fit_im must be 0, 1 or 2");
+    const int B = c->B, S = o->swarmsize, D = c->D;
+    const int nb = o->bounds_per_spectrum ? B : 1;
+    for (int i = 0; i < nb * D; ++i)      // pyswarm: assert np.all(ub > lb)
+        if (!(ub[i] > lb[i])) return fail(NMRFIT_ERR_ARG, "All upper-bound values must be greater than lower-bound values");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    size_t nsd = (size_t)B * S * D, ns = (size_t)B * S;
+    CK(c->sx.reserve(nsd)); CK(c->sv.reserve(nsd)); CK(c->sp.reserve(nsd));
+    CK(c->sfx.reserve(ns)); CK(c->sfp.reserve(ns));
+    CK(c->sg.reserve((size_t)B * D)); CK(c->sfg.reserve(B)); CK(c->sbx.reserve((size_t)B * D)); CK(c->sbf.reserve(B));
+    CK(c->slb.reserve((size_t)B * D)); CK(c->sub.reserve((size_t)B * D)); CK(c->srec.reserve((size_t)B * (D + 2)));
+    CK(c->sstop.reserve(B)); CK(c->sit.reserve(B));
+    std::vector<double> hl((size_t)B * D), hu((size_t)B * D);
+    for (int b = 0; b < B; ++b)
+        for (int d = 0; d < D; ++d) {
+            hl[(size_t)b * D + d] = lb[(o->bounds_per_spectrum ? (size_t)b * D : 0) + d];
+            hu[(size_t)b * D + d] = ub[(o->bounds_per_spectrum ? (size_t)b * D : 0) + d];
+        }
+    CK(cudaMemcpyAsync(c->slb.ptr, hl.data(), hl.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(c->sub.ptr, hu.data(), hu.size() * sizeof(double), cudaMemcpyHostToDevice, st));
+    CK(cudaStreamSynchronize(st));      // hl/hu go out of scope
+    CK(cudaMemsetAsync(c->sstop.ptr, 0, sizeof(int) * B, st));
+    CK(cudaMemsetAsync(c->sit.ptr, 0, sizeof(int) * B, st));
+    SwarmState& s = c->sw;
+    s.B = B; s.S = S; s.D = D;
+    s.x = c->sx.ptr; s.v = c->sv.ptr; s.p = c->sp.ptr; s.fx = c->sfx.ptr; s.fp = c->sfp.ptr;
+    s.g = c->sg.ptr; s.fg = c->sfg.ptr; s.best_x = c->sbx.ptr; s.best_f = c->sbf.ptr;
+    s.lb = c->slb.ptr; s.ub = c->sub.ptr; s.rec = c->srec.ptr; s.stop = c->sstop.ptr; s.it = c->sit.ptr;
+    s.omega = o->omega; s.phip = o->phip; s.phig = o->phig; s.minstep = o->minstep; s.minfunc = o->minfunc;
+    s.seed = o->seed; s.index0 = o->particle_offset;
+    c->maxiter = o->maxiter; c->kk = o->fit_im; c->generation = 0; c->swarm = true;
+
+    const double *rp_d = nullptr, *rv_d = nullptr;
+    if (int rc = stage(r_pos, nsd, c->rnd_a, st, &rp_d)) return rc;
+    if (int rc = stage(r_vel, nsd, c->rnd_b, st, &rv_d)) return rc;
+    cudaError_t e = launch_swarm_init(s, rp_d, nullptr, st);
+    if (e == cudaSuccess) e = launch_swarm_init_velocity(s, rv_d, st);
+    if (e != cudaSuccess) return fail_cuda(e, "swarm init");
+    if (int rc = run_objective(c, s.x, S, c->kk, s.fx, nullptr, st)) return rc;
+    e = launch_swarm_local_best(s, s.rec, st);
+    if (e != cudaSuccess) return fail_cuda(e, "swarm local best");
+    return NMRFIT_OK;
+}
+
+int nmrfit_pso_advance(nmrfit_ctx* c, const double* rp, const double* rg, void* stream) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    if ((rp == nullptr) != (rg == nullptr)) return fail(NMRFIT_ERR_ARG, "rp and rg must both be given or both be NULL");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SwarmState& s = c->sw;
+    size_t nsd = (size_t)s.B * s.S * s.D;
+    const double *rp_d = nullptr, *rg_d = nullptr;
+    if (int rc = stage(rp, nsd, c->rnd_a, st, &rp_d)) return rc;
+    if (int rc = stage(rg, nsd, c->rnd_b, st, &rg_d)) return rc;
+    c->generation += 1;
+    cudaError_t e = launch_swarm_move(s, rp_d, rg_d, c->generation, st);
+    if (e != cudaSuccess) return fail_cuda(e, "swarm move");
+    if (int rc = run_objective(c, s.x, s.S, c->kk, s.fx, s.stop, st)) return rc;
+    e = launch_swarm_local_best(s, s.rec, st);
+    if (e != cudaSuccess) return fail_cuda(e, "swarm local best");
+    return NMRFIT_OK;
+}
+
+int nmrfit_pso_record(nmrfit_ctx* c, double** rec_dev, int* n_doubles) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    if (rec_dev) *rec_dev = c->sw.rec;
+    if (n_doubles) *n_doubles = c->B * (c->D + 2);
+    return NMRFIT_OK;
+}
+
+int nmrfit_pso_commit(nmrfit_ctx* c, const double* recs_dev, int n_ranks, void* stream) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    if (recs_dev && n_ranks < 1) return fail(NMRFIT_ERR_ARG, "n_ranks must be >= 1");
+    CK(cudaSetDevice(c->device));
+    const double* recs = recs_dev ? recs_dev : c->sw.rec;
+    cudaError_t e = launch_swarm_commit(c->sw, recs, recs_dev ? n_ranks : 1, c->generation == 0, c->maxiter,
+                                        (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "swarm commit");
+    return NMRFIT_OK;
+}
+
+int nmrfit_pso_run(nmrfit_ctx* c, int n_generations, const double* rp_all, const double* rg_all, int* n_running,
+                   void* stream) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    if ((rp_all == nullptr) != (rg_all == nullptr)) return fail(NMRFIT_ERR_ARG, "rp_all and rg_all must both be given or both be NULL");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SwarmState& s = c->sw;
+    size_t nsd = (size_t)s.B * s.S * s.D;
+    const double *rp_d = nullptr, *rg_d = nullptr;
+    if (n_generations > 0) {
+        if (int rc = stage(rp_all, nsd * n_generations, c->rnd_a, st, &rp_d)) return rc;
+        if (int rc = stage(rg_all, nsd * n_generations, c->rnd_b, st, &rg_d)) return rc;
+    }
+    for (int k = 0; k < n_generations; ++k) {
+        c->generation += 1;
+        cudaError_t e = launch_swarm_move(s, rp_d ? rp_d + nsd * k : nullptr, rg_d ? rg_d + nsd * k : nullptr,
+                                          c->generation, st);
+        if (e != cudaSuccess) return fail_cuda(e, "swarm move");
+        if (int rc = run_objective(c, s.x, s.S, c->kk, s.fx, s.stop, st)) return rc;
+        e = launch_swarm_local_best(s, s.rec, st);
+        if (e == cudaSuccess) e = launch_swarm_commit(s, s.rec, 1, 0, c->maxiter, st);
+        if (e != cudaSuccess) return fail_cuda(e, "swarm best");
+    }
+    CK(cudaMemcpyAsync(c->h_flags, s.stop, sizeof(int) * s.B, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int running = 0;
+    for (int b = 0; b < s.B; ++b) running += c->h_flags[b] == 0;
+    if (n_running) *n_running = running;
+    return NMRFIT_OK;
+}
+
+int nmrfit_pso_get_best(nmrfit_ctx* c, double* x_best, double* f_best, int* generations, int* stop_reason) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    const SwarmState& s = c->sw;
+    if (x_best) CK(cudaMemcpy(x_best, s.best_x, sizeof(double) * s.B * s.D, cudaMemcpyDeviceToHost));
+    if (f_best) CK(cudaMemcpy(f_best, s.best_f, sizeof(double) * s.B, cudaMemcpyDeviceToHost));
+    if (generations) CK(cudaMemcpy(generations, s.it, sizeof(int) * s.B, cudaMemcpyDeviceToHost));
+    if (stop_reason) CK(cudaMemcpy(stop_reason, s.stop, sizeof(int) * s.B, cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
+}
+
+int nmrfit_pso_get_state(nmrfit_ctx* c, double* x, double* v, double* p, double* fx, double* fp) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    CK(cudaSetDevice(c->device));
+    CK(cudaDeviceSynchronize());
+    const SwarmState& s = c->sw;
+    size_t nsd = sizeof(double) * s.B * s.S * s.D, ns = sizeof(double) * s.B * s.S;
+    if (x) CK(cudaMemcpy(x, s.x, nsd, cudaMemcpyDeviceToHost));
+    if (v) CK(cudaMemcpy(v, s.v, nsd, cudaMemcpyDeviceToHost));
+    if (p) CK(cudaMemcpy(p, s.p, nsd, cudaMemcpyDeviceToHost));
+    if (fx) CK(cudaMemcpy(fx, s.fx, ns, cudaMemcpyDeviceToHost));
+    if (fp) CK(cudaMemcpy(fp, s.fp, ns, cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
+}
+
+// ---- curves --------------------------------------------------------------------------------------
+
+int nmrfit_ps2(const double* u, const double* v, int n, double p0, double p1, int inv, double* re, double* im,
+               void* stream) {
+    if (n < 0 || (n > 0 && (!u || !v || !re || !im))) return fail(NMRFIT_ERR_ARG, "bad ps2 arguments");
+    cudaError_t e = launch_ps2(u, v, n, p0, p1, inv, re, im, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "ps2 launch");
+    return NMRFIT_OK;
+}
+
+int nmrfit_voigt(const double* w, int n, double r, double yoff, double width, double loc, double a, double* out,
+                 void* stream) {
+    if (n < 0 || (n > 0 && (!w || !out))) return fail(NMRFIT_ERR_ARG, "bad voigt arguments");
+    cudaError_t e = launch_voigt(w, n, r, yoff, width, loc, a, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "voigt launch");
+    return NMRFIT_OK;
+}
+
+int nmrfit_kk(const double* w, int n, double r, double yoff, double width, double loc, double a, double* out,
+              void* stream) {
+    (void)yoff;   // cancels in the Kramers-Kronig integrand (equations.py:40,45,48)
+    if (n < 0 || (n > 0 && (!w || !out))) return fail(NMRFIT_ERR_ARG, "bad kk arguments");
+    cudaError_t e = launch_kk(w, n, r, width, loc, a, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return fail_cuda(e, "kk launch");
+    return NMRFIT_OK;
+}
+
+int nmrfit_generate_result(const double* params, int P, const double* w, int n, double* real, double* imag, double* V,
+                           double* I, double* u, double* v, void* stream) {
+    if (!params || P < 1 || n < 0) return fail(NMRFIT_ERR_ARG, "bad generate_result arguments");
+    if (n > 0 && (!w || !real || !imag || !V || !I || !u || !v)) return fail(NMRFIT_ERR_ARG, "NULL output buffer");
+    if (n == 0) return NMRFIT_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    double* pd = nullptr;
+    const int D = 4 + 3 * P;
+    CK(cudaMallocAsync(&pd, sizeof(double) * D, st));
+    CK(cudaMemcpyAsync(pd, params, sizeof(double) * D, cudaMemcpyHostToDevice, st));
+    cudaError_t e = launch_generate_result(pd, P, w, n, real, imag, V, I, u, v, st);
+    cudaFreeAsync(pd, st);
+    if (e != cudaSuccess) return fail_cuda(e, "generate_result launch");
+    return NMRFIT_OK;
+}
+
+// host-staged variants: allocate, copy in, run, copy out, free
+namespace {
+struct Scratch {
+    std::vector<double*> ptrs;
+    ~Scratch() { for (double* p : ptrs) cudaFree(p); }
+    cudaError_t get(size_t n, double** out) {
+        cudaError_t e = cudaMalloc(out, std::max<size_t>(n, 1) * sizeof(double));
+        if (e == cudaSuccess) ptrs.push_back(*out);
+        return e;
+    }
+};
+}  // namespace
+
+int nmrfit_ps2_host(int device, const double* u, const double* v, int n, double p0, double p1, int inv, double* re,
+                    double* im) {
+    if (n < 0 || (n > 0 && (!u || !v || !re || !im))) return fail(NMRFIT_ERR_ARG, "bad ps2 arguments");
+    if (n == 0) return NMRFIT_OK;
+    CK(cudaSetDevice(device));
+    Scratch s;
+    double *du, *dv, *dr, *di;
+    CK(s.get(n, &du)); CK(s.get(n, &dv)); CK(s.get(n, &dr)); CK(s.get(n, &di));
+    CK(cudaMemcpy(du, u, sizeof(double) * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dv, v, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (int rc = nmrfit_ps2(du, dv, n, p0, p1, inv, dr, di, nullptr)) return rc;
+    CK(cudaMemcpy(re, dr, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(im, di, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
+}
+
+int nmrfit_voigt_host(int device, const double* w, int n, double r, double yoff, double width, double loc, double a,
+                      double* out) {
+    if (n < 0 || (n > 0 && (!w || !out))) return fail(NMRFIT_ERR_ARG, "bad voigt arguments");
+    if (n == 0) return NMRFIT_OK;
+    CK(cudaSetDevice(device));
+    Scratch s;
+    double *dw, *dout;
+    CK(s.get(n, &dw)); CK(s.get(n, &dout));
+    CK(cudaMemcpy(dw, w, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (int rc = nmrfit_voigt(dw, n, r, yoff, width, loc, a, dout, nullptr)) return rc;
+    CK(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
+}
+
+int nmrfit_kk_host(int device, const double* w, int n, double r, double yoff, double width, double loc, double a,
+                   double* out) {
+    if (n < 0 || (n > 0 && (!w || !out))) return fail(NMRFIT_ERR_ARG, "bad kk arguments");
+    if (n == 0) return NMRFIT_OK;
+    CK(cudaSetDevice(device));
+    Scratch s;
+    double *dw, *dout;
+    CK(s.get(n, &dw)); CK(s.get(n, &dout));
+    CK(cudaMemcpy(dw, w, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (int rc = nmrfit_kk(dw, n, r, yoff, width, loc, a, dout, nullptr)) return rc;
+    CK(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
+}
+
+int nmrfit_generate_result_host(int device, const double* params, int P, const double* w, int n, double* real,
+                                double* imag, double* V, double* I, double* u, double* v) {
+    if (!params || P < 1 || n < 0) return fail(NMRFIT_ERR_ARG, "bad generate_result arguments");
+    if (n > 0 && (!w || !real || !imag || !V || !I || !u || !v)) return fail(NMRFIT_ERR_ARG, "NULL output buffer");
+    if (n == 0) return NMRFIT_OK;
+    CK(cudaSetDevice(device));
+    Scratch s;
+    double *dw, *dreal, *dimag, *dV, *dI, *du, *dv;
+    size_t pn = (size_t)P * n;
+    CK(s.get(n, &dw)); CK(s.get(pn, &dreal)); CK(s.get(pn, &dimag));
+    CK(s.get(n, &dV)); CK(s.get(n, &dI)); CK(s.get(n, &du)); CK(s.get(n, &dv));
+    CK(cudaMemcpy(dw, w, sizeof(double) * n, cudaMemcpyHostToDevice));
+    if (int rc = nmrfit_generate_result(params, P, dw, n, dreal, dimag, dV, dI, du, dv, nullptr)) return rc;
+    CK(cudaMemcpy(real, dreal, sizeof(double) * pn, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(imag, dimag, sizeof(double) * pn, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(V, dV, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(I, dI, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(u, du, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(v, dv, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
+}
+
+int nmrfit_fp64_peak(int device, int iters, int repeats, double* burst, double* sustained) {
+    if (!burst || !sustained || iters < 1 || repeats < 1) return fail(NMRFIT_ERR_ARG, "bad probe arguments");
+    CK(cudaSetDevice(device));
+    cudaError_t e = fp64_peak_probe(iters, repeats, burst, sustained, nullptr);
+    if (e != cudaSuccess) return fail_cuda(e, "fp64 probe");
+    return NMRFIT_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// K4/K5: curve evaluation on a grid - the pieces FitUtility.generate_result strings
+// together on the host in the reference (utils.py:226-295), plus the standalone
+// ps2 / voigt / Kramers-Kronig entry points that stay importable from Python.
+//
+// The Kramers-Kronig counterpart (reference equations.py:9-80: adaptive quadrature
+// of [V(w-x) - V(w+x)]/x over [0, inf), ~6.6 ms per grid point on a CPU core) is
+// evaluated in closed form: the Hilbert transform of the Lorentzian is the
+// dispersion Lorentzian t/(1+t^2), that of the Gaussian is (2/sqrt(pi)) Dawson(s);
+// yoff cancels in the integrand.
+//
+// generate_result is bound by HBM writes: (2P + 4) doubles out and 1 double in per
+// grid point ((2*24+5)*8 B * 262,144 = 111 MB at BASELINE config 5).
+#include <cuda_runtime.h>
+#include "nmrfit_internal.h"
+#include "nmrfit_math.cuh"
+
+namespace nmrfit {
+
+// phi_i = p0 + (p1*i)/n  (proc_autophase.py:30-31); forward: (u + iv) e^{i phi}; inverse: (u + iv) e^{-i phi}
+__global__ void ps2_kernel(const double* __restrict__ u, const double* __restrict__ v, int n, double p0, double p1,
+                           int inv, double* __restrict__ re, double* __restrict__ im) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double sn, cs;
+    sincos(p0 + (p1 * (double)i) / (double)n, &sn, &cs);
+    if (inv) sn = -sn;
+    double a = u[i], b = v[i];
+    re[i] = a * cs - b * sn;
+    im[i] = a * sn + b * cs;
+}
+
+__device__ __forceinline__ double body_real(const PeakCoef& c, double w) {
+    double d = w - c.loc, d2 = d * d;
+    double rq = rcp_pos(fma(d2, c.kL2, 1.0));
+    return fma(c.aG, exp_neg<0>(d2 * c.nkG2, nullptr), c.aL * rq);
+}
+
+__device__ __forceinline__ double body_imag(const PeakCoef& c, double kL, double kG, double w) {
+    double d = w - c.loc;
+    double rq = rcp_pos(fma(d * d, c.kL2, 1.0));
+    double daw = dawson(d * kG, NMRFIT_DAW_TAB, NMRFIT_DAW_TAIL);
+    return fma(c.aL * (d * kL), rq, (c.aG * kTwoOverSqrtPi) * daw);
+}
+
+__global__ void voigt_kernel(const double* __restrict__ w, int n, double r, double yoff, double width, double loc,
+                             double a, double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PeakCoef c = make_coef(r, width, loc, a);
+    out[i] = yoff + body_real(c, w[i]);
+}
+
+__global__ void kk_kernel(const double* __restrict__ w, int n, double r, double width, double loc, double a,
+                          double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    PeakCoef c = make_coef(r, width, loc, a);
+    double iw = 2.0 / width;
+    out[i] = body_imag(c, iw, iw * kSqrtLn2, w[i]);
+}
+
+// one thread per grid point, all peaks; every store is coalesced along the grid
+constexpr int kGenThreads = 256;
+constexpr int kGenMaxPeaks = 256;
+__global__ void __launch_bounds__(kGenThreads)
+generate_result_kernel(const double* __restrict__ params, int P, const double* __restrict__ w, int n,
+                       double* __restrict__ real, double* __restrict__ imag, double* __restrict__ V,
+                       double* __restrict__ I, double* __restrict__ u, double* __restrict__ v) {
+    extern __shared__ __align__(16) double sm[];   // [P][8]
+    const double p0 = params[0], p1 = params[1], r = params[2], yoff = params[3];
+    for (int k = threadIdx.x; k < P; k += kGenThreads) {
+        double width = params[4 + 3 * k], loc = params[5 + 3 * k], a = params[6 + 3 * k];
+        PeakCoef c = make_coef(r, width, loc, a);
+        double iw = 2.0 / width;
+        double* o = sm + k * 8;
+        o[0] = c.loc; o[1] = c.kL2; o[2] = c.aL; o[3] = c.nkG2; o[4] = c.aG; o[5] = iw; o[6] = iw * kSqrtLn2; o[7] = 0;
+    }
+    __syncthreads();
+    int i = blockIdx.x * kGenThreads + threadIdx.x;
+    if (i >= n) return;
+    const double wi = w[i];
+    double vs = 0.0, is = 0.0;
+    for (int k = 0; k < P; ++k) {
+        const double* o = sm + k * 8;
+        PeakCoef c;
+        c.loc = o[0]; c.kL2 = o[1]; c.aL = o[2]; c.nkG2 = o[3]; c.aG = o[4];
+        double re = yoff + body_real(c, wi);        // utils.py:267: every contribution carries yoff
+        double im = body_imag(c, o[5], o[6], wi);
+        real[(size_t)k * n + i] = re;
+        imag[(size_t)k * n + i] = im;
+        vs += re;                                    // utils.py:276-277: both sums accumulate
+        is += im;
+    }
+    V[i] = vs;
+    I[i] = is;
+    double sn, cs;
+    sincos(p0 + (p1 * (double)i) / (double)n, &sn, &cs);   // utils.py:284: ramp over the UPSAMPLED length
+    u[i] = vs * cs + is * sn;
+    v[i] = is * cs - vs * sn;
+}
+
+cudaError_t launch_ps2(const double* u, const double* v, int n, double p0, double p1, int inv, double* re, double* im,
+                       cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    count_launches(1);
+    ps2_kernel<<<(n + 255) / 256, 256, 0, st>>>(u, v, n, p0, p1, inv, re, im);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_voigt(const double* w, int n, double r, double yoff, double width, double loc, double a, double* out,
+                         cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    count_launches(1);
+    voigt_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, n, r, yoff, width, loc, a, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_kk(const double* w, int n, double r, double width, double loc, double a, double* out,
+                      cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    count_launches(1);
+    kk_kernel<<<(n + 255) / 256, 256, 0, st>>>(w, n, r, width, loc, a, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_generate_result(const double* params_dev, int P, const double* w, int n, double* real,
+                                   double* imag, double* V, double* I, double* u, double* v, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    if (P > kGenMaxPeaks) return cudaErrorInvalidValue;
+    count_launches(1);
+    generate_result_kernel<<<(n + kGenThreads - 1) / kGenThreads, kGenThreads, (size_t)P * 8 * sizeof(double), st>>>(
+        params_dev, P, w, n, real, imag, V, I, u, v);
+    return cudaGetLastError();
+}
+
+}  // namespace nmrfit

@@ -1,0 +1,72 @@
+// Internal declarations shared by the translation units of libnmrfit_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+
+#define NMRFIT_MAX_DEVICES 16
+
+namespace nmrfit {
+
+void count_launches(int n);   // bookkeeping for nmrfit_launch_count()
+
+// ---- K1 objective -------------------------------------------------------------
+struct ObjArgs {
+    const double* spec;     // [B][4][N]: w, u, v, weights
+    const double* x;        // [B][S][D] particle positions, D = 4 + 3P
+    double* partials;       // [B][S][n_tiles][nsum]
+    const int* frozen;      // [B] or null: spectra whose swarm has stopped are skipped
+    int N, P, S;
+    int kk;                 // 0 real only, 1 reference fit_im (last peak), 2 sum over peaks
+    int sp;                 // particles per CTA (filled by the launcher)
+};
+
+struct ObjTune {
+    int threads;            // 128 | 256
+    int r;                  // grid points per thread: 2 | 4 | 8
+    int tb;                 // exp table bits: 0 | 6 | 8 | 10
+    int sp;                 // particles per CTA
+};
+
+int objective_tiles(int N, const ObjTune& t);
+size_t objective_smem_bytes(int P, const ObjTune& t, int kk);
+cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st);
+
+// opt-in FP32 objective (same launch geometry)
+cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st);
+
+// ---- K2/K3 swarm --------------------------------------------------------------
+struct SwarmState {
+    int B, S, D;
+    double *x, *v, *p;      // [B][S][D]
+    double *fx, *fp;        // [B][S]
+    double *g, *fg;         // [B][D], [B]   running global best
+    double *best_x, *best_f;// [B][D], [B]   what pso() returns (p_min on an early stop)
+    double *lb, *ub;        // [B][D]
+    double *rec;            // [B][D+2] local best record: f, global index, position
+    int *stop, *it;         // [B] stop reason (0 running), generation counter
+    double omega, phip, phig, minstep, minfunc;
+    unsigned long long seed;
+    long long index0;       // global index of local particle 0 (particle sharding)
+};
+
+cudaError_t launch_swarm_init(const SwarmState& s, const double* r_pos, const double* r_vel, cudaStream_t st);
+cudaError_t launch_swarm_init_velocity(const SwarmState& s, const double* r_vel, cudaStream_t st);
+cudaError_t launch_swarm_move(const SwarmState& s, const double* rp, const double* rg, int generation, cudaStream_t st);
+cudaError_t launch_swarm_local_best(const SwarmState& s, double* rec, cudaStream_t st);
+cudaError_t launch_swarm_commit(const SwarmState& s, const double* recs, int n_ranks, int initial, int maxiter,
+                                cudaStream_t st);
+
+// ---- K4/K5 curves -------------------------------------------------------------
+cudaError_t launch_ps2(const double* u, const double* v, int n, double p0, double p1, int inv, double* re, double* im,
+                       cudaStream_t st);
+cudaError_t launch_voigt(const double* w, int n, double r, double yoff, double width, double loc, double a, double* out,
+                         cudaStream_t st);
+cudaError_t launch_kk(const double* w, int n, double r, double width, double loc, double a, double* out,
+                      cudaStream_t st);
+cudaError_t launch_generate_result(const double* params_dev, int P, const double* w, int n, double* real,
+                                   double* imag, double* V, double* I, double* u, double* v, cudaStream_t st);
+
+// ---- probes -------------------------------------------------------------------
+cudaError_t fp64_peak_probe(int iters, int repeats, double* tflops, double* sustained, cudaStream_t st);
+
+}  // namespace nmrfit

@@ -1,0 +1,221 @@
+// Device math for the Voigt / Kramers-Kronig lineshapes (sm_100a).
+//
+// Everything the inner loops evaluate lives here so that it can also be compiled
+// for the host (tests/host_math_harness.cpp defines NMRFIT_HOST_MATH and empties
+// the CUDA qualifiers) and checked against libm/mpmath without a GPU.  The host
+// build exists only for those accuracy tests; the product never runs it.
+//
+// Cost accounting (FP64-pipe issue slots; DFMA/DMUL/DADD = 1 slot each):
+//   rcp_pos      3 slots + 1 MUFU.RCP64H
+//   exp_neg<0>   15 slots   (degree-11 polynomial, no table)
+//   exp_neg<6>    9 slots   (64-entry 2^(j/64) table in shared memory, degree 5)
+//   exp_neg<8>    8 slots   (256-entry table, degree 4)
+//   exp_neg<10>   7 slots   (1024-entry table, degree 3)
+#pragma once
+#include "nmrfit_coeffs.cuh"
+
+#ifdef NMRFIT_HOST_MATH
+#include <cmath>
+#include <cstring>
+#include <cstdint>
+#define NMRFIT_HD inline
+static inline int nmrfit_hi(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b >> 32); }
+static inline int nmrfit_lo(double x) { int64_t b; std::memcpy(&b, &x, 8); return (int)(b & 0xffffffff); }
+static inline double nmrfit_mk(int hi, int lo) {
+    int64_t b = ((int64_t)hi << 32) | (uint32_t)lo; double x; std::memcpy(&x, &b, 8); return x;
+}
+static inline double nmrfit_rcp_seed(double q) {
+    // emulate MUFU.RCP64H: only the high word of the operand is seen and only a
+    // high word is produced (20 mantissa bits each way)
+    double t = 1.0 / nmrfit_mk(nmrfit_hi(q), 0);
+    return nmrfit_mk(nmrfit_hi(t), 0);
+}
+#define NMRFIT_FMA(a, b, c) std::fma((a), (b), (c))
+#else
+#define NMRFIT_HD __device__ __forceinline__
+__device__ __forceinline__ int nmrfit_hi(double x) { return __double2hiint(x); }
+__device__ __forceinline__ int nmrfit_lo(double x) { return __double2loint(x); }
+__device__ __forceinline__ double nmrfit_mk(int hi, int lo) { return __hiloint2double(hi, lo); }
+__device__ __forceinline__ double nmrfit_rcp_seed(double q) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+    return y;
+}
+#define NMRFIT_FMA(a, b, c) fma((a), (b), (c))
+#endif
+
+namespace nmrfit {
+
+constexpr double kPi = 3.14159265358979323846;
+constexpr double kLn2 = 0.69314718055994530942;
+constexpr double kSqrtLn2 = 0.83255461115769775635;          // sqrt(ln 2)
+constexpr double kSqrtLn2OverPi = 0.46971863934982566689;    // sqrt(ln 2 / pi)
+constexpr double kTwoOverSqrtPi = 1.12837916709551257390;    // 2 / sqrt(pi)
+constexpr double kMagic = 6755399441055744.0;                // 1.5 * 2^52: round-to-nearest-int shifter
+constexpr int kExpClampHi = (int)0xC085E000;                 // high word of -700.0
+
+// 1/q for q >= 1 (the Lorentzian denominator 1 + t^2).  One MUFU seed with
+// ~2^-20 relative error, then a cubic correction y0*(1 + e + e^2), e = 1 - q*y0:
+// error ~ e^3 < 2^-57.
+NMRFIT_HD double rcp_pos(double q) {
+    double y0 = nmrfit_rcp_seed(q);
+    double e = NMRFIT_FMA(-q, y0, 1.0);
+    double g = NMRFIT_FMA(e, e, e);
+    return NMRFIT_FMA(g, y0, y0);
+}
+
+template <int TB> struct ExpPoly;
+template <> struct ExpPoly<0> {
+    static NMRFIT_HD double eval(double r) {   // (e^r - 1)/r, degree 10
+        double p = NMRFIT_EXP_T0_C10;
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C9);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C8);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C7);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C6);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C5);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C4);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C3);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C2);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C1);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T0_C0);
+        return p;
+    }
+};
+template <> struct ExpPoly<6> {
+    static NMRFIT_HD double eval(double r) {
+        double p = NMRFIT_EXP_T6_C4;
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C3);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C2);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C1);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C0);
+        return p;
+    }
+};
+template <> struct ExpPoly<8> {
+    static NMRFIT_HD double eval(double r) {
+        double p = NMRFIT_EXP_T8_C3;
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T8_C2);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T8_C1);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T8_C0);
+        return p;
+    }
+};
+template <> struct ExpPoly<10> {
+    static NMRFIT_HD double eval(double r) {
+        double p = NMRFIT_EXP_T10_C2;
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T10_C1);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T10_C0);
+        return p;
+    }
+};
+
+// exp(x) for x <= 0.  Arguments below -700 are clamped there (exp(-700) ~ 1e-304
+// is zero for every purpose of a sum of peaks); the clamp is an unsigned min on
+// the high word, i.e. integer-pipe work, not an FP64 slot.
+//   n = rint(x * 2^TB / ln2);  r = x - n * ln2/2^TB  (one FMA: n*ln2/2^TB is not
+//   exact, but its error n*ulp(ln2/2^TB)/2 is < 1e-16 * |x| and enters the result
+//   only as a relative error of exp(x), which is itself < e^x <= 1)
+//   exp(x) = 2^(n >> TB) * tab[n & (2^TB-1)] * (1 + r*P(r))
+template <int TB>
+NMRFIT_HD double exp_neg(double x, const double* __restrict__ tab) {
+    unsigned hi = (unsigned)nmrfit_hi(x);
+    hi = hi < (unsigned)kExpClampHi ? hi : (unsigned)kExpClampHi;
+    x = nmrfit_mk((int)hi, nmrfit_lo(x));
+    constexpr double scale = (double)(1 << TB) / kLn2;
+    constexpr double step = kLn2 / (double)(1 << TB);
+    double t = NMRFIT_FMA(x, scale, kMagic);
+    int n = nmrfit_lo(t);
+    double nd = t - kMagic;
+    double r = NMRFIT_FMA(nd, -step, x);
+    double p = ExpPoly<TB>::eval(r);
+    double res;
+    if (TB == 0) {
+        res = NMRFIT_FMA(p, r, 1.0);
+    } else {
+        double tj = tab[n & ((1 << TB) - 1)];
+        res = NMRFIT_FMA(tj * r, p, tj);
+    }
+    int q = n >> TB;   // arithmetic shift: floor division for negative n
+    return nmrfit_mk(nmrfit_hi(res) + (q << 20), nmrfit_lo(res));
+}
+
+// Dawson's integral F(s) = exp(-s^2) * int_0^s exp(t^2) dt, any real s (odd).
+// Piecewise degree-12 polynomials on |s| < 8 (table read through the read-only
+// path: lanes sit in different intervals), asymptotic form beyond.
+NMRFIT_HD double dawson(double s, const double* __restrict__ core, const double* __restrict__ tail) {
+    double as = s < 0 ? -s : s;
+    double res;
+    if (as < NMRFIT_DAW_SMAX) {
+        int k = (int)(as * NMRFIT_DAW_INV_WIDTH);
+        k = k > NMRFIT_DAW_NINT - 1 ? NMRFIT_DAW_NINT - 1 : k;
+        const double* c = core + k * (NMRFIT_DAW_DEG + 1);
+        double t = as - ((double)k + 0.5) * NMRFIT_DAW_WIDTH;
+        double p = c[NMRFIT_DAW_DEG];
+#pragma unroll
+        for (int i = NMRFIT_DAW_DEG - 1; i >= 0; --i) p = NMRFIT_FMA(p, t, c[i]);
+        res = p;
+    } else {
+        double inv = 1.0 / as;
+        double y = inv * inv - NMRFIT_DAW_TAIL_MID;
+        double p = tail[NMRFIT_DAW_TAIL_DEG];
+#pragma unroll
+        for (int i = NMRFIT_DAW_TAIL_DEG - 1; i >= 0; --i) p = NMRFIT_FMA(p, y, tail[i]);
+        res = 0.5 * inv * p;
+    }
+    return s < 0 ? -res : res;
+}
+
+// ---- per-peak constants --------------------------------------------------
+// voigt (reference equations.py:141-147), rewritten so the inner loop needs
+// d = w - loc and d2 = d*d only:
+//   L = (2/(pi W)) / (1 + d2 * (2/W)^2)            G = (2/W) sqrt(ln2/pi) exp(-d2 * (2 sqrt(ln2)/W)^2)
+//   body = aL / (1 + d2*kL2) + aG * exp(d2 * nkG2)
+struct PeakCoef {
+    double loc;    // centre
+    double kL2;    // (2/W)^2
+    double aL;     // a * r * 2/(pi W)
+    double nkG2;   // -(2 sqrt(ln2)/W)^2
+    double aG;     // a * (1-r) * (2/W) * sqrt(ln2/pi)
+};
+
+NMRFIT_HD PeakCoef make_coef(double r, double width, double loc, double a) {
+    PeakCoef c;
+    double iw = 2.0 / width;
+    double kg = iw * kSqrtLn2;
+    c.loc = loc;
+    c.kL2 = iw * iw;
+    c.aL = a * r * (iw / kPi);
+    c.nkG2 = -(kg * kg);
+    c.aG = a * (1.0 - r) * (iw * kSqrtLn2OverPi);
+    return c;
+}
+
+// Philox4x32-10 (Salmon et al., SC'11) -> two uniform doubles in [0, 1) with 53
+// random bits each, built as MT19937's genrand_res53 builds them:
+// (a >> 5) * 2^26 + (b >> 6), scaled by 2^-53.
+struct Philox2 { double a, b; };
+NMRFIT_HD void philox_round(unsigned& c0, unsigned& c1, unsigned& c2, unsigned& c3, unsigned k0, unsigned k1) {
+    unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+    unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    unsigned n0 = (unsigned)(p1 >> 32) ^ c1 ^ k0;
+    unsigned n1 = (unsigned)p1;
+    unsigned n2 = (unsigned)(p0 >> 32) ^ c3 ^ k1;
+    unsigned n3 = (unsigned)p0;
+    c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+}
+NMRFIT_HD Philox2 philox_uniform2(unsigned long long seed, unsigned long long ctr_lo, unsigned long long ctr_hi) {
+    unsigned c0 = (unsigned)ctr_lo, c1 = (unsigned)(ctr_lo >> 32);
+    unsigned c2 = (unsigned)ctr_hi, c3 = (unsigned)(ctr_hi >> 32);
+    unsigned k0 = (unsigned)seed, k1 = (unsigned)(seed >> 32);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    Philox2 o;
+    o.a = ((double)(c0 >> 5) * 67108864.0 + (double)(c1 >> 6)) * (1.0 / 9007199254740992.0);
+    o.b = ((double)(c2 >> 5) * 67108864.0 + (double)(c3 >> 6)) * (1.0 / 9007199254740992.0);
+    return o;
+}
+
+}  // namespace nmrfit

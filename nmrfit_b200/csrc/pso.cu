@@ -1,0 +1,228 @@
+// K2/K3: the particle-swarm bookkeeping that pyswarm.pso does in numpy on the host
+// (called from the reference at nmrfit/utils.py:176-182; algorithm restated in
+// oracle/pso_oracle.py), kept on the device so that a generation is
+// move -> objective -> personal best -> swarm best without a host round trip.
+//
+// The position/velocity update reproduces numpy's evaluation order
+//   v = ((omega*v) + ((phip*rp)*(p-x))) + ((phig*rg)*(g-x));  x = x + v
+// with explicitly rounded multiplies/adds (no FMA contraction), so that with
+// host-supplied random numbers the trajectory is bit-identical to the CPU one as
+// long as the objective values compare the same way.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include "nmrfit_internal.h"
+#include "nmrfit_math.cuh"
+
+namespace nmrfit {
+
+enum { kStopRunning = 0, kStopMinFunc = 1, kStopMinStep = 2, kStopMaxIter = 3 };
+
+__device__ __forceinline__ unsigned long long elem_counter(const SwarmState& s, int b, int sl, int d) {
+    // global (sharding-independent) element number
+    return ((unsigned long long)b << 40) ^ ((unsigned long long)(s.index0 + sl) * (unsigned long long)s.D + d);
+}
+
+// generation 0, part 1: x = lb + r*(ub - lb); fp = inf   (pyswarm: x = rand(S,D); x = lb + x*(ub-lb))
+__global__ void swarm_init_kernel(SwarmState s, const double* __restrict__ r_pos) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)s.B * s.S * s.D;
+    if (idx >= total) return;
+    int d = idx % s.D;
+    size_t bs = idx / s.D;
+    int sl = bs % s.S, b = bs / s.S;
+    double r = r_pos ? r_pos[idx] : philox_uniform2(s.seed, elem_counter(s, b, sl, d), 0ull).a;
+    double lb = s.lb[b * s.D + d], ub = s.ub[b * s.D + d];
+    s.x[idx] = __dadd_rn(lb, __dmul_rn(r, __dsub_rn(ub, lb)));
+    s.p[idx] = 0.0;
+    if (d == 0) s.fp[bs] = CUDART_INF;
+}
+
+// generation 0, part 2 (after the first evaluation): v = vlow + r*(vhigh - vlow),
+// vhigh = |ub - lb|, vlow = -vhigh
+__global__ void swarm_init_velocity_kernel(SwarmState s, const double* __restrict__ r_vel) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)s.B * s.S * s.D;
+    if (idx >= total) return;
+    int d = idx % s.D;
+    size_t bs = idx / s.D;
+    int sl = bs % s.S, b = bs / s.S;
+    double r = r_vel ? r_vel[idx] : philox_uniform2(s.seed, elem_counter(s, b, sl, d), 0ull).b;
+    double vhigh = fabs(__dsub_rn(s.ub[b * s.D + d], s.lb[b * s.D + d]));
+    double vlow = -vhigh;
+    s.v[idx] = __dadd_rn(vlow, __dmul_rn(r, __dsub_rn(vhigh, vlow)));
+}
+
+__global__ void swarm_move_kernel(SwarmState s, const double* __restrict__ rp_in, const double* __restrict__ rg_in,
+                                  int generation) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)s.B * s.S * s.D;
+    if (idx >= total) return;
+    int d = idx % s.D;
+    size_t bs = idx / s.D;
+    int sl = bs % s.S, b = bs / s.S;
+    if (s.stop[b]) return;
+    double rp, rg;
+    if (rp_in) {
+        rp = rp_in[idx];
+        rg = rg_in[idx];
+    } else {
+        Philox2 u = philox_uniform2(s.seed, elem_counter(s, b, sl, d), (unsigned long long)generation);
+        rp = u.a;
+        rg = u.b;
+    }
+    double x = s.x[idx], v = s.v[idx], p = s.p[idx], g = s.g[b * s.D + d];
+    double t1 = __dmul_rn(s.omega, v);
+    double t2 = __dmul_rn(__dmul_rn(s.phip, rp), __dsub_rn(p, x));
+    double t3 = __dmul_rn(__dmul_rn(s.phig, rg), __dsub_rn(g, x));
+    v = __dadd_rn(__dadd_rn(t1, t2), t3);
+    x = __dadd_rn(x, v);
+    double lb = s.lb[b * s.D + d], ub = s.ub[b * s.D + d];
+    x = x < lb ? lb : (x > ub ? ub : x);
+    s.v[idx] = v;
+    s.x[idx] = x;
+}
+
+// personal best positions (elementwise; fp itself is updated by the reduction kernel that follows)
+__global__ void swarm_pbest_kernel(SwarmState s) {
+    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t total = (size_t)s.B * s.S * s.D;
+    if (idx >= total) return;
+    size_t bs = idx / s.D;
+    int b = bs / s.S;
+    if (s.stop[b]) return;
+    if (s.fx[bs] < s.fp[bs]) s.p[idx] = s.x[idx];
+}
+
+// fp update + argmin(fp) with first-index tie-break (np.argmin semantics) -> record
+__global__ void __launch_bounds__(256) swarm_local_best_kernel(SwarmState s, double* __restrict__ rec) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (s.stop[b]) return;
+    __shared__ double sf[256];
+    __shared__ int si[256];
+    double bf = CUDART_INF;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < s.S; i += 256) {
+        size_t bs = (size_t)b * s.S + i;
+        double fx = s.fx[bs], fp = s.fp[bs];
+        if (fx < fp) { fp = fx; s.fp[bs] = fx; }
+        if (fp < bf || (fp == bf && i < bi)) { bf = fp; bi = i; }
+    }
+    sf[tid] = bf; si[tid] = bi;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) {
+            double of = sf[tid + o]; int oi = si[tid + o];
+            if (of < sf[tid] || (of == sf[tid] && oi < si[tid])) { sf[tid] = of; si[tid] = oi; }
+        }
+        __syncthreads();
+    }
+    int best = si[0];
+    const double* src = s.p;
+    if (best == 0x7fffffff) { best = 0; src = s.x; }   // nothing finite yet: pyswarm falls back to x[0]
+    double* r = rec + (size_t)b * (s.D + 2);
+    if (tid == 0) { r[0] = sf[0]; r[1] = (double)(s.index0 + best); }
+    for (int d = tid; d < s.D; d += 256) r[2 + d] = src[((size_t)b * s.S + best) * s.D + d];
+}
+
+// swarm-best update and the minfunc/minstep stop tests.  `recs` holds one record
+// per rank ([n_ranks][B][D+2]); every rank runs this redundantly on identical
+// input, so g/fg stay bit-identical everywhere.
+__global__ void __launch_bounds__(128) swarm_commit_kernel(SwarmState s, const double* __restrict__ recs, int n_ranks,
+                                                           int initial, int maxiter) {
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (s.stop[b]) return;
+    const int W = s.D + 2;
+    __shared__ int s_win;
+    __shared__ double s_step;
+    __shared__ int s_action;   // 0 nothing, 1 adopt as g, 2 stop (return p_min)
+    if (tid == 0) {
+        int win = 0;
+        double wf = recs[(size_t)b * W], wi = recs[(size_t)b * W + 1];
+        for (int r = 1; r < n_ranks; ++r) {
+            const double* q = recs + ((size_t)r * s.B + b) * W;
+            if (q[0] < wf || (q[0] == wf && q[1] < wi)) { wf = q[0]; wi = q[1]; win = r; }
+        }
+        s_win = win;
+    }
+    __syncthreads();
+    const double* q = recs + ((size_t)s_win * s.B + b) * W;
+    const double fmin = q[0];
+    double* g = s.g + (size_t)b * s.D;
+    if (initial) {
+        // pyswarm: fg = fp[i_min]; g = p[i_min] (else g = x[0] when nothing is finite)
+        for (int d = tid; d < s.D; d += 128) { g[d] = q[2 + d]; s.best_x[(size_t)b * s.D + d] = q[2 + d]; }
+        if (tid == 0) { s.fg[b] = fmin; s.best_f[b] = fmin; s.it[b] = 0; }
+        return;
+    }
+    const double fg = s.fg[b];
+    if (tid == 0) {
+        int action = 0;
+        if (fmin < fg) {
+            double acc = 0.0;
+            for (int d = 0; d < s.D; ++d) {
+                double df = __dsub_rn(g[d], q[2 + d]);
+                acc = __dadd_rn(acc, __dmul_rn(df, df));
+            }
+            s_step = sqrt(acc);
+            if (fabs(__dsub_rn(fg, fmin)) <= s.minfunc) { action = 2; s.stop[b] = kStopMinFunc; }
+            else if (s_step <= s.minstep) { action = 2; s.stop[b] = kStopMinStep; }
+            else action = 1;
+        }
+        s_action = action;
+        s.it[b] += 1;
+        if (action == 0 || action == 1) {
+            if (s.it[b] >= maxiter) s.stop[b] = kStopMaxIter;
+        }
+    }
+    __syncthreads();
+    if (s_action == 0) return;
+    for (int d = tid; d < s.D; d += 128) {
+        s.best_x[(size_t)b * s.D + d] = q[2 + d];
+        if (s_action == 1) g[d] = q[2 + d];
+    }
+    if (tid == 0) {
+        s.best_f[b] = fmin;
+        if (s_action == 1) s.fg[b] = fmin;
+    }
+}
+
+static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+cudaError_t launch_swarm_init(const SwarmState& s, const double* r_pos, const double*, cudaStream_t st) {
+    size_t total = (size_t)s.B * s.S * s.D;
+    swarm_init_kernel<<<blocks_for(total, 256), 256, 0, st>>>(s, r_pos);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_swarm_init_velocity(const SwarmState& s, const double* r_vel, cudaStream_t st) {
+    size_t total = (size_t)s.B * s.S * s.D;
+    swarm_init_velocity_kernel<<<blocks_for(total, 256), 256, 0, st>>>(s, r_vel);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_swarm_move(const SwarmState& s, const double* rp, const double* rg, int generation,
+                              cudaStream_t st) {
+    size_t total = (size_t)s.B * s.S * s.D;
+    swarm_move_kernel<<<blocks_for(total, 256), 256, 0, st>>>(s, rp, rg, generation);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_swarm_local_best(const SwarmState& s, double* rec, cudaStream_t st) {
+    size_t total = (size_t)s.B * s.S * s.D;
+    swarm_pbest_kernel<<<blocks_for(total, 256), 256, 0, st>>>(s);
+    swarm_local_best_kernel<<<s.B, 256, 0, st>>>(s, rec);
+    count_launches(2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_swarm_commit(const SwarmState& s, const double* recs, int n_ranks, int initial, int maxiter,
+                                cudaStream_t st) {
+    swarm_commit_kernel<<<s.B, 128, 0, st>>>(s, recs, n_ranks, initial, maxiter);
+    count_launches(1);
+    return cudaGetLastError();
+}
+
+}  // namespace nmrfit

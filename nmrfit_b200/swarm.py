@@ -1,0 +1,286 @@
+"""Host-side driver of the on-device particle swarm.
+
+Replaces ``pyswarm.pso`` as the reference calls it (utils.py:176-182).  The swarm
+state (positions, velocities, personal/global bests) lives in the library's
+context on the GPU; this module only sequences generations, feeds random numbers
+when the reference's host RNG stream is to be reproduced, and polls the stop flags.
+
+Three shapes of the same loop:
+  ``pso_single``   one spectrum, one GPU (what ``nmrfit.fit`` needs);
+  ``pso_batch``    B independent spectra, one swarm each, one GPU - spectra shard
+                   across ranks with no communication (BASELINE config 3);
+  ``pso_sharded``  one spectrum, the particles of one swarm sharded over the ranks
+                   of a ``torch.distributed`` group; per generation each rank
+                   contributes its best record (f, global index, x[D]) to one
+                   all-gather and every rank applies the same first-index argmin
+                   (BASELINE config 4).
+"""
+import numpy as np
+
+from . import _cabi
+
+STOP_TEXT = {
+    _cabi.STOP_MINFUNC: 'Stopping search: Swarm best objective change less than {minfunc}',
+    _cabi.STOP_MINSTEP: 'Stopping search: Swarm best position change less than {minstep}',
+    _cabi.STOP_MAXITER: 'Stopping search: maximum iterations reached --> {maxiter}',
+    _cabi.RUNNING: 'Stopping search: maximum iterations reached --> {maxiter}',
+}
+
+
+def _precision(p):
+    if p in ('fp64', 'f64', _cabi.FP64, None):
+        return _cabi.FP64
+    if p in ('fp32', 'f32', _cabi.FP32):
+        return _cabi.FP32
+    raise ValueError("precision must be 'fp64' or 'fp32'")
+
+
+def _fit_im_mode(fit_im):
+    from .equations import _fit_im_mode as f
+    return f(fit_im)
+
+
+def _check_bounds(lower, upper):
+    lb = np.array(lower, dtype=np.float64)
+    ub = np.array(upper, dtype=np.float64)
+    # pyswarm's own argument checks, same messages
+    assert lb.shape == ub.shape, 'Lower- and upper-bounds must be the same length'
+    assert np.all(ub > lb), 'All upper-bound values must be greater than lower-bound values'
+    return lb, ub
+
+
+def _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed, offset=0):
+    o = _cabi.PsoOpts()
+    o.swarmsize, o.maxiter = int(S), int(maxiter)
+    o.omega, o.phip, o.phig = float(omega), float(phip), float(phig)
+    o.minstep, o.minfunc = float(minstep), float(minfunc)
+    o.fit_im = _fit_im_mode(fit_im)
+    o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    o.particle_offset = int(offset)
+    return o
+
+
+def _draw_generations(rnd, n, S, D):
+    """rp then rg per generation, from the legacy stream - pyswarm's order."""
+    rp = np.empty((n, S, D))
+    rg = np.empty((n, S, D))
+    for k in range(n):
+        rp[k] = rnd.uniform(size=(S, D))
+        rg[k] = rnd.uniform(size=(S, D))
+    return rp, rg
+
+
+def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxiter=100, omega=0.5, phip=0.5,
+               phig=0.5, minstep=1e-8, minfunc=1e-8, rng='host', seed=0, precision='fp64', chunk=16, device=None,
+               quiet=False, trace=None, tuning=None):
+    """Minimise the nmrfit objective for one spectrum.  Returns (x_best, f_best, info).
+
+    rng='host' consumes ``np.random`` exactly as pyswarm does (rand(S,D) for the
+    positions, rand(S,D) for the velocities, then uniform(size=(S,D)) twice per
+    generation), and leaves the global stream where pyswarm would have left it.
+    """
+    lb, ub = _check_bounds(lower, upper)
+    D = lb.size
+    if D < 7 or (D - 4) % 3:
+        raise ValueError('bounds must have 4 + 3*n_peaks entries')
+    w = _cabi.as_f64(w)
+    S = int(swarmsize)
+    host = rng == 'host'
+    if rng not in ('host', 'device'):
+        raise ValueError("rng must be 'host' or 'device'")
+    with _cabi.Context(1, w.size, (D - 4) // 3, device=device, precision=_precision(precision)) as ctx:
+        if tuning:
+            ctx.set_tuning(**tuning)
+        ctx.set_spectrum(0, w, u, v, weights)
+        opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed)
+        r_pos = np.random.rand(S, D) if host else None
+        r_vel = np.random.rand(S, D) if host else None
+        ctx.pso_begin(lb, ub, opts, r_pos, r_vel)
+        ctx.pso_commit()
+        if trace is not None:
+            x, f, it, stop = ctx.pso_best()
+            trace.append((0, x[0].copy(), float(f[0])))
+        done = 0
+        chunk = max(1, int(chunk)) if trace is None else 1
+        while done < maxiter:
+            n = min(chunk, maxiter - done)
+            if host:
+                state = np.random.get_state()
+                rp, rg = _draw_generations(np.random, n, S, D)
+            else:
+                rp = rg = None
+            running = ctx.pso_run(n, rp, rg)
+            if trace is not None:
+                x, f, it, stop = ctx.pso_best()
+                trace.append((int(it[0]), x[0].copy(), float(f[0])))
+            if running == 0:
+                if host:
+                    # leave the legacy stream where pyswarm would have: it stops drawing
+                    # at the generation that tripped the test
+                    x, f, it, stop = ctx.pso_best()
+                    used = int(it[0]) - done
+                    if used < n:
+                        np.random.set_state(state)
+                        _draw_generations(np.random, used, S, D)
+                break
+            done += n
+        x, f, it, stop = ctx.pso_best()
+    info = dict(generations=int(it[0]), stop=int(stop[0]), evaluations=S * (int(it[0]) + 1))
+    if not quiet:
+        print(STOP_TEXT[info['stop']].format(minfunc=minfunc, minstep=minstep, maxiter=maxiter))
+    return x[0].copy(), float(f[0]), info
+
+
+def pso_batch(spectra, lowers, uppers, fit_im=False, swarmsize=100, maxiter=100, omega=0.5, phip=0.5, phig=0.5,
+              minstep=1e-8, minfunc=1e-8, rng='device', seeds=None, seed=0, precision='fp64', chunk=16, device=None,
+              tuning=None):
+    """B independent fits in one context.  ``spectra``: sequence of (w, u, v, weights),
+    all of one length; ``lowers``/``uppers``: [B][D].
+
+    rng='host' gives spectrum b its own legacy stream ``RandomState(seeds[b])``, drawn
+    in pyswarm's order - i.e. the result equals running the reference fit b after
+    ``np.random.seed(seeds[b])``.  rng='device' uses Philox keyed by ``seed``.
+    Returns (x_best [B][D], f_best [B], generations [B], stop [B]).
+    """
+    B = len(spectra)
+    lb = np.array(lowers, dtype=np.float64)
+    ub = np.array(uppers, dtype=np.float64)
+    assert lb.shape == ub.shape and lb.ndim == 2 and lb.shape[0] == B, 'bounds must be [B][D]'
+    assert np.all(ub > lb), 'All upper-bound values must be greater than lower-bound values'
+    D = lb.shape[1]
+    N = len(spectra[0][0])
+    S = int(swarmsize)
+    host = rng == 'host'
+    if host:
+        if seeds is None or len(seeds) != B:
+            raise ValueError("rng='host' needs one seed per spectrum")
+        streams = [np.random.RandomState(int(s)) for s in seeds]
+    with _cabi.Context(B, N, (D - 4) // 3, device=device, precision=_precision(precision)) as ctx:
+        if tuning:
+            ctx.set_tuning(**tuning)
+        for b, (w, u, v, wt) in enumerate(spectra):
+            ctx.set_spectrum(b, w, u, v, wt)
+        opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed)
+        r_pos = r_vel = None
+        if host:
+            r_pos = np.empty((B, S, D))
+            r_vel = np.empty((B, S, D))
+            for b, st in enumerate(streams):
+                r_pos[b] = st.rand(S, D)
+                r_vel[b] = st.rand(S, D)
+        ctx.pso_begin(lb, ub, opts, r_pos, r_vel)
+        ctx.pso_commit()
+        done = 0
+        while done < maxiter:
+            n = min(max(1, int(chunk)), maxiter - done)
+            rp = rg = None
+            if host:
+                rp = np.empty((n, B, S, D))
+                rg = np.empty((n, B, S, D))
+                for b, st in enumerate(streams):
+                    for k in range(n):
+                        rp[k, b] = st.uniform(size=(S, D))
+                        rg[k, b] = st.uniform(size=(S, D))
+            if ctx.pso_run(n, rp, rg) == 0:
+                break
+            done += n
+        return ctx.pso_best()
+
+
+# ---- particle sharding over torch.distributed ------------------------------------------------------
+
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ carrier so torch can alias library-owned memory."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {'shape': (n,), 'typestr': '<f8', 'data': (int(ptr), False), 'version': 2}
+
+
+def shard_range(total, rank, world):
+    """Contiguous rank-major split of ``total`` items: (offset, count)."""
+    base, extra = divmod(int(total), int(world))
+    count = base + (1 if rank < extra else 0)
+    offset = rank * base + min(rank, extra)
+    return offset, count
+
+
+def gather_records(rec, group=None):
+    """All-gather one record tensor per rank into [world, n], rank order (works for
+    NCCL device tensors and for gloo CPU tensors)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    out = torch.empty((world, rec.numel()), dtype=rec.dtype, device=rec.device)
+    if rec.is_cuda:
+        dist.all_gather_into_tensor(out, rec.contiguous(), group=group)
+    else:
+        parts = [torch.empty_like(rec) for _ in range(world)]
+        dist.all_gather(parts, rec.contiguous(), group=group)
+        out = torch.stack(parts)
+    return out
+
+
+def select_record(recs):
+    """The winning record among ranks: smallest f, ties to the lowest global particle
+    index (np.argmin's first-occurrence rule).  Host mirror of the device commit rule,
+    used by the CPU tests of the exchange logic.  recs: [world, D+2]."""
+    recs = np.asarray(recs)
+    order = np.lexsort((recs[:, 1], recs[:, 0]))
+    return recs[order[0]]
+
+
+def pso_sharded(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxiter=100, omega=0.5, phip=0.5,
+                phig=0.5, minstep=1e-8, minfunc=1e-8, seed=0, precision='fp64', check_every=8, device=None,
+                group=None, host_random=None, tuning=None):
+    """One swarm of ``swarmsize`` particles sharded over the ranks of ``group``.
+
+    Every rank holds the spectrum and a contiguous block of particles.  Random numbers
+    come from device Philox keyed by the GLOBAL particle index, so the trajectory does
+    not depend on the number of ranks; ``host_random`` (dict with 'pos', 'vel' [S,D] and a
+    callable 'gen'(k) -> (rp, rg) [S,D]) substitutes host numbers for lock-step tests.
+    Returns (x_best, f_best, info) - identical on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    lb, ub = _check_bounds(lower, upper)
+    D = lb.size
+    off, cnt = shard_range(swarmsize, rank, world)
+    if cnt < 1:
+        raise ValueError('swarmsize must be at least the number of ranks')
+    dev = _cabi.default_device() if device is None else int(device)
+    torch.cuda.set_device(dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    w = _cabi.as_f64(w)
+    with _cabi.Context(1, w.size, (D - 4) // 3, device=dev, precision=_precision(precision)) as ctx:
+        if tuning:
+            ctx.set_tuning(**tuning)
+        ctx.set_spectrum(0, w, u, v, weights)
+        opts = _make_opts(cnt, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed, offset=off)
+        sl = slice(off, off + cnt)
+        r_pos = host_random['pos'][sl] if host_random else None
+        r_vel = host_random['vel'][sl] if host_random else None
+        ctx.pso_begin(lb, ub, opts, r_pos, r_vel, stream=stream)
+        ptr, n = ctx.pso_record()
+        rec = torch.as_tensor(_DeviceArray(ptr, n), device='cuda:%d' % dev)
+        recs = gather_records(rec, group)
+        ctx.pso_commit(recs, world, stream=stream)
+        gen = 0
+        stop = np.zeros(1, dtype=np.int32)
+        while gen < maxiter:
+            for _ in range(min(check_every, maxiter - gen)):
+                gen += 1
+                if host_random:
+                    rp, rg = host_random['gen'](gen)
+                    ctx.pso_advance(rp[sl], rg[sl], stream=stream)
+                else:
+                    ctx.pso_advance(stream=stream)
+                recs = gather_records(rec, group)
+                ctx.pso_commit(recs, world, stream=stream)
+            x, f, it, stop = ctx.pso_best()
+            if stop[0] != _cabi.RUNNING:
+                break
+        x, f, it, stop = ctx.pso_best()
+    info = dict(generations=int(it[0]), stop=int(stop[0]), evaluations=int(swarmsize) * (int(it[0]) + 1),
+                world=world, local_particles=cnt)
+    return x[0].copy(), float(f[0]), info

@@ -1,0 +1,177 @@
+"""Fit driver, mirroring ``nmrfit.utils`` for the hot path.
+
+``FitUtility`` keeps the reference's constructor, methods and result attributes
+(utils.py:96-339); what changes is underneath: the swarm lives on the GPU and a
+generation is one batched launch instead of ``swarmsize`` Python callbacks.
+
+``Peak`` / ``Peaks`` are the plain records the driver reads (utils.py:14-93).  The
+interactive selectors of the reference (BoundsSelector, PeakSelector,
+AutoPeakSelector: utils.py:342-816) are outside the accelerated path and are not
+provided.
+"""
+import numpy as np
+
+from . import _cabi
+from . import equations
+from . import swarm as _swarm
+
+
+class Peaks(list):
+    """List of ``Peak`` records (utils.py:14-55)."""
+
+    def average_height(self):
+        return sum(abs(p.height) for p in self) / len(self)
+
+    def split(self):
+        """(main peaks, satellites) by height relative to the average."""
+        h = self.average_height()
+        mains, sats = Peaks(), Peaks()
+        for p in self:
+            (mains if abs(p.height) >= h else sats).append(p)
+        return mains, sats
+
+
+class Peak:
+    """Metadata of one peak: ``loc``, ``height``, ``bounds`` [lo, hi], ``width`` (FWHM), ``area``."""
+
+    def __repr__(self):
+        return 'Peak(loc=%s, height=%s, bounds=[%s, %s], width=%s, area=%s)' % (
+            getattr(self, 'loc', None), getattr(self, 'height', None),
+            *(getattr(self, 'bounds', [None, None])), getattr(self, 'width', None), getattr(self, 'area', None))
+
+
+def compute_weights(w, peaks, expon=0.5):
+    """Frequency-dependent residual weights (utils.py:191-224): 1 everywhere,
+    (tallest/|height|)**expon inside each peak's index window (later peaks
+    overwrite earlier ones), then 10 Jacobi smoothing sweeps.  Host-side: it runs
+    once per fit and costs microseconds."""
+    n_pk = len(peaks)
+    lo = np.zeros(n_pk, dtype=int)
+    hi = np.zeros(n_pk, dtype=int)
+    mag = np.zeros(n_pk)
+    for i, pk in enumerate(peaks):
+        a = int(np.argmin(np.abs(w - pk.bounds[0])))
+        b = int(np.argmin(np.abs(w - pk.bounds[1])))
+        lo[i], hi[i] = min(a, b), max(a, b)
+        mag[i] = np.abs(pk.height)
+    tallest = np.amax(mag)
+    weights = np.ones(len(w))
+    for i in range(n_pk):
+        weights[lo[i]:hi[i] + 1] = np.power(tallest / mag[i], expon)
+    return equations.laplace1d(weights)
+
+
+class FitUtility:
+    """Interface used to perform a fit of the data (drop-in for utils.py:96-339).
+
+    Attributes after ``fit()``: ``params`` (ndarray D), ``error`` (float),
+    ``weights``; after ``generate_result()``: ``w, u, v, V, I`` and the per-peak
+    lists ``real_contribs`` / ``imag_contribs``.
+
+    ``options`` understands the reference's keys (``swarmsize`` 204, ``maxiter``
+    2000, ``omega`` -0.2134, ``phip`` -0.3344, ``phig`` 2.3259; utils.py:177-181)
+    plus optional extras that do not exist upstream:
+      ``rng``       'host' (default): random numbers are drawn from numpy's legacy
+                    global stream in pyswarm's order, so ``np.random.seed(k)`` gives
+                    the reference's trajectory; 'device': Philox on the GPU.
+      ``seed``      Philox seed for rng='device'.
+      ``minstep``, ``minfunc``   pyswarm's stop tolerances (1e-8).
+      ``precision`` 'fp64' (default) or 'fp32'.
+      ``chunk``     generations queued between host checks of the stop flag.
+      ``device``    CUDA device index.
+    ``processes`` is accepted and ignored (the GPU evaluates every particle at once).
+    """
+
+    def __init__(self, data, lower, upper, expon=0.5, dynamic_weighting=True, fit_im=False, processes=1,
+                 summary=True, options={}):
+        self.data = data
+        self.lower = lower
+        self.upper = upper
+        self.expon = expon
+        self.dynamic_weighting = dynamic_weighting
+        self.fit_im = fit_im
+        self.summary = summary
+        self.processes = processes
+        self.options = options
+
+    def fit(self):
+        """Minimise the objective over the box [lower, upper] with the swarm."""
+        self.weights = self._compute_weights()
+        if self.dynamic_weighting is False:
+            self.weights = np.ones_like(self.weights)
+
+        opt = self.options
+        xopt, fopt, info = _swarm.pso_single(
+            self.data.w, self.data.u, self.data.v, self.weights, self.lower, self.upper,
+            fit_im=self.fit_im,
+            swarmsize=opt.get('swarmsize', 204), maxiter=opt.get('maxiter', 2000),
+            omega=opt.get('omega', -0.2134), phip=opt.get('phip', -0.3344), phig=opt.get('phig', 2.3259),
+            minstep=opt.get('minstep', 1e-8), minfunc=opt.get('minfunc', 1e-8),
+            rng=opt.get('rng', 'host'), seed=opt.get('seed', 0), precision=opt.get('precision', 'fp64'),
+            chunk=opt.get('chunk', 16), device=opt.get('device', None))
+
+        self.params = xopt
+        self.error = fopt
+        self.fit_info = info
+
+        if self.summary is True:
+            self._print_summary()
+
+    def _compute_weights(self):
+        return compute_weights(self.data.w, self.data.peaks, self.expon)
+
+    def generate_result(self, scale=1):
+        """Evaluate the fitted curves, optionally upsampled by ``scale`` (utils.py:226-295)."""
+        if scale == 1.0:
+            w = self.data.w
+        else:
+            w = np.linspace(self.data.w.min(), self.data.w.max(), int(scale * self.data.w.shape[0]))
+
+        p0, p1 = self.params[0], self.params[1]
+        # the reference re-phases the data object here (utils.py:252)
+        self.data.shift_phase(method='manual', p0=p0, p1=p1)
+
+        params = _cabi.as_f64(self.params)
+        n_peaks = (params.size - 4) // 3
+        w = _cabi.as_f64(w)
+        n = w.size
+        real = np.empty((n_peaks, n))
+        imag = np.empty((n_peaks, n))
+        V, I, u, v = (np.empty(n) for _ in range(4))
+        dev = self.options.get('device', None)
+        _cabi.check(_cabi.lib().nmrfit_generate_result_host(
+            _cabi.default_device() if dev is None else int(dev), _cabi.ptr(params), n_peaks, _cabi.ptr(w), n,
+            _cabi.ptr(real), _cabi.ptr(imag), _cabi.ptr(V), _cabi.ptr(I), _cabi.ptr(u), _cabi.ptr(v)))
+
+        self.u = u
+        self.v = v
+        self.V = V
+        self.I = I
+        self.w = w
+        self.real_contribs = [real[k] for k in range(n_peaks)]
+        self.imag_contribs = [imag[k] for k in range(n_peaks)]
+
+    def calculate_area_fraction(self):
+        """Satellite area / total area, satellites = areas below the mean (utils.py:297-310)."""
+        areas = self.get_areas()
+        m = np.mean(areas)
+        mains = areas[areas >= m].sum()
+        sats = areas[areas < m].sum()
+        return sats / (mains + sats)
+
+    def get_areas(self):
+        """Fitted areas: every third parameter from index 6 (utils.py:322)."""
+        return np.array([self.params[i] for i in range(6, len(self.params), 3)])
+
+    def _print_summary(self):
+        import pandas as pd
+        res = np.array(self.params)
+        res_globals = pd.DataFrame(res[:4].reshape((1, -1)), columns=['p0', 'p1', 'r', 'y-off'])
+        res_peaks = pd.DataFrame(res[4:].reshape((-1, 3)), columns=['width', 'location', 'area'])
+        print('\nFit Summary:')
+        print('------------')
+        print('Global parameters')
+        print(res_globals.to_string(index=False))
+        print('\nPeak parameters')
+        print(res_peaks.to_string(index=False))
+        print("Error:\t", self.error)

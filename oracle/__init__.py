@@ -1,0 +1,20 @@
+"""CPU oracle for the nmrfit objective-evaluation hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``nmrfit_b200/`` may import this
+package; the only permitted importers are ``tests/``, ``__graft_entry__.smoke()``
+and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``, and there
+only as the checker or as the CPU arm being timed, never as the product path.
+
+Parity status
+-------------
+* ``nmrfit_oracle`` (ps2 / voigt / objective / laplace1d / weights /
+  generate_result / Kramers-Kronig): PINNED.  The reference ships no tests or
+  golden vectors, so the pins are outputs of the unmodified
+  reference itself, imported from /root/reference in the build container by
+  ``tests/golden/make_golden.py`` and committed under ``tests/golden/``.
+* ``pso_oracle`` (pyswarm.pso): PARITY UNPINNED.  pyswarm is a third-party,
+  un-vendored, un-pinned dependency of the reference (README.md:13-17 installs
+  git master of tisimst/pyswarm; it is absent from requirements.txt and from this
+  image).  The loop is restated from its published algorithm and anchored only on
+  the reference's call site (nmrfit/utils.py:176-182).
+"""

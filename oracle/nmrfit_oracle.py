@@ -1,0 +1,226 @@
+"""numpy float64 restatement of the reference's objective hot path.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``).  Every function cites the
+reference lines it follows.  The arithmetic keeps the reference's operation
+order so that, on the same inputs, results agree with the unmodified reference
+to the last bit (checked by ``tests/golden/make_golden.py`` when it is run in
+the build container, and by ``tests/test_oracle_golden.py`` against the
+committed fixtures everywhere else).
+
+Parity: PINNED against outputs of the unmodified reference (tests/golden/).
+"""
+import numpy as np
+import scipy.integrate
+import scipy.special
+
+LN2 = np.log(2)
+
+
+# --------------------------------------------------------------------------
+# phase rotation  (reference: nmrfit/proc_autophase.py:9-36, ``ps2``)
+# --------------------------------------------------------------------------
+def phase_ramp(n, p0, p1):
+    """phi_i = p0 + (p1 * i) / n, radians  (proc_autophase.py:30-31)."""
+    return p0 + (p1 * np.arange(n) / n)
+
+
+def ps2(u, v, p0=0.0, p1=0.0, inv=False):
+    """Rotate (u, v) by the linear phase ramp; ``inv`` divides instead.
+
+    proc_autophase.py:29-36.  The reference builds a complex vector, multiplies
+    by exp(1j*phi) (or its reciprocal) and splits real/imag; the same complex
+    numpy ops are used here so rounding is identical.
+    """
+    z = u + 1j * v
+    rot = np.exp(1.0j * phase_ramp(z.shape[-1], p0, p1)).astype(z.dtype)
+    if inv:
+        rot = 1 / rot
+    z = rot * z
+    return z.real, z.imag
+
+
+# --------------------------------------------------------------------------
+# lineshape  (reference: nmrfit/equations.py:115-149, ``voigt``)
+# --------------------------------------------------------------------------
+def voigt(w, r, yoff, width, loc, a):
+    """Area-parameterised pseudo-Voigt: yoff + a*(r*Lorentz + (1-r)*Gauss).
+
+    equations.py:141 (Lorentzian), :144 (Gaussian), :147 (mix; ``r`` weighs the
+    Lorentzian, ``yoff`` is added per peak).
+    """
+    lor = (2 / (np.pi * width)) * 1 / (1 + ((w - loc) / (0.5 * width))**2)
+    gau = (2 / width) * np.sqrt(LN2 / np.pi) * np.exp(-((w - loc) / (width / (2 * np.sqrt(LN2))))**2)
+    return yoff + a * (r * lor + (1 - r) * gau)
+
+
+# --------------------------------------------------------------------------
+# Kramers-Kronig counterpart  (reference: equations.py:9-80, 242)
+# --------------------------------------------------------------------------
+def _kk_integrand(x, r, yoff, width, loc, a, w):
+    """[V(w - x) - V(w + x)] / x   (equations.py:37-49)."""
+    plus = voigt(x + w, r, yoff, width, loc, a)
+    minus = voigt(-x + w, r, yoff, width, loc, a)
+    return 1 / x * (minus - plus)
+
+
+def kk_quad(w, r, yoff, width, loc, a):
+    """(1/pi) * integral_0^inf of the integrand, scipy ``quad`` defaults
+    (equations.py:79-80).  Scalar ``w``.  ~6 ms per call."""
+    val, _ = scipy.integrate.quad(_kk_integrand, 0, np.inf, args=(r, yoff, width, loc, a, w))
+    return val / np.pi
+
+
+kk_quad_vectorized = np.vectorize(kk_quad, otypes=[float])  # equations.py:242
+
+
+def kk_closed(w, r, yoff, width, loc, a):
+    """Closed form of the integral above (Hilbert transform of the Voigt body).
+
+    Lorentzian part -> dispersion Lorentzian t/(1+t^2); Gaussian part ->
+    (2/sqrt(pi)) * Dawson(s).  ``yoff`` cancels in the integrand.  Agreement
+    with ``kk_quad`` is limited by quad's own tolerance (~1e-9 absolute); see
+    tests/test_oracle_golden.py::test_kk_closed_matches_reference_quad.
+    """
+    del yoff
+    t = (w - loc) / (0.5 * width)
+    s = (w - loc) * (2 * np.sqrt(LN2)) / width
+    lor = (2 / (np.pi * width)) * t / (1 + t * t)
+    gau = (2 / width) * np.sqrt(LN2 / np.pi) * (2 / np.sqrt(np.pi)) * scipy.special.dawsn(s)
+    return a * (r * lor + (1 - r) * gau)
+
+
+# --------------------------------------------------------------------------
+# objective  (reference: equations.py:152-212)
+# --------------------------------------------------------------------------
+def objective(x, w, u, v, weights, fit_im=False, kk=kk_closed):
+    """Weighted RMSE between the phase-rotated data and the sum of peaks.
+
+    equations.py:177 (unpack), :180 (ps2), :188-199 (peak loop; with
+    ``fit_im is True`` the imaginary fit is OVERWRITTEN by each peak, so only the
+    last peak's curve survives - reproduced), :202 (real RMSE), :205-209
+    (imaginary RMSE added, then halved).
+
+    ``kk`` picks the imaginary-lineshape evaluator: ``kk_closed`` (default,
+    fast) or ``kk_quad_vectorized`` (what the reference literally runs).
+    """
+    p0, p1, r, yoff = x[:4]
+    v_data, i_data = ps2(u, v, p0=p0, p1=p1)
+    v_fit = np.zeros_like(v_data)
+    if fit_im is True:
+        i_fit = np.zeros_like(i_data)
+    for k in range(4, len(x), 3):
+        width, loc, a = x[k], x[k + 1], x[k + 2]
+        v_fit = v_fit + voigt(w, r, yoff, width, loc, a)
+        if fit_im is True:
+            i_fit = kk(w, r, yoff, width, loc, a)
+    rmse = np.sqrt(np.square(np.multiply(weights, (v_data - v_fit))).mean(axis=None))
+    if fit_im is True:
+        rmse += np.sqrt(np.square(np.multiply(weights, (i_data - i_fit))).mean(axis=None))
+        rmse /= 2.0
+    return rmse
+
+
+def objective_swarm(xs, w, u, v, weights, fit_im=False):
+    """One call per particle, as pyswarm drives it (utils.py:176-182)."""
+    return np.array([objective(x, w, u, v, weights, fit_im) for x in xs])
+
+
+# --------------------------------------------------------------------------
+# weights  (reference: equations.py:215-238 ``laplace1d``;
+#           utils.py:191-224 ``FitUtility._compute_weights``)
+# --------------------------------------------------------------------------
+def laplace1d(x, n=10, omega=0.33333333):
+    """n Jacobi sweeps, endpoints pinned, in place (equations.py:236-238)."""
+    for _ in range(n):
+        x[1:-1] = (1. - omega) * x[1:-1] + omega * 0.5 * (x[2:] + x[:-2])
+    return x
+
+
+def compute_weights(w, peaks, expon=0.5):
+    """Per-peak windows weighted by (tallest/|height|)**expon, then smoothed.
+
+    utils.py:201-211 (index windows from ``peak.bounds``, swapped if reversed),
+    :213-215 (tallest), :217-221 (fill; later peaks overwrite earlier), :223.
+    """
+    lo = np.zeros(len(peaks), dtype=int)
+    hi = np.zeros(len(peaks), dtype=int)
+    mag = np.zeros(len(peaks))
+    for i, pk in enumerate(peaks):
+        lo[i] = np.argmin(np.abs(w - pk.bounds[0]))
+        hi[i] = np.argmin(np.abs(w - pk.bounds[1]))
+        if lo[i] > hi[i]:
+            lo[i], hi[i] = hi[i], lo[i]
+        mag[i] = np.abs(pk.height)
+    tallest = np.amax(mag)
+    weights = np.ones(len(w)) * 1.0
+    for i in range(len(peaks)):
+        weights[lo[i]:hi[i] + 1] = np.power(tallest / mag[i], expon)
+    return laplace1d(weights)
+
+
+# --------------------------------------------------------------------------
+# final curves  (reference: utils.py:226-295 ``FitUtility.generate_result``)
+# --------------------------------------------------------------------------
+def generate_result(params, w_data, scale=1, kk=kk_closed):
+    """Per-peak real/imag contributions, their sums, and the inverse-phased
+    (u, v) on the (optionally upsampled) grid.
+
+    utils.py:236-241 (grid: ``scale == 1.0`` keeps ``w``; otherwise an ascending
+    linspace of int(scale*N) points), :248-249, :262-277 (each real contribution
+    includes yoff; imag contributions ACCUMULATE here), :284 (inverse ps2 whose
+    ramp uses the upsampled length).  Returns a dict with the attributes the
+    reference sets at :289-295.  The side effect on ``data`` (:252) is the
+    caller's business.
+    """
+    if scale == 1.0:
+        w = w_data
+    else:
+        w = np.linspace(w_data.min(), w_data.max(), int(scale * w_data.shape[0]))
+    v_fit = np.zeros_like(w)
+    i_fit = np.zeros_like(w)
+    p0, p1, r, yoff = params[:4]
+    rest = params[4:]
+    real_contribs, imag_contribs = [], []
+    for k in range(0, len(rest), 3):
+        width, loc, a = rest[k], rest[k + 1], rest[k + 2]
+        real = voigt(w, r, yoff, width, loc, a)
+        imag = kk(w, r, yoff, width, loc, a)
+        real_contribs.append(real)
+        imag_contribs.append(imag)
+        v_fit = v_fit + real
+        i_fit = i_fit + imag
+    u_fit, v_fit2 = ps2(v_fit, i_fit, inv=True, p0=p0, p1=p1)
+    return dict(w=w, V=v_fit, I=i_fit, u=u_fit, v=v_fit2,
+                real_contribs=real_contribs, imag_contribs=imag_contribs)
+
+
+def get_areas(params):
+    """utils.py:322: params[6::3]."""
+    return np.array([params[i] for i in range(6, len(params), 3)])
+
+
+def area_fraction(areas):
+    """utils.py:302-310 / containers.py:246-252: sum(areas < mean) / sum(all)."""
+    areas = np.asarray(areas)
+    m = np.mean(areas)
+    big = areas[areas >= m].sum()
+    small = areas[areas < m].sum()
+    return small / (big + small)
+
+
+def solution_bounds(peaks, p0=None, p1=None):
+    """containers.py:193-215.  ``p0``/``p1`` not None == force_p0/force_p1."""
+    lower, upper = [], []
+    for ph in (p0, p1):
+        if ph is not None:
+            upper.append(ph + 0.001)
+            lower.append(ph - 0.001)
+        else:
+            upper.append(np.pi)
+            lower.append(-np.pi)
+    upper.extend([1.0, 0.01])
+    lower.extend([0.0, -0.01])
+    for pk in peaks:
+        lower.extend([pk.width * 0.5, pk.loc - 0.1 * (pk.loc - pk.bounds[0]), pk.area * 0.5])
+        upper.extend([pk.width * 1.5, pk.loc - 0.1 * (pk.loc - pk.bounds[1]), pk.area * 1.5])
+    return lower, upper
