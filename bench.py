@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""Benchmark of the nmrfit objective-evaluation hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Workload (BASELINE.json configs[1], "C2"): one fit with 12 peaks on a 32,768-point window,
+swarm of 4,096 particles per GPU, FP64 objective.  A *step* is one swarm generation on the
+device: velocity/position update (device Philox), objective for every particle, personal
+bests, swarm best (+ one record all-gather when particles are sharded over N > 1 GPUs; weak
+scaling: each rank holds 4,096 particles of one 4,096*N-particle swarm).
+
+One JSON line on stdout (rank 0).  `value` = objective evaluations per second over all GPUs
+with everything resident in HBM; `e2e` = the same metric through the public host-buffer call
+(`equations.objective_batch`: spectrum + particle positions copied H2D and objective values
+copied D2H inside the timed region, every step).
+
+`--impl reference` times the CPU arm on the same config: the numpy oracle port of the
+reference objective (oracle/nmrfit_oracle.py, bit-identical to the unmodified reference on the
+golden vectors), called once per particle over a multiprocessing pool with every host core -
+what `nmrfit.fit(..., processes=N)` does through pyswarm.  Each step is a bounded sample of
+the generation (a fixed number of particles), not the 4,096.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (n_peaks, n_points, particles per GPU, synth seed)
+    'c2': (12, 32768, 4096, 2000),
+    'c1': (6, 4096, 100, 1000),
+    'c4': (24, 65536, 8192, 4000),
+}
+METRIC = 'voigt_objective_evals_per_s'
+PSO = dict(omega=-0.2134, phip=-0.3344, phig=2.3259)
+
+
+def flop_per_eval(n_points, n_peaks):
+    """SURVEY.md section 8(d) canonical cost model: 50 FP64 flop per peak-point + 20 per (particle, point)."""
+    return n_points * (50 * n_peaks + 20)
+
+
+def make_inputs(name):
+    from nmrfit_b200 import synth, utils
+    P, N, S, seed = WORKLOADS[name]
+    data, true = synth.multiplet(N, P, seed=seed)
+    weights = utils.compute_weights(data.w, data.peaks)
+    lo, up = data.generate_solution_bounds()
+    return data, weights, np.array(lo), np.array(up), true
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU arm: oracle port over all host cores
+# ---------------------------------------------------------------------------------------------
+_pool_args = None
+
+
+def _pool_init(w, u, v, weights):
+    global _pool_args
+    _pool_args = (w, u, v, weights)
+
+
+def _pool_eval(x):
+    from oracle import nmrfit_oracle as orc      # CPU baseline leg: the one place bench.py runs the oracle
+    return orc.objective(x, *_pool_args, False)
+
+
+def cpu_arm(name, n_particles, repeats, cores=None):
+    """evals/s of the numpy objective, one call per particle, Pool.map over `cores` processes."""
+    import multiprocessing as mp
+    from nmrfit_b200 import synth
+    data, weights, lo, up, _ = make_inputs(name)
+    xs = synth.particles(lo, up, n_particles, seed=7)
+    cores = cores or os.cpu_count() or 1
+    ctx = mp.get_context('fork')
+    times = []
+    with ctx.Pool(cores, initializer=_pool_init, initargs=(data.w, data.u, data.v, weights)) as pool:
+        pool.map(_pool_eval, list(xs[:cores]))                     # warm the workers
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            pool.map(_pool_eval, list(xs))
+            times.append(time.perf_counter() - t0)
+    return n_particles / np.array(times), cores
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return 0
+    P, N, S, _ = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    # bounded sample: ~1 s of wall time per step (the numpy objective costs ~8 ms per evaluation per
+    # core at 12 peaks x 32,768 points and scales with n_points * n_peaks)
+    sample = min(S, max(cores, int(125 * cores * 393216.0 / (N * P))))
+    rates, cores = cpu_arm(args.workload, sample, args.warmup + args.steps)
+    rates = rates[args.warmup:]
+    value = float(sample * len(rates) / np.sum(sample / rates))
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(1e3 * np.mean(sample / rates)),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': workload_config(args.workload, args.gpus),
+        'cpu_baseline': {'value': value, 'unit': 'evals/s', 'cores': cores, 'kind': 'port',
+                         'sample': '%d particles per step (of %d), numpy objective once per particle over a '
+                                   '%d-process pool' % (sample, S, cores)},
+        'e2e': {'value': value, 'unit': 'evals/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'peak_points_per_s': value * N * P,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(name, gpus):
+    P, N, S, _ = WORKLOADS[name]
+    return {'workload': 'BASELINE config[1] C2: single fit, 12 peaks, 32,768-point window, swarmsize 4,096 per GPU, '
+                        'FP64 objective' if name == 'c2' else 'workload %s' % name,
+            'n_peaks': P, 'n_points': N, 'particles_per_gpu': S, 'swarm_total': S * gpus,
+            'parallelism': 'particles sharded over %d GPU(s), one best-record all-gather per generation' % gpus,
+            'l2': 'flushed between timed steps (256 MiB fill outside the per-step event brackets)'}
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+              'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', '-i', str(self.index), '--query-gpu=' + self.FIELDS, '--format=csv,noheader,nounits',
+                 '-lms', '50'], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        self.t = threading.Thread(target=self._read, daemon=True)
+        self.t.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, smax, power, reasons = [], None, [], set()
+        for t, row in self.rows:
+            parts = [p.strip() for p in row.split(',')]
+            if len(parts) < 7 or not (t0 <= t <= t1 + 0.15):
+                continue
+            try:
+                sm.append(float(parts[0])); smax = float(parts[1]); power.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), parts[3:7]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax,
+                'power_w_max': max(power) if power else None, 'samples': len(sm), 'reasons': sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from nmrfit_b200 import _cabi, equations, swarm
+
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world != args.gpus:
+        raise SystemExit('--gpus %d but WORLD_SIZE=%d (launch N>1 with torch.distributed.run)' % (args.gpus, world))
+    P, N, S, _ = WORKLOADS[args.workload]
+    D = 4 + 3 * P
+
+    # CPU baseline first (rank 0, N == 1): fork-based pool must not inherit a CUDA context
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        n_cores = os.cpu_count() or 1
+        sample = min(S, max(n_cores, 32 * n_cores))
+        rates, n_cores = cpu_arm(args.workload, sample, 3)
+        one, _ = cpu_arm(args.workload, max(8, sample // n_cores // 2), 2, cores=1)
+        cpu = {'value': float(np.median(rates)), 'unit': 'evals/s', 'cores': n_cores, 'kind': 'port',
+               'sample': '%d of %d particles, numpy objective once per particle, %d-process pool, median of 3'
+                         % (sample, S, n_cores),
+               'one_core_value': float(np.median(one))}
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=torch.device('cuda', local))
+    stream = torch.cuda.current_stream().cuda_stream
+    data, weights, lo, up, true = make_inputs(args.workload)
+
+    ctx = _cabi.Context(1, N, P, device=local)
+    if args.tune:
+        th, r, tb, sp = (int(t) for t in args.tune.split(','))
+        ctx.set_tuning(th, r, tb, sp)
+    ctx.set_spectrum(0, data.w, data.u, data.v, weights)
+    off = rank * S
+    opts = swarm._make_opts(S, 10 ** 9, PSO['omega'], PSO['phip'], PSO['phig'], 0.0, 0.0, False, 1234, offset=off)
+    opts.minstep = -1.0      # never stop early: every timed step does the full generation's work
+    opts.minfunc = -1.0
+    ctx.pso_begin(lo, up, opts, stream=stream)
+    rec = None
+    if world > 1:
+        ptr, nrec = ctx.pso_record()
+        rec = torch.as_tensor(swarm._DeviceArray(ptr, nrec), device='cuda:%d' % local)
+
+    def commit():
+        if world > 1:
+            ctx.pso_commit(swarm.gather_records(rec), world, stream=stream)
+        else:
+            ctx.pso_commit(stream=stream)
+
+    def step():
+        ctx.pso_advance(stream=stream)
+        commit()
+
+    commit()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    sync_all()
+
+    # ---- timed region: K steps, per-step CUDA events on the launching stream, L2 flushed between steps
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.25)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ctx.profile(True)
+    launches0 = _cabi.launch_count()
+    sync_all()
+    t0 = time.perf_counter()
+    for a, b in ev:
+        flush.fill_(1)
+        a.record()
+        step()
+        b.record()
+    sync_all()
+    t1 = time.perf_counter()
+    launches = _cabi.launch_count() - launches0
+    kernel_ms, kernel_launches = ctx.profile_read()
+    ctx.profile(False)
+    clocks = sampler.stop(t0, t1)
+    step_ms = np.array([a.elapsed_time(b) for a, b in ev])
+    total_ms = torch.tensor([float(step_ms.sum())], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    value = S * world * args.steps / (total_ms * 1e-3)
+
+    x, f, it, stop = ctx.pso_best()
+    assert int(it[0]) == args.warmup + args.steps and np.isfinite(f[0]) and int(stop[0]) == 0
+
+    # ---- end to end through the public host-buffer API
+    from nmrfit_b200 import synth
+    xs_pinned = torch.empty((S, D), dtype=torch.float64).pin_memory()
+    xs = xs_pinned.numpy()
+    xs[:] = synth.particles(lo, up, S, seed=7 + rank)
+    for _ in range(max(3, args.warmup)):
+        equations.objective_batch(xs, data.w, data.u, data.v, weights)
+    sync_all()
+    e0 = time.perf_counter()
+    for _ in range(args.steps):
+        fx = equations.objective_batch(xs, data.w, data.u, data.v, weights)
+    torch.cuda.synchronize()
+    e_ms = torch.tensor([(time.perf_counter() - e0) * 1e3], dtype=torch.float64, device='cuda')
+    if world > 1:
+        dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = S * world * args.steps / (float(e_ms.item()) * 1e-3)
+    assert fx.shape == (S,) and np.all(np.isfinite(fx))
+
+    # ---- roofline of the dominant kernel (objective_kernel), denominators measured on this box
+    burst, sustained = _cabi.fp64_peak(local, iters=4096, repeats=20)
+    per_launch_ms = kernel_ms / max(kernel_launches, 1)
+    achieved = S * flop_per_eval(N, P) / (per_launch_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, 'profiles', 'objective_traffic.json')
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get(args.workload)
+    peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    hbm_peak = json.load(open(peaks_path)).get('hbm_gbs') if os.path.exists(peaks_path) else 6650.0
+    algo_bytes = 4 * N * 8 + S * D * 8 + S * 8
+
+    if rank == 0:
+        tune = ctx.get_tuning(S)
+        line = {
+            'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': dict(workload_config(args.workload, world), kernel=tune),
+            'peak_points_per_s': value * N * P,
+            'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s',
+                         'frac': achieved / sustained, 'traffic': traffic,
+                         'kernel': 'objective_kernel', 'kernel_ms_per_launch': per_launch_ms,
+                         'kernel_share_of_step': kernel_ms / float(step_ms.sum()),
+                         'flop_per_eval': flop_per_eval(N, P),
+                         'peak_source': 'DFMA probe (nmrfit_fp64_peak) measured in this run, back-to-back average; '
+                                        'burst %.2f TFLOP/s; MEASURED_PEAKS.json has no FP64 entry' % burst,
+                         'peak_burst': burst,
+                         'hbm': {'algorithmic_bytes_per_launch': algo_bytes,
+                                 'achieved_gbs': algo_bytes / (per_launch_ms * 1e-3) / 1e9, 'peak_gbs': hbm_peak}},
+            'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(xs.nbytes + 4 * N * 8),
+                    'd2h_bytes_per_step': int(S * 8),
+                    'api': 'nmrfit_b200.equations.objective_batch(xs, w, u, v, weights) with host arrays'},
+            'gpu_launches': int(launches),
+            'clocks': clocks,
+        }
+        if cpu:
+            line['cpu_baseline'] = cpu
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--tune', default='', help='threads,points_per_thread,exp_table_bits,particles_per_cta')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    return run_reference(args) if args.impl == 'reference' else run_b200(args)
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -77,6 +77,11 @@ int nmrfit_ctx_set_tuning(nmrfit_ctx* ctx, int threads, int points_per_thread, i
 int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* points_per_thread, int* exp_table_bits,
                           int* particles_per_cta, int* n_point_tiles);
 
+/* Per-launch timing of the objective kernel with CUDA events on the launching stream (for bench.py's
+ * roofline: enable, run, then read the summed duration and the launch count; read resets). */
+int nmrfit_ctx_profile(nmrfit_ctx* ctx, int enable);
+int nmrfit_ctx_profile_read(nmrfit_ctx* ctx, double* total_ms, long long* launches);
+
 /* ---- objective: equations.objective (equations.py:152-212) for a whole swarm generation -------
  * x [n_spectra][n_particles][D] -> f [n_spectra][n_particles].  One call replaces the
  * n_particles Python callbacks pyswarm makes per generation (utils.py:176-182). */

@@ -48,6 +48,8 @@ SIGNATURES = {
     'nmrfit_ctx_set_spectrum': (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
     'nmrfit_ctx_set_tuning': (_i, [_vp, _i, _i, _i, _i]),
     'nmrfit_ctx_get_tuning': (_i, [_vp, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    'nmrfit_ctx_profile': (_i, [_vp, _i]),
+    'nmrfit_ctx_profile_read': (_i, [_vp, c_double_p, ctypes.POINTER(ctypes.c_longlong)]),
     'nmrfit_objective_batch': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'nmrfit_objective_batch_host': (_i, [_vp, _vp, _i, _i, _vp]),
     'nmrfit_pso_begin': (_i, [_vp, _vp, _vp, ctypes.POINTER(PsoOpts), _vp, _vp, _vp]),
@@ -168,6 +170,15 @@ class Context:
         check(lib().nmrfit_ctx_get_tuning(self._h, int(n_particles), *[ctypes.byref(v) for v in vals]))
         keys = ('threads', 'points_per_thread', 'exp_table_bits', 'particles_per_cta', 'n_point_tiles')
         return dict(zip(keys, (v.value for v in vals)))
+
+    def profile(self, enable=True):
+        check(lib().nmrfit_ctx_profile(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        """(summed objective-kernel milliseconds, launches) since the last read."""
+        ms, n = ctypes.c_double(0), ctypes.c_longlong(0)
+        check(lib().nmrfit_ctx_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)))
+        return ms.value, n.value
 
     # -- objective
     def objective_host(self, x, fit_im=REAL_ONLY):

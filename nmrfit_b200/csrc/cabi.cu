@@ -66,18 +66,6 @@ bool is_device_pointer(const void* p) {
     return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
 }
 
-struct DeviceGuard {
-    int prev = -1;
-    explicit DeviceGuard(int dev) {
-        cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
-        else prev = -1;
-    }
-    ~DeviceGuard() {
-        if (prev >= 0) cudaSetDevice(prev);
-    }
-};
-
 }  // namespace
 
 struct nmrfit_ctx {
@@ -93,6 +81,10 @@ struct nmrfit_ctx {
     DevBuf<double> sx, sv, sp, sfx, sfp, sg, sfg, sbx, sbf, slb, sub, srec, rnd_a, rnd_b;
     DevBuf<int> sstop, sit;
     int* h_flags = nullptr;            // pinned [2*B]
+    // optional per-launch timing of the objective kernel (nmrfit_ctx_profile)
+    bool profiling = false;
+    std::vector<cudaEvent_t> prof_events;   // pairs
+    size_t prof_used = 0;
 };
 
 namespace {
@@ -139,8 +131,21 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     a.partials = c->partials.ptr;
     a.frozen = frozen;
     a.N = c->N; a.P = c->P; a.S = S; a.kk = fit_im; a.sp = t.sp;
-    cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, st)
-                                                : launch_objective(a, t, c->B, f_dev, st);
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    if (c->profiling) {
+        if (c->prof_used + 2 > c->prof_events.size()) {
+            for (int k = 0; k < 2; ++k) {
+                cudaEvent_t ev;
+                CK(cudaEventCreate(&ev));
+                c->prof_events.push_back(ev);
+            }
+        }
+        ev0 = c->prof_events[c->prof_used];
+        ev1 = c->prof_events[c->prof_used + 1];
+        c->prof_used += 2;
+    }
+    cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, st, ev0, ev1)
+                                                : launch_objective(a, t, c->B, f_dev, st, ev0, ev1);
     if (e != cudaSuccess) return fail_cuda(e, "objective launch");
     return NMRFIT_OK;
 }
@@ -206,6 +211,7 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->sstop.release();
     c->sit.release();
     if (c->h_flags) cudaFreeHost(c->h_flags);
+    for (cudaEvent_t ev : c->prof_events) cudaEventDestroy(ev);
     delete c;
 }
 
@@ -242,6 +248,29 @@ int nmrfit_ctx_get_tuning(nmrfit_ctx* c, int S, int* threads, int* r, int* tb, i
     if (tb) *tb = t.tb;
     if (sp) *sp = t.sp;
     if (n_tiles) *n_tiles = objective_tiles(c->N, t);
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_profile(nmrfit_ctx* c, int enable) {
+    if (int rc = check_ctx(c)) return rc;
+    c->profiling = enable != 0;
+    c->prof_used = 0;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_profile_read(nmrfit_ctx* c, double* total_ms, long long* launches) {
+    if (int rc = check_ctx(c)) return rc;
+    CK(cudaSetDevice(c->device));
+    double sum = 0.0;
+    for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
+        CK(cudaEventSynchronize(c->prof_events[i + 1]));
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
+        sum += ms;
+    }
+    if (total_ms) *total_ms = sum;
+    if (launches) *launches = (long long)(c->prof_used / 2);
+    c->prof_used = 0;
     return NMRFIT_OK;
 }
 

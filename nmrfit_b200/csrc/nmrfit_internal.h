@@ -29,10 +29,13 @@ struct ObjTune {
 
 int objective_tiles(int N, const ObjTune& t);
 size_t objective_smem_bytes(int P, const ObjTune& t, int kk);
-cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st);
+// ev0/ev1 (nullable) are recorded immediately before/after the main kernel on `st`
+cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0 = nullptr,
+                             cudaEvent_t ev1 = nullptr);
 
 // opt-in FP32 objective (same launch geometry)
-cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st);
+cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0 = nullptr,
+                                 cudaEvent_t ev1 = nullptr);
 
 // ---- K2/K3 swarm --------------------------------------------------------------
 struct SwarmState {

@@ -56,7 +56,7 @@ objective_kernel(ObjArgs a) {
     if (a.frozen && a.frozen[b]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.P, N = a.N, D = 4 + 3 * P;
-    const int s0 = blockIdx.y * a.sp;
+    const int s0 = blockIdx.x * a.sp;          // particle tiles on x (no 65,535 limit), point tiles on y
     const int nsp = min(a.sp, a.S - s0);
     const ObjSmem L(a.sp, P, NW, R, TB, NSUM);
     double* coef = smem + L.coef;
@@ -67,7 +67,7 @@ objective_kernel(ObjArgs a) {
     double* wpart = smem + L.wpart;
 
     // ---- this thread's grid points
-    const int tile0 = blockIdx.x * (THREADS * R);
+    const int tile0 = blockIdx.y * (THREADS * R);
     const double* sw = a.spec + (size_t)b * 4 * N;
     double w[R], u[R], v[R], wt[R];
 #pragma unroll
@@ -98,7 +98,6 @@ objective_kernel(ObjArgs a) {
     }
     {
         const int per = 32 + NW * R;
-        const double invN = 1.0;  (void)invN;
         for (int idx = tid; idx < nsp * per; idx += THREADS) {
             int sp = idx / per, e = idx - sp * per;
             const double* xs = xb + (size_t)sp * D;
@@ -197,7 +196,7 @@ objective_kernel(ObjArgs a) {
         double t = 0.0;
 #pragma unroll
         for (int wi = 0; wi < NW; ++wi) t += wpart[(sp * NW + wi) * NSUM + c];
-        a.partials[(((size_t)b * a.S + s0 + sp) * gridDim.x + blockIdx.x) * NSUM + c] = t;
+        a.partials[(((size_t)b * a.S + s0 + sp) * gridDim.y + blockIdx.y) * NSUM + c] = t;
     }
 }
 
@@ -263,17 +262,20 @@ size_t objective_smem_bytes(int P, const ObjTune& t, int kk) {
     return (size_t)ObjSmem(t.sp, P, t.threads / 32, t.r, t.tb, kk ? 2 : 1).total * sizeof(double);
 }
 
-cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st) {
+cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0,
+                             cudaEvent_t ev1) {
     a.sp = t.sp;
     const int n_tiles = objective_tiles(a.N, t);
-    dim3 grid(n_tiles, (a.S + t.sp - 1) / t.sp, B);
+    dim3 grid((a.S + t.sp - 1) / t.sp, n_tiles, B);
     cudaError_t e = cudaErrorInvalidValue;
+    if (ev0) cudaEventRecord(ev0, st);
     if (t.threads == 128 && t.r == 2) e = launch_tb<128, 2>(a, t.tb, grid, st);
     else if (t.threads == 128 && t.r == 4) e = launch_tb<128, 4>(a, t.tb, grid, st);
     else if (t.threads == 128 && t.r == 8) e = launch_tb<128, 8>(a, t.tb, grid, st);
     else if (t.threads == 256 && t.r == 2) e = launch_tb<256, 2>(a, t.tb, grid, st);
     else if (t.threads == 256 && t.r == 4) e = launch_tb<256, 4>(a, t.tb, grid, st);
     else if (t.threads == 256 && t.r == 8) e = launch_tb<256, 8>(a, t.tb, grid, st);
+    if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) return e;
     const int total = B * a.S;
     objective_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(a.partials, n_tiles, a.kk ? 2 : 1, a.N, a.S, B,

@@ -3,5 +3,7 @@
 #include "nmrfit_internal.h"
 
 namespace nmrfit {
-cudaError_t launch_objective_f32(ObjArgs, const ObjTune&, int, double*, cudaStream_t) { return cudaErrorNotSupported; }
+cudaError_t launch_objective_f32(ObjArgs, const ObjTune&, int, double*, cudaStream_t, cudaEvent_t, cudaEvent_t) {
+    return cudaErrorNotSupported;
+}
 }  // namespace nmrfit

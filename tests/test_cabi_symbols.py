@@ -1,0 +1,57 @@
+"""The shared library builds for sm_100a without a GPU, loads, and exports every symbol
+include/nmrfit_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def built():
+    import __graft_entry__ as g
+    g.build()
+    return g.LIB
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, 'include', 'nmrfit_b200.h')).read()
+    text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+    return sorted(set(re.findall(r'\b(nmrfit_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_exports_match_header(built):
+    from nmrfit_b200 import _cabi
+    names = declared_symbols()
+    assert len(names) >= 25
+    handle = ctypes.CDLL(built)
+    for n in names:
+        assert hasattr(handle, n), n
+    # the ctypes table binds exactly the declared set
+    assert sorted(_cabi.SIGNATURES) == names
+
+
+def test_abi_version_and_error_string(built):
+    from nmrfit_b200 import _cabi
+    lib = _cabi.lib()
+    assert lib.nmrfit_abi_version() == 1
+    assert isinstance(lib.nmrfit_last_error(), bytes)
+    assert _cabi.launch_count() >= 0
+
+
+def test_pso_opts_layout_matches_header():
+    from nmrfit_b200 import _cabi
+    # struct nmrfit_pso_opts: 2 int, 5 double, 2 int, u64, i64  -> 72 bytes with natural alignment
+    assert ctypes.sizeof(_cabi.PsoOpts) == 72
+    assert _cabi.PsoOpts.omega.offset == 8 and _cabi.PsoOpts.fit_im.offset == 48
+    assert _cabi.PsoOpts.seed.offset == 56 and _cabi.PsoOpts.particle_offset.offset == 64
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    from nmrfit_b200 import _cabi
+    monkeypatch.setattr(_cabi, '_lib', None)
+    monkeypatch.setattr(_cabi, 'LIB_PATH', str(tmp_path / 'nope.so'))
+    with pytest.raises(ImportError, match='no CPU fallback'):
+        _cabi.lib()

@@ -1,0 +1,100 @@
+"""Accuracy of the device math (nmrfit_b200/csrc/nmrfit_math.cuh) compiled for the host.
+The header is the single source of the lineshape arithmetic; compiling it with g++
+lets the polynomial tables, the range reduction and the reciprocal refinement be
+checked against libm / mpmath without a GPU.  (The MUFU reciprocal seed is emulated
+by truncating to the 20 mantissa bits of a high word.)"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+from scipy.special import dawsn
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+dp = ctypes.POINTER(ctypes.c_double)
+
+
+def P(a):
+    return a.ctypes.data_as(dp)
+
+
+@pytest.fixture(scope='module')
+def hm(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp('hm') / 'host_math.so')
+    subprocess.run(['g++', '-O2', '-ffp-contract=off', '-shared', '-fPIC', '-o', so,
+                    os.path.join(ROOT, 'tests', 'host_math_harness.cpp')], check=True)
+    return ctypes.CDLL(so)
+
+
+@pytest.mark.parametrize('tb', [0, 6, 8, 10])
+def test_exp_neg(hm, tb):
+    rng = np.random.default_rng(tb)
+    x = -np.concatenate([rng.random(100000) * 40, 10.0 ** rng.uniform(-14, 1, 20000), [0.0, 1e-300]])
+    out = np.empty_like(x)
+    hm.h_exp_neg(tb, P(x), len(x), P(out))
+    rel = np.abs(out / np.exp(x) - 1)
+    assert rel.max() < 2e-15, rel.max()
+    # deep tail: single-FMA reduction costs accuracy proportional to |x|, irrelevant in absolute terms
+    x = -rng.uniform(40, 700, 50000)
+    hm.h_exp_neg(tb, P(x), len(x), P(out[:len(x)]))
+    assert np.abs(out[:len(x)] / np.exp(x) - 1).max() < 5e-14
+    # below the clamp everything collapses to ~exp(-700): finite, tiny, never NaN/inf
+    x = -np.array([700.0, 701.0, 1e4, 1e9, 1e300])
+    hm.h_exp_neg(tb, P(x), len(x), P(out[:len(x)]))
+    assert np.all(np.isfinite(out[:len(x)])) and np.all(out[:len(x)] < 1e-300) and np.all(out[:len(x)] > 0)
+
+
+def test_rcp_pos(hm):
+    rng = np.random.default_rng(1)
+    q = 1 + 10.0 ** rng.uniform(-9, 12, 200000)
+    out = np.empty_like(q)
+    hm.h_rcp_pos(P(q), len(q), P(out))
+    assert np.abs(out * q - 1).max() < 3e-16
+
+
+def test_dawson(hm):
+    rng = np.random.default_rng(2)
+    s = np.concatenate([rng.uniform(-12, 12, 200000), 10.0 ** rng.uniform(-12, 5, 20000),
+                        [0.0, 8.0, np.nextafter(8.0, 0), -8.0, 0.25, 0.5]])
+    out = np.empty_like(s)
+    hm.h_dawson(P(s), len(s), P(out))
+    assert np.abs(out - dawsn(s)).max() < 4e-16
+    assert np.array_equal(out[:1000], -_daw(hm, -s[:1000]))      # odd
+
+
+def _daw(hm, s):
+    s = np.ascontiguousarray(s)
+    out = np.empty_like(s)
+    hm.h_dawson(P(s), len(s), P(out))
+    return out
+
+
+@pytest.mark.parametrize('tb', [0, 6])
+def test_voigt_body_matches_reference_formula(hm, tb):
+    from oracle import nmrfit_oracle as orc
+    w = np.linspace(3.23, 3.60, 5000)
+    for r, width, loc, a in ((0.55, 0.004, 3.41, 0.012), (0.0, 0.002, 3.3, 1.5), (1.0, 0.006, 3.59, 0.2)):
+        out = np.empty_like(w)
+        hm.h_voigt_body.argtypes = [dp, ctypes.c_int] + [ctypes.c_double] * 4 + [ctypes.c_int, dp]
+        hm.h_voigt_body(P(w), len(w), r, width, loc, a, tb, P(out))
+        want = orc.voigt(w, r, 0.0, width, loc, a)
+        assert np.abs(out - want).max() < 4e-16 * np.abs(want).max() + 1e-300
+        assert np.abs(out / want - 1)[want > 1e-12 * want.max()].max() < 1e-13
+
+
+def test_philox_known_answer_and_range(hm):
+    # Random123 known-answer test for philox4x32-10: counter = key = 0
+    out = np.empty(2)
+    hm.h_philox.argtypes = [ctypes.c_ulonglong] * 3 + [dp]
+    hm.h_philox(0, 0, 0, P(out))
+    c = [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    want = [((c[0] >> 5) * 67108864.0 + (c[1] >> 6)) / 9007199254740992.0,
+            ((c[2] >> 5) * 67108864.0 + (c[3] >> 6)) / 9007199254740992.0]
+    assert list(out) == want
+    vals = []
+    for i in range(2000):
+        hm.h_philox(12345, i, 7, P(out))
+        vals.extend(out)
+    vals = np.array(vals)
+    assert vals.min() >= 0 and vals.max() < 1 and abs(vals.mean() - 0.5) < 0.02
