@@ -43,6 +43,12 @@ extern "C" {
 #define NMRFIT_FP64 0
 #define NMRFIT_FP32 1          /* opt-in: FP32 lineshape math, FP64 residual accumulation */
 
+/* objective kernel selection (nmrfit_ctx_set_algorithm) */
+#define NMRFIT_ALGO_AUTO 0     /* uniform-axis kernel when every spectrum's w is uniformly spaced, the fit is
+                                  real-only and FP64; the general kernel otherwise */
+#define NMRFIT_ALGO_GENERAL 1  /* always the general kernel (any w) */
+#define NMRFIT_ALGO_UNIFORM 2  /* require the uniform-axis kernel; launches fail with NMRFIT_ERR_STATE if it cannot run */
+
 /* fit_im argument of the objective entry points */
 #define NMRFIT_REAL_ONLY 0     /* fit_im is not True: equations.py:202 only */
 #define NMRFIT_IM_REFERENCE 1  /* fit_im is True, reference semantics: equations.py:199 overwrites I_fit,
@@ -70,8 +76,15 @@ void nmrfit_ctx_destroy(nmrfit_ctx* ctx);
 int nmrfit_ctx_set_spectrum(nmrfit_ctx* ctx, int b, const double* w, const double* u, const double* v,
                             const double* weights);
 
+/* Which objective kernel runs (default NMRFIT_ALGO_AUTO), and which one a launch with this fit_im would use.
+ * Both kernels evaluate equations.objective (equations.py:152-212); the uniform-axis one exploits
+ * w_i = w_0 + i*h (what core.load builds, core.py:58-60) to replace most exponentials by a recurrence. */
+int nmrfit_ctx_set_algorithm(nmrfit_ctx* ctx, int algorithm);
+int nmrfit_ctx_get_algorithm(nmrfit_ctx* ctx, int fit_im, int* algorithm);
+
 /* Launch geometry of the objective kernel; 0 keeps the automatic choice for that field.
- * threads in {128, 256}; points_per_thread in {2, 4, 8}; exp_table_bits in {0, 6, 8, 10}. */
+ * threads in {128, 256}; points_per_thread in {2, 4, 8} (general kernel) or {4, 8, 16} (uniform-axis
+ * kernel); exp_table_bits in {-1 (no table), 6, 8, 10}. */
 int nmrfit_ctx_set_tuning(nmrfit_ctx* ctx, int threads, int points_per_thread, int exp_table_bits,
                           int particles_per_cta);
 int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* points_per_thread, int* exp_table_bits,

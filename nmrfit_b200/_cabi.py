@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, 'csrc', 'libnmrfit_b200.so')
 OK = 0
 FP64, FP32 = 0, 1
 REAL_ONLY, IM_REFERENCE, IM_SUM = 0, 1, 2
+ALGO_AUTO, ALGO_GENERAL, ALGO_UNIFORM = 0, 1, 2
 RUNNING, STOP_MINFUNC, STOP_MINSTEP, STOP_MAXITER = 0, 1, 2, 3
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -46,6 +47,8 @@ SIGNATURES = {
     'nmrfit_ctx_create': (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i]),
     'nmrfit_ctx_destroy': (None, [_vp]),
     'nmrfit_ctx_set_spectrum': (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    'nmrfit_ctx_set_algorithm': (_i, [_vp, _i]),
+    'nmrfit_ctx_get_algorithm': (_i, [_vp, _i, c_int_p]),
     'nmrfit_ctx_set_tuning': (_i, [_vp, _i, _i, _i, _i]),
     'nmrfit_ctx_get_tuning': (_i, [_vp, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     'nmrfit_ctx_profile': (_i, [_vp, _i]),
@@ -161,6 +164,16 @@ class Context:
             if a.shape != (self.N,):
                 raise ValueError('spectrum arrays must have shape (%d,), got %s' % (self.N, a.shape))
         check(lib().nmrfit_ctx_set_spectrum(self._h, int(b), *[ptr(a) for a in arrs]))
+
+    def set_algorithm(self, algorithm=ALGO_AUTO):
+        """ALGO_AUTO (default), ALGO_GENERAL (any axis) or ALGO_UNIFORM (require the uniform-axis kernel)."""
+        check(lib().nmrfit_ctx_set_algorithm(self._h, int(algorithm)))
+
+    def get_algorithm(self, fit_im=REAL_ONLY):
+        """Which objective kernel a launch with this ``fit_im`` would run."""
+        a = ctypes.c_int(0)
+        check(lib().nmrfit_ctx_get_algorithm(self._h, int(fit_im), ctypes.byref(a)))
+        return a.value
 
     def set_tuning(self, threads=0, points_per_thread=0, exp_table_bits=0, particles_per_cta=0):
         check(lib().nmrfit_ctx_set_tuning(self._h, threads, points_per_thread, exp_table_bits, particles_per_cta))

@@ -1,6 +1,7 @@
 // extern "C" surface of libnmrfit_b200.so (declared in include/nmrfit_b200.h).
 #include <cuda_runtime.h>
 #include <algorithm>
+#include <cmath>
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -72,6 +73,9 @@ struct nmrfit_ctx {
     int device = 0, B = 0, N = 0, P = 0, D = 0, precision = 0;
     DevBuf<double> spec;               // [B][4][N]
     std::vector<char> spec_set;
+    DevBuf<double> grid_h;             // [B][2] axis spacing h and 2^-52*max|w| of each spectrum
+    std::vector<char> uniform;         // [B] stored w is w_0 + i*h to within 4 ulp
+    int algorithm = NMRFIT_ALGO_AUTO;
     DevBuf<double> partials, x_stage, f_stage;
     ObjTune user_tune{0, 0, 0, 0};
     // swarm
@@ -89,13 +93,28 @@ struct nmrfit_ctx {
 
 namespace {
 
-ObjTune pick_tune(const nmrfit_ctx* c, int S) {
+// Which objective kernel a launch uses: the uniform-axis kernel needs every spectrum of the batch on a
+// uniform axis, the real-only fit and FP64; anything else runs the general kernel.
+bool use_uniform(const nmrfit_ctx* c, int fit_im) {
+    if (c->algorithm == NMRFIT_ALGO_GENERAL || fit_im != NMRFIT_REAL_ONLY || c->precision != NMRFIT_FP64) return false;
+    for (char u : c->uniform)
+        if (!u) return false;
+    return true;
+}
+
+ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
     ObjTune t;
     // The point tiling fixes the summation order of the residual, so it may depend on
     // N alone (never on how many particles or spectra a rank happens to hold).
-    if (c->N >= 8192) { t.threads = 256; t.r = 4; }
-    else if (c->N >= 1024) { t.threads = 128; t.r = 4; }
-    else { t.threads = 128; t.r = 2; }
+    if (uni) {
+        if (c->N >= 8192) { t.threads = 256; t.r = 8; }
+        else if (c->N >= 2048) { t.threads = 128; t.r = 8; }
+        else { t.threads = 128; t.r = 4; }
+    } else {
+        if (c->N >= 8192) { t.threads = 256; t.r = 4; }
+        else if (c->N >= 1024) { t.threads = 128; t.r = 4; }
+        else { t.threads = 128; t.r = 2; }
+    }
     t.tb = 6;
     if (c->user_tune.threads) t.threads = c->user_tune.threads;
     if (c->user_tune.r) t.r = c->user_tune.r;
@@ -109,6 +128,9 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S) {
     sp = std::min(sp, std::max(1, S));
     if (c->user_tune.sp > 0) sp = std::min(c->user_tune.sp, std::max(1, S));
     t.sp = sp;
+    // per-particle coefficients live in shared memory: keep the CTA under the 200 KB opt-in limit
+    while (t.sp > 1 && (uni ? objective_uniform_smem_bytes(c->P, t) : objective_smem_bytes(c->P, t, 2)) > 200 * 1024)
+        t.sp /= 2;
     return t;
 }
 
@@ -122,7 +144,13 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     for (int b = 0; b < c->B; ++b)
         if (!c->spec_set[b]) return fail(NMRFIT_ERR_STATE, "spectrum " + std::to_string(b) + " was never set");
     if (fit_im < 0 || fit_im > 2) return fail(NMRFIT_ERR_ARG, "fit_im must be 0, 1 or 2");
-    ObjTune t = pick_tune(c, S);
+    const bool uni = use_uniform(c, fit_im);
+    if (c->algorithm == NMRFIT_ALGO_UNIFORM && !uni)
+        return fail(NMRFIT_ERR_STATE, "the uniform-axis kernel needs uniformly spaced w in every spectrum, fit_im off and FP64");
+    ObjTune t = pick_tune(c, S, uni);
+    if (uni ? (t.r != 4 && t.r != 8 && t.r != 16) : (t.r != 2 && t.r != 4 && t.r != 8))
+        return fail(NMRFIT_ERR_ARG, uni ? "points_per_thread must be 4, 8 or 16 for the uniform-axis kernel"
+                                        : "points_per_thread must be 2, 4 or 8 for the general kernel");
     int n_tiles = objective_tiles(c->N, t);
     CK(c->partials.reserve((size_t)c->B * S * n_tiles * 2));
     ObjArgs a;
@@ -130,6 +158,7 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     a.x = x_dev;
     a.partials = c->partials.ptr;
     a.frozen = frozen;
+    a.grid_h = c->grid_h.ptr;
     a.N = c->N; a.P = c->P; a.S = S; a.kk = fit_im; a.sp = t.sp;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     if (c->profiling) {
@@ -145,6 +174,7 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
         c->prof_used += 2;
     }
     cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, st, ev0, ev1)
+                    : uni                       ? launch_objective_uniform(a, t, c->B, f_dev, st, ev0, ev1)
                                                 : launch_objective(a, t, c->B, f_dev, st, ev0, ev1);
     if (e != cudaSuccess) return fail_cuda(e, "objective launch");
     return NMRFIT_OK;
@@ -191,7 +221,9 @@ int nmrfit_ctx_create(nmrfit_ctx** out, int device, int n_spectra, int n_points,
     c->device = device; c->B = n_spectra; c->N = n_points; c->P = n_peaks; c->D = 4 + 3 * n_peaks;
     c->precision = precision;
     c->spec_set.assign(n_spectra, 0);
+    c->uniform.assign(n_spectra, 0);
     cudaError_t e = c->spec.reserve((size_t)n_spectra * 4 * n_points);
+    if (e == cudaSuccess) e = c->grid_h.reserve(2 * (size_t)n_spectra);
     if (e == cudaSuccess) e = cudaMallocHost(&c->h_flags, sizeof(int) * 2 * n_spectra);
     if (e != cudaSuccess) {
         nmrfit_ctx_destroy(c);
@@ -204,7 +236,7 @@ int nmrfit_ctx_create(nmrfit_ctx** out, int device, int n_spectra, int n_points,
 void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (DevBuf<double>* b : {&c->spec, &c->partials, &c->x_stage, &c->f_stage, &c->sx, &c->sv, &c->sp, &c->sfx,
+    for (DevBuf<double>* b : {&c->spec, &c->grid_h, &c->partials, &c->x_stage, &c->f_stage, &c->sx, &c->sv, &c->sp, &c->sfx,
                               &c->sfp, &c->sg, &c->sfg, &c->sbx, &c->sbf, &c->slb, &c->sub, &c->srec, &c->rnd_a,
                               &c->rnd_b})
         b->release();
@@ -225,14 +257,45 @@ int nmrfit_ctx_set_spectrum(nmrfit_ctx* c, int b, const double* w, const double*
     const double* src[4] = {w, u, v, weights};
     for (int k = 0; k < 4; ++k)
         CK(cudaMemcpy(dst + (size_t)k * c->N, src[k], sizeof(double) * c->N, cudaMemcpyDefault));
+    // Is the axis uniform?  h = (w_last - w_0)/(N-1); every stored w_i within 4 ulp of w_0 + i*h.
+    std::vector<double> hw(c->N);
+    CK(cudaMemcpy(hw.data(), dst, sizeof(double) * c->N, cudaMemcpyDeviceToHost));
+    double h = 0.0, big = 0.0;
+    bool uni = c->N >= 2;
+    if (uni) {
+        h = (hw[c->N - 1] - hw[0]) / (double)(c->N - 1);
+        big = std::max(std::fabs(hw[0]), std::fabs(hw[c->N - 1]));
+        const double tol = 4.0 * 2.220446049250313e-16 * big;
+        uni = std::isfinite(h) && h != 0.0 && std::isfinite(big);
+        for (int i = 0; uni && i < c->N; ++i) uni = std::fabs(hw[i] - std::fma((double)i, h, hw[0])) <= tol;
+    }
+    c->uniform[b] = uni ? 1 : 0;
+    const double grid[2] = {h, 2.220446049250313e-16 * big};
+    CK(cudaMemcpy(c->grid_h.ptr + 2 * (size_t)b, grid, sizeof(grid), cudaMemcpyHostToDevice));
     c->spec_set[b] = 1;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_set_algorithm(nmrfit_ctx* c, int algorithm) {
+    if (int r = check_ctx(c)) return r;
+    if (algorithm != NMRFIT_ALGO_AUTO && algorithm != NMRFIT_ALGO_GENERAL && algorithm != NMRFIT_ALGO_UNIFORM)
+        return fail(NMRFIT_ERR_ARG, "algorithm must be NMRFIT_ALGO_AUTO, _GENERAL or _UNIFORM");
+    c->algorithm = algorithm;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_get_algorithm(nmrfit_ctx* c, int fit_im, int* algorithm) {
+    if (int r = check_ctx(c)) return r;
+    if (!algorithm) return fail(NMRFIT_ERR_ARG, "algorithm is NULL");
+    *algorithm = use_uniform(c, fit_im) ? NMRFIT_ALGO_UNIFORM : NMRFIT_ALGO_GENERAL;
     return NMRFIT_OK;
 }
 
 int nmrfit_ctx_set_tuning(nmrfit_ctx* c, int threads, int r, int tb, int sp) {
     if (int rc = check_ctx(c)) return rc;
     if (threads != 0 && threads != 128 && threads != 256) return fail(NMRFIT_ERR_ARG, "threads must be 0, 128 or 256");
-    if (r != 0 && r != 2 && r != 4 && r != 8) return fail(NMRFIT_ERR_ARG, "points_per_thread must be 0, 2, 4 or 8");
+    if (r != 0 && r != 2 && r != 4 && r != 8 && r != 16)
+        return fail(NMRFIT_ERR_ARG, "points_per_thread must be 0, 2, 4, 8 or 16");
     if (tb != 0 && tb != 6 && tb != 8 && tb != 10 && tb != -1)
         return fail(NMRFIT_ERR_ARG, "exp_table_bits must be 0 (auto), -1 (no table), 6, 8 or 10");
     if (sp < 0 || sp > 64) return fail(NMRFIT_ERR_ARG, "particles_per_cta must be 0..64");
@@ -242,7 +305,7 @@ int nmrfit_ctx_set_tuning(nmrfit_ctx* c, int threads, int r, int tb, int sp) {
 
 int nmrfit_ctx_get_tuning(nmrfit_ctx* c, int S, int* threads, int* r, int* tb, int* sp, int* n_tiles) {
     if (int rc = check_ctx(c)) return rc;
-    ObjTune t = pick_tune(c, S < 1 ? 1 : S);
+    ObjTune t = pick_tune(c, S < 1 ? 1 : S, use_uniform(c, NMRFIT_REAL_ONLY));
     if (threads) *threads = t.threads;
     if (r) *r = t.r;
     if (tb) *tb = t.tb;

@@ -15,6 +15,7 @@ struct ObjArgs {
     const double* x;        // [B][S][D] particle positions, D = 4 + 3P
     double* partials;       // [B][S][n_tiles][nsum]
     const int* frozen;      // [B] or null: spectra whose swarm has stopped are skipped
+    const double* grid_h;   // [B][2] axis spacing h and ulp scale 2^-52*max|w| (uniform-axis kernel only)
     int N, P, S;
     int kk;                 // 0 real only, 1 reference fit_im (last peak), 2 sum over peaks
     int sp;                 // particles per CTA (filled by the launcher)
@@ -22,7 +23,7 @@ struct ObjArgs {
 
 struct ObjTune {
     int threads;            // 128 | 256
-    int r;                  // grid points per thread: 2 | 4 | 8
+    int r;                  // grid points per thread: 2 | 4 | 8 (general kernel), 4 | 8 | 16 (uniform-grid kernel)
     int tb;                 // exp table bits: 0 | 6 | 8 | 10
     int sp;                 // particles per CTA
 };
@@ -32,6 +33,15 @@ size_t objective_smem_bytes(int P, const ObjTune& t, int kk);
 // ev0/ev1 (nullable) are recorded immediately before/after the main kernel on `st`
 cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0 = nullptr,
                              cudaEvent_t ev1 = nullptr);
+
+// fixed-order sum over point tiles + sqrt(mean) (shared by the objective kernels)
+cudaError_t launch_objective_finalize(const double* partials, int n_tiles, int nsum, int N, int S, int B,
+                                      const int* frozen, double* f, cudaStream_t st);
+
+// uniform-axis objective (objective_uniform.cu): real-only fit, FP64
+size_t objective_uniform_smem_bytes(int P, const ObjTune& t);
+cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st,
+                                     cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 
 // opt-in FP32 objective (same launch geometry)
 cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0 = nullptr,

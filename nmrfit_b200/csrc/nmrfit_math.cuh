@@ -109,9 +109,11 @@ template <> struct ExpPoly<10> {
     }
 };
 
-// exp(x) for x <= 0.  Arguments below -700 are clamped there (exp(-700) ~ 1e-304
-// is zero for every purpose of a sum of peaks); the clamp is an unsigned min on
-// the high word, i.e. integer-pipe work, not an FP64 slot.
+// exp(x) for x <= 0 (the Gaussian) and for moderate positive x (the step ratios of
+// peak_span, bounded there to < 300; nothing clamps the positive side).  Arguments
+// below -700 are clamped there (exp(-700) ~ 1e-304 is zero for every purpose of a sum
+// of peaks); the clamp is an unsigned min on the high word - positive doubles have a
+// smaller high word and pass unchanged - i.e. integer-pipe work, not an FP64 slot.
 //   n = rint(x * 2^TB / ln2);  r = x - n * ln2/2^TB  (one FMA: n*ln2/2^TB is not
 //   exact, but its error n*ulp(ln2/2^TB)/2 is < 1e-16 * |x| and enters the result
 //   only as a relative error of exp(x), which is itself < e^x <= 1)
@@ -188,6 +190,92 @@ NMRFIT_HD PeakCoef make_coef(double r, double width, double loc, double a) {
     c.nkG2 = -(kg * kg);
     c.aG = a * (1.0 - r) * (iw * kSqrtLn2OverPi);
     return c;
+}
+
+// ---- uniform-grid span evaluation --------------------------------------------
+// On a uniformly spaced axis (w_i = w_0 + i*h: what np.linspace / a spectrometer
+// ppm scale gives) the Gaussian at consecutive points needs no exponential:
+//   s_j = s_0 + j*hG,  hG = h*kG,   G_j = exp(-s_j^2)
+//   G_{j+1} = G_j * rho_j,   rho_j = exp(-hG*(2*s_j + hG)),   rho_{j+1} = rho_j * c2,   c2 = exp(-2*hG^2)
+// so a thread that owns R consecutive points pays two exponentials (G_0, rho_0) per
+// peak and two multiplies per further point.  The Lorentzian argument advances as
+// t_j = t_0 + j*dT, dT = h*kL.  Per peak-point: t, q, rcp (3), 2 accumulating FMAs,
+// 2 recurrence multiplies = 9 FP64 issue slots + 1 MUFU.
+//
+// A peak takes the recurrence only when it is safe and accurate; the coefficient builder marks it
+// `exact` (c2 < 0) otherwise, and such peaks are evaluated point by point from the STORED abscissae
+// with one exponential each (peak_exact - the arithmetic of the general kernel):
+//   * R*|hG| > 4: the R points of a thread span more than 4 units of s (a peak narrower than ~3 grid
+//     points); the product chain could then be asked to climb from a clamped, underflowed anchor;
+//   * kL*ulp(w) > 1e-11: treating the axis as exactly uniform moves an abscissa by up to one ulp(w)
+//     against its stored value, i.e. up to kL*ulp(w) relative in a curve value - 4e-13 for a 0.004 ppm
+//     line at 3.4 ppm, but it grows as the width shrinks;
+//   * non-finite coefficients.
+// On the recurrence path, if the anchor is already in the far tail (x_0 = -s_0^2 < -650, |s_0| > 25.5)
+// every point of the span has |s_j| > 21.5 and G_j < 1e-200: the chain is forced to zero
+// (rho_0 := exp(-700)) instead of being multiplied up from the clamped anchor.  Otherwise
+// |ln rho_j| <= |hG|*(2*(25.5 + 4) + |hG|), and R of them sum to < 4*63: no overflow.
+struct SpanCoef {
+    double loc, kL, kG, aL;   // centre, 2/W, 2 sqrt(ln2)/W, a r 2/(pi W)
+    double aG, dT, hG, c2;    // a (1-r) (2/W) sqrt(ln2/pi), h kL, h kG, exp(-2 hG^2)  (c2 < 0: exact path)
+};
+
+// h: axis spacing; w_ulp: 2^-52 * max|w| of the axis
+NMRFIT_HD SpanCoef make_span_coef(double r, double width, double loc, double a, double h, double w_ulp, int R) {
+    SpanCoef c;
+    double iw = 2.0 / width;
+    c.loc = loc;
+    c.kL = iw;
+    c.kG = iw * kSqrtLn2;
+    c.aL = a * r * (iw / kPi);
+    c.aG = a * (1.0 - r) * (iw * kSqrtLn2OverPi);
+    c.dT = h * c.kL;
+    c.hG = h * c.kG;
+    double ah = c.hG < 0 ? -c.hG : c.hG;
+    double ak = c.kL < 0 ? -c.kL : c.kL;
+    if ((double)R * ah <= 4.0 && ak * w_ulp <= 1e-11) c.c2 = exp_neg<0>(-2.0 * (c.hG * c.hG), nullptr);
+    else c.c2 = -1.0;          // also taken for NaN / inf
+    return c;
+}
+
+// acc[j] += aL / (1 + t_j^2) + aG * exp(-s_j^2) for the R consecutive points that start at
+// distance d0 = w_first - loc from the centre (recurrence path, c.c2 >= 0).
+template <int R, int TB>
+NMRFIT_HD void peak_span(double d0, const SpanCoef& c, const double* __restrict__ tab, double (&acc)[R]) {
+    const double t0 = d0 * c.kL;
+    const double s0 = d0 * c.kG;
+    const double x0 = -(s0 * s0);
+    double a2 = -(c.hG * NMRFIT_FMA(2.0, s0, c.hG));
+    a2 = x0 < -650.0 ? -700.0 : a2;
+    double g = exp_neg<TB>(x0, tab);
+    double rho = exp_neg<TB>(a2, tab);
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        double t = j == 0 ? t0 : NMRFIT_FMA((double)j, c.dT, t0);
+        double rq = rcp_pos(NMRFIT_FMA(t, t, 1.0));
+        acc[j] = NMRFIT_FMA(c.aL, rq, acc[j]);
+        acc[j] = NMRFIT_FMA(c.aG, g, acc[j]);
+        if (j + 1 < R) {
+            g *= rho;
+            if (j + 2 < R) rho *= c.c2;
+        }
+    }
+}
+
+// Same sum from the stored abscissae w[0..n_valid) (points past the end of the axis are extrapolated
+// with h; they carry zero weight): one exponential per point, any spacing, any width.
+template <int R, int TB>
+NMRFIT_HD void peak_exact(const double* __restrict__ w, int n_valid, double w_first, double h, const SpanCoef& c,
+                          const double* __restrict__ tab, double (&acc)[R]) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        double wj = j < n_valid ? w[j] : NMRFIT_FMA((double)j, h, w_first);
+        double d = wj - c.loc;
+        double t = d * c.kL, s = d * c.kG;
+        double rq = rcp_pos(NMRFIT_FMA(t, t, 1.0));
+        acc[j] = NMRFIT_FMA(c.aL, rq, acc[j]);
+        acc[j] = NMRFIT_FMA(c.aG, exp_neg<TB>(-(s * s), tab), acc[j]);
+    }
 }
 
 // Philox4x32-10 (Salmon et al., SC'11) -> two uniform doubles in [0, 1) with 53

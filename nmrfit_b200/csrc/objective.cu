@@ -277,10 +277,15 @@ cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cuda
     else if (t.threads == 256 && t.r == 8) e = launch_tb<256, 8>(a, t.tb, grid, st);
     if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) return e;
-    const int total = B * a.S;
-    objective_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(a.partials, n_tiles, a.kk ? 2 : 1, a.N, a.S, B,
-                                                                   a.frozen, f);
+    e = launch_objective_finalize(a.partials, n_tiles, a.kk ? 2 : 1, a.N, a.S, B, a.frozen, f, st);
     count_launches(2);
+    return e;
+}
+
+cudaError_t launch_objective_finalize(const double* partials, int n_tiles, int nsum, int N, int S, int B,
+                                      const int* frozen, double* f, cudaStream_t st) {
+    const int total = B * S;
+    objective_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(partials, n_tiles, nsum, N, S, B, frozen, f);
     return cudaGetLastError();
 }
 

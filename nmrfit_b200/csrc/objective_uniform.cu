@@ -1,0 +1,227 @@
+// K1u: batched objective on a UNIFORM frequency axis (w_i = w_0 + i*h, what np.linspace and
+// every spectrometer ppm scale produce) - the kernel a fit normally runs.
+//
+// Same result definition as objective.cu (reference equations.py:152-212 with ps2,
+// proc_autophase.py:29-36, and voigt, equations.py:141-147); different arithmetic.  The general
+// kernel pays one exponential per peak-point; here a thread owns R CONSECUTIVE grid points, so the
+// Gaussian of a peak advances along them by a two-multiply recurrence (peak_span in
+// nmrfit_math.cuh) and only its two anchors need an exponential.  FP64 issue slots per peak-point:
+// 9 (t, q, 3 rcp, 2 accumulate, 2 recurrence) + anchors/R, against 19 in the general kernel;
+// non-FP64 instructions per peak-point: 2 (MUFU seed + its zero low word) against 18.
+//
+// Mapping: grid (particle tiles, point tiles, spectra).  A CTA stages its THREADS*R points of
+// (u, v) and weights in shared memory once ([j][thread] order: conflict-free for the per-point
+// reads) and loops over SP particles; per particle the per-peak span coefficients are built into
+// shared memory by the first threads and broadcast.  The squared residual is reduced by a fixed
+// xor-shuffle tree, a fixed-order sum over warps and (objective_finalize_kernel) over point tiles:
+// no atomics, bit-reproducible, independent of how particles or spectra are sharded.
+//
+// The axis is treated as exactly uniform: the anchor uses the stored w of the thread's first
+// point and the other R-1 abscissae are anchor + j*h.  That moves an abscissa by at most one
+// ulp(w) (4.4e-16 ppm at w ~ 3.4) against the stored value, i.e. <= 5e-13 relative in a curve
+// value for a 0.004 ppm line at 3.4 ppm.  Peaks for which that bound (kL * ulp(w)) would exceed 1e-11,
+// and peaks narrower than ~3 grid points, are evaluated point by point from the stored w instead
+// (peak_exact).  nmrfit_ctx_set_spectrum only enables this kernel when every stored w_i is within
+// 4 ulp of w_0 + i*h, otherwise the general kernel runs.
+#include <cuda_runtime.h>
+#include "nmrfit_internal.h"
+#include "nmrfit_math.cuh"
+
+namespace nmrfit {
+
+template <int TB> struct ExpTabU { static __device__ __forceinline__ const double* src() { return nullptr; } };
+template <> struct ExpTabU<6> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB6; } };
+template <> struct ExpTabU<8> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB8; } };
+template <> struct ExpTabU<10> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB10; } };
+
+// shared-memory carve-up (in doubles), shared by kernel and launcher
+struct UniSmem {
+    int tab, coef, uv, wt, ewarp, elane, misc, wpart, total;
+    __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB) {
+        const int nw = threads / 32;
+        int o = 0;
+        tab = o;   o += TB ? (1 << TB) : 0;
+        coef = o;  o += sp * P * 8;
+        uv = o;    o += threads * R * 2;
+        wt = o;    o += threads * R;
+        ewarp = o; o += sp * nw * 2;
+        elane = o; o += sp * 32 * 2;
+        misc = o;  o += sp * 4;          // cos(p1/N), sin(p1/N), P*yoff, pad
+        wpart = o; o += sp * nw;
+        total = o;
+    }
+};
+
+template <int THREADS, int R, int TB>
+__global__ void __launch_bounds__(THREADS)
+objective_uniform_kernel(ObjArgs a) {
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) double smem[];
+    const int b = blockIdx.z;
+    if (a.frozen && a.frozen[b]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = a.P, N = a.N, D = 4 + 3 * P;
+    const int s0 = blockIdx.x * a.sp;
+    const int nsp = min(a.sp, a.S - s0);
+    const UniSmem L(a.sp, P, THREADS, R, TB);
+    double* tab = smem + L.tab;
+    double* coef = smem + L.coef;
+    double2* suv = reinterpret_cast<double2*>(smem + L.uv);
+    double* swt = smem + L.wt;
+    double2* ewarp = reinterpret_cast<double2*>(smem + L.ewarp);
+    double2* elane = reinterpret_cast<double2*>(smem + L.elane);
+    double* misc = smem + L.misc;
+    double* wpart = smem + L.wpart;
+
+    const int tile0 = blockIdx.y * (THREADS * R);
+    const double* sw = a.spec + (size_t)b * 4 * N;
+    const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
+
+    // ---- stage the tile: coalesced reads, [j][thread] placement (point i0 + t*R + j -> slot j*THREADS + t)
+    for (int e = tid; e < THREADS * R; e += THREADS) {
+        const int i = tile0 + e;
+        const bool ok = i < N;
+        const int slot = (e % R) * THREADS + e / R;
+        suv[slot] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
+        swt[slot] = ok ? sw[3 * N + i] : 0.0;              // zero weight: padding contributes nothing
+    }
+    const int i_first = tile0 + tid * R;                   // this thread's first point
+    const double w_first = i_first < N ? sw[i_first] : fma((double)i_first, h, sw[0]);
+
+    if (TB) {
+        const double* src = ExpTabU<TB>::src();
+        for (int i = tid; i < (1 << TB); i += THREADS) tab[i] = src[i];
+    }
+    // ---- per-particle constants
+    const double* xb = a.x + ((size_t)b * a.S + s0) * D;
+    for (int idx = tid; idx < nsp * P; idx += THREADS) {
+        const int sp = idx / P, k = idx - sp * P;
+        const double* xs = xb + (size_t)sp * D;
+        const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+        double* o = coef + (size_t)idx * 8;
+        o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.hG; o[7] = c.c2;
+    }
+    {
+        // phi_i = p0 + (p1*i)/N, i = tile0 + (32*warp + lane)*R + j, split as
+        // [p0 + p1*(tile0 + 32*R*warp)/N] + [p1*(lane*R)/N] + j*[p1/N]
+        const int per = NW + 32 + 1;
+        for (int idx = tid; idx < nsp * per; idx += THREADS) {
+            const int sp = idx / per, e = idx - sp * per;
+            const double* xs = xb + (size_t)sp * D;
+            const double p0 = xs[0], p1 = xs[1];
+            double ang;
+            if (e < NW) ang = p0 + (p1 * (double)(tile0 + 32 * R * e)) / (double)N;
+            else if (e < NW + 32) ang = (p1 * (double)((e - NW) * R)) / (double)N;
+            else ang = p1 / (double)N;
+            double sn, cs;
+            sincos(ang, &sn, &cs);
+            if (e < NW) ewarp[sp * NW + e] = make_double2(cs, sn);
+            else if (e < NW + 32) elane[sp * 32 + (e - NW)] = make_double2(cs, sn);
+            else { misc[sp * 4] = cs; misc[sp * 4 + 1] = sn; misc[sp * 4 + 2] = (double)P * xs[3]; }
+        }
+    }
+    __syncthreads();
+
+    for (int sp = 0; sp < nsp; ++sp) {
+        double acc[R];
+        const double py = misc[sp * 4 + 2];                // yoff is added once per peak (equations.py:147,195)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] = py;
+        const double* cf = coef + (size_t)sp * P * 8;
+        for (int k = 0; k < P; ++k) {
+            const double2 c01 = *reinterpret_cast<const double2*>(cf + k * 8);
+            const double2 c23 = *reinterpret_cast<const double2*>(cf + k * 8 + 2);
+            const double2 c45 = *reinterpret_cast<const double2*>(cf + k * 8 + 4);
+            const double2 c67 = *reinterpret_cast<const double2*>(cf + k * 8 + 6);
+            SpanCoef c;
+            c.loc = c01.x; c.kL = c01.y; c.kG = c23.x; c.aL = c23.y;
+            c.aG = c45.x; c.dT = c45.y; c.hG = c67.x; c.c2 = c67.y;
+            if (c.c2 >= 0.0) peak_span<R, TB>(w_first - c.loc, c, tab, acc);        // CTA-uniform branch
+            else peak_exact<R, TB>(sw + i_first, N - i_first, w_first, h, c, tab, acc);
+        }
+        // residual against the phase-rotated data; the rotation advances by p1/N per point
+        const double2 ew = ewarp[sp * NW + warp], el = elane[sp * 32 + lane];
+        const double cd = misc[sp * 4], sd = misc[sp * 4 + 1];
+        double cr = fma(ew.x, el.x, -(ew.y * el.y));
+        double ci = fma(ew.y, el.x, ew.x * el.y);
+        double ss = 0.0;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const double2 uv = suv[j * THREADS + tid];
+            const double wt = swt[j * THREADS + tid];
+            const double vd = fma(uv.x, cr, -(uv.y * ci));
+            const double res = wt * (vd - acc[j]);
+            ss = fma(res, res, ss);
+            if (j + 1 < R) {
+                const double c2 = fma(cr, cd, -(ci * sd));
+                ci = fma(ci, cd, cr * sd);
+                cr = c2;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (lane == 0) wpart[sp * NW + warp] = ss;
+    }
+    __syncthreads();
+    for (int sp = tid; sp < nsp; sp += THREADS) {
+        double t = 0.0;
+#pragma unroll
+        for (int wi = 0; wi < NW; ++wi) t += wpart[sp * NW + wi];
+        a.partials[((size_t)b * a.S + s0 + sp) * gridDim.y + blockIdx.y] = t;
+    }
+}
+
+// ---- launcher -----------------------------------------------------------------
+template <int THREADS, int R, int TB>
+static cudaError_t launch_one(const ObjArgs& a, dim3 grid, cudaStream_t st) {
+    static bool attr_set[NMRFIT_MAX_DEVICES] = {};
+    UniSmem L(a.sp, a.P, THREADS, R, TB);
+    size_t bytes = (size_t)L.total * sizeof(double);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!attr_set[dev % NMRFIT_MAX_DEVICES]) {
+        cudaError_t e = cudaFuncSetAttribute(objective_uniform_kernel<THREADS, R, TB>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[dev % NMRFIT_MAX_DEVICES] = true;
+    }
+    objective_uniform_kernel<THREADS, R, TB><<<grid, THREADS, bytes, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int THREADS, int R>
+static cudaError_t launch_tb(const ObjArgs& a, int tb, dim3 grid, cudaStream_t st) {
+    switch (tb) {
+        case 0: return launch_one<THREADS, R, 0>(a, grid, st);
+        case 6: return launch_one<THREADS, R, 6>(a, grid, st);
+        case 8: return launch_one<THREADS, R, 8>(a, grid, st);
+        case 10: return launch_one<THREADS, R, 10>(a, grid, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+size_t objective_uniform_smem_bytes(int P, const ObjTune& t) {
+    return (size_t)UniSmem(t.sp, P, t.threads, t.r, t.tb).total * sizeof(double);
+}
+
+cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0,
+                                     cudaEvent_t ev1) {
+    a.sp = t.sp;
+    const int n_tiles = objective_tiles(a.N, t);
+    dim3 grid((a.S + t.sp - 1) / t.sp, n_tiles, B);
+    cudaError_t e = cudaErrorInvalidValue;
+    if (ev0) cudaEventRecord(ev0, st);
+    if (t.threads == 128 && t.r == 4) e = launch_tb<128, 4>(a, t.tb, grid, st);
+    else if (t.threads == 128 && t.r == 8) e = launch_tb<128, 8>(a, t.tb, grid, st);
+    else if (t.threads == 128 && t.r == 16) e = launch_tb<128, 16>(a, t.tb, grid, st);
+    else if (t.threads == 256 && t.r == 4) e = launch_tb<256, 4>(a, t.tb, grid, st);
+    else if (t.threads == 256 && t.r == 8) e = launch_tb<256, 8>(a, t.tb, grid, st);
+    else if (t.threads == 256 && t.r == 16) e = launch_tb<256, 16>(a, t.tb, grid, st);
+    if (ev1) cudaEventRecord(ev1, st);
+    if (e != cudaSuccess) return e;
+    e = launch_objective_finalize(a.partials, n_tiles, 1, a.N, a.S, B, a.frozen, f, st);
+    count_launches(2);
+    return e;
+}
+
+}  // namespace nmrfit

@@ -8,6 +8,24 @@
 #define __forceinline__ inline
 #include "../nmrfit_b200/csrc/nmrfit_math.cuh"
 
+// Sum of peaks over a uniform grid w_i = w[0] + i*h, evaluated span by span exactly as
+// objective_uniform_kernel does it: anchors at the true w of every R-th point.
+template <int R, int TB>
+static void spans(const double* w, int n, double h, const double* x, int P, const double* tab, double* vfit) {
+    double big = std::fabs(w[0]) > std::fabs(w[n - 1]) ? std::fabs(w[0]) : std::fabs(w[n - 1]);
+    const double w_ulp = 2.220446049250313e-16 * big;
+    for (int i0 = 0; i0 < n; i0 += R) {
+        double acc[R];
+        for (int j = 0; j < R; ++j) acc[j] = (double)P * x[3];
+        for (int k = 0; k < P; ++k) {
+            nmrfit::SpanCoef c = nmrfit::make_span_coef(x[2], x[4 + 3 * k], x[5 + 3 * k], x[6 + 3 * k], h, w_ulp, R);
+            if (c.c2 >= 0.0) nmrfit::peak_span<R, TB>(w[i0] - c.loc, c, tab, acc);
+            else nmrfit::peak_exact<R, TB>(w + i0, n - i0, w[i0], h, c, tab, acc);
+        }
+        for (int j = 0; j < R && i0 + j < n; ++j) vfit[i0 + j] = acc[j];
+    }
+}
+
 extern "C" {
 
 void h_exp_neg(int tb, const double* x, int n, double* out) {
@@ -38,6 +56,18 @@ void h_voigt_body(const double* w, int n, double r, double width, double loc, do
         double acc = c.aL * nmrfit::rcp_pos(q);
         double e = tb == 0 ? nmrfit::exp_neg<0>(d2 * c.nkG2, nullptr) : nmrfit::exp_neg<6>(d2 * c.nkG2, NMRFIT_EXP2_TAB6);
         out[i] = NMRFIT_FMA(c.aG, e, acc);
+    }
+}
+
+void h_span_fit(const double* w, int n, double h, const double* x, int P, int R, int tb, double* vfit) {
+    if (tb == 6) {
+        if (R == 4) spans<4, 6>(w, n, h, x, P, NMRFIT_EXP2_TAB6, vfit);
+        else if (R == 8) spans<8, 6>(w, n, h, x, P, NMRFIT_EXP2_TAB6, vfit);
+        else spans<16, 6>(w, n, h, x, P, NMRFIT_EXP2_TAB6, vfit);
+    } else {
+        if (R == 4) spans<4, 10>(w, n, h, x, P, NMRFIT_EXP2_TAB10, vfit);
+        else if (R == 8) spans<8, 10>(w, n, h, x, P, NMRFIT_EXP2_TAB10, vfit);
+        else spans<16, 10>(w, n, h, x, P, NMRFIT_EXP2_TAB10, vfit);
     }
 }
 

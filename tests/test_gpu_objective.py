@@ -30,6 +30,7 @@ def test_every_kernel_variant(threads, r, tb):
     g = load_golden('objective_ragged_1000x6')
     with _cabi.Context(1, g['w'].size, 6) as ctx:
         ctx.set_spectrum(0, g['w'], g['u'], g['v'], g['weights'])
+        ctx.set_algorithm(_cabi.ALGO_GENERAL)           # the uniform-axis kernel has its own file
         for sp in (1, 3, 16):
             ctx.set_tuning(threads, r, tb, sp)
             t = ctx.get_tuning(len(g['xs']))

@@ -98,3 +98,51 @@ def test_philox_known_answer_and_range(hm):
         vals.extend(out)
     vals = np.array(vals)
     assert vals.min() >= 0 and vals.max() < 1 and abs(vals.mean() - 0.5) < 0.02
+
+
+def _span_fit(hm, w, h, x, n_peaks, R, tb):
+    hm.h_span_fit.argtypes = [dp, ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_int, ctypes.c_int, dp]
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    out = np.empty(len(w))
+    hm.h_span_fit(P(w), len(w), h, P(x), n_peaks, R, tb, P(out))
+    return out
+
+
+@pytest.mark.parametrize('R', [4, 8, 16])
+@pytest.mark.parametrize('shape', [(4096, 6, 1000), (1024, 6, 3), (301, 6, 4), (8192, 12, 2000)])
+def test_uniform_axis_span_recurrence(hm, R, shape):
+    """peak_span (two exponentials per peak and R points, then a multiplicative recurrence) against the
+    reference formula on the uniform axes the synthetic spectra use.  The axis is treated as exactly
+    uniform, which moves an abscissa by <= 1 ulp(w): <= 5e-13 of the curve's scale."""
+    from oracle import nmrfit_oracle as orc
+    from nmrfit_b200 import synth
+    N, n_peaks, seed = shape
+    data, true = synth.multiplet(N, n_peaks, seed=seed)
+    lo, up = data.generate_solution_bounds()
+    xs = synth.particles(lo, up, 5, seed=11)
+    xs[0] = true
+    w = data.w
+    h = (w[-1] - w[0]) / (N - 1)
+    for x in xs:
+        want = sum(orc.voigt(w, x[2], x[3], *x[4 + 3 * k:7 + 3 * k]) for k in range(n_peaks))
+        for tb in (6, 10):
+            got = _span_fit(hm, w, h, x, n_peaks, R, tb)
+            assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+
+
+def test_uniform_axis_span_edge_cases(hm):
+    """Descending axes, coarse grids (every point its own exponential), far tails and absurd widths:
+    finite everywhere and equal to the reference formula."""
+    from oracle import nmrfit_oracle as orc
+    N = 512
+    for w in (np.linspace(3.6, 3.23, N), np.linspace(-1.0, 1.0, N), np.linspace(3.23, 3.60, N)):
+        h = (w[-1] - w[0]) / (N - 1)
+        mid = 0.5 * (w[0] + w[-1])
+        for width in (1e-6, 2e-4, 1e-3, 4e-3, 0.05, 10.0):
+            for loc in (mid + 0.01, w[0] - 50 * abs(h), mid + 100.0):
+                x = np.array([0.1, 0.2, 0.4, 0.003, width, loc, 0.7])
+                want = orc.voigt(w, x[2], x[3], width, loc, x[6])
+                for R in (4, 8, 16):
+                    got = _span_fit(hm, w, h, x, 1, R, 6)
+                    assert np.all(np.isfinite(got))
+                    assert np.abs(got - want).max() < 2e-12 * max(np.abs(want).max(), 1e-3), (width, loc, R)

@@ -34,8 +34,11 @@ def main():
         with _cabi.Context(1, N, P) as ctx:
             ctx.set_spectrum(0, data.w, data.u, data.v, weights)
             ref = None
-            sps = (1, 2, 4, 8, 16, 32) if name != 'c1' else (1, 2, 4)
-            for threads, r, tb, sp in itertools.product((128, 256), (2, 4, 8), (-1, 6, 8, 10), sps):
+            sps = (4, 8, 16, 32) if name != 'c1' else (1, 2, 4)
+            general = [(_cabi.ALGO_GENERAL,) + t for t in itertools.product((128, 256), (4,), (6, 10), sps)]
+            uniform = [(_cabi.ALGO_UNIFORM,) + t for t in itertools.product((128, 256), (4, 8, 16), (6, 10), sps)]
+            for algo, threads, r, tb, sp in general + uniform:
+                ctx.set_algorithm(algo)
                 ctx.set_tuning(threads, r, tb, sp)
                 for _ in range(2):
                     ctx.objective_device(xs, S, f)
@@ -52,10 +55,11 @@ def main():
                 err = float(np.max(np.abs(got - ref) / np.abs(ref)))
                 evals = S / (ms * 1e-3)
                 frac = evals * bench.flop_per_eval(N, P) / 1e12 / sustained
-                rows.append(dict(workload=name, threads=threads, r=r, tb=tb, sp=sp, ms=ms, evals_per_s=evals,
+                rows.append(dict(workload=name, algo=algo, threads=threads, r=r, tb=tb, sp=sp, ms=ms, evals_per_s=evals,
                                  peak_points_per_s=evals * N * P, frac=frac, rel_dev=err))
-                print('%s T=%3d R=%d TB=%2d SP=%2d  %8.4f ms  %.3e evals/s  %.3e pp/s  frac %.3f  dev %.1e'
-                      % (name, threads, r, tb, sp, ms, evals, evals * N * P, frac, err), flush=True)
+                print('%s %s T=%3d R=%2d TB=%2d SP=%2d  %8.4f ms  %.3e evals/s  %.3e pp/s  frac %.3f  dev %.1e'
+                      % (name, 'uni' if algo == _cabi.ALGO_UNIFORM else 'gen', threads, r, tb, sp, ms, evals,
+                         evals * N * P, frac, err), flush=True)
     best = {}
     for row in rows:
         if row['workload'] not in best or row['ms'] < best[row['workload']]['ms']:
