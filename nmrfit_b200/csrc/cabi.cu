@@ -107,7 +107,7 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
     // The point tiling fixes the summation order of the residual, so it may depend on
     // N alone (never on how many particles or spectra a rank happens to hold).
     if (uni) {
-        if (c->N >= 8192) { t.threads = 256; t.r = 8; }
+        if (c->N >= 8192) { t.threads = 256; t.r = 8; }          // 2,048-point tiles
         else if (c->N >= 2048) { t.threads = 128; t.r = 8; }
         else { t.threads = 128; t.r = 4; }
     } else {

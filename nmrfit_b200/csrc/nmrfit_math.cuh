@@ -31,6 +31,7 @@ static inline double nmrfit_rcp_seed(double q) {
     return nmrfit_mk(nmrfit_hi(t), 0);
 }
 #define NMRFIT_FMA(a, b, c) std::fma((a), (b), (c))
+#define NMRFIT_ABS(a) std::fabs(a)
 #else
 #define NMRFIT_HD __device__ __forceinline__
 __device__ __forceinline__ int nmrfit_hi(double x) { return __double2hiint(x); }
@@ -42,6 +43,7 @@ __device__ __forceinline__ double nmrfit_rcp_seed(double q) {
     return y;
 }
 #define NMRFIT_FMA(a, b, c) fma((a), (b), (c))
+#define NMRFIT_ABS(a) fabs(a)
 #endif
 
 namespace nmrfit {
@@ -193,31 +195,39 @@ NMRFIT_HD PeakCoef make_coef(double r, double width, double loc, double a) {
 }
 
 // ---- uniform-grid span evaluation --------------------------------------------
-// On a uniformly spaced axis (w_i = w_0 + i*h: what np.linspace / a spectrometer
-// ppm scale gives) the Gaussian at consecutive points needs no exponential:
-//   s_j = s_0 + j*hG,  hG = h*kG,   G_j = exp(-s_j^2)
-//   G_{j+1} = G_j * rho_j,   rho_j = exp(-hG*(2*s_j + hG)),   rho_{j+1} = rho_j * c2,   c2 = exp(-2*hG^2)
-// so a thread that owns R consecutive points pays two exponentials (G_0, rho_0) per
-// peak and two multiplies per further point.  The Lorentzian argument advances as
-// t_j = t_0 + j*dT, dT = h*kL.  Per peak-point: t, q, rcp (3), 2 accumulating FMAs,
-// 2 recurrence multiplies = 9 FP64 issue slots + 1 MUFU.
+// On a uniformly spaced axis (w_i = w_0 + i*h: what np.linspace / a spectrometer ppm scale gives) a
+// thread that owns R consecutive points evaluates a peak with far fewer instructions than one
+// exponential and one reciprocal per point:
 //
-// A peak takes the recurrence only when it is safe and accurate; the coefficient builder marks it
-// `exact` (c2 < 0) otherwise, and such peaks are evaluated point by point from the STORED abscissae
-// with one exponential each (peak_exact - the arithmetic of the general kernel):
+// Gaussian.  s_j = s_0 + j*hG (hG = h*kG), G_j = exp(-s_j^2):
+//   * if no point of the span can come within |s| <= 6.5 of the centre (|s_0| > 6.5 + (R-1)|hG|), every
+//     G_j < exp(-42.25) = 4.5e-19
+//     of the Gaussian's height - below half an ulp of anything it is added to - and the Gaussian is
+//     skipped.  With FWHM = 1.665 in s units that is ~92 % of the window for a 0.004 ppm line in a
+//     0.37 ppm window;
+//   * otherwise G_{j+1} = G_j * rho_j, rho_{j+1} = rho_j * c2 with rho_0 = exp(-hG*(2*s_0 + hG)),
+//     c2 = exp(-2*hG^2): two exponentials per span, two multiplies per further point.  Inside the cut
+//     |s_0| <= 6.5 + 4, so nothing under- or overflows.
+// Lorentzian.  t_j = t_0 + j*dT (dT = h*kL), q_j = 1 + t_j^2; the reciprocals are taken four at a time
+// from ONE reciprocal of q_a*q_b*q_c*q_d (Montgomery's batch inversion, with aL folded in): 13 FP64
+// slots + 1 MUFU per four points instead of 16 + 4.
+//
+// A peak takes this path only when it is safe and accurate; the coefficient builder marks it `exact`
+// otherwise, and such peaks are evaluated point by point from the STORED abscissae with one
+// exponential each (peak_exact - the arithmetic of the general kernel):
 //   * R*|hG| > 4: the R points of a thread span more than 4 units of s (a peak narrower than ~3 grid
-//     points); the product chain could then be asked to climb from a clamped, underflowed anchor;
+//     points);
 //   * kL*ulp(w) > 1e-11: treating the axis as exactly uniform moves an abscissa by up to one ulp(w)
 //     against its stored value, i.e. up to kL*ulp(w) relative in a curve value - 4e-13 for a 0.004 ppm
 //     line at 3.4 ppm, but it grows as the width shrinks;
+//   * |t| could exceed 1e60 somewhere on the axis (the product of four q would overflow);
 //   * non-finite coefficients.
-// On the recurrence path, if the anchor is already in the far tail (x_0 = -s_0^2 < -650, |s_0| > 25.5)
-// every point of the span has |s_j| > 21.5 and G_j < 1e-200: the chain is forced to zero
-// (rho_0 := exp(-700)) instead of being multiplied up from the clamped anchor.  Otherwise
-// |ln rho_j| <= |hG|*(2*(25.5 + 4) + |hG|), and R of them sum to < 4*63: no overflow.
+constexpr double kGaussCut = 6.5;
+
 struct SpanCoef {
     double loc, kL, kG, aL;   // centre, 2/W, 2 sqrt(ln2)/W, a r 2/(pi W)
-    double aG, dT, hG, c2;    // a (1-r) (2/W) sqrt(ln2/pi), h kL, h kG, exp(-2 hG^2)  (c2 < 0: exact path)
+    double aG, dT, thr, c2;   // a (1-r) (2/W) sqrt(ln2/pi), h kL, Gaussian cut for |s_0| (incl. the span), exp(-2 hG^2)
+    bool exact;               // evaluate from the stored abscissae instead (peak_exact)
 };
 
 // h: axis spacing; w_ulp: 2^-52 * max|w| of the axis
@@ -230,34 +240,61 @@ NMRFIT_HD SpanCoef make_span_coef(double r, double width, double loc, double a, 
     c.aL = a * r * (iw / kPi);
     c.aG = a * (1.0 - r) * (iw * kSqrtLn2OverPi);
     c.dT = h * c.kL;
-    c.hG = h * c.kG;
-    double ah = c.hG < 0 ? -c.hG : c.hG;
-    double ak = c.kL < 0 ? -c.kL : c.kL;
-    if ((double)R * ah <= 4.0 && ak * w_ulp <= 1e-11) c.c2 = exp_neg<0>(-2.0 * (c.hG * c.hG), nullptr);
-    else c.c2 = -1.0;          // also taken for NaN / inf
+    double hG = c.dT * kSqrtLn2;
+    double ah = NMRFIT_ABS(hG), ak = NMRFIT_ABS(c.kL), al = NMRFIT_ABS(loc);
+    double reach = (al + w_ulp * 4503599627370496.0) * ak;     // >= |t| anywhere on the axis
+    c.exact = !((double)R * ah <= 4.0 && ak * w_ulp <= 1e-11 && reach <= 1e60);   // also for NaN / inf
+    c.thr = NMRFIT_FMA((double)(R - 1), ah, kGaussCut);
+    c.c2 = c.exact ? 1.0 : exp_neg<0>(-2.0 * (hG * hG), nullptr);
+    return c;
+}
+
+// What the span loop sees for a peak that takes the exact path: contributes exactly zero.
+NMRFIT_HD SpanCoef null_span_coef() {
+    SpanCoef c;
+    c.loc = c.kL = c.kG = c.aL = c.aG = c.dT = 0.0;
+    c.thr = -1.0;             // Gaussian never entered
+    c.c2 = 1.0;
+    c.exact = true;
     return c;
 }
 
 // acc[j] += aL / (1 + t_j^2) + aG * exp(-s_j^2) for the R consecutive points that start at
-// distance d0 = w_first - loc from the centre (recurrence path, c.c2 >= 0).
+// distance d0 = w_first - loc from the centre (recurrence path).
 template <int R, int TB>
 NMRFIT_HD void peak_span(double d0, const SpanCoef& c, const double* __restrict__ tab, double (&acc)[R]) {
+    static_assert(R % 4 == 0, "R must be a multiple of 4");
     const double t0 = d0 * c.kL;
     const double s0 = d0 * c.kG;
-    const double x0 = -(s0 * s0);
-    double a2 = -(c.hG * NMRFIT_FMA(2.0, s0, c.hG));
-    a2 = x0 < -650.0 ? -700.0 : a2;
-    double g = exp_neg<TB>(x0, tab);
-    double rho = exp_neg<TB>(a2, tab);
 #pragma unroll
-    for (int j = 0; j < R; ++j) {
-        double t = j == 0 ? t0 : NMRFIT_FMA((double)j, c.dT, t0);
-        double rq = rcp_pos(NMRFIT_FMA(t, t, 1.0));
-        acc[j] = NMRFIT_FMA(c.aL, rq, acc[j]);
-        acc[j] = NMRFIT_FMA(c.aG, g, acc[j]);
-        if (j + 1 < R) {
-            g *= rho;
-            if (j + 2 < R) rho *= c.c2;
+    for (int j0 = 0; j0 < R; j0 += 4) {
+        const double ta = j0 == 0 ? t0 : NMRFIT_FMA((double)j0, c.dT, t0);
+        const double tb = NMRFIT_FMA((double)(j0 + 1), c.dT, t0);
+        const double tc = NMRFIT_FMA((double)(j0 + 2), c.dT, t0);
+        const double td = NMRFIT_FMA((double)(j0 + 3), c.dT, t0);
+        const double qa = NMRFIT_FMA(ta, ta, 1.0), qb = NMRFIT_FMA(tb, tb, 1.0);
+        const double qc = NMRFIT_FMA(tc, tc, 1.0), qd = NMRFIT_FMA(td, td, 1.0);
+        const double qab = qa * qb, qcd = qc * qd;
+        const double ay = c.aL * rcp_pos(qab * qcd);
+        const double yab = ay * qcd, ycd = ay * qab;      // aL/(qa qb), aL/(qc qd)
+        acc[j0] = NMRFIT_FMA(yab, qb, acc[j0]);
+        acc[j0 + 1] = NMRFIT_FMA(yab, qa, acc[j0 + 1]);
+        acc[j0 + 2] = NMRFIT_FMA(ycd, qd, acc[j0 + 2]);
+        acc[j0 + 3] = NMRFIT_FMA(ycd, qc, acc[j0 + 3]);
+    }
+    // Gaussian only if the span can come within the cut.  Compared on the high words (integer pipe):
+    // a larger high word means a larger magnitude, equality falls on the safe side; NaN skips.
+    if ((nmrfit_hi(s0) & 0x7fffffff) <= nmrfit_hi(c.thr)) {
+        const double hG = c.dT * kSqrtLn2;
+        double g = exp_neg<TB>(-(s0 * s0), tab);
+        double rho = exp_neg<TB>(-(hG * NMRFIT_FMA(2.0, s0, hG)), tab);
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            acc[j] = NMRFIT_FMA(c.aG, g, acc[j]);
+            if (j + 1 < R) {
+                g *= rho;
+                if (j + 2 < R) rho *= c.c2;
+            }
         }
     }
 }

@@ -14,8 +14,10 @@
 // finalize kernel) a fixed-order sum over point tiles - no atomics, so results
 // are bit-reproducible and independent of how particles are sharded over GPUs.
 //
-// Bound: FP64 pipe.  FP64 issue slots per peak-point (TB = exp-table bits):
-//   d, d2, q (3) + rcp (3) + acc (1) + arg (1) + exp (15 | 9 | 8 | 7) + acc (1).
+// Bound: FP64 pipe issue.  FP64 slots per peak-point (TB = exp-table bits):
+//   d, d2, q (3) + rcp (3) + acc (1) + arg (1) + [exp (15 | 9 | 8 | 7) + acc (1) where |s| <= 6.5].
+// This kernel serves arbitrary (non-uniform) axes and the fit_im modes; fits on a uniform axis run
+// objective_uniform.cu.
 #include <cuda_runtime.h>
 #include "nmrfit_internal.h"
 #include "nmrfit_math.cuh"
@@ -143,8 +145,9 @@ objective_kernel(ObjArgs a) {
                 double q = fma(d2, kL2, 1.0);
                 double rq = rcp_pos(q);
                 acc[j] = fma(aL, rq, acc[j]);
-                double g = exp_neg<TB>(d2 * nkG2, tab);
-                acc[j] = fma(aG, g, acc[j]);
+                // beyond |s| = 6.5 the Gaussian is < 4.5e-19 of its height: below half an ulp of the sum
+                const double xg = d2 * nkG2;
+                if (xg > -(kGaussCut * kGaussCut)) acc[j] = fma(aG, exp_neg<TB>(xg, tab), acc[j]);
                 if (KK == 2) {
                     const double kL = cf[k * kCoefStride + 5], kG = cf[k * kCoefStride + 6];
                     double daw = dawson(d * kG, NMRFIT_DAW_TAB, NMRFIT_DAW_TAIL);

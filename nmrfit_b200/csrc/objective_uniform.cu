@@ -36,7 +36,7 @@ template <> struct ExpTabU<10> { static __device__ __forceinline__ const double*
 
 // shared-memory carve-up (in doubles), shared by kernel and launcher
 struct UniSmem {
-    int tab, coef, uv, wt, ewarp, elane, misc, wpart, total;
+    int tab, coef, uv, wt, ewarp, elane, misc, wpart, nex, total;
     __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB) {
         const int nw = threads / 32;
         int o = 0;
@@ -48,6 +48,7 @@ struct UniSmem {
         elane = o; o += sp * 32 * 2;
         misc = o;  o += sp * 4;          // cos(p1/N), sin(p1/N), P*yoff, pad
         wpart = o; o += sp * nw;
+        nex = o;   o += (sp + 1) / 2;    // int per particle: peaks on the exact path
         total = o;
     }
 };
@@ -72,6 +73,7 @@ objective_uniform_kernel(ObjArgs a) {
     double2* elane = reinterpret_cast<double2*>(smem + L.elane);
     double* misc = smem + L.misc;
     double* wpart = smem + L.wpart;
+    int* nex = reinterpret_cast<int*>(smem + L.nex);
 
     const int tile0 = blockIdx.y * (THREADS * R);
     const double* sw = a.spec + (size_t)b * 4 * N;
@@ -97,9 +99,10 @@ objective_uniform_kernel(ObjArgs a) {
     for (int idx = tid; idx < nsp * P; idx += THREADS) {
         const int sp = idx / P, k = idx - sp * P;
         const double* xs = xb + (size_t)sp * D;
-        const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+        SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+        if (c.exact) c = null_span_coef();       // the span loop adds zero; the peak is handled after it
         double* o = coef + (size_t)idx * 8;
-        o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.hG; o[7] = c.c2;
+        o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.thr; o[7] = c.c2;
     }
     {
         // phi_i = p0 + (p1*i)/N, i = tile0 + (32*warp + lane)*R + j, split as
@@ -121,12 +124,17 @@ objective_uniform_kernel(ObjArgs a) {
         }
     }
     __syncthreads();
+    for (int sp = tid; sp < nsp; sp += THREADS) {          // thr < 0 marks a nulled (exact-path) peak
+        int n = 0;
+        for (int k = 0; k < P; ++k) n += coef[(size_t)(sp * P + k) * 8 + 6] < 0.0;
+        nex[sp] = n;
+    }
+    __syncthreads();
 
     for (int sp = 0; sp < nsp; ++sp) {
         double acc[R];
-        const double py = misc[sp * 4 + 2];                // yoff is added once per peak (equations.py:147,195)
 #pragma unroll
-        for (int j = 0; j < R; ++j) acc[j] = py;
+        for (int j = 0; j < R; ++j) acc[j] = 0.0;
         const double* cf = coef + (size_t)sp * P * 8;
         for (int k = 0; k < P; ++k) {
             const double2 c01 = *reinterpret_cast<const double2*>(cf + k * 8);
@@ -135,13 +143,21 @@ objective_uniform_kernel(ObjArgs a) {
             const double2 c67 = *reinterpret_cast<const double2*>(cf + k * 8 + 6);
             SpanCoef c;
             c.loc = c01.x; c.kL = c01.y; c.kG = c23.x; c.aL = c23.y;
-            c.aG = c45.x; c.dT = c45.y; c.hG = c67.x; c.c2 = c67.y;
-            if (c.c2 >= 0.0) peak_span<R, TB>(w_first - c.loc, c, tab, acc);        // CTA-uniform branch
-            else peak_exact<R, TB>(sw + i_first, N - i_first, w_first, h, c, tab, acc);
+            c.aG = c45.x; c.dT = c45.y; c.thr = c67.x; c.c2 = c67.y;
+            peak_span<R, TB>(w_first - c.loc, c, tab, acc);
+        }
+        if (nex[sp]) {                                     // rare: peaks too narrow for the uniform-axis shortcuts
+            const double* xs = xb + (size_t)sp * D;
+            for (int k = 0; k < P; ++k) {
+                if (!(cf[k * 8 + 6] < 0.0)) continue;
+                const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+                peak_exact<R, TB>(sw + i_first, N - i_first, w_first, h, c, tab, acc);
+            }
         }
         // residual against the phase-rotated data; the rotation advances by p1/N per point
         const double2 ew = ewarp[sp * NW + warp], el = elane[sp * 32 + lane];
         const double cd = misc[sp * 4], sd = misc[sp * 4 + 1];
+        const double py = misc[sp * 4 + 2];                // yoff is added once per peak (equations.py:147,195)
         double cr = fma(ew.x, el.x, -(ew.y * el.y));
         double ci = fma(ew.y, el.x, ew.x * el.y);
         double ss = 0.0;
@@ -149,7 +165,7 @@ objective_uniform_kernel(ObjArgs a) {
         for (int j = 0; j < R; ++j) {
             const double2 uv = suv[j * THREADS + tid];
             const double wt = swt[j * THREADS + tid];
-            const double vd = fma(uv.x, cr, -(uv.y * ci));
+            const double vd = fma(uv.x, cr, -fma(uv.y, ci, py));     // V_data - P*yoff
             const double res = wt * (vd - acc[j]);
             ss = fma(res, res, ss);
             if (j + 1 < R) {

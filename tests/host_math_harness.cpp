@@ -19,7 +19,7 @@ static void spans(const double* w, int n, double h, const double* x, int P, cons
         for (int j = 0; j < R; ++j) acc[j] = (double)P * x[3];
         for (int k = 0; k < P; ++k) {
             nmrfit::SpanCoef c = nmrfit::make_span_coef(x[2], x[4 + 3 * k], x[5 + 3 * k], x[6 + 3 * k], h, w_ulp, R);
-            if (c.c2 >= 0.0) nmrfit::peak_span<R, TB>(w[i0] - c.loc, c, tab, acc);
+            if (!c.exact) nmrfit::peak_span<R, TB>(w[i0] - c.loc, c, tab, acc);
             else nmrfit::peak_exact<R, TB>(w + i0, n - i0, w[i0], h, c, tab, acc);
         }
         for (int j = 0; j < R && i0 + j < n; ++j) vfit[i0 + j] = acc[j];

@@ -91,5 +91,39 @@ def full(src, dst):
             f.write('| %s | %s |\n' % (name, ' | '.join('%.3f' % v for v in vals)))
 
 
+def objective_json(src, dst, workload='c2', peak_points=4096 * 32768 * 12):
+    """profiles/objective_ncu.json: what bench.py attaches to its roofline (traffic + executed-instruction view).
+    peak_points = peak-points one launch processes (particles * points * peaks)."""
+    raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True, check=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units, r = rows[0], rows[1], rows[-1]
+
+    def g(name):
+        return num(r[hdr.index(name)])
+
+    def to_bytes(name):
+        v, u = g(name), units[hdr.index(name)]
+        return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
+    cycles = g('sm__cycles_elapsed.avg')
+    fp64 = sum(g('smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed' % k) for k in ('dfma', 'dmul', 'dadd')) * cycles
+    d = {
+        'kernel': r[hdr.index('Kernel Name')], 'source': src,
+        'duration_ms_under_ncu': g('gpu__time_duration.sum') * {'ms': 1, 'us': 1e-3, 'ns': 1e-6, 'usecond': 1e-3, 'msecond': 1}[units[hdr.index('gpu__time_duration.sum')]],
+        'dram_bytes_per_launch': to_bytes('dram__bytes_read.sum') + to_bytes('dram__bytes_write.sum'),
+        'fp64_pipe_active_pct': g('sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active'),
+        'issue_slots_busy_pct': g('smsp__issue_active.avg.pct_of_peak_sustained_active'),
+        'warp_inst_per_peak_point': g('smsp__inst_executed.sum') * 32 / peak_points,
+        'fp64_arith_inst_per_peak_point': fp64 / peak_points,
+        'registers_per_thread': g('launch__registers_per_thread'),
+        'warps_active_pct': g('sm__warps_active.avg.pct_of_peak_sustained_active'),
+    }
+    try:
+        out = json.load(open(dst))
+    except (OSError, ValueError):
+        out = {}
+    out[workload] = d
+    json.dump(out, open(dst, 'w'), indent=1)
+
+
 if __name__ == '__main__':
-    {'launches': launches, 'full': full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {'launches': launches, 'full': full, 'objective_json': objective_json}[sys.argv[1]](*sys.argv[2:4])

@@ -43,7 +43,7 @@ def main():
                 for _ in range(2):
                     ctx.objective_device(xs, S, f)
                 ctx.profile(True)
-                reps = 5 if name != 'c1' else 50
+                reps = 12 if name != "c1" else 50
                 for _ in range(reps):
                     ctx.objective_device(xs, S, f)
                 ms, n = ctx.profile_read()
