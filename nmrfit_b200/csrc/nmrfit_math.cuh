@@ -315,6 +315,59 @@ NMRFIT_HD void peak_exact(const double* __restrict__ w, int n_valid, double w_fi
     }
 }
 
+// ---- far field of the Lorentzians -----------------------------------------------
+// Over a REGION of 2*H consecutive points (one warp's 32*R points; H = 16*R) a peak whose centre is
+// far away compared with the region's half-width is a smooth function, and the sum of all such peaks
+// is one polynomial.  With xi in (-1, 1) the position inside the region (xi = (i - i_c)/H), A = H*dT the
+// region's half-width in t units and t_c = kL*(w_c - loc) the centre's offset,
+//     aL / (1 + t^2),  t = t_c + A*xi
+//   = aL * Im[ 1 / ((t_c - i) + A*xi) ]                       (1/(t - i) = (t + i)/(1 + t^2))
+//   = (aL/A) * sum_n (-xi)^n Im[u^(n+1)],   u = A/(t_c - i) = A (t_c + i)/(1 + t_c^2),  |u|^2 = A^2/(1 + t_c^2)
+// and v_n = Im[u^(n+1)]/A obeys v_{n+1} = 2 Re(u) v_n - |u|^2 v_{n-1}, v_{-1} = 0, v_0 = 1/(1 + t_c^2).
+// A peak is FAR when |u| <= 1/16 (kFarRhoInv2 = 256) and its Gaussian cannot reach the region; the series
+// is cut after kFarTerms = 12 terms, leaving < |u|^12/(1 - |u|) = 4e-15 of the Lorentzian's HEIGHT (the
+// prefactor 1/A is bounded by 1/|u|).  Everything else is NEAR and is evaluated by peak_span.
+constexpr int kFarTerms = 12;
+constexpr double kFarRhoInv2 = 256.0;
+
+// Classify one peak for a region whose centre sits Dc = w_c - loc from the peak's centre; H = half the
+// region's point count.  Far: adds the peak's expansion to C and returns true.  Near: returns false.
+NMRFIT_HD bool far_accumulate(double Dc, const SpanCoef& c, double H, double (&C)[kFarTerms]) {
+    const double A = H * c.dT;
+    const double tc = Dc * c.kL;
+    const double qc = NMRFIT_FMA(tc, tc, 1.0);
+    const double sc = Dc * c.kG;
+    const double reach = NMRFIT_FMA(H * kSqrtLn2, NMRFIT_ABS(c.dT), kGaussCut);   // 6.5 + H*|hG|
+    if (NMRFIT_ABS(sc) <= reach) return false;                // the Gaussian reaches the region
+    if (!(kFarRhoInv2 * (A * A) <= qc)) return false;         // too close for the series (or NaN)
+    if (!(qc <= 1e300)) return true;                          // infinitely far: contributes nothing
+    const double iq = rcp_pos(qc);
+    const double two_p = 2.0 * (A * tc) * iq;                 // 2 Re(u)
+    const double rho2 = (A * A) * iq;                         // |u|^2
+    double vm = 0.0, v = iq;
+#pragma unroll
+    for (int n = 0; n < kFarTerms; ++n) {
+        C[n] = NMRFIT_FMA((n & 1) ? -c.aL : c.aL, v, C[n]);
+        const double vn = NMRFIT_FMA(two_p, v, -(rho2 * vm));
+        vm = v;
+        v = vn;
+    }
+    return true;
+}
+
+// acc[j] += sum_n C[n] xi_j^n for the R consecutive points xi_j = xi0 + j*dxi.
+template <int R>
+NMRFIT_HD void far_eval(const double (&C)[kFarTerms], double xi0, double dxi, double (&acc)[R]) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const double xi = j == 0 ? xi0 : NMRFIT_FMA((double)j, dxi, xi0);
+        double p = C[kFarTerms - 1];
+#pragma unroll
+        for (int n = kFarTerms - 2; n >= 1; --n) p = NMRFIT_FMA(p, xi, C[n]);
+        acc[j] = NMRFIT_FMA(p, xi, acc[j] + C[0]);
+    }
+}
+
 // Philox4x32-10 (Salmon et al., SC'11) -> two uniform doubles in [0, 1) with 53
 // random bits each, built as MT19937's genrand_res53 builds them:
 // (a >> 5) * 2^26 + (b >> 6), scaled by 2^-53.

@@ -9,6 +9,12 @@
 // 9 (t, q, 3 rcp, 2 accumulate, 2 recurrence) + anchors/R, against 19 in the general kernel;
 // non-FP64 instructions per peak-point: 2 (MUFU seed + its zero low word) against 18.
 //
+// Lorentzians of peaks far from a warp's 32*R points are not evaluated peak by peak at all: per
+// (particle, warp region) the prologue sums their Taylor series about the region's centre into ONE
+// degree-11 polynomial (far_accumulate), which costs 12 FMAs per point for all far peaks together; only
+// the peaks near the region (1.5 of 12 on average at BASELINE config 2, 2.2 of 24 at config 4) go
+// through peak_span.
+//
 // Mapping: grid (particle tiles, point tiles, spectra).  A CTA stages its THREADS*R points of
 // (u, v) and weights in shared memory once ([j][thread] order: conflict-free for the per-point
 // reads) and loops over SP particles; per particle the per-peak span coefficients are built into
@@ -36,7 +42,7 @@ template <> struct ExpTabU<10> { static __device__ __forceinline__ const double*
 
 // shared-memory carve-up (in doubles), shared by kernel and launcher
 struct UniSmem {
-    int tab, coef, uv, wt, ewarp, elane, misc, wpart, nex, total;
+    int tab, coef, uv, wt, ewarp, elane, misc, wpart, nex, far, mask, mw, total;
     __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB) {
         const int nw = threads / 32;
         int o = 0;
@@ -48,7 +54,10 @@ struct UniSmem {
         elane = o; o += sp * 32 * 2;
         misc = o;  o += sp * 4;          // cos(p1/N), sin(p1/N), P*yoff, pad
         wpart = o; o += sp * nw;
-        nex = o;   o += (sp + 1) / 2;    // int per particle: peaks on the exact path
+        nex = o;   o += ((sp + 3) / 4) * 2;           // int per particle: peaks on the exact path (keeps 16-byte alignment)
+        far = o;   o += sp * nw * kFarTerms;          // far-field polynomial per (particle, warp region)
+        mw = (P + 31) / 32;                           // near-peak bit mask per (particle, warp region) + a has-far word
+        mask = o;  o += (sp * nw * (mw + 1) + 1) / 2;
         total = o;
     }
 };
@@ -74,6 +83,10 @@ objective_uniform_kernel(ObjArgs a) {
     double* misc = smem + L.misc;
     double* wpart = smem + L.wpart;
     int* nex = reinterpret_cast<int*>(smem + L.nex);
+    double* farc = smem + L.far;
+    unsigned* mask = reinterpret_cast<unsigned*>(smem + L.mask);
+    const int MW = L.mw;
+    constexpr double H = 16.0 * R;                         // half a warp region, in points
 
     const int tile0 = blockIdx.y * (THREADS * R);
     const double* sw = a.spec + (size_t)b * 4 * N;
@@ -129,14 +142,46 @@ objective_uniform_kernel(ObjArgs a) {
         for (int k = 0; k < P; ++k) n += coef[(size_t)(sp * P + k) * 8 + 6] < 0.0;
         nex[sp] = n;
     }
+    // near / far split of the peaks for every (particle, warp region) of this tile
+    for (int idx = tid; idx < nsp * NW; idx += THREADS) {
+        const int sp = idx / NW, r = idx - sp * NW;
+        const int ir = tile0 + r * 32 * R;
+        const double w_r = ir < N ? sw[ir] : fma((double)ir, h, sw[0]);
+        const double w_c = fma(0.5 * (32 * R - 1), h, w_r);
+        double C[kFarTerms];
+#pragma unroll
+        for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
+        unsigned any_far = 0;
+        unsigned* mk = mask + (size_t)idx * (MW + 1);
+        for (int wd = 0; wd < MW; ++wd) {
+            unsigned m = 0;
+            const int kend = min(P, wd * 32 + 32);
+            for (int k = wd * 32; k < kend; ++k) {
+                const double* o = coef + (size_t)(sp * P + k) * 8;
+                SpanCoef c;
+                c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
+                if (c.thr < 0.0) continue;                 // exact-path peak: neither near nor far here
+                if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
+                else m |= 1u << (k & 31);
+            }
+            mk[wd] = m;
+        }
+        mk[MW] = any_far;
+#pragma unroll
+        for (int n = 0; n < kFarTerms; ++n) farc[(size_t)idx * kFarTerms + n] = C[n];
+    }
     __syncthreads();
+    const double xi0 = ((double)(lane * R) - 0.5 * (32 * R - 1)) / H;   // this thread's first point inside its region
 
     for (int sp = 0; sp < nsp; ++sp) {
         double acc[R];
 #pragma unroll
         for (int j = 0; j < R; ++j) acc[j] = 0.0;
         const double* cf = coef + (size_t)sp * P * 8;
-        for (int k = 0; k < P; ++k) {
+        const unsigned* mk = mask + (size_t)(sp * NW + warp) * (MW + 1);
+        for (int wd = 0; wd < MW; ++wd)
+        for (unsigned m = mk[wd]; m; m &= m - 1) {         // peaks near this warp's region
+            const int k = wd * 32 + __ffs(m) - 1;
             const double2 c01 = *reinterpret_cast<const double2*>(cf + k * 8);
             const double2 c23 = *reinterpret_cast<const double2*>(cf + k * 8 + 2);
             const double2 c45 = *reinterpret_cast<const double2*>(cf + k * 8 + 4);
@@ -145,6 +190,16 @@ objective_uniform_kernel(ObjArgs a) {
             c.loc = c01.x; c.kL = c01.y; c.kG = c23.x; c.aL = c23.y;
             c.aG = c45.x; c.dT = c45.y; c.thr = c67.x; c.c2 = c67.y;
             peak_span<R, TB>(w_first - c.loc, c, tab, acc);
+        }
+        if (mk[MW]) {                                      // all far peaks at once
+            const double* fc = farc + (size_t)(sp * NW + warp) * kFarTerms;
+            double C[kFarTerms];
+#pragma unroll
+            for (int n = 0; n < kFarTerms; n += 2) {
+                const double2 t = *reinterpret_cast<const double2*>(fc + n);
+                C[n] = t.x; C[n + 1] = t.y;
+            }
+            far_eval<R>(C, xi0, 1.0 / H, acc);
         }
         if (nex[sp]) {                                     // rare: peaks too narrow for the uniform-axis shortcuts
             const double* xs = xb + (size_t)sp * D;

@@ -6,6 +6,7 @@
 #define __host__
 #define __constant__
 #define __forceinline__ inline
+#include <vector>
 #include "../nmrfit_b200/csrc/nmrfit_math.cuh"
 
 // Sum of peaks over a uniform grid w_i = w[0] + i*h, evaluated span by span exactly as
@@ -26,7 +27,52 @@ static void spans(const double* w, int n, double h, const double* x, int P, cons
     }
 }
 
+// The same sum as `spans`, with the far-field split of objective_uniform_kernel: regions of 32*R points,
+// near peaks by peak_span / peak_exact, far peaks through one polynomial per region.
+template <int R, int TB>
+static void regions(const double* w, int n, double h, const double* x, int P, const double* tab, double* vfit,
+                    int* n_near_total) {
+    double big = std::fabs(w[0]) > std::fabs(w[n - 1]) ? std::fabs(w[0]) : std::fabs(w[n - 1]);
+    const double w_ulp = 2.220446049250313e-16 * big;
+    const int RG = 32 * R;
+    const double H = 16.0 * R;
+    int near_total = 0;
+    for (int r0 = 0; r0 < n; r0 += RG) {
+        const double wc = std::fma(0.5 * (RG - 1), h, w[r0]);
+        double C[nmrfit::kFarTerms] = {0};
+        std::vector<int> near;
+        std::vector<nmrfit::SpanCoef> cs(P);
+        for (int k = 0; k < P; ++k) {
+            cs[k] = nmrfit::make_span_coef(x[2], x[4 + 3 * k], x[5 + 3 * k], x[6 + 3 * k], h, w_ulp, R);
+            if (cs[k].exact || !nmrfit::far_accumulate(wc - cs[k].loc, cs[k], H, C)) near.push_back(k);
+        }
+        near_total += (int)near.size();
+        for (int lane = 0; lane < 32; ++lane) {
+            const int i0 = r0 + lane * R;
+            if (i0 >= n) break;
+            double acc[R];
+            for (int j = 0; j < R; ++j) acc[j] = 0.0;
+            for (int k : near) {
+                if (!cs[k].exact) nmrfit::peak_span<R, TB>(w[i0] - cs[k].loc, cs[k], tab, acc);
+                else nmrfit::peak_exact<R, TB>(w + i0, n - i0, w[i0], h, cs[k], tab, acc);
+            }
+            const double xi0 = ((double)(lane * R) - 0.5 * (RG - 1)) / H;
+            nmrfit::far_eval<R>(C, xi0, 1.0 / H, acc);
+            for (int j = 0; j < R && i0 + j < n; ++j) vfit[i0 + j] = acc[j] + (double)P * x[3];
+        }
+    }
+    *n_near_total = near_total;
+}
+
 extern "C" {
+
+int h_region_fit(const double* w, int n, double h, const double* x, int P, int R, double* vfit) {
+    int near = 0;
+    if (R == 4) regions<4, 6>(w, n, h, x, P, NMRFIT_EXP2_TAB6, vfit, &near);
+    else if (R == 8) regions<8, 6>(w, n, h, x, P, NMRFIT_EXP2_TAB6, vfit, &near);
+    else regions<16, 6>(w, n, h, x, P, NMRFIT_EXP2_TAB6, vfit, &near);
+    return near;
+}
 
 void h_exp_neg(int tb, const double* x, int n, double* out) {
     for (int i = 0; i < n; ++i) {

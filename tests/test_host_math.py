@@ -146,3 +146,53 @@ def test_uniform_axis_span_edge_cases(hm):
                     got = _span_fit(hm, w, h, x, 1, R, 6)
                     assert np.all(np.isfinite(got))
                     assert np.abs(got - want).max() < 2e-12 * max(np.abs(want).max(), 1e-3), (width, loc, R)
+
+
+@pytest.mark.parametrize('R', [4, 8, 16])
+@pytest.mark.parametrize('shape', [(4096, 6, 1000), (32768, 12, 2000), (300, 6, 4), (16384, 24, 4000)])
+def test_far_field_split(hm, R, shape):
+    """Near peaks by peak_span, far peaks through one degree-11 polynomial per 32*R-point region
+    (far_accumulate / far_eval): same curve as the reference formula, and on fine grids most peaks are far."""
+    from oracle import nmrfit_oracle as orc
+    from nmrfit_b200 import synth
+    N, n_peaks, seed = shape
+    data, true = synth.multiplet(N, n_peaks, seed=seed)
+    lo, up = data.generate_solution_bounds()
+    xs = synth.particles(lo, up, 4, seed=5)
+    xs[0] = true
+    w = data.w
+    h = (w[-1] - w[0]) / (N - 1)
+    hm.h_region_fit.argtypes = [dp, ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_int, dp]
+    n_regions = (N + 32 * R - 1) // (32 * R)
+    for x in xs:
+        x = np.ascontiguousarray(x)
+        got = np.empty(N)
+        near = hm.h_region_fit(P(w), N, h, P(x), n_peaks, R, P(got))
+        want = sum(orc.voigt(w, x[2], x[3], *x[4 + 3 * k:7 + 3 * k]) for k in range(n_peaks))
+        assert np.abs(got - want).max() < 1e-12 * np.abs(want).max()
+        if N >= 16384 and R <= 8:
+            assert near / n_regions < 0.25 * n_peaks
+
+
+def test_far_field_extremes(hm):
+    """Broad peaks (far because smooth), peaks outside the window, mixed widths, descending axis."""
+    from oracle import nmrfit_oracle as orc
+    hm.h_region_fit.argtypes = [dp, ctypes.c_int, ctypes.c_double, dp, ctypes.c_int, ctypes.c_int, dp]
+    N = 8192
+    for w in (np.linspace(3.23, 3.60, N), np.linspace(3.60, 3.23, N), np.linspace(-200.0, 200.0, N)):
+        h = (w[-1] - w[0]) / (N - 1)
+        span = abs(w[-1] - w[0])
+        mid = 0.5 * (w[0] + w[-1])
+        x = np.array([0.3, -0.2, 0.45, 1e-3,
+                      0.011 * span, mid + 0.1 * span, 0.5,        # ordinary line
+                      2.0 * span, mid - 0.2 * span, 3.0,          # broader than the window
+                      0.004 * span, mid + 30 * span, 1.0,         # far outside
+                      1e-7 * span, mid, 1e-4,                     # narrower than the grid: exact path
+                      0.02 * span, w[0], 0.2, 0.02 * span, w[-1], 0.2])   # on the edges
+        n_peaks = (len(x) - 4) // 3
+        want = sum(orc.voigt(w, x[2], x[3], *x[4 + 3 * k:7 + 3 * k]) for k in range(n_peaks))
+        for R in (4, 8, 16):
+            got = np.empty(N)
+            hm.h_region_fit(P(w), N, h, P(x), n_peaks, R, P(got))
+            assert np.all(np.isfinite(got))
+            assert np.abs(got - want).max() < 2e-12 * np.abs(want).max(), R
