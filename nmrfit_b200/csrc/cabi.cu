@@ -77,6 +77,8 @@ struct nmrfit_ctx {
     std::vector<char> uniform;         // [B] stored w is w_0 + i*h to within 4 ulp
     int algorithm = NMRFIT_ALGO_AUTO;
     DevBuf<double> partials, x_stage, f_stage;
+    DevBuf<double> prep_coef, prep_part, prep_far, prep_anchor;   // uniform-axis kernel, per-particle constants
+    DevBuf<unsigned> prep_mask;
     ObjTune user_tune{0, 0, 0, 0};
     // swarm
     bool swarm = false;
@@ -156,7 +158,19 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
                                         : "points_per_thread must be 2, 4 or 8 for the general kernel");
     int n_tiles = objective_tiles(c->N, t);
     CK(c->partials.reserve((size_t)c->B * S * n_tiles * 2));
-    ObjArgs a;
+    ObjArgs a{};
+    if (uni) {
+        size_t nc, np, nf, na, nm;
+        objective_uniform_prep_sizes(c->N, c->P, t, &a.NR, &nc, &np, &nf, &na, &nm);
+        const size_t slots = (size_t)c->B * S;
+        CK(c->prep_coef.reserve(slots * nc));
+        CK(c->prep_part.reserve(slots * np));
+        CK(c->prep_far.reserve(slots * nf));
+        CK(c->prep_anchor.reserve(slots * na));
+        CK(c->prep_mask.reserve(slots * nm));
+        a.prep_coef = c->prep_coef.ptr; a.prep_part = c->prep_part.ptr; a.prep_far = c->prep_far.ptr;
+        a.prep_anchor = c->prep_anchor.ptr; a.prep_mask = c->prep_mask.ptr;
+    }
     a.spec = c->spec.ptr;
     a.x = x_dev;
     a.partials = c->partials.ptr;
@@ -239,7 +253,8 @@ int nmrfit_ctx_create(nmrfit_ctx** out, int device, int n_spectra, int n_points,
 void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    for (DevBuf<double>* b : {&c->spec, &c->grid_h, &c->partials, &c->x_stage, &c->f_stage, &c->sx, &c->sv, &c->sp, &c->sfx,
+    c->prep_mask.release();
+    for (DevBuf<double>* b : {&c->prep_coef, &c->prep_part, &c->prep_far, &c->prep_anchor, &c->spec, &c->grid_h, &c->partials, &c->x_stage, &c->f_stage, &c->sx, &c->sv, &c->sp, &c->sfx,
                               &c->sfp, &c->sg, &c->sfg, &c->sbx, &c->sbf, &c->slb, &c->sub, &c->srec, &c->rnd_a,
                               &c->rnd_b})
         b->release();

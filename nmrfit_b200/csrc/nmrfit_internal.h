@@ -16,6 +16,13 @@ struct ObjArgs {
     double* partials;       // [B][S][n_tiles][nsum]
     const int* frozen;      // [B] or null: spectra whose swarm has stopped are skipped
     const double* grid_h;   // [B][2] axis spacing h and ulp scale 2^-52*max|w| (uniform-axis kernel only)
+    // uniform-axis kernel: per-particle constants written by its prepare pass (see objective_uniform.cu)
+    double* prep_coef;      // [B][S][P][8]
+    double* prep_part;      // [B][S][68]
+    double* prep_far;       // [B][S][NR][12]
+    double* prep_anchor;    // [B][S][NR][2]
+    unsigned* prep_mask;    // [B][S][NR][ceil(P/32)+1]
+    int NR;                 // regions of 32*r points on the axis
     int N, P, S;
     int kk;                 // 0 real only, 1 reference fit_im (last peak), 2 sum over peaks
     int sp;                 // particles per CTA (filled by the launcher)
@@ -40,6 +47,9 @@ cudaError_t launch_objective_finalize(const double* partials, int n_tiles, int n
 
 // uniform-axis objective (objective_uniform.cu): real-only fit, FP64
 size_t objective_uniform_smem_bytes(int P, const ObjTune& t);
+// per-particle sizes (in doubles / 32-bit words) of the prepare pass's outputs
+void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, int* n_regions, size_t* coef, size_t* part, size_t* far,
+                                  size_t* anchor, size_t* mask_words);
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st,
                                      cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 

@@ -10,7 +10,7 @@
 // non-FP64 instructions per peak-point: 2 (MUFU seed + its zero low word) against 18.
 //
 // Lorentzians of peaks far from a warp's 32*R points are not evaluated peak by peak at all: per
-// (particle, warp region) the prologue sums their Taylor series about the region's centre into ONE
+// (particle, warp region) objective_prepare_kernel sums their Taylor series about the region's centre into ONE
 // degree-11 polynomial (far_accumulate), which costs 12 FMAs per point for all far peaks together; only
 // the peaks near the region (1.5 of 12 on average at BASELINE config 2, 2.2 of 24 at config 4) go
 // through peak_span.
@@ -40,24 +40,101 @@ template <> struct ExpTabU<6> { static __device__ __forceinline__ const double* 
 template <> struct ExpTabU<8> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB8; } };
 template <> struct ExpTabU<10> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB10; } };
 
-// shared-memory carve-up (in doubles), shared by kernel and launcher
+constexpr int kPartDoubles = 68;   // per particle: e^{i p1 lane R/N} for 32 lanes (64), cos/sin(p1/N), P*yoff, #exact peaks
+
+// ---- pass 1: per-particle constants, once per swarm generation ------------------------------------
+// One CTA per particle.  Phase 1 builds the span coefficients of its P peaks and the phase tables;
+// phase 2 walks the regions of the axis (32*R points each), classifies every peak as near or far for
+// that region, sums the far Lorentzians into the region's polynomial and takes the phase anchor
+// e^{i(p0 + p1*i_r/N)} of the region's first point.  Everything lands in global memory (a few KB per
+// particle); the evaluation kernel's prologue is then a plain copy.
+template <int R>
+__global__ void __launch_bounds__(128)
+objective_prepare_kernel(ObjArgs a) {
+    extern __shared__ __align__(16) double cs[];           // [P][8]
+    const int b = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
+    if (a.frozen && a.frozen[b]) return;
+    const int P = a.P, N = a.N, D = 4 + 3 * P, NR = a.NR, MW = (P + 31) / 32;
+    const size_t ps = (size_t)b * a.S + s;
+    const double* xs = a.x + ps * D;
+    const double* sw = a.spec + (size_t)b * 4 * N;
+    const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
+    const double p0 = xs[0], p1 = xs[1];
+    double* part = a.prep_part + ps * kPartDoubles;
+    constexpr double H = 16.0 * R;
+
+    for (int k = tid; k < P; k += 128) {
+        SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+        if (c.exact) c = null_span_coef();                 // the span loop adds zero; the peak is handled after it
+        double* o = cs + k * 8;
+        o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.thr; o[7] = c.c2;
+        double* g = a.prep_coef + (ps * P + k) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = o[i];
+    }
+    // phi_i = p0 + (p1*i)/N with i = i_r + lane*R + j:  anchor(i_r) * [p1*(lane*R)/N] * j*[p1/N]
+    for (int e = 127 - tid; e < 33; e += 128) {            // the last warp does these while the first does the peaks
+        double sn, cn;
+        sincos(e < 32 ? (p1 * (double)(e * R)) / (double)N : p1 / (double)N, &sn, &cn);
+        part[2 * e] = cn;
+        part[2 * e + 1] = sn;
+    }
+    if (tid == 64) part[66] = (double)P * xs[3];           // yoff is added once per peak (equations.py:147,195)
+    __syncthreads();
+    if (tid == 64) {
+        int n = 0;
+        for (int k = 0; k < P; ++k) n += cs[k * 8 + 6] < 0.0;      // thr < 0 marks a nulled (exact-path) peak
+        part[67] = (double)n;
+    }
+    for (int r = tid; r < NR; r += 128) {
+        const int ir = r * 32 * R;
+        const double w_c = fma(0.5 * (32 * R - 1), h, sw[ir]);
+        double C[kFarTerms];
+#pragma unroll
+        for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
+        unsigned any_far = 0;
+        unsigned* mk = a.prep_mask + (ps * NR + r) * (MW + 1);
+        for (int wd = 0; wd < MW; ++wd) {
+            unsigned m = 0;
+            const int kend = min(P, wd * 32 + 32);
+            for (int k = wd * 32; k < kend; ++k) {
+                const double* o = cs + k * 8;
+                SpanCoef c;
+                c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
+                if (c.thr < 0.0) continue;                 // exact-path peak: neither near nor far
+                if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
+                else m |= 1u << (k & 31);
+            }
+            mk[wd] = m;
+        }
+        mk[MW] = any_far;
+        double* fc = a.prep_far + (ps * NR + r) * kFarTerms;
+#pragma unroll
+        for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
+        double sn, cn;
+        sincos(p0 + (p1 * (double)ir) / (double)N, &sn, &cn);
+        a.prep_anchor[(ps * NR + r) * 2] = cn;
+        a.prep_anchor[(ps * NR + r) * 2 + 1] = sn;
+    }
+}
+
+// ---- pass 2: evaluation ------------------------------------------------------------------------------
+// shared-memory carve-up (in doubles), shared by kernel and launcher; every offset is even (16-byte loads)
 struct UniSmem {
-    int tab, coef, uv, wt, ewarp, elane, misc, wpart, nex, far, mask, mw, total;
+    int tab, coef, uv, wt, part, far, anchor, wpart, mask, mw, total;
     __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB) {
         const int nw = threads / 32;
         int o = 0;
-        tab = o;   o += TB ? (1 << TB) : 0;
-        coef = o;  o += sp * P * 8;
-        uv = o;    o += threads * R * 2;
-        wt = o;    o += threads * R;
-        ewarp = o; o += sp * nw * 2;
-        elane = o; o += sp * 32 * 2;
-        misc = o;  o += sp * 4;          // cos(p1/N), sin(p1/N), P*yoff, pad
-        wpart = o; o += sp * nw;
-        nex = o;   o += ((sp + 3) / 4) * 2;           // int per particle: peaks on the exact path (keeps 16-byte alignment)
-        far = o;   o += sp * nw * kFarTerms;          // far-field polynomial per (particle, warp region)
-        mw = (P + 31) / 32;                           // near-peak bit mask per (particle, warp region) + a has-far word
-        mask = o;  o += (sp * nw * (mw + 1) + 1) / 2;
+        tab = o;    o += TB ? (1 << TB) : 0;
+        coef = o;   o += sp * P * 8;
+        uv = o;     o += threads * R * 2;
+        wt = o;     o += threads * R;
+        part = o;   o += sp * kPartDoubles;
+        far = o;    o += sp * nw * kFarTerms;          // far-field polynomial per (particle, warp region)
+        anchor = o; o += sp * nw * 2;                  // phase at the first point of each warp region
+        wpart = o;  o += sp * nw;
+        mw = (P + 31) / 32;                            // near-peak bit mask per (particle, warp region) + a has-far word
+        mask = o;   o += (sp * nw * (mw + 1) + 1) / 2;
         total = o;
     }
 };
@@ -70,7 +147,7 @@ objective_uniform_kernel(ObjArgs a) {
     const int b = blockIdx.z;
     if (a.frozen && a.frozen[b]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int P = a.P, N = a.N, D = 4 + 3 * P;
+    const int P = a.P, N = a.N, D = 4 + 3 * P, NR = a.NR;
     const int s0 = blockIdx.x * a.sp;
     const int nsp = min(a.sp, a.S - s0);
     const UniSmem L(a.sp, P, THREADS, R, TB);
@@ -78,19 +155,19 @@ objective_uniform_kernel(ObjArgs a) {
     double* coef = smem + L.coef;
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
     double* swt = smem + L.wt;
-    double2* ewarp = reinterpret_cast<double2*>(smem + L.ewarp);
-    double2* elane = reinterpret_cast<double2*>(smem + L.elane);
-    double* misc = smem + L.misc;
-    double* wpart = smem + L.wpart;
-    int* nex = reinterpret_cast<int*>(smem + L.nex);
+    double* part = smem + L.part;
     double* farc = smem + L.far;
+    double2* anchor = reinterpret_cast<double2*>(smem + L.anchor);
+    double* wpart = smem + L.wpart;
     unsigned* mask = reinterpret_cast<unsigned*>(smem + L.mask);
     const int MW = L.mw;
     constexpr double H = 16.0 * R;                         // half a warp region, in points
 
     const int tile0 = blockIdx.y * (THREADS * R);
+    const int rg0 = blockIdx.y * NW;                       // first region of this tile
     const double* sw = a.spec + (size_t)b * 4 * N;
     const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
+    const size_t ps0 = (size_t)b * a.S + s0;
 
     // ---- stage the tile: coalesced reads, [j][thread] placement (point i0 + t*R + j -> slot j*THREADS + t)
     for (int e = tid; e < THREADS * R; e += THREADS) {
@@ -102,73 +179,37 @@ objective_uniform_kernel(ObjArgs a) {
     }
     const int i_first = tile0 + tid * R;                   // this thread's first point
     const double w_first = i_first < N ? sw[i_first] : fma((double)i_first, h, sw[0]);
-
     if (TB) {
         const double* src = ExpTabU<TB>::src();
         for (int i = tid; i < (1 << TB); i += THREADS) tab[i] = src[i];
     }
-    // ---- per-particle constants
-    const double* xb = a.x + ((size_t)b * a.S + s0) * D;
-    for (int idx = tid; idx < nsp * P; idx += THREADS) {
-        const int sp = idx / P, k = idx - sp * P;
-        const double* xs = xb + (size_t)sp * D;
-        SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
-        if (c.exact) c = null_span_coef();       // the span loop adds zero; the peak is handled after it
-        double* o = coef + (size_t)idx * 8;
-        o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.thr; o[7] = c.c2;
-    }
+    // ---- per-particle constants: copies of what objective_prepare_kernel left in global memory
     {
-        // phi_i = p0 + (p1*i)/N, i = tile0 + (32*warp + lane)*R + j, split as
-        // [p0 + p1*(tile0 + 32*R*warp)/N] + [p1*(lane*R)/N] + j*[p1/N]
-        const int per = NW + 32 + 1;
-        for (int idx = tid; idx < nsp * per; idx += THREADS) {
-            const int sp = idx / per, e = idx - sp * per;
-            const double* xs = xb + (size_t)sp * D;
-            const double p0 = xs[0], p1 = xs[1];
-            double ang;
-            if (e < NW) ang = p0 + (p1 * (double)(tile0 + 32 * R * e)) / (double)N;
-            else if (e < NW + 32) ang = (p1 * (double)((e - NW) * R)) / (double)N;
-            else ang = p1 / (double)N;
-            double sn, cs;
-            sincos(ang, &sn, &cs);
-            if (e < NW) ewarp[sp * NW + e] = make_double2(cs, sn);
-            else if (e < NW + 32) elane[sp * 32 + (e - NW)] = make_double2(cs, sn);
-            else { misc[sp * 4] = cs; misc[sp * 4 + 1] = sn; misc[sp * 4 + 2] = (double)P * xs[3]; }
+        const double2* g = reinterpret_cast<const double2*>(a.prep_coef + ps0 * P * 8);
+        double2* d = reinterpret_cast<double2*>(coef);
+        for (int i = tid; i < nsp * P * 4; i += THREADS) d[i] = g[i];
+        g = reinterpret_cast<const double2*>(a.prep_part + ps0 * kPartDoubles);
+        d = reinterpret_cast<double2*>(part);
+        for (int i = tid; i < nsp * (kPartDoubles / 2); i += THREADS) d[i] = g[i];
+        for (int i = tid; i < nsp * NW * (kFarTerms / 2); i += THREADS) {
+            const int sp = i / (NW * (kFarTerms / 2)), rem = i - sp * (NW * (kFarTerms / 2));
+            const int r = rem / (kFarTerms / 2), q = rem - r * (kFarTerms / 2);
+            double2 v = make_double2(0.0, 0.0);
+            if (rg0 + r < NR)
+                v = reinterpret_cast<const double2*>(a.prep_far + ((ps0 + sp) * NR + rg0 + r) * kFarTerms)[q];
+            reinterpret_cast<double2*>(farc)[i] = v;
         }
-    }
-    __syncthreads();
-    for (int sp = tid; sp < nsp; sp += THREADS) {          // thr < 0 marks a nulled (exact-path) peak
-        int n = 0;
-        for (int k = 0; k < P; ++k) n += coef[(size_t)(sp * P + k) * 8 + 6] < 0.0;
-        nex[sp] = n;
-    }
-    // near / far split of the peaks for every (particle, warp region) of this tile
-    for (int idx = tid; idx < nsp * NW; idx += THREADS) {
-        const int sp = idx / NW, r = idx - sp * NW;
-        const int ir = tile0 + r * 32 * R;
-        const double w_r = ir < N ? sw[ir] : fma((double)ir, h, sw[0]);
-        const double w_c = fma(0.5 * (32 * R - 1), h, w_r);
-        double C[kFarTerms];
-#pragma unroll
-        for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
-        unsigned any_far = 0;
-        unsigned* mk = mask + (size_t)idx * (MW + 1);
-        for (int wd = 0; wd < MW; ++wd) {
-            unsigned m = 0;
-            const int kend = min(P, wd * 32 + 32);
-            for (int k = wd * 32; k < kend; ++k) {
-                const double* o = coef + (size_t)(sp * P + k) * 8;
-                SpanCoef c;
-                c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
-                if (c.thr < 0.0) continue;                 // exact-path peak: neither near nor far here
-                if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
-                else m |= 1u << (k & 31);
-            }
-            mk[wd] = m;
+        for (int i = tid; i < nsp * NW; i += THREADS) {
+            const int sp = i / NW, r = i - sp * NW;
+            double2 v = make_double2(1.0, 0.0);
+            if (rg0 + r < NR) v = reinterpret_cast<const double2*>(a.prep_anchor)[(ps0 + sp) * NR + rg0 + r];
+            anchor[i] = v;
         }
-        mk[MW] = any_far;
-#pragma unroll
-        for (int n = 0; n < kFarTerms; ++n) farc[(size_t)idx * kFarTerms + n] = C[n];
+        for (int i = tid; i < nsp * NW * (MW + 1); i += THREADS) {
+            const int sr = i / (MW + 1), wd = i - sr * (MW + 1);
+            const int sp = sr / NW, r = sr - sp * NW;
+            mask[i] = rg0 + r < NR ? a.prep_mask[((ps0 + sp) * NR + rg0 + r) * (MW + 1) + wd] : 0u;
+        }
     }
     __syncthreads();
     const double xi0 = ((double)(lane * R) - 0.5 * (32 * R - 1)) / H;   // this thread's first point inside its region
@@ -178,6 +219,7 @@ objective_uniform_kernel(ObjArgs a) {
 #pragma unroll
         for (int j = 0; j < R; ++j) acc[j] = 0.0;
         const double* cf = coef + (size_t)sp * P * 8;
+        const double* pt = part + sp * kPartDoubles;
         const unsigned* mk = mask + (size_t)(sp * NW + warp) * (MW + 1);
         for (int wd = 0; wd < MW; ++wd)
         for (unsigned m = mk[wd]; m; m &= m - 1) {         // peaks near this warp's region
@@ -201,8 +243,8 @@ objective_uniform_kernel(ObjArgs a) {
             }
             far_eval<R>(C, xi0, 1.0 / H, acc);
         }
-        if (nex[sp]) {                                     // rare: peaks too narrow for the uniform-axis shortcuts
-            const double* xs = xb + (size_t)sp * D;
+        if (pt[67] != 0.0) {                               // rare: peaks too narrow for the uniform-axis shortcuts
+            const double* xs = a.x + (ps0 + sp) * D;
             for (int k = 0; k < P; ++k) {
                 if (!(cf[k * 8 + 6] < 0.0)) continue;
                 const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
@@ -210,9 +252,9 @@ objective_uniform_kernel(ObjArgs a) {
             }
         }
         // residual against the phase-rotated data; the rotation advances by p1/N per point
-        const double2 ew = ewarp[sp * NW + warp], el = elane[sp * 32 + lane];
-        const double cd = misc[sp * 4], sd = misc[sp * 4 + 1];
-        const double py = misc[sp * 4 + 2];                // yoff is added once per peak (equations.py:147,195)
+        const double2 ew = anchor[sp * NW + warp];
+        const double2 el = *reinterpret_cast<const double2*>(pt + 2 * lane);
+        const double cd = pt[64], sd = pt[65], py = pt[66];
         double cr = fma(ew.x, el.x, -(ew.y * el.y));
         double ci = fma(ew.y, el.x, ew.x * el.y);
         double ss = 0.0;
@@ -271,6 +313,17 @@ static cudaError_t launch_tb(const ObjArgs& a, int tb, dim3 grid, cudaStream_t s
     }
 }
 
+void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, int* n_regions, size_t* coef, size_t* part, size_t* far,
+                                  size_t* anchor, size_t* mask_words) {
+    const int nr = (N + 32 * t.r - 1) / (32 * t.r);
+    *n_regions = nr;
+    *coef = (size_t)P * 8;                      // doubles per particle
+    *part = kPartDoubles;
+    *far = (size_t)nr * kFarTerms;
+    *anchor = (size_t)nr * 2;
+    *mask_words = (size_t)nr * ((P + 31) / 32 + 1);
+}
+
 size_t objective_uniform_smem_bytes(int P, const ObjTune& t) {
     return (size_t)UniSmem(t.sp, P, t.threads, t.r, t.tb).total * sizeof(double);
 }
@@ -282,6 +335,17 @@ cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double*
     dim3 grid((a.S + t.sp - 1) / t.sp, n_tiles, B);
     cudaError_t e = cudaErrorInvalidValue;
     if (ev0) cudaEventRecord(ev0, st);
+    {
+        dim3 pgrid(a.S, B);
+        const size_t pbytes = (size_t)a.P * 8 * sizeof(double);
+        if (t.r == 4) objective_prepare_kernel<4><<<pgrid, 128, pbytes, st>>>(a);
+        else if (t.r == 8) objective_prepare_kernel<8><<<pgrid, 128, pbytes, st>>>(a);
+        else if (t.r == 16) objective_prepare_kernel<16><<<pgrid, 128, pbytes, st>>>(a);
+        else return cudaErrorInvalidValue;
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        e = cudaErrorInvalidValue;
+    }
     if (t.threads == 128 && t.r == 4) e = launch_tb<128, 4>(a, t.tb, grid, st);
     else if (t.threads == 128 && t.r == 8) e = launch_tb<128, 8>(a, t.tb, grid, st);
     else if (t.threads == 128 && t.r == 16) e = launch_tb<128, 16>(a, t.tb, grid, st);
@@ -291,7 +355,7 @@ cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double*
     if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) return e;
     e = launch_objective_finalize(a.partials, n_tiles, 1, a.N, a.S, B, a.frozen, f, st);
-    count_launches(2);
+    count_launches(3);
     return e;
 }
 
