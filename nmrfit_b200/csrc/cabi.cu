@@ -161,8 +161,9 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     ObjArgs a{};
     if (uni) {
         size_t nc, np, nf, na, nm;
-        objective_uniform_prep_sizes(c->N, c->P, t, &a.NR, &nc, &np, &nf, &na, &nm);
-        const size_t slots = (size_t)c->B * S;
+        int pad = 0;
+        objective_uniform_prep_sizes(c->N, c->P, t, &nc, &np, &nf, &na, &nm, &pad);
+        const size_t slots = (size_t)c->B * S + pad;
         CK(c->prep_coef.reserve(slots * nc));
         CK(c->prep_part.reserve(slots * np));
         CK(c->prep_far.reserve(slots * nf));

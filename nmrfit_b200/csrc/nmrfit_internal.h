@@ -19,10 +19,10 @@ struct ObjArgs {
     // uniform-axis kernel: per-particle constants written by its prepare pass (see objective_uniform.cu)
     double* prep_coef;      // [B][S][P][8]
     double* prep_part;      // [B][S][68]
-    double* prep_far;       // [B][S][NR][12]
-    double* prep_anchor;    // [B][S][NR][2]
-    unsigned* prep_mask;    // [B][S][NR][ceil(P/32)+1]
-    int NR;                 // regions of 32*r points on the axis
+    double* prep_far;       // [B][S][n_tiles*nw][12]   regions in tile-major order
+    double* prep_anchor;    // [B][S][n_tiles*nw][2]
+    unsigned* prep_mask;    // [B][S][n_tiles*nw][ceil(P/32)+1]
+    int n_tiles, nw;        // point tiles, warps (= regions) per tile (filled by the launcher)
     int N, P, S;
     int kk;                 // 0 real only, 1 reference fit_im (last peak), 2 sum over peaks
     int sp;                 // particles per CTA (filled by the launcher)
@@ -48,8 +48,8 @@ cudaError_t launch_objective_finalize(const double* partials, int n_tiles, int n
 // uniform-axis objective (objective_uniform.cu): real-only fit, FP64
 size_t objective_uniform_smem_bytes(int P, const ObjTune& t);
 // per-particle sizes (in doubles / 32-bit words) of the prepare pass's outputs
-void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, int* n_regions, size_t* coef, size_t* part, size_t* far,
-                                  size_t* anchor, size_t* mask_words);
+void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, size_t* coef, size_t* part, size_t* far, size_t* anchor,
+                                  size_t* mask_words, int* pad_particles);
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st,
                                      cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 

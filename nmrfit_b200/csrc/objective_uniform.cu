@@ -1,35 +1,45 @@
 // K1u: batched objective on a UNIFORM frequency axis (w_i = w_0 + i*h, what np.linspace and
-// every spectrometer ppm scale produce) - the kernel a fit normally runs.
+// every spectrometer ppm scale produce) - the kernels a fit normally runs.
 //
 // Same result definition as objective.cu (reference equations.py:152-212 with ps2,
-// proc_autophase.py:29-36, and voigt, equations.py:141-147); different arithmetic.  The general
-// kernel pays one exponential per peak-point; here a thread owns R CONSECUTIVE grid points, so the
-// Gaussian of a peak advances along them by a two-multiply recurrence (peak_span in
-// nmrfit_math.cuh) and only its two anchors need an exponential.  FP64 issue slots per peak-point:
-// 9 (t, q, 3 rcp, 2 accumulate, 2 recurrence) + anchors/R, against 19 in the general kernel;
-// non-FP64 instructions per peak-point: 2 (MUFU seed + its zero low word) against 18.
+// proc_autophase.py:29-36, and voigt, equations.py:141-147); different arithmetic (nmrfit_math.cuh):
+//   * a thread owns R CONSECUTIVE grid points, so the Gaussian of a peak advances along them by a
+//     two-multiply recurrence and only its two anchors need an exponential; beyond 6.5 units of s it
+//     is skipped (< 4.5e-19 of its height);
+//   * Lorentzian reciprocals are taken four at a time from one reciprocal of the product;
+//   * Lorentzians of peaks FAR from a warp's region of 32*R points are not evaluated peak by peak at
+//     all: their Taylor series about the region's centre are summed into ONE degree-11 polynomial per
+//     (particle, region), 12 FMAs per point for all far peaks together; only the peaks near the region
+//     (1.5 of 12 on average at BASELINE config 2, 2.2 of 24 at config 4) are evaluated individually.
 //
-// Lorentzians of peaks far from a warp's 32*R points are not evaluated peak by peak at all: per
-// (particle, warp region) objective_prepare_kernel sums their Taylor series about the region's centre into ONE
-// degree-11 polynomial (far_accumulate), which costs 12 FMAs per point for all far peaks together; only
-// the peaks near the region (1.5 of 12 on average at BASELINE config 2, 2.2 of 24 at config 4) go
-// through peak_span.
+// Two passes per swarm generation:
+//   objective_prepare_kernel   one CTA per particle: span coefficients of its peaks, phase tables, and
+//                              per region the near-peak mask, the far-field polynomial and the phase
+//                              anchor -> a few KB per particle in global memory;
+//   objective_uniform_kernel   grid (particle groups, point tiles, spectra).  A CTA owns THREADS*R
+//                              consecutive points (one region of 32*R per warp) and SP particles.  Its
+//                              per-particle constants arrive by TMA bulk copies (cp.async.bulk completing
+//                              on an mbarrier) issued by one thread while all threads stage the tile's
+//                              (u, v, weights) in shared memory; after that the CTA touches no global
+//                              memory until it writes SP partial sums.
+// (A persistent variant - one CTA per SM slot looping over groups with double-buffered bulk copies - was
+// measured 5-10 % slower at BASELINE config 2: a region's cost depends on how many peaks are near it, the
+// same regions for every particle, and the hardware's CTA scheduler balances that better than a static
+// assignment of tiles to persistent CTAs.)
 //
-// Mapping: grid (particle tiles, point tiles, spectra).  A CTA stages its THREADS*R points of
-// (u, v) and weights in shared memory once ([j][thread] order: conflict-free for the per-point
-// reads) and loops over SP particles; per particle the per-peak span coefficients are built into
-// shared memory by the first threads and broadcast.  The squared residual is reduced by a fixed
-// xor-shuffle tree, a fixed-order sum over warps and (objective_finalize_kernel) over point tiles:
-// no atomics, bit-reproducible, independent of how particles or spectra are sharded.
+// The squared residual is reduced by a fixed xor-shuffle tree, a fixed-order sum over the warps of a
+// tile and (objective_finalize_kernel) over tiles: no atomics, bit-reproducible, independent of how
+// particles or spectra are sharded and of how many CTAs run.
 //
-// The axis is treated as exactly uniform: the anchor uses the stored w of the thread's first
-// point and the other R-1 abscissae are anchor + j*h.  That moves an abscissa by at most one
-// ulp(w) (4.4e-16 ppm at w ~ 3.4) against the stored value, i.e. <= 5e-13 relative in a curve
-// value for a 0.004 ppm line at 3.4 ppm.  Peaks for which that bound (kL * ulp(w)) would exceed 1e-11,
-// and peaks narrower than ~3 grid points, are evaluated point by point from the stored w instead
-// (peak_exact).  nmrfit_ctx_set_spectrum only enables this kernel when every stored w_i is within
-// 4 ulp of w_0 + i*h, otherwise the general kernel runs.
+// The axis is treated as exactly uniform: the anchor uses the stored w of the thread's first point and
+// the other R-1 abscissae are anchor + j*h.  That moves an abscissa by at most one ulp(w) (4.4e-16 ppm
+// at w ~ 3.4) against the stored value, i.e. <= 5e-13 relative in a curve value for a 0.004 ppm line.
+// Peaks for which that bound (kL * ulp(w)) would exceed 1e-11, and peaks narrower than ~3 grid points,
+// are evaluated point by point from the stored w instead (peak_exact).  nmrfit_ctx_set_spectrum only
+// enables these kernels when every stored w_i is within 4 ulp of w_0 + i*h; otherwise the general kernel runs.
 #include <cuda_runtime.h>
+#include <algorithm>
+#include <cstdint>
 #include "nmrfit_internal.h"
 #include "nmrfit_math.cuh"
 
@@ -41,20 +51,19 @@ template <> struct ExpTabU<8> { static __device__ __forceinline__ const double* 
 template <> struct ExpTabU<10> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB10; } };
 
 constexpr int kPartDoubles = 68;   // per particle: e^{i p1 lane R/N} for 32 lanes (64), cos/sin(p1/N), P*yoff, #exact peaks
+constexpr int kPadParticles = 64;  // slack at the end of the prepare buffers: the last group is copied whole
 
 // ---- pass 1: per-particle constants, once per swarm generation ------------------------------------
-// One CTA per particle.  Phase 1 builds the span coefficients of its P peaks and the phase tables;
-// phase 2 walks the regions of the axis (32*R points each), classifies every peak as near or far for
-// that region, sums the far Lorentzians into the region's polynomial and takes the phase anchor
-// e^{i(p0 + p1*i_r/N)} of the region's first point.  Everything lands in global memory (a few KB per
-// particle); the evaluation kernel's prologue is then a plain copy.
+// Regions (32*R points each) are stored in axis order, padded to a whole number of tiles; the slots of
+// regions past the end of the axis are neutral.
 template <int R>
 __global__ void __launch_bounds__(128)
 objective_prepare_kernel(ObjArgs a) {
     extern __shared__ __align__(16) double cs[];           // [P][8]
     const int b = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
     if (a.frozen && a.frozen[b]) return;
-    const int P = a.P, N = a.N, D = 4 + 3 * P, NR = a.NR, MW = (P + 31) / 32;
+    const int P = a.P, N = a.N, D = 4 + 3 * P, MW = (P + 31) / 32;
+    const int NR = (N + 32 * R - 1) / (32 * R), NRP = a.n_tiles * a.nw;
     const size_t ps = (size_t)b * a.S + s;
     const double* xs = a.x + ps * D;
     const double* sw = a.spec + (size_t)b * 4 * N;
@@ -72,8 +81,8 @@ objective_prepare_kernel(ObjArgs a) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) g[i] = o[i];
     }
-    // phi_i = p0 + (p1*i)/N with i = i_r + lane*R + j:  anchor(i_r) * [p1*(lane*R)/N] * j*[p1/N]
-    for (int e = 127 - tid; e < 33; e += 128) {            // the last warp does these while the first does the peaks
+    // phi_i = p0 + (p1*i)/N with i = i_r + lane*R + j:  anchor(i_r) * e^{i p1 (lane R)/N} * (e^{i p1/N})^j
+    for (int e = 127 - tid; e < 33; e += 128) {            // the last warps do these while the first does the peaks
         double sn, cn;
         sincos(e < 32 ? (p1 * (double)(e * R)) / (double)N : p1 / (double)N, &sn, &cn);
         part[2 * e] = cn;
@@ -86,90 +95,138 @@ objective_prepare_kernel(ObjArgs a) {
         for (int k = 0; k < P; ++k) n += cs[k * 8 + 6] < 0.0;      // thr < 0 marks a nulled (exact-path) peak
         part[67] = (double)n;
     }
-    for (int r = tid; r < NR; r += 128) {
-        const int ir = r * 32 * R;
-        const double w_c = fma(0.5 * (32 * R - 1), h, sw[ir]);
+    for (int r = tid; r < NRP; r += 128) {
+        const size_t slot = ps * NRP + r;
         double C[kFarTerms];
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
         unsigned any_far = 0;
-        unsigned* mk = a.prep_mask + (ps * NR + r) * (MW + 1);
-        for (int wd = 0; wd < MW; ++wd) {
-            unsigned m = 0;
-            const int kend = min(P, wd * 32 + 32);
-            for (int k = wd * 32; k < kend; ++k) {
-                const double* o = cs + k * 8;
-                SpanCoef c;
-                c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
-                if (c.thr < 0.0) continue;                 // exact-path peak: neither near nor far
-                if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
-                else m |= 1u << (k & 31);
+        unsigned* mk = a.prep_mask + slot * (MW + 1);
+        double sn = 0.0, cn = 1.0;
+        if (r < NR) {
+            const int ir = r * 32 * R;
+            const double w_c = fma(0.5 * (32 * R - 1), h, sw[ir]);
+            for (int wd = 0; wd < MW; ++wd) {
+                unsigned m = 0;
+                const int kend = min(P, wd * 32 + 32);
+                for (int k = wd * 32; k < kend; ++k) {
+                    const double* o = cs + k * 8;
+                    SpanCoef c;
+                    c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
+                    if (c.thr < 0.0) continue;             // exact-path peak: neither near nor far
+                    if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
+                    else m |= 1u << (k & 31);
+                }
+                mk[wd] = m;
             }
-            mk[wd] = m;
+            sincos(p0 + (p1 * (double)ir) / (double)N, &sn, &cn);
+        } else {
+            for (int wd = 0; wd < MW; ++wd) mk[wd] = 0u;
         }
         mk[MW] = any_far;
-        double* fc = a.prep_far + (ps * NR + r) * kFarTerms;
+        double* fc = a.prep_far + slot * kFarTerms;
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
-        double sn, cn;
-        sincos(p0 + (p1 * (double)ir) / (double)N, &sn, &cn);
-        a.prep_anchor[(ps * NR + r) * 2] = cn;
-        a.prep_anchor[(ps * NR + r) * 2 + 1] = sn;
+        a.prep_anchor[slot * 2] = cn;
+        a.prep_anchor[slot * 2 + 1] = sn;
     }
 }
 
 // ---- pass 2: evaluation ------------------------------------------------------------------------------
-// shared-memory carve-up (in doubles), shared by kernel and launcher; every offset is even (16-byte loads)
+// TMA bulk copy (global -> shared, 1-D) completing on an mbarrier, and the barrier's own operations.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+// shared-memory carve-up (in doubles), shared by kernel and launcher; every offset is even (16-byte alignment)
 struct UniSmem {
-    int tab, coef, uv, wt, part, far, anchor, wpart, mask, mw, total;
+    int tab, uv, wt, bar, wpart, coef, part, far, anchor, mask, mw, total;
     __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB) {
         const int nw = threads / 32;
+        mw = (P + 31) / 32;                               // near-peak mask words per region, + 1 has-far word
         int o = 0;
         tab = o;    o += TB ? (1 << TB) : 0;
-        coef = o;   o += sp * P * 8;
         uv = o;     o += threads * R * 2;
         wt = o;     o += threads * R;
-        part = o;   o += sp * kPartDoubles;
-        far = o;    o += sp * nw * kFarTerms;          // far-field polynomial per (particle, warp region)
-        anchor = o; o += sp * nw * 2;                  // phase at the first point of each warp region
+        bar = o;    o += 2;                               // one mbarrier
         wpart = o;  o += sp * nw;
-        mw = (P + 31) / 32;                            // near-peak bit mask per (particle, warp region) + a has-far word
-        mask = o;   o += (sp * nw * (mw + 1) + 1) / 2;
+        coef = o;   o += sp * P * 8;
+        part = o;   o += sp * kPartDoubles;
+        far = o;    o += sp * nw * kFarTerms;             // far-field polynomial per (particle, warp region)
+        anchor = o; o += sp * nw * 2;                     // phase at the first point of each warp region
+        mask = o;   o += ((sp * nw * (mw + 1) + 3) / 4) * 2;
         total = o;
     }
 };
 
 template <int THREADS, int R, int TB>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (R <= 8 ? 768 : 512) / THREADS)    // 24 (16 for R = 16) resident warps per SM
 objective_uniform_kernel(ObjArgs a) {
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.z;
     if (a.frozen && a.frozen[b]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int P = a.P, N = a.N, D = 4 + 3 * P, NR = a.NR;
-    const int s0 = blockIdx.x * a.sp;
-    const int nsp = min(a.sp, a.S - s0);
-    const UniSmem L(a.sp, P, THREADS, R, TB);
+    const int P = a.P, N = a.N, D = 4 + 3 * P, SP = a.sp;
+    const int n_tiles = a.n_tiles, tile = blockIdx.y, NRP = n_tiles * NW;
+    const int s0 = blockIdx.x * SP, nsp = min(SP, a.S - s0);
+    const UniSmem L(SP, P, THREADS, R, TB);
     double* tab = smem + L.tab;
-    double* coef = smem + L.coef;
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
     double* swt = smem + L.wt;
-    double* part = smem + L.part;
-    double* farc = smem + L.far;
-    double2* anchor = reinterpret_cast<double2*>(smem + L.anchor);
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
     double* wpart = smem + L.wpart;
-    unsigned* mask = reinterpret_cast<unsigned*>(smem + L.mask);
+    const double* coef = smem + L.coef;
+    const double* part = smem + L.part;
+    const double* farc = smem + L.far;
+    const double2* anchor = reinterpret_cast<const double2*>(smem + L.anchor);
+    const unsigned* mask = reinterpret_cast<const unsigned*>(smem + L.mask);
     const int MW = L.mw;
-    constexpr double H = 16.0 * R;                         // half a warp region, in points
+    constexpr double H = 16.0 * R;                         // half a region, in points
 
-    const int tile0 = blockIdx.y * (THREADS * R);
-    const int rg0 = blockIdx.y * NW;                       // first region of this tile
+    const int tile0 = tile * (THREADS * R);
     const double* sw = a.spec + (size_t)b * 4 * N;
     const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
-    const size_t ps0 = (size_t)b * a.S + s0;
+    const size_t q0 = (size_t)b * a.S + s0;                // first particle slot of this group
 
-    // ---- stage the tile: coalesced reads, [j][thread] placement (point i0 + t*R + j -> slot j*THREADS + t)
+    // ---- one thread asks the TMA for the group's constants; they complete on the mbarrier.  Whole
+    // groups are copied (the prepare buffers are padded), only nsp particles are evaluated.
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const uint32_t b_coef = SP * P * 8 * 8, b_part = SP * kPartDoubles * 8, b_far = NW * kFarTerms * 8;
+        const uint32_t b_anchor = NW * 2 * 8, b_mask = NW * (MW + 1) * 4;
+        mbar_expect_tx(bar, b_coef + b_part + SP * (b_far + b_anchor + b_mask));
+        bulk_g2s(smem + L.coef, a.prep_coef + q0 * P * 8, b_coef, bar);
+        bulk_g2s(smem + L.part, a.prep_part + q0 * kPartDoubles, b_part, bar);
+        for (int sp = 0; sp < SP; ++sp) {
+            const size_t rs = (q0 + sp) * NRP + (size_t)tile * NW;
+            bulk_g2s(smem + L.far + sp * NW * kFarTerms, a.prep_far + rs * kFarTerms, b_far, bar);
+            bulk_g2s(smem + L.anchor + sp * NW * 2, a.prep_anchor + rs * 2, b_anchor, bar);
+            bulk_g2s(reinterpret_cast<unsigned*>(smem + L.mask) + sp * NW * (MW + 1), a.prep_mask + rs * (MW + 1), b_mask, bar);
+        }
+    }
+
+    // ---- meanwhile stage the tile: coalesced reads, [j][thread] placement (point tile0 + t*R + j -> slot j*THREADS + t)
     for (int e = tid; e < THREADS * R; e += THREADS) {
         const int i = tile0 + e;
         const bool ok = i < N;
@@ -183,36 +240,9 @@ objective_uniform_kernel(ObjArgs a) {
         const double* src = ExpTabU<TB>::src();
         for (int i = tid; i < (1 << TB); i += THREADS) tab[i] = src[i];
     }
-    // ---- per-particle constants: copies of what objective_prepare_kernel left in global memory
-    {
-        const double2* g = reinterpret_cast<const double2*>(a.prep_coef + ps0 * P * 8);
-        double2* d = reinterpret_cast<double2*>(coef);
-        for (int i = tid; i < nsp * P * 4; i += THREADS) d[i] = g[i];
-        g = reinterpret_cast<const double2*>(a.prep_part + ps0 * kPartDoubles);
-        d = reinterpret_cast<double2*>(part);
-        for (int i = tid; i < nsp * (kPartDoubles / 2); i += THREADS) d[i] = g[i];
-        for (int i = tid; i < nsp * NW * (kFarTerms / 2); i += THREADS) {
-            const int sp = i / (NW * (kFarTerms / 2)), rem = i - sp * (NW * (kFarTerms / 2));
-            const int r = rem / (kFarTerms / 2), q = rem - r * (kFarTerms / 2);
-            double2 v = make_double2(0.0, 0.0);
-            if (rg0 + r < NR)
-                v = reinterpret_cast<const double2*>(a.prep_far + ((ps0 + sp) * NR + rg0 + r) * kFarTerms)[q];
-            reinterpret_cast<double2*>(farc)[i] = v;
-        }
-        for (int i = tid; i < nsp * NW; i += THREADS) {
-            const int sp = i / NW, r = i - sp * NW;
-            double2 v = make_double2(1.0, 0.0);
-            if (rg0 + r < NR) v = reinterpret_cast<const double2*>(a.prep_anchor)[(ps0 + sp) * NR + rg0 + r];
-            anchor[i] = v;
-        }
-        for (int i = tid; i < nsp * NW * (MW + 1); i += THREADS) {
-            const int sr = i / (MW + 1), wd = i - sr * (MW + 1);
-            const int sp = sr / NW, r = sr - sp * NW;
-            mask[i] = rg0 + r < NR ? a.prep_mask[((ps0 + sp) * NR + rg0 + r) * (MW + 1) + wd] : 0u;
-        }
-    }
-    __syncthreads();
-    const double xi0 = ((double)(lane * R) - 0.5 * (32 * R - 1)) / H;   // this thread's first point inside its region
+    const double xi0 = ((double)(lane * R) - 0.5 * (32 * R - 1)) / H;      // first point's position inside its region
+    __syncthreads();                                       // tile, table and the mbarrier initialisation are visible
+    mbar_wait(bar, 0);                                     // the constants have landed
 
     for (int sp = 0; sp < nsp; ++sp) {
         double acc[R];
@@ -244,7 +274,7 @@ objective_uniform_kernel(ObjArgs a) {
             far_eval<R>(C, xi0, 1.0 / H, acc);
         }
         if (pt[67] != 0.0) {                               // rare: peaks too narrow for the uniform-axis shortcuts
-            const double* xs = a.x + (ps0 + sp) * D;
+            const double* xs = a.x + (q0 + sp) * D;
             for (int k = 0; k < P; ++k) {
                 if (!(cf[k * 8 + 6] < 0.0)) continue;
                 const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
@@ -276,20 +306,20 @@ objective_uniform_kernel(ObjArgs a) {
         if (lane == 0) wpart[sp * NW + warp] = ss;
     }
     __syncthreads();
-    for (int sp = tid; sp < nsp; sp += THREADS) {
+    if (tid < nsp) {
         double t = 0.0;
 #pragma unroll
-        for (int wi = 0; wi < NW; ++wi) t += wpart[sp * NW + wi];
-        a.partials[((size_t)b * a.S + s0 + sp) * gridDim.y + blockIdx.y] = t;
+        for (int wi = 0; wi < NW; ++wi) t += wpart[tid * NW + wi];
+        a.partials[(q0 + tid) * n_tiles + tile] = t;
     }
 }
 
 // ---- launcher -----------------------------------------------------------------
 template <int THREADS, int R, int TB>
-static cudaError_t launch_one(const ObjArgs& a, dim3 grid, cudaStream_t st) {
+static cudaError_t launch_one(const ObjArgs& a, int B, cudaStream_t st) {
     static bool attr_set[NMRFIT_MAX_DEVICES] = {};
     UniSmem L(a.sp, a.P, THREADS, R, TB);
-    size_t bytes = (size_t)L.total * sizeof(double);
+    const size_t bytes = (size_t)L.total * sizeof(double);
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev % NMRFIT_MAX_DEVICES]) {
@@ -298,30 +328,31 @@ static cudaError_t launch_one(const ObjArgs& a, dim3 grid, cudaStream_t st) {
         if (e != cudaSuccess) return e;
         attr_set[dev % NMRFIT_MAX_DEVICES] = true;
     }
+    dim3 grid((a.S + a.sp - 1) / a.sp, a.n_tiles, B);
     objective_uniform_kernel<THREADS, R, TB><<<grid, THREADS, bytes, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int THREADS, int R>
-static cudaError_t launch_tb(const ObjArgs& a, int tb, dim3 grid, cudaStream_t st) {
+static cudaError_t launch_tb(const ObjArgs& a, int tb, int B, cudaStream_t st) {
     switch (tb) {
-        case 0: return launch_one<THREADS, R, 0>(a, grid, st);
-        case 6: return launch_one<THREADS, R, 6>(a, grid, st);
-        case 8: return launch_one<THREADS, R, 8>(a, grid, st);
-        case 10: return launch_one<THREADS, R, 10>(a, grid, st);
+        case 0: return launch_one<THREADS, R, 0>(a, B, st);
+        case 6: return launch_one<THREADS, R, 6>(a, B, st);
+        case 8: return launch_one<THREADS, R, 8>(a, B, st);
+        case 10: return launch_one<THREADS, R, 10>(a, B, st);
         default: return cudaErrorInvalidValue;
     }
 }
 
-void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, int* n_regions, size_t* coef, size_t* part, size_t* far,
-                                  size_t* anchor, size_t* mask_words) {
-    const int nr = (N + 32 * t.r - 1) / (32 * t.r);
-    *n_regions = nr;
+void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, size_t* coef, size_t* part, size_t* far, size_t* anchor,
+                                  size_t* mask_words, int* pad_particles) {
+    const size_t nrp = (size_t)objective_tiles(N, t) * (t.threads / 32);
     *coef = (size_t)P * 8;                      // doubles per particle
     *part = kPartDoubles;
-    *far = (size_t)nr * kFarTerms;
-    *anchor = (size_t)nr * 2;
-    *mask_words = (size_t)nr * ((P + 31) / 32 + 1);
+    *far = nrp * kFarTerms;
+    *anchor = nrp * 2;
+    *mask_words = nrp * ((P + 31) / 32 + 1);    // 32-bit words per particle
+    *pad_particles = kPadParticles;
 }
 
 size_t objective_uniform_smem_bytes(int P, const ObjTune& t) {
@@ -330,9 +361,10 @@ size_t objective_uniform_smem_bytes(int P, const ObjTune& t) {
 
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0,
                                      cudaEvent_t ev1) {
+    if (t.sp > kPadParticles) return cudaErrorInvalidValue;
     a.sp = t.sp;
-    const int n_tiles = objective_tiles(a.N, t);
-    dim3 grid((a.S + t.sp - 1) / t.sp, n_tiles, B);
+    a.n_tiles = objective_tiles(a.N, t);
+    a.nw = t.threads / 32;
     cudaError_t e = cudaErrorInvalidValue;
     if (ev0) cudaEventRecord(ev0, st);
     {
@@ -346,15 +378,15 @@ cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double*
         if (e != cudaSuccess) return e;
         e = cudaErrorInvalidValue;
     }
-    if (t.threads == 128 && t.r == 4) e = launch_tb<128, 4>(a, t.tb, grid, st);
-    else if (t.threads == 128 && t.r == 8) e = launch_tb<128, 8>(a, t.tb, grid, st);
-    else if (t.threads == 128 && t.r == 16) e = launch_tb<128, 16>(a, t.tb, grid, st);
-    else if (t.threads == 256 && t.r == 4) e = launch_tb<256, 4>(a, t.tb, grid, st);
-    else if (t.threads == 256 && t.r == 8) e = launch_tb<256, 8>(a, t.tb, grid, st);
-    else if (t.threads == 256 && t.r == 16) e = launch_tb<256, 16>(a, t.tb, grid, st);
+    if (t.threads == 128 && t.r == 4) e = launch_tb<128, 4>(a, t.tb, B, st);
+    else if (t.threads == 128 && t.r == 8) e = launch_tb<128, 8>(a, t.tb, B, st);
+    else if (t.threads == 128 && t.r == 16) e = launch_tb<128, 16>(a, t.tb, B, st);
+    else if (t.threads == 256 && t.r == 4) e = launch_tb<256, 4>(a, t.tb, B, st);
+    else if (t.threads == 256 && t.r == 8) e = launch_tb<256, 8>(a, t.tb, B, st);
+    else if (t.threads == 256 && t.r == 16) e = launch_tb<256, 16>(a, t.tb, B, st);
     if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) return e;
-    e = launch_objective_finalize(a.partials, n_tiles, 1, a.N, a.S, B, a.frozen, f, st);
+    e = launch_objective_finalize(a.partials, a.n_tiles, 1, a.N, a.S, B, a.frozen, f, st);
     count_launches(3);
     return e;
 }
