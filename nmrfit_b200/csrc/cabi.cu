@@ -95,10 +95,10 @@ struct nmrfit_ctx {
 
 namespace {
 
-// Which objective kernel a launch uses: the uniform-axis kernel needs every spectrum of the batch on a
-// uniform axis, the real-only fit and FP64; anything else runs the general kernel.
+// Which objective kernel a launch uses: the uniform-axis kernels (FP64 or FP32) need every spectrum of the
+// batch on a uniform axis and the real-only fit; anything else runs the general kernel of that precision.
 bool use_uniform(const nmrfit_ctx* c, int fit_im) {
-    if (c->algorithm == NMRFIT_ALGO_GENERAL || fit_im != NMRFIT_REAL_ONLY || c->precision != NMRFIT_FP64) return false;
+    if (c->algorithm == NMRFIT_ALGO_GENERAL || fit_im != NMRFIT_REAL_ONLY) return false;
     for (char u : c->uniform)
         if (!u) return false;
     return true;
@@ -151,8 +151,11 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     if (fit_im < 0 || fit_im > 2) return fail(NMRFIT_ERR_ARG, "fit_im must be 0, 1 or 2");
     const bool uni = use_uniform(c, fit_im);
     if (c->algorithm == NMRFIT_ALGO_UNIFORM && !uni)
-        return fail(NMRFIT_ERR_STATE, "the uniform-axis kernel needs uniformly spaced w in every spectrum, fit_im off and FP64");
+        return fail(NMRFIT_ERR_STATE, "the uniform-axis kernel needs uniformly spaced w in every spectrum and fit_im off");
+    if (c->precision == NMRFIT_FP32 && fit_im != NMRFIT_REAL_ONLY)
+        return fail(NMRFIT_ERR_ARG, "fit_im is not available in FP32 mode (the Kramers-Kronig term runs in FP64 only)");
     ObjTune t = pick_tune(c, S, uni);
+    if (uni && c->precision == NMRFIT_FP32 && t.r == 16) t.r = 8;      // the FP32 kernel is built for 4 and 8
     if (uni ? (t.r != 4 && t.r != 8 && t.r != 16) : (t.r != 2 && t.r != 4 && t.r != 8))
         return fail(NMRFIT_ERR_ARG, uni ? "points_per_thread must be 4, 8 or 16 for the uniform-axis kernel"
                                         : "points_per_thread must be 2, 4 or 8 for the general kernel");
@@ -191,7 +194,7 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
         ev1 = c->prof_events[c->prof_used + 1];
         c->prof_used += 2;
     }
-    cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, st, ev0, ev1)
+    cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, uni, st, ev0, ev1)
                     : uni                       ? launch_objective_uniform(a, t, c->B, f_dev, st, ev0, ev1)
                                                 : launch_objective(a, t, c->B, f_dev, st, ev0, ev1);
     if (e != cudaSuccess) return fail_cuda(e, "objective launch");

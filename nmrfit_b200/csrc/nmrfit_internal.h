@@ -53,9 +53,12 @@ void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, size_t* coef, 
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st,
                                      cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 
-// opt-in FP32 objective (same launch geometry)
-cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0 = nullptr,
-                                 cudaEvent_t ev1 = nullptr);
+cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaStream_t st);
+
+// opt-in FP32 objective: uniform-axis kernel when `uniform`, else a plain FP32 kernel for any axis (real-only fit)
+size_t objective_f32_smem_bytes(int P, const ObjTune& t);
+cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, bool uniform, cudaStream_t st,
+                                 cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
 
 // ---- K2/K3 swarm --------------------------------------------------------------
 struct SwarmState {

@@ -42,6 +42,7 @@
 #include <cstdint>
 #include "nmrfit_internal.h"
 #include "nmrfit_math.cuh"
+#include "uniform_common.cuh"
 
 namespace nmrfit {
 
@@ -50,8 +51,6 @@ template <> struct ExpTabU<6> { static __device__ __forceinline__ const double* 
 template <> struct ExpTabU<8> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB8; } };
 template <> struct ExpTabU<10> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB10; } };
 
-constexpr int kPartDoubles = 68;   // per particle: e^{i p1 lane R/N} for 32 lanes (64), cos/sin(p1/N), P*yoff, #exact peaks
-constexpr int kPadParticles = 64;  // slack at the end of the prepare buffers: the last group is copied whole
 
 // ---- pass 1: per-particle constants, once per swarm generation ------------------------------------
 // Regions (32*R points each) are stored in axis order, padded to a whole number of tiles; the slots of
@@ -133,30 +132,6 @@ objective_prepare_kernel(ObjArgs a) {
 }
 
 // ---- pass 2: evaluation ------------------------------------------------------------------------------
-// TMA bulk copy (global -> shared, 1-D) completing on an mbarrier, and the barrier's own operations.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t done = 0;
-    while (!done) {
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    }
-}
-
 // shared-memory carve-up (in doubles), shared by kernel and launcher; every offset is even (16-byte alignment)
 struct UniSmem {
     int tab, uv, wt, bar, wpart, coef, part, far, anchor, mask, mw, total;
@@ -359,25 +334,27 @@ size_t objective_uniform_smem_bytes(int P, const ObjTune& t) {
     return (size_t)UniSmem(t.sp, P, t.threads, t.r, t.tb).total * sizeof(double);
 }
 
-cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0,
-                                     cudaEvent_t ev1) {
+// pass 1 (shared with the FP32 evaluation kernel); fills a.sp / a.n_tiles / a.nw
+cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaStream_t st) {
     if (t.sp > kPadParticles) return cudaErrorInvalidValue;
     a.sp = t.sp;
     a.n_tiles = objective_tiles(a.N, t);
     a.nw = t.threads / 32;
-    cudaError_t e = cudaErrorInvalidValue;
+    dim3 pgrid(a.S, B);
+    const size_t pbytes = (size_t)a.P * 8 * sizeof(double);
+    if (t.r == 4) objective_prepare_kernel<4><<<pgrid, 128, pbytes, st>>>(a);
+    else if (t.r == 8) objective_prepare_kernel<8><<<pgrid, 128, pbytes, st>>>(a);
+    else if (t.r == 16) objective_prepare_kernel<16><<<pgrid, 128, pbytes, st>>>(a);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0,
+                                     cudaEvent_t ev1) {
     if (ev0) cudaEventRecord(ev0, st);
-    {
-        dim3 pgrid(a.S, B);
-        const size_t pbytes = (size_t)a.P * 8 * sizeof(double);
-        if (t.r == 4) objective_prepare_kernel<4><<<pgrid, 128, pbytes, st>>>(a);
-        else if (t.r == 8) objective_prepare_kernel<8><<<pgrid, 128, pbytes, st>>>(a);
-        else if (t.r == 16) objective_prepare_kernel<16><<<pgrid, 128, pbytes, st>>>(a);
-        else return cudaErrorInvalidValue;
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        e = cudaErrorInvalidValue;
-    }
+    cudaError_t e = launch_objective_prepare(a, t, B, st);
+    if (e != cudaSuccess) return e;
+    e = cudaErrorInvalidValue;
     if (t.threads == 128 && t.r == 4) e = launch_tb<128, 4>(a, t.tb, B, st);
     else if (t.threads == 128 && t.r == 8) e = launch_tb<128, 8>(a, t.tb, B, st);
     else if (t.threads == 128 && t.r == 16) e = launch_tb<128, 16>(a, t.tb, B, st);

@@ -1,0 +1,35 @@
+// Pieces shared by the uniform-axis evaluation kernels (objective_uniform.cu: FP64, objective_f32.cu: FP32).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace nmrfit {
+
+constexpr int kPartDoubles = 68;   // per particle: e^{i p1 lane R/N} for 32 lanes (64), cos/sin(p1/N), P*yoff, #exact peaks
+constexpr int kPadParticles = 64;  // slack at the end of the prepare buffers: the last group is copied whole
+
+// TMA bulk copy (global -> shared, 1-D) completing on an mbarrier, and the barrier's own operations.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    }
+}
+
+}  // namespace nmrfit
