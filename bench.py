@@ -396,6 +396,28 @@ def extra_measurements(device):
                                           'peak_points_per_s': S * N * P / (ms / n * 1e-3)}
     out['shape_6peaks_4096pts'] = dict(shapes, note='objective kernel alone, inputs resident; 100 particles is '
                                                     'configs[0] (launch-latency bound), 65,536 shows the throughput')
+    # opt-in FP32 mode on the headline shape (configs[1]) and its error against the FP64 kernel, same particles
+    P2, N2, S2, _ = WORKLOADS['c2']
+    d2, w2, lo2, up2, _ = make_inputs('c2')
+    xs = torch.from_numpy(synth.particles(lo2, up2, S2, seed=7)).cuda()
+    res = {}
+    for name, prec in (('fp64', _cabi.FP64), ('fp32', _cabi.FP32)):
+        with _cabi.Context(1, N2, P2, device=device, precision=prec) as ctx:
+            ctx.set_spectrum(0, d2.w, d2.u, d2.v, w2)
+            f = torch.empty(S2, dtype=torch.float64, device='cuda')
+            for _ in range(5):
+                ctx.objective_device(xs, S2, f)
+            ctx.profile(True)
+            for _ in range(50):
+                ctx.objective_device(xs, S2, f)
+            ms, n = ctx.profile_read()
+            res[name] = (f.cpu().numpy(), ms / n)
+    rel = np.abs(res['fp32'][0] / res['fp64'][0] - 1)
+    out['fp32_mode'] = {'workload': 'configs[1] shape, 4,096 particles, objective kernels alone',
+                        'evals_per_s': S2 / (res['fp32'][1] * 1e-3), 'kernel_ms': res['fp32'][1],
+                        'fp64_kernel_ms': res['fp64'][1], 'speedup_vs_fp64': res['fp64'][1] / res['fp32'][1],
+                        'max_rel_err_vs_fp64': float(rel.max()), 'median_rel_err_vs_fp64': float(np.median(rel)),
+                        'tolerance': 1e-5}
     # fits/s, configs[0]: one fit at a time through nmrfit_b200.fit, then 256 fits advanced together
     opts = {'swarmsize': 100, 'maxiter': 100}
     sink = io.StringIO()

@@ -7,10 +7,12 @@
 //     ulp_f32(3.4)/width = 6e-5 of its shape if the subtraction were done in FP32;
 //   * the per-particle constants (objective_prepare_kernel: coefficients, near/far split, far-field
 //     polynomial, phase anchors) - computed once per particle, converted on load;
-//   * the sum of squared residuals across a warp, a tile and the axis.
-// Everything per point - Lorentzian (reciprocals four at a time, one MUFU.RCP), Gaussian (two
+//   * the data side of the residual - phase rotation of (u, v), the subtraction V_data - V_fit, the weight and
+//     the sum of squares: near the optimum the residual is the noise (1e-4 of the signal), and forming it
+//     from two FP32 numbers of size 1 would cost three of its digits.
+// The fitted curve itself - Lorentzian (reciprocals four at a time, one MUFU.RCP), Gaussian (two
 // ex2.approx anchors + multiplicative recurrence, skipped beyond 6.5 units of s), far-field polynomial
-// (12 FFMA), phase rotation, residual - is FP32.
+// (12 FFMA) - is FP32, i.e. carries ~1e-7 of the curve's size.
 //
 // Two kernels: objective_uniform_f32_kernel mirrors objective_uniform_kernel (uniform axis; TMA bulk
 // prologue, regions, near masks); objective_general_f32_kernel takes any axis and evaluates every
@@ -68,15 +70,15 @@ __device__ __forceinline__ void peak_span_f32(float t0, float s0, float dT, floa
     }
 }
 
-// shared-memory carve-up (in doubles): as UniSmem, with the tile held as float2 (u, v) + float weights
+// shared-memory carve-up (in doubles): as UniSmem without the exp table
 struct F32Smem {
     int uv, wt, bar, wpart, coef, part, far, anchor, mask, mw, total;
     __host__ __device__ F32Smem(int sp, int P, int threads, int R) {
         const int nw = threads / 32;
         mw = (P + 31) / 32;
         int o = 0;
-        uv = o;     o += threads * R;                     // float2 per point
-        wt = o;     o += threads * R / 2;                 // float per point
+        uv = o;     o += threads * R * 2;
+        wt = o;     o += threads * R;
         bar = o;    o += 2;
         wpart = o;  o += sp * nw;
         coef = o;   o += sp * P * 8;
@@ -100,8 +102,8 @@ objective_uniform_f32_kernel(ObjArgs a) {
     const int n_tiles = a.n_tiles, tile = blockIdx.y, NRP = n_tiles * NW;
     const int s0 = blockIdx.x * SP, nsp = min(SP, a.S - s0);
     const F32Smem L(SP, P, THREADS, R);
-    float2* suv = reinterpret_cast<float2*>(smem + L.uv);
-    float* swt = reinterpret_cast<float*>(smem + L.wt);
+    double2* suv = reinterpret_cast<double2*>(smem + L.uv);
+    double* swt = smem + L.wt;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
     double* wpart = smem + L.wpart;
     const double* coef = smem + L.coef;
@@ -136,8 +138,8 @@ objective_uniform_f32_kernel(ObjArgs a) {
         const int i = tile0 + e;
         const bool ok = i < N;
         const int slot = (e % R) * THREADS + e / R;
-        suv[slot] = make_float2(ok ? (float)sw[N + i] : 0.f, ok ? (float)sw[2 * N + i] : 0.f);
-        swt[slot] = ok ? (float)sw[3 * N + i] : 0.f;
+        suv[slot] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
+        swt[slot] = ok ? sw[3 * N + i] : 0.0;
     }
     const int i_first = tile0 + tid * R;
     const double w_first = i_first < N ? sw[i_first] : fma((double)i_first, h, sw[0]);
@@ -195,24 +197,23 @@ objective_uniform_f32_kernel(ObjArgs a) {
         }
         const double2 ew = anchor[sp * NW + warp];
         const double2 el = *reinterpret_cast<const double2*>(pt + 2 * lane);
-        const float cd = (float)pt[64], sd = (float)pt[65], py = (float)pt[66];
-        float cr = (float)fma(ew.x, el.x, -(ew.y * el.y));
-        float ci = (float)fma(ew.y, el.x, ew.x * el.y);
-        float ssf = 0.f;
+        const double cd = pt[64], sd = pt[65], py = pt[66];
+        double cr = fma(ew.x, el.x, -(ew.y * el.y));
+        double ci = fma(ew.y, el.x, ew.x * el.y);
+        double ss = 0.0;
 #pragma unroll
         for (int j = 0; j < R; ++j) {
-            const float2 uv = suv[j * THREADS + tid];
-            const float wt = swt[j * THREADS + tid];
-            const float vd = fmaf(uv.x, cr, -fmaf(uv.y, ci, py));
-            const float res = wt * (vd - acc[j]);
-            ssf = fmaf(res, res, ssf);
+            const double2 uv = suv[j * THREADS + tid];
+            const double wt = swt[j * THREADS + tid];
+            const double vd = fma(uv.x, cr, -fma(uv.y, ci, py));
+            const double res = wt * (vd - (double)acc[j]);
+            ss = fma(res, res, ss);
             if (j + 1 < R) {
-                const float c2 = fmaf(cr, cd, -(ci * sd));
-                ci = fmaf(ci, cd, cr * sd);
+                const double c2 = fma(cr, cd, -(ci * sd));
+                ci = fma(ci, cd, cr * sd);
                 cr = c2;
             }
         }
-        double ss = (double)ssf;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
         if (lane == 0) wpart[sp * NW + warp] = ss;
