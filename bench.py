@@ -38,7 +38,11 @@ WORKLOADS = {
     'c2': (12, 32768, 4096, 2000),
     'c1': (6, 4096, 100, 1000),
     'c4': (24, 65536, 8192, 4000),
+    # BASELINE configs[2]: 1,024 independent spectra, one swarm of 204 (the reference default) each; the
+    # spectra are split over the ranks (strong scaling, no data-path collective)
+    'c3': (6, 16384, 204, 3000),
 }
+C3_SPECTRA = 1024
 METRIC = 'voigt_objective_evals_per_s'
 PSO = dict(omega=-0.2134, phip=-0.3344, phig=2.3259)
 
@@ -132,6 +136,13 @@ def run_reference(args):
 
 def workload_config(name, gpus):
     P, N, S, _ = WORKLOADS[name]
+    if name == 'c3':
+        return {'workload': 'BASELINE config[2] C3: %d independent spectra (6 peaks, 16,384 points), one swarm of 204 '
+                            'particles each, FP64 objective' % C3_SPECTRA,
+                'n_peaks': P, 'n_points': N, 'particles_per_swarm': S, 'spectra_total': C3_SPECTRA,
+                'spectra_per_gpu': C3_SPECTRA // gpus,
+                'parallelism': 'spectra sharded over %d GPU(s), no data-path collective' % gpus,
+                'l2': 'working set (spectra + swarm constants) exceeds L2; also flushed between timed steps'}
     return {'workload': 'BASELINE config[1] C2: single fit, 12 peaks, 32,768-point window, swarmsize 4,096 per GPU, '
                         'FP64 objective' if name == 'c2' else 'workload %s' % name,
             'n_peaks': P, 'n_points': N, 'particles_per_gpu': S, 'swarm_total': S * gpus,
@@ -220,23 +231,35 @@ def run_b200(args):
     stream = torch.cuda.current_stream().cuda_stream
     data, weights, lo, up, true = make_inputs(args.workload)
 
-    ctx = _cabi.Context(1, N, P, device=local)
+    batched = args.workload == 'c3'
+    B = C3_SPECTRA // world if batched else 1
+    ctx = _cabi.Context(B, N, P, device=local)
     if args.tune:
         th, r, tb, sp = (int(t) for t in args.tune.split(','))
         ctx.set_tuning(th, r, tb, sp)
-    ctx.set_spectrum(0, data.w, data.u, data.v, weights)
-    off = rank * S
+    if batched:
+        from nmrfit_b200 import synth as _synth, utils as _utils
+        los, ups = [], []
+        for bb in range(B):
+            d, _ = _synth.multiplet(N, P, seed=3000 + rank * B + bb)
+            ctx.set_spectrum(bb, d.w, d.u, d.v, _utils.compute_weights(d.w, d.peaks))
+            l, u_ = d.generate_solution_bounds()
+            los.append(l); ups.append(u_)
+        lo, up = np.array(los), np.array(ups)
+    else:
+        ctx.set_spectrum(0, data.w, data.u, data.v, weights)
+    off = 0 if batched else rank * S
     opts = swarm._make_opts(S, 10 ** 9, PSO['omega'], PSO['phip'], PSO['phig'], 0.0, 0.0, False, 1234, offset=off)
     opts.minstep = -1.0      # never stop early: every timed step does the full generation's work
     opts.minfunc = -1.0
     ctx.pso_begin(lo, up, opts, stream=stream)
     rec = None
-    if world > 1:
+    if world > 1 and not batched:
         ptr, nrec = ctx.pso_record()
         rec = torch.as_tensor(swarm._DeviceArray(ptr, nrec), device='cuda:%d' % local)
 
     def commit():
-        if world > 1:
+        if world > 1 and not batched:
             ctx.pso_commit(swarm.gather_records(rec), world, stream=stream)
         else:
             ctx.pso_commit(stream=stream)
@@ -282,33 +305,48 @@ def run_b200(args):
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
-    value = S * world * args.steps / (total_ms * 1e-3)
+    value = S * B * world * args.steps / (total_ms * 1e-3)
 
     x, f, it, stop = ctx.pso_best()
-    assert int(it[0]) == args.warmup + args.steps and np.isfinite(f[0]) and int(stop[0]) == 0
+    assert np.all(it == args.warmup + args.steps) and np.all(np.isfinite(f)) and np.all(stop == 0)
 
     # ---- end to end through the public host-buffer API
     from nmrfit_b200 import synth
-    xs_pinned = torch.empty((S, D), dtype=torch.float64).pin_memory()
-    xs = xs_pinned.numpy()
-    xs[:] = synth.particles(lo, up, S, seed=7 + rank)
+    if batched:
+        # the B spectra stay resident in the context (a fit uploads them once); every step copies the
+        # generation's positions [B][S][D] host -> device and the objective values [B][S] back
+        xs_pinned = torch.empty((B, S, D), dtype=torch.float64).pin_memory()
+        xs = xs_pinned.numpy()
+        for bb in range(B):
+            xs[bb] = synth.particles(lo[bb], up[bb], S, seed=7 + rank * B + bb)
+        e2e_call = lambda: ctx.objective_host(xs)
+        e2e_api = ('nmrfit_b200._cabi.Context.objective_host(xs[B][S][D]) with host arrays; the %d spectra are '
+                   'resident in the context (uploaded once per fit)' % B)
+        e2e_h2d, e2e_d2h = B * S * D * 8, B * S * 8
+    else:
+        xs_pinned = torch.empty((S, D), dtype=torch.float64).pin_memory()
+        xs = xs_pinned.numpy()
+        xs[:] = synth.particles(lo, up, S, seed=7 + rank)
+        e2e_call = lambda: equations.objective_batch(xs, data.w, data.u, data.v, weights)
+        e2e_api = 'nmrfit_b200.equations.objective_batch(xs, w, u, v, weights) with host arrays'
+        e2e_h2d, e2e_d2h = 4 * N * 8 + S * D * 8, S * 8
     for _ in range(max(3, args.warmup)):
-        equations.objective_batch(xs, data.w, data.u, data.v, weights)
+        e2e_call()
     sync_all()
     e0 = time.perf_counter()
     for _ in range(args.steps):
-        fx = equations.objective_batch(xs, data.w, data.u, data.v, weights)
+        fx = e2e_call()
     torch.cuda.synchronize()
     e_ms = torch.tensor([(time.perf_counter() - e0) * 1e3], dtype=torch.float64, device='cuda')
     if world > 1:
         dist.all_reduce(e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = S * world * args.steps / (float(e_ms.item()) * 1e-3)
-    assert fx.shape == (S,) and np.all(np.isfinite(fx))
+    e2e_value = S * B * world * args.steps / (float(e_ms.item()) * 1e-3)
+    assert fx.size == S * B and np.all(np.isfinite(fx))
 
     # ---- roofline of the dominant kernel (objective_kernel), denominators measured on this box
     burst, sustained = _cabi.fp64_peak(local, iters=4096, repeats=20)
     per_launch_ms = kernel_ms / max(kernel_launches, 1)
-    achieved = S * flop_per_eval(N, P) / (per_launch_ms * 1e-3) / 1e12
+    achieved = S * B * flop_per_eval(N, P) / (per_launch_ms * 1e-3) / 1e12
     traffic, ncu = None, None
     tpath = os.path.join(ROOT, 'profiles', 'objective_ncu.json')
     if os.path.exists(tpath):
@@ -316,7 +354,7 @@ def run_b200(args):
         traffic = ncu.get('dram_bytes_per_launch') if ncu else None
     peaks_path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     hbm_peak = json.load(open(peaks_path)).get('hbm_gbs') if os.path.exists(peaks_path) else 6650.0
-    algo_bytes = 4 * N * 8 + S * D * 8 + S * 8
+    algo_bytes = B * (4 * N * 8 + S * D * 8 + S * 8)
 
     extras = None
     if world == 1 and not args.quick:
@@ -326,10 +364,12 @@ def run_b200(args):
         tune = ctx.get_tuning(S)
         line = {
             'metric': METRIC, 'value': value, 'unit': 'evals/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
+            'scaling': 'strong' if batched else 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': dict(workload_config(args.workload, world), kernel=tune),
             'peak_points_per_s': value * N * P,
+            'spectra_generations_per_s': (B * world * args.steps / (total_ms * 1e-3)) if batched else None,
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s',
                          'frac': achieved / sustained, 'traffic': traffic,
                          'kernel': 'objective_prepare_kernel + objective_uniform_kernel (one CUDA-event bracket around both)'
@@ -350,9 +390,8 @@ def run_b200(args):
                          'peak_burst': burst,
                          'hbm': {'algorithmic_bytes_per_launch': algo_bytes,
                                  'achieved_gbs': algo_bytes / (per_launch_ms * 1e-3) / 1e9, 'peak_gbs': hbm_peak}},
-            'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(xs.nbytes + 4 * N * 8),
-                    'd2h_bytes_per_step': int(S * 8),
-                    'api': 'nmrfit_b200.equations.objective_batch(xs, w, u, v, weights) with host arrays'},
+            'e2e': {'value': e2e_value, 'unit': 'evals/s', 'h2d_bytes_per_step': int(e2e_h2d),
+                    'd2h_bytes_per_step': int(e2e_d2h), 'api': e2e_api},
             'gpu_launches': int(launches),
             'clocks': clocks,
         }
