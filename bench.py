@@ -461,16 +461,28 @@ def extra_measurements(device):
     opts = {'swarmsize': 100, 'maxiter': 100}
     sink = io.StringIO()
     fits = {}
-    for rng in ('host', 'device'):
+    for rng, fused in (('host', 'auto'), ('device', 'auto'), ('device', 'off')):
         times = []
         for rep in range(4):
             np.random.seed(rep)
             t0 = time.perf_counter()
             with contextlib.redirect_stdout(sink):
-                fit = nmrfit_b200.fit(data, lo, up, summary=False, options=dict(opts, rng=rng, seed=rep))
+                fit = nmrfit_b200.fit(data, lo, up, summary=False, options=dict(opts, rng=rng, seed=rep, fused=fused))
             times.append(time.perf_counter() - t0)
-        fits['single_fit_ms_rng_%s' % rng] = 1e3 * float(np.median(times[1:]))
-        fits['single_fit_generations_rng_%s' % rng] = int(fit.fit_info['generations'])
+        tag = 'rng_%s' % rng + ('' if fused == 'auto' else '_per_step_kernels')
+        fits['single_fit_ms_' + tag] = 1e3 * float(np.median(times[1:]))
+        fits['single_fit_generations_' + tag] = int(fit.fit_info['generations'])
+    # the reference's defaults (swarmsize 204, maxiter 2000, stops on minfunc/minstep) on the same spectrum
+    for fused in ('auto', 'off'):
+        times = []
+        for rep in range(3):
+            t0 = time.perf_counter()
+            with contextlib.redirect_stdout(sink):
+                fit = nmrfit_b200.fit(data, lo, up, summary=False, options=dict(rng='device', seed=rep, fused=fused))
+            times.append(time.perf_counter() - t0)
+        tag = 'default_fit' + ('' if fused == 'auto' else '_per_step_kernels')
+        fits[tag + '_ms'] = 1e3 * float(np.median(times[1:]))
+        fits[tag + '_generations'] = int(fit.fit_info['generations'])
     B = 256
     datas, los, ups = [], [], []
     for b in range(B):
@@ -487,7 +499,9 @@ def extra_measurements(device):
     fits['batched_fits_per_s'] = B / float(np.median(times[1:]))
     fits['single_fits_per_s'] = 1e3 / fits['single_fit_ms_rng_device']
     fits['note'] = ('configs[0]: 6 peaks, 4,096 points, swarmsize 100, maxiter 100, wall clock through the public API '
-                    'incl. weights, uploads and result readback; rng=host replays numpy\'s legacy stream (parity mode)')
+                    'incl. weights, uploads and result readback; rng=host replays numpy\'s legacy stream (parity mode); single fits run '
+                    'the fused swarm kernel (one cooperative launch per 16 generations), *_per_step_kernels = 7 launches '
+                    'per generation; default_fit = swarmsize 204, maxiter 2000, pyswarm stop rules')
     out['fits'] = fits
     return out
 

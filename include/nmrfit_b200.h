@@ -90,6 +90,17 @@ int nmrfit_ctx_set_tuning(nmrfit_ctx* ctx, int threads, int points_per_thread, i
 int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* points_per_thread, int* exp_table_bits,
                           int* particles_per_cta, int* n_point_tiles);
 
+/* Small swarms: nmrfit_pso_run executes its generations in ONE cooperative launch (one CTA per particle,
+ * one barrier per generation) instead of seven launches per generation - the loop pyswarm.pso runs on the host
+ * (call site utils.py:176-182).  Bit-identical to the per-step kernels.  AUTO uses it whenever it can run
+ * (FP64, uniform axis, real-only fit, n_spectra * swarmsize CTAs co-resident); REQUIRE makes nmrfit_pso_run
+ * fail with NMRFIT_ERR_STATE otherwise. */
+#define NMRFIT_FUSED_AUTO 0
+#define NMRFIT_FUSED_OFF 1
+#define NMRFIT_FUSED_REQUIRE 2
+int nmrfit_ctx_set_fused(nmrfit_ctx* ctx, int mode);
+int nmrfit_ctx_fused_launches(nmrfit_ctx* ctx, long long* launches);
+
 /* Per-launch timing of the objective kernel with CUDA events on the launching stream (for bench.py's
  * roofline: enable, run, then read the summed duration and the launch count; read resets). */
 int nmrfit_ctx_profile(nmrfit_ctx* ctx, int enable);

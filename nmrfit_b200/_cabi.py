@@ -16,6 +16,7 @@ OK = 0
 FP64, FP32 = 0, 1
 REAL_ONLY, IM_REFERENCE, IM_SUM = 0, 1, 2
 ALGO_AUTO, ALGO_GENERAL, ALGO_UNIFORM = 0, 1, 2
+FUSED_AUTO, FUSED_OFF, FUSED_REQUIRE = 0, 1, 2
 RUNNING, STOP_MINFUNC, STOP_MINSTEP, STOP_MAXITER = 0, 1, 2, 3
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
@@ -51,6 +52,8 @@ SIGNATURES = {
     'nmrfit_ctx_get_algorithm': (_i, [_vp, _i, c_int_p]),
     'nmrfit_ctx_set_tuning': (_i, [_vp, _i, _i, _i, _i]),
     'nmrfit_ctx_get_tuning': (_i, [_vp, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    'nmrfit_ctx_set_fused': (_i, [_vp, _i]),
+    'nmrfit_ctx_fused_launches': (_i, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
     'nmrfit_ctx_profile': (_i, [_vp, _i]),
     'nmrfit_ctx_profile_read': (_i, [_vp, c_double_p, ctypes.POINTER(ctypes.c_longlong)]),
     'nmrfit_objective_batch': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -184,6 +187,16 @@ class Context:
         keys = ('threads', 'points_per_thread', 'exp_table_bits', 'particles_per_cta', 'n_point_tiles')
         return dict(zip(keys, (v.value for v in vals)))
 
+    def set_fused(self, mode=FUSED_AUTO):
+        """FUSED_AUTO: ``pso_run`` uses the one-launch fused swarm kernel whenever the shape allows;
+        FUSED_OFF: always the per-step kernels; FUSED_REQUIRE: fail if the fused kernel cannot run."""
+        check(lib().nmrfit_ctx_set_fused(self._h, int(mode)))
+
+    def fused_launches(self):
+        n = ctypes.c_longlong(0)
+        check(lib().nmrfit_ctx_fused_launches(self._h, ctypes.byref(n)))
+        return n.value
+
     def profile(self, enable=True):
         check(lib().nmrfit_ctx_profile(self._h, int(bool(enable))))
 
@@ -270,6 +283,61 @@ class Context:
                    fx=np.empty((self.B, S)), fp=np.empty((self.B, S)))
         check(lib().nmrfit_pso_get_state(self._h, *[ptr(out[k]) for k in ('x', 'v', 'p', 'fx', 'fp')]))
         return out
+
+
+# ---- context pool ---------------------------------------------------------------------------------
+# Creating and destroying a context costs tens of milliseconds (pinned-host and device allocations, and
+# every cudaFree synchronises) - far more than a small fit itself - so the fit drivers borrow contexts from
+# this pool and hand them back with default settings.  A pooled context keeps its device buffers.
+_pool = {}
+_POOL_PER_KEY = 2
+_POOL_KEYS = 8
+
+
+class pooled_context:
+    """``with pooled_context(B, N, P, device, precision) as ctx:`` - a cached context of that shape, or a new one."""
+
+    def __init__(self, n_spectra, n_points, n_peaks, device=None, precision=FP64):
+        dev = default_device() if device is None else int(device)
+        self.key = (dev, int(n_spectra), int(n_points), int(n_peaks), int(precision))
+        self.ctx = None
+
+    def __enter__(self):
+        idle = _pool.get(self.key)
+        if idle:
+            self.ctx = idle.pop()
+        else:
+            dev, B, N, P, prec = self.key
+            self.ctx = Context(B, N, P, device=dev, precision=prec)
+        return self.ctx
+
+    def __exit__(self, exc_type, exc, tb):
+        ctx, self.ctx = self.ctx, None
+        if exc_type is not None:
+            ctx.close()                    # do not reuse a context an error may have left half way
+            return
+        ctx.set_tuning()
+        ctx.set_fused(FUSED_AUTO)
+        ctx.set_algorithm(ALGO_AUTO)
+        ctx.profile(False)
+        if self.key not in _pool and len(_pool) >= _POOL_KEYS:
+            _, old = _pool.popitem()
+            for c in old:
+                c.close()
+        idle = _pool.setdefault(self.key, [])
+        small = self.key[1] * self.key[2] * 32 <= (256 << 20)      # big batches give their memory back
+        if small and len(idle) < _POOL_PER_KEY:
+            idle.append(ctx)
+        else:
+            ctx.close()
+
+
+def clear_pool():
+    """Destroy every idle pooled context (frees their device memory)."""
+    while _pool:
+        _, idle = _pool.popitem()
+        for c in idle:
+            c.close()
 
 
 def fp64_peak(device=None, iters=4096, repeats=10):

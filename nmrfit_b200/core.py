@@ -49,7 +49,8 @@ def fit_batch(datas, lowers, uppers, expon=0.5, dynamic_weighting=True, fit_im=F
         omega=opt.get('omega', -0.2134), phip=opt.get('phip', -0.3344), phig=opt.get('phig', 2.3259),
         minstep=opt.get('minstep', 1e-8), minfunc=opt.get('minfunc', 1e-8),
         rng=opt.get('rng', 'device'), seeds=opt.get('seeds'), seed=opt.get('seed', 0),
-        precision=opt.get('precision', 'fp64'), chunk=opt.get('chunk', 16), device=opt.get('device'))
+        precision=opt.get('precision', 'fp64'), chunk=opt.get('chunk', 16), device=opt.get('device'),
+        fused=opt.get('fused', 'auto'))
     for b, f in enumerate(fits):
         f.params = x[b].copy()
         f.error = float(fbest[b])

@@ -86,6 +86,10 @@ struct nmrfit_ctx {
     int maxiter = 0, kk = 0, generation = 0;
     DevBuf<double> sx, sv, sp, sfx, sfp, sg, sfg, sbx, sbf, slb, sub, srec, rnd_a, rnd_b;
     DevBuf<int> sstop, sit;
+    DevBuf<double> frec_f, frec_x;     // fused swarm kernel: published records
+    DevBuf<unsigned> fbarrier;
+    int fused_mode = NMRFIT_FUSED_AUTO;
+    long long fused_launches = 0;
     int* h_flags = nullptr;            // pinned [2*B]
     // optional per-launch timing of the objective kernel (nmrfit_ctx_profile)
     bool profiling = false;
@@ -211,6 +215,38 @@ int stage(const double* src, size_t n, DevBuf<double>& buf, cudaStream_t st, con
     return NMRFIT_OK;
 }
 
+// Fill the fused kernel's arguments for `n_gen` generations and decide whether it can run (FP64, uniform axis,
+// real-only fit, default exp table, and every CTA co-resident).
+int fused_setup(nmrfit_ctx* c, int n_gen, const double* rp_d, const double* rg_d, FusedArgs* a, FusedPlan* plan) {
+    plan->ok = false;
+    if (c->fused_mode == NMRFIT_FUSED_OFF) return NMRFIT_OK;
+    if (c->precision != NMRFIT_FP64 || c->kk != NMRFIT_REAL_ONLY || !use_uniform(c, NMRFIT_REAL_ONLY)) return NMRFIT_OK;
+    const SwarmState& s = c->sw;
+    ObjTune t = pick_tune(c, s.S, true);
+    *a = FusedArgs{};
+    a->s = s;
+    a->spec = c->spec.ptr;
+    a->grid_h = c->grid_h.ptr;
+    a->rp = rp_d;
+    a->rg = rg_d;
+    a->N = c->N; a->P = c->P;
+    a->n_vtiles = objective_tiles(c->N, t);
+    a->vw = t.threads / 32;
+    a->n_gen = n_gen;
+    a->gen0 = c->generation + 1;
+    a->maxiter = c->maxiter;
+    cudaError_t e = swarm_fused_plan(*a, c->D, s.B, s.S, t, c->device, plan);
+    if (e != cudaSuccess) return fail_cuda(e, "fused swarm plan");
+    if (!plan->ok) return NMRFIT_OK;
+    CK(c->frec_f.reserve(2 * (size_t)s.B * s.S));
+    CK(c->frec_x.reserve(2 * (size_t)s.B * s.S * s.D));
+    CK(c->fbarrier.reserve(s.B));
+    a->rec_f = c->frec_f.ptr;
+    a->rec_x = c->frec_x.ptr;
+    a->barrier = c->fbarrier.ptr;
+    return NMRFIT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -264,6 +300,9 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
         b->release();
     c->sstop.release();
     c->sit.release();
+    c->frec_f.release();
+    c->frec_x.release();
+    c->fbarrier.release();
     if (c->h_flags) cudaFreeHost(c->h_flags);
     for (cudaEvent_t ev : c->prof_events) cudaEventDestroy(ev);
     delete c;
@@ -333,6 +372,21 @@ int nmrfit_ctx_get_tuning(nmrfit_ctx* c, int S, int* threads, int* r, int* tb, i
     if (tb) *tb = t.tb;
     if (sp) *sp = t.sp;
     if (n_tiles) *n_tiles = objective_tiles(c->N, t);
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_set_fused(nmrfit_ctx* c, int mode) {
+    if (int rc = check_ctx(c)) return rc;
+    if (mode != NMRFIT_FUSED_AUTO && mode != NMRFIT_FUSED_OFF && mode != NMRFIT_FUSED_REQUIRE)
+        return fail(NMRFIT_ERR_ARG, "mode must be NMRFIT_FUSED_AUTO, _OFF or _REQUIRE");
+    c->fused_mode = mode;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_fused_launches(nmrfit_ctx* c, long long* launches) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!launches) return fail(NMRFIT_ERR_ARG, "launches is NULL");
+    *launches = c->fused_launches;
     return NMRFIT_OK;
 }
 
@@ -489,6 +543,20 @@ int nmrfit_pso_run(nmrfit_ctx* c, int n_generations, const double* rp_all, const
     if (n_generations > 0) {
         if (int rc = stage(rp_all, nsd * n_generations, c->rnd_a, st, &rp_d)) return rc;
         if (int rc = stage(rg_all, nsd * n_generations, c->rnd_b, st, &rg_d)) return rc;
+    }
+    FusedArgs fa;
+    FusedPlan plan{};
+    if (n_generations > 0)
+        if (int rc = fused_setup(c, n_generations, rp_d, rg_d, &fa, &plan)) return rc;
+    if (c->fused_mode == NMRFIT_FUSED_REQUIRE && n_generations > 0 && !plan.ok)
+        return fail(NMRFIT_ERR_STATE, "the fused swarm kernel cannot run this shape (needs FP64, a uniform axis, the real-only "
+                                      "fit and n_spectra * swarmsize CTAs co-resident)");
+    if (plan.ok) {
+        cudaError_t e = launch_swarm_fused(fa, plan, s.B, s.S, st);
+        if (e != cudaSuccess) return fail_cuda(e, "fused swarm launch");
+        c->generation += n_generations;
+        c->fused_launches += 1;
+        n_generations = 0;
     }
     for (int k = 0; k < n_generations; ++k) {
         c->generation += 1;

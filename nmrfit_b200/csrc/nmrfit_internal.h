@@ -82,6 +82,32 @@ cudaError_t launch_swarm_local_best(const SwarmState& s, double* rec, cudaStream
 cudaError_t launch_swarm_commit(const SwarmState& s, const double* recs, int n_ranks, int initial, int maxiter,
                                 cudaStream_t st);
 
+// ---- K7 fused swarm generations (swarm_fused.cu) ------------------------------------
+struct FusedArgs {
+    SwarmState s;
+    const double* spec;     // [B][4][N]
+    const double* grid_h;   // [B][2]
+    const double* rp;       // [n_gen][B][S][D] host-stream uniforms, or null for device Philox
+    const double* rg;
+    double* rec_f;          // [2][B][S]     published personal-best values, double-buffered by generation parity
+    double* rec_x;          // [2][B][S][D]  ... and positions
+    unsigned* barrier;      // [B] arrival counters (zeroed by the launcher)
+    int N, P;
+    int n_vtiles, vw;       // point tiles and warps per tile of the per-step kernels (fixes the summation order)
+    int n_gen;              // generations to run in this launch
+    int gen0;               // absolute number of the first of them (Philox counter)
+    int maxiter;
+    int slots;              // supertiles of (u, v, weights) held in shared memory (filled by the launcher)
+};
+struct FusedPlan {
+    bool ok;
+    int threads, r, slots;
+    size_t smem;
+};
+// can B*S CTAs be co-resident for this shape?  plan->ok says so; never launches
+cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjTune& t, int device, FusedPlan* plan);
+cudaError_t launch_swarm_fused(FusedArgs a, const FusedPlan& plan, int B, int S, cudaStream_t st);
+
 // ---- K4/K5 curves -------------------------------------------------------------
 cudaError_t launch_ps2(const double* u, const double* v, int n, double p0, double p1, int inv, double* re, double* im,
                        cudaStream_t st);

@@ -43,6 +43,7 @@
 #include "nmrfit_internal.h"
 #include "nmrfit_math.cuh"
 #include "uniform_common.cuh"
+#include "uniform_eval.cuh"
 
 namespace nmrfit {
 
@@ -64,71 +65,10 @@ objective_prepare_kernel(ObjArgs a) {
     const int P = a.P, N = a.N, D = 4 + 3 * P, MW = (P + 31) / 32;
     const int NR = (N + 32 * R - 1) / (32 * R), NRP = a.n_tiles * a.nw;
     const size_t ps = (size_t)b * a.S + s;
-    const double* xs = a.x + ps * D;
-    const double* sw = a.spec + (size_t)b * 4 * N;
-    const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
-    const double p0 = xs[0], p1 = xs[1];
-    double* part = a.prep_part + ps * kPartDoubles;
-    constexpr double H = 16.0 * R;
-
-    for (int k = tid; k < P; k += 128) {
-        SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
-        if (c.exact) c = null_span_coef();                 // the span loop adds zero; the peak is handled after it
-        double* o = cs + k * 8;
-        o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.thr; o[7] = c.c2;
-        double* g = a.prep_coef + (ps * P + k) * 8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) g[i] = o[i];
-    }
-    // phi_i = p0 + (p1*i)/N with i = i_r + lane*R + j:  anchor(i_r) * e^{i p1 (lane R)/N} * (e^{i p1/N})^j
-    for (int e = 127 - tid; e < 33; e += 128) {            // the last warps do these while the first does the peaks
-        double sn, cn;
-        sincos(e < 32 ? (p1 * (double)(e * R)) / (double)N : p1 / (double)N, &sn, &cn);
-        part[2 * e] = cn;
-        part[2 * e + 1] = sn;
-    }
-    if (tid == 64) part[66] = (double)P * xs[3];           // yoff is added once per peak (equations.py:147,195)
-    __syncthreads();
-    if (tid == 64) {
-        int n = 0;
-        for (int k = 0; k < P; ++k) n += cs[k * 8 + 6] < 0.0;      // thr < 0 marks a nulled (exact-path) peak
-        part[67] = (double)n;
-    }
-    for (int r = tid; r < NRP; r += 128) {
-        const size_t slot = ps * NRP + r;
-        double C[kFarTerms];
-#pragma unroll
-        for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
-        unsigned any_far = 0;
-        unsigned* mk = a.prep_mask + slot * (MW + 1);
-        double sn = 0.0, cn = 1.0;
-        if (r < NR) {
-            const int ir = r * 32 * R;
-            const double w_c = fma(0.5 * (32 * R - 1), h, sw[ir]);
-            for (int wd = 0; wd < MW; ++wd) {
-                unsigned m = 0;
-                const int kend = min(P, wd * 32 + 32);
-                for (int k = wd * 32; k < kend; ++k) {
-                    const double* o = cs + k * 8;
-                    SpanCoef c;
-                    c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
-                    if (c.thr < 0.0) continue;             // exact-path peak: neither near nor far
-                    if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
-                    else m |= 1u << (k & 31);
-                }
-                mk[wd] = m;
-            }
-            sincos(p0 + (p1 * (double)ir) / (double)N, &sn, &cn);
-        } else {
-            for (int wd = 0; wd < MW; ++wd) mk[wd] = 0u;
-        }
-        mk[MW] = any_far;
-        double* fc = a.prep_far + slot * kFarTerms;
-#pragma unroll
-        for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
-        a.prep_anchor[slot * 2] = cn;
-        a.prep_anchor[slot * 2 + 1] = sn;
-    }
+    prepare_particle<R>(a.x + ps * D, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid,
+                        128, cs, a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles,
+                        a.prep_far + ps * NRP * kFarTerms, a.prep_anchor + ps * NRP * 2,
+                        a.prep_mask + ps * NRP * (MW + 1));
 }
 
 // ---- pass 2: evaluation ------------------------------------------------------------------------------
@@ -220,64 +160,10 @@ objective_uniform_kernel(ObjArgs a) {
     mbar_wait(bar, 0);                                     // the constants have landed
 
     for (int sp = 0; sp < nsp; ++sp) {
-        double acc[R];
-#pragma unroll
-        for (int j = 0; j < R; ++j) acc[j] = 0.0;
-        const double* cf = coef + (size_t)sp * P * 8;
-        const double* pt = part + sp * kPartDoubles;
-        const unsigned* mk = mask + (size_t)(sp * NW + warp) * (MW + 1);
-        for (int wd = 0; wd < MW; ++wd)
-        for (unsigned m = mk[wd]; m; m &= m - 1) {         // peaks near this warp's region
-            const int k = wd * 32 + __ffs(m) - 1;
-            const double2 c01 = *reinterpret_cast<const double2*>(cf + k * 8);
-            const double2 c23 = *reinterpret_cast<const double2*>(cf + k * 8 + 2);
-            const double2 c45 = *reinterpret_cast<const double2*>(cf + k * 8 + 4);
-            const double2 c67 = *reinterpret_cast<const double2*>(cf + k * 8 + 6);
-            SpanCoef c;
-            c.loc = c01.x; c.kL = c01.y; c.kG = c23.x; c.aL = c23.y;
-            c.aG = c45.x; c.dT = c45.y; c.thr = c67.x; c.c2 = c67.y;
-            peak_span<R, TB>(w_first - c.loc, c, tab, acc);
-        }
-        if (mk[MW]) {                                      // all far peaks at once
-            const double* fc = farc + (size_t)(sp * NW + warp) * kFarTerms;
-            double C[kFarTerms];
-#pragma unroll
-            for (int n = 0; n < kFarTerms; n += 2) {
-                const double2 t = *reinterpret_cast<const double2*>(fc + n);
-                C[n] = t.x; C[n + 1] = t.y;
-            }
-            far_eval<R>(C, xi0, 1.0 / H, acc);
-        }
-        if (pt[67] != 0.0) {                               // rare: peaks too narrow for the uniform-axis shortcuts
-            const double* xs = a.x + (q0 + sp) * D;
-            for (int k = 0; k < P; ++k) {
-                if (!(cf[k * 8 + 6] < 0.0)) continue;
-                const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
-                peak_exact<R, TB>(sw + i_first, N - i_first, w_first, h, c, tab, acc);
-            }
-        }
-        // residual against the phase-rotated data; the rotation advances by p1/N per point
-        const double2 ew = anchor[sp * NW + warp];
-        const double2 el = *reinterpret_cast<const double2*>(pt + 2 * lane);
-        const double cd = pt[64], sd = pt[65], py = pt[66];
-        double cr = fma(ew.x, el.x, -(ew.y * el.y));
-        double ci = fma(ew.y, el.x, ew.x * el.y);
-        double ss = 0.0;
-#pragma unroll
-        for (int j = 0; j < R; ++j) {
-            const double2 uv = suv[j * THREADS + tid];
-            const double wt = swt[j * THREADS + tid];
-            const double vd = fma(uv.x, cr, -fma(uv.y, ci, py));     // V_data - P*yoff
-            const double res = wt * (vd - acc[j]);
-            ss = fma(res, res, ss);
-            if (j + 1 < R) {
-                const double c2 = fma(cr, cd, -(ci * sd));
-                ci = fma(ci, cd, cr * sd);
-                cr = c2;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        const double ss = eval_region<R, TB>(
+            coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + warp) * (MW + 1),
+            farc + (size_t)(sp * NW + warp) * kFarTerms, anchor[sp * NW + warp], MW, P, lane, w_first, xi0, suv + tid,
+            swt + tid, THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp);
         if (lane == 0) wpart[sp * NW + warp] = ss;
     }
     __syncthreads();

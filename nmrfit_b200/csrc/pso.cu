@@ -12,15 +12,9 @@
 #include <math_constants.h>
 #include "nmrfit_internal.h"
 #include "nmrfit_math.cuh"
+#include "swarm_common.cuh"
 
 namespace nmrfit {
-
-enum { kStopRunning = 0, kStopMinFunc = 1, kStopMinStep = 2, kStopMaxIter = 3 };
-
-__device__ __forceinline__ unsigned long long elem_counter(const SwarmState& s, int b, int sl, int d) {
-    // global (sharding-independent) element number
-    return ((unsigned long long)b << 40) ^ ((unsigned long long)(s.index0 + sl) * (unsigned long long)s.D + d);
-}
 
 // generation 0, part 1: x = lb + r*(ub - lb); fp = inf   (pyswarm: x = rand(S,D); x = lb + x*(ub-lb))
 __global__ void swarm_init_kernel(SwarmState s, const double* __restrict__ r_pos) {
@@ -71,13 +65,7 @@ __global__ void swarm_move_kernel(SwarmState s, const double* __restrict__ rp_in
         rg = u.b;
     }
     double x = s.x[idx], v = s.v[idx], p = s.p[idx], g = s.g[b * s.D + d];
-    double t1 = __dmul_rn(s.omega, v);
-    double t2 = __dmul_rn(__dmul_rn(s.phip, rp), __dsub_rn(p, x));
-    double t3 = __dmul_rn(__dmul_rn(s.phig, rg), __dsub_rn(g, x));
-    v = __dadd_rn(__dadd_rn(t1, t2), t3);
-    x = __dadd_rn(x, v);
-    double lb = s.lb[b * s.D + d], ub = s.ub[b * s.D + d];
-    x = x < lb ? lb : (x > ub ? ub : x);
+    move_element(s.omega, s.phip, s.phig, rp, rg, p, g, s.lb[b * s.D + d], s.ub[b * s.D + d], x, v);
     s.v[idx] = v;
     s.x[idx] = x;
 }

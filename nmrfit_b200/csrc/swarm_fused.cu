@@ -1,0 +1,388 @@
+// K7: swarm generations fused into ONE cooperative launch - the fit loop of a small swarm.
+//
+// pyswarm.pso (called from the reference at utils.py:176-182) is a host loop: move every particle, call the
+// objective once per particle, update personal and swarm bests, test for convergence, repeat.  The per-step
+// kernels (pso.cu + objective_uniform.cu) already keep that loop on the device, but a generation is still
+// seven launches, and for the swarm sizes a single nmrfit.fit uses (100-204 particles, 4k-16k points) every one
+// of them is shorter than its own launch latency: ~40 us per generation for ~1 us of arithmetic.
+//
+// Here one CTA owns one particle for the whole run of generations.  Its state (x, v, p, fp, and replicas of the
+// swarm best g, fg and of the box) lives in shared memory; when the spectrum fits it is staged in shared memory
+// once per launch.  A generation is: move -> per-particle constants -> objective over every region of the axis ->
+// personal best -> publish (fp, p) -> ONE barrier among the CTAs of the same spectrum -> every CTA finds the
+// swarm's argmin and applies pyswarm's update/stop rules redundantly (identical inputs, identical result), so
+// no second barrier and no broadcast are needed.  Published records are double-buffered by generation parity:
+// a CTA can run at most one generation ahead of the slowest one.
+//
+// The arithmetic is the per-step kernels' own (uniform_eval.cuh, swarm_common.cuh) and the squared residual is
+// summed in the same order (warp tree, then the warps of a point tile, then the tiles), so a fused run is
+// bit-identical to the same generations stepped kernel by kernel (tests/test_gpu_fused.py).
+//
+// Requires every CTA of the grid to be co-resident: launched with cudaLaunchCooperativeKernel, and the host
+// falls back to the per-step kernels when n_spectra * swarmsize exceeds what the device can hold.
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <algorithm>
+#include <cstdint>
+#include "nmrfit_internal.h"
+#include "nmrfit_math.cuh"
+#include "uniform_common.cuh"
+#include "uniform_eval.cuh"
+#include "swarm_common.cuh"
+
+namespace nmrfit {
+
+namespace {
+
+// shared-memory carve-up in doubles; every offset is even (16-byte alignment)
+struct FusedSmem {
+    int tab, uv, wt, cs, part, far, anchor, mask, wpart, state, red, misc, total;
+    __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP) {
+        const int mw = (P + 31) / 32;
+        const int De = (D + 1) & ~1;
+        int o = 0;
+        tab = o;    o += 64;
+        uv = o;     o += slots * threads * R * 2;
+        wt = o;     o += slots * threads * R;
+        cs = o;     o += P * 8;
+        part = o;   o += kPartDoubles;
+        far = o;    o += NRP * kFarTerms;
+        anchor = o; o += NRP * 2;
+        mask = o;   o += ((NRP * (mw + 1) + 3) / 4) * 2;
+        wpart = o;  o += (NRP + 1) & ~1;
+        state = o;  o += 9 * De;         // x, v, p, g, lb, ub, best_x, p_min, spare
+        red = o;    o += 64;             // per-warp argmin values and indices
+        misc = o;   o += 8;
+        total = o;
+    }
+};
+
+__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+// first-occurrence argmin rule of np.argmin on (value, index) pairs
+__device__ __forceinline__ void take_min(double& bf, int& bi, double f, int i) {
+    if (f < bf || (f == bf && i < bi)) { bf = f; bi = i; }
+}
+
+}  // namespace
+
+template <int THREADS, int R, int TB>
+__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+swarm_fused_kernel(FusedArgs a) {
+    constexpr int NW = THREADS / 32;
+    extern __shared__ __align__(16) double smem[];
+    const SwarmState& s = a.s;
+    const int S = s.S, D = s.D, De = (D + 1) & ~1;
+    const int b = blockIdx.x / S, sl = blockIdx.x % S;
+    if (s.stop[b]) return;                                 // this spectrum's swarm has already stopped
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int P = a.P, N = a.N, MW = (P + 31) / 32;
+    const int VW = a.vw, NRP = a.n_vtiles * VW;            // warps per point tile of the per-step kernels; region slots
+    const int NR = (N + 32 * R - 1) / (32 * R);
+    const int n_super = (NRP + NW - 1) / NW;
+    const bool resident = a.slots >= n_super;
+    const FusedSmem L(P, D, THREADS, R, a.slots, NRP);
+    double* tab = smem + L.tab;
+    double2* suv = reinterpret_cast<double2*>(smem + L.uv);
+    double* swt = smem + L.wt;
+    double* cs = smem + L.cs;
+    double* part = smem + L.part;
+    double* farc = smem + L.far;
+    double* anchor = smem + L.anchor;
+    unsigned* mask = reinterpret_cast<unsigned*>(smem + L.mask);
+    double* wpart = smem + L.wpart;
+    double* xs = smem + L.state;
+    double* vs = xs + De;
+    double* ps = vs + De;
+    double* gs = ps + De;
+    double* lbs = gs + De;
+    double* ubs = lbs + De;
+    double* bxs = ubs + De;                                // what pso() returns (p_min on an early stop)
+    double* pm = bxs + De;                                 // the generation's best personal-best position
+    double* redf = smem + L.red;
+    int* redi = reinterpret_cast<int*>(smem + L.red + 32);
+    double* misc = smem + L.misc;                          // 0 fx, 1 fp, 2 fg, 3 best_f, 4 improved, 5 action, 6 fmin
+
+    const double* sw = a.spec + (size_t)b * 4 * N;
+    const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
+    const size_t bs = (size_t)b * S + sl;
+    constexpr double H = 16.0 * R;
+    const double xi0 = ((double)(lane * R) - 0.5 * (32 * R - 1)) / H;
+
+    // ---- load the particle and the swarm's shared state
+    for (int d = tid; d < D; d += THREADS) {
+        xs[d] = s.x[bs * D + d];
+        vs[d] = s.v[bs * D + d];
+        ps[d] = s.p[bs * D + d];
+        gs[d] = s.g[(size_t)b * D + d];
+        lbs[d] = s.lb[(size_t)b * D + d];
+        ubs[d] = s.ub[(size_t)b * D + d];
+        bxs[d] = s.best_x[(size_t)b * D + d];
+    }
+    if (tid == 0) {
+        misc[0] = s.fx[bs];
+        misc[1] = s.fp[bs];
+        misc[2] = s.fg[b];
+        misc[3] = s.best_f[b];
+    }
+    for (int i = tid; i < 64; i += THREADS) tab[i] = NMRFIT_EXP2_TAB6[i];
+    int it = s.it[b];
+    int stop = 0;
+
+    auto stage = [&](int st, int slot) {                   // (u, v, weights) of supertile st -> slot
+        const int base = st * THREADS * R;
+        for (int e = tid; e < THREADS * R; e += THREADS) {
+            const int i = base + e;
+            const bool ok = i < N;
+            const int o = slot * THREADS * R + (e % R) * THREADS + e / R;
+            suv[o] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
+            swt[o] = ok ? sw[3 * N + i] : 0.0;             // zero weight: padding contributes nothing
+        }
+    };
+    if (resident)
+        for (int st = 0; st < n_super; ++st) stage(st, st);
+    __syncthreads();
+
+    for (int k = 0; k < a.n_gen && !stop; ++k) {
+        const int par = k & 1;
+        // ---- move (pyswarm: v = omega v + phip rp (p - x) + phig rg (g - x); x += v; clamp)
+        for (int d = tid; d < D; d += THREADS) {
+            double rp, rg;
+            if (a.rp) {
+                const size_t idx = ((size_t)k * s.B * S + bs) * D + d;
+                rp = a.rp[idx];
+                rg = a.rg[idx];
+            } else {
+                const Philox2 u = philox_uniform2(s.seed, elem_counter(s, b, sl, d), (unsigned long long)(a.gen0 + k));
+                rp = u.a;
+                rg = u.b;
+            }
+            double x = xs[d], v = vs[d];
+            move_element(s.omega, s.phip, s.phig, rp, rg, ps[d], gs[d], lbs[d], ubs[d], x, v);
+            xs[d] = x;
+            vs[d] = v;
+        }
+        __syncthreads();
+
+        // ---- objective (equations.py:152-212) of the moved particle
+        prepare_particle<R>(xs, sw, h, w_ulp, N, P, NR, NRP, tid, THREADS, cs, nullptr, part, farc, anchor, mask);
+        __syncthreads();
+        for (int st = 0; st < n_super; ++st) {
+            if (!resident) {
+                __syncthreads();
+                stage(st, 0);
+                __syncthreads();
+            }
+            const int rgn = st * NW + warp;
+            if (rgn < NRP) {
+                const int slot = resident ? st : 0;
+                const int i_first = (st * THREADS + tid) * R;
+                const double w_first = i_first < N ? __ldg(sw + i_first) : fma((double)i_first, h, __ldg(sw));
+                const double2 ew = *reinterpret_cast<const double2*>(anchor + 2 * rgn);
+                const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rgn * (MW + 1), farc + (size_t)rgn * kFarTerms,
+                                                     ew, MW, P, lane, w_first, xi0, suv + slot * THREADS * R + tid,
+                                                     swt + slot * THREADS * R + tid, THREADS, tab, xs, sw + i_first,
+                                                     N - i_first, h, w_ulp);
+                if (lane == 0) wpart[rgn] = ss;
+            }
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // same order as the per-step path: the warps of a point tile, then the tiles, then sqrt(mean)
+            double total = 0.0;
+            for (int t = 0; t < a.n_vtiles; ++t) {
+                double tt = 0.0;
+                for (int wi = 0; wi < VW; ++wi) tt += wpart[t * VW + wi];
+                total += tt;
+            }
+            const double fx = sqrt(total / (double)N);
+            const bool better = fx < misc[1];
+            misc[0] = fx;
+            if (better) misc[1] = fx;
+            misc[4] = better ? 1.0 : 0.0;
+            a.rec_f[((size_t)par * s.B + b) * S + sl] = misc[1];
+        }
+        __syncthreads();
+        {
+            const bool better = misc[4] != 0.0;
+            double* rx = a.rec_x + (((size_t)par * s.B + b) * S + sl) * D;
+            for (int d = tid; d < D; d += THREADS) {
+                if (better) ps[d] = xs[d];
+                rx[d] = ps[d];
+            }
+        }
+
+        // ---- barrier among the S CTAs of this spectrum
+        __syncthreads();
+        if (tid == 0) {
+            // release: this CTA's record (ordered before by the bar.sync above) is visible to whoever acquires the count
+            red_release_add(a.barrier + b, 1u);
+            const unsigned target = (unsigned)S * (unsigned)(k + 1);
+            while (ld_acquire(a.barrier + b) < target) { }
+        }
+        __syncthreads();
+
+        // ---- swarm best: argmin over the personal bests, first index wins (np.argmin)
+        {
+            const double* rf = a.rec_f + ((size_t)par * s.B + b) * S;
+            double bf = CUDART_INF;
+            int bi = 0x7fffffff;
+            for (int i = tid; i < S; i += THREADS) take_min(bf, bi, __ldcg(rf + i), i);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double of = __shfl_xor_sync(0xffffffffu, bf, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                take_min(bf, bi, of, oi);
+            }
+            if (lane == 0) { redf[warp] = bf; redi[warp] = bi; }
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double bf = lane < NW ? redf[lane] : CUDART_INF;
+            int bi = lane < NW ? redi[lane] : 0x7fffffff;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double of = __shfl_xor_sync(0xffffffffu, bf, o);
+                const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                take_min(bf, bi, of, oi);
+            }
+            const int win = bi == 0x7fffffff ? 0 : bi;
+            if (bf < misc[2]) {                            // only a new swarm best needs its position
+                const double* rx = a.rec_x + (((size_t)par * s.B + b) * S + win) * D;
+                for (int d = lane; d < D; d += 32) pm[d] = __ldcg(rx + d);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                // pyswarm: if fp[i_min] < fg: test |fg - fp[i_min]| <= minfunc, then ||g - p_min|| <= minstep, else adopt
+                const double fmin = bf, fg = misc[2];
+                int action = 0;
+                if (fmin < fg) {
+                    double acc = 0.0;
+                    for (int d = 0; d < D; ++d) {
+                        const double df = __dsub_rn(gs[d], pm[d]);
+                        acc = __dadd_rn(acc, __dmul_rn(df, df));
+                    }
+                    const double step = sqrt(acc);
+                    if (fabs(__dsub_rn(fg, fmin)) <= s.minfunc) action = 2 + kStopMinFunc;
+                    else if (step <= s.minstep) action = 2 + kStopMinStep;
+                    else action = 1;
+                }
+                misc[5] = (double)action;
+                misc[6] = fmin;
+            }
+        }
+        __syncthreads();
+        {
+            const int action = (int)misc[5];
+            it += 1;
+            if (action >= 2) stop = action - 2;
+            else if (it >= a.maxiter) stop = kStopMaxIter;
+            if (action != 0) {
+                for (int d = tid; d < D; d += THREADS) {
+                    bxs[d] = pm[d];
+                    if (action == 1) gs[d] = pm[d];
+                }
+                if (tid == 0) {
+                    misc[3] = misc[6];
+                    if (action == 1) misc[2] = misc[6];
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- write the state back for the host (and for further generations by either path)
+    for (int d = tid; d < D; d += THREADS) {
+        s.x[bs * D + d] = xs[d];
+        s.v[bs * D + d] = vs[d];
+        s.p[bs * D + d] = ps[d];
+        if (sl == 0) {
+            s.g[(size_t)b * D + d] = gs[d];
+            s.best_x[(size_t)b * D + d] = bxs[d];
+        }
+    }
+    if (tid == 0) {
+        s.fx[bs] = misc[0];
+        s.fp[bs] = misc[1];
+        if (sl == 0) {
+            s.fg[b] = misc[2];
+            s.best_f[b] = misc[3];
+            s.it[b] = it;
+            s.stop[b] = stop;
+        }
+    }
+}
+
+// ---- host side ------------------------------------------------------------------------------------------
+
+template <int THREADS, int R>
+static cudaError_t plan_one(const FusedArgs& a, int D, int grid, int device, FusedPlan* plan) {
+    auto kern = swarm_fused_kernel<THREADS, R, 6>;
+    static bool attr_set[NMRFIT_MAX_DEVICES] = {};
+    if (!attr_set[device % NMRFIT_MAX_DEVICES]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) return e;
+        attr_set[device % NMRFIT_MAX_DEVICES] = true;
+    }
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    const int NRP = a.n_vtiles * a.vw, n_super = (NRP + THREADS / 32 - 1) / (THREADS / 32);
+    // the whole spectrum stays in shared memory when that still leaves room for enough CTAs; else one supertile
+    for (int slots : {n_super, 1}) {
+        const size_t bytes = (size_t)FusedSmem(a.P, D, THREADS, R, slots, NRP).total * sizeof(double);
+        if (bytes > 200 * 1024) continue;
+        int per_sm = 0;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, bytes);
+        if (e != cudaSuccess) return e;
+        if ((long long)per_sm * sms >= grid) {
+            plan->ok = true; plan->threads = THREADS; plan->r = R; plan->slots = slots; plan->smem = bytes;
+            return cudaSuccess;
+        }
+        if (slots == 1) break;
+    }
+    return cudaSuccess;
+}
+
+cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjTune& t, int device, FusedPlan* plan) {
+    plan->ok = false;
+    if (t.tb != 6 || (t.r != 4 && t.r != 8) || (t.threads != 128 && t.threads != 256)) return cudaSuccess;
+    const long long grid = (long long)B * S;
+    if (grid > 4096) return cudaSuccess;
+    int sms = 0;
+    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    // one CTA per SM can afford 16 warps; more CTAs than SMs share an SM two (or more) at a time with 8 warps each
+    const bool wide = grid <= sms && a.n_vtiles * a.vw > 8;
+    if (wide) {
+        e = t.r == 8 ? plan_one<512, 8>(a, D, (int)grid, device, plan) : plan_one<512, 4>(a, D, (int)grid, device, plan);
+        if (e != cudaSuccess || plan->ok) return e;
+    }
+    return t.r == 8 ? plan_one<256, 8>(a, D, (int)grid, device, plan) : plan_one<256, 4>(a, D, (int)grid, device, plan);
+}
+
+cudaError_t launch_swarm_fused(FusedArgs a, const FusedPlan& plan, int B, int S, cudaStream_t st) {
+    a.slots = plan.slots;
+    void* args[] = {&a};
+    dim3 grid((unsigned)(B * S)), block((unsigned)plan.threads);
+    const void* kern = nullptr;
+    if (plan.threads == 512 && plan.r == 8) kern = (const void*)swarm_fused_kernel<512, 8, 6>;
+    else if (plan.threads == 512 && plan.r == 4) kern = (const void*)swarm_fused_kernel<512, 4, 6>;
+    else if (plan.threads == 256 && plan.r == 8) kern = (const void*)swarm_fused_kernel<256, 8, 6>;
+    else if (plan.threads == 256 && plan.r == 4) kern = (const void*)swarm_fused_kernel<256, 4, 6>;
+    else return cudaErrorInvalidValue;
+    cudaError_t e = cudaMemsetAsync(a.barrier, 0, sizeof(unsigned) * B, st);
+    if (e != cudaSuccess) return e;
+    e = cudaLaunchCooperativeKernel(kern, grid, block, args, plan.smem, st);
+    count_launches(1);
+    return e;
+}
+
+}  // namespace nmrfit

@@ -1,0 +1,162 @@
+// The two device routines of the uniform-axis objective, shared by the two-pass kernels
+// (objective_uniform.cu) and the fused swarm kernel (swarm_fused.cu) so that both evaluate a particle
+// with the SAME arithmetic in the SAME order - their objective values are bit-identical.
+//
+//   prepare_particle  per-particle constants: span coefficients of its peaks, phase tables and, per
+//                     region of 32*R points, the near-peak mask, the far-field polynomial and the
+//                     phase anchor.  The destinations are plain pointers: global memory in the
+//                     two-pass path, shared memory in the fused kernel.
+//   eval_region       one warp's squared weighted residual over its region, from those constants
+//                     and the staged (u, v, weights) of the tile.
+#pragma once
+#include <cuda_runtime.h>
+#include "nmrfit_math.cuh"
+#include "uniform_common.cuh"
+
+namespace nmrfit {
+
+// xs: the particle's D parameters; sw: its spectrum's w plane (N points); cs: shared [P][8] scratch that ends up
+// holding the span coefficients; coef_out: optional second copy of them; part [kPartDoubles]; far [NRP][kFarTerms];
+// anchor [NRP][2]; mask [NRP][MW+1].  NR regions cover the axis, NRP >= NR slots are filled (the rest neutral).
+// Called by all `nthreads` (>= 128) threads of a CTA; contains one __syncthreads().
+template <int R>
+__device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, const double* __restrict__ sw, double h,
+                                                 double w_ulp, int N, int P, int NR, int NRP, int tid, int nthreads,
+                                                 double* __restrict__ cs, double* __restrict__ coef_out,
+                                                 double* __restrict__ part, double* __restrict__ far,
+                                                 double* __restrict__ anchor, unsigned* __restrict__ mask) {
+    const int MW = (P + 31) / 32;
+    const double p0 = xs[0], p1 = xs[1];
+    constexpr double H = 16.0 * R;
+
+    for (int k = tid; k < P; k += nthreads) {
+        SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+        if (c.exact) c = null_span_coef();                 // the span loop adds zero; the peak is handled after it
+        double* o = cs + k * 8;
+        o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.thr; o[7] = c.c2;
+        if (coef_out) {
+            double* g = coef_out + k * 8;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) g[i] = o[i];
+        }
+    }
+    // phi_i = p0 + (p1*i)/N with i = i_r + lane*R + j:  anchor(i_r) * e^{i p1 (lane R)/N} * (e^{i p1/N})^j
+    for (int e = nthreads - 1 - tid; e < 33; e += nthreads) {   // the last warps do these while the first does the peaks
+        double sn, cn;
+        sincos(e < 32 ? (p1 * (double)(e * R)) / (double)N : p1 / (double)N, &sn, &cn);
+        part[2 * e] = cn;
+        part[2 * e + 1] = sn;
+    }
+    if (tid == 64) part[66] = (double)P * xs[3];           // yoff is added once per peak (equations.py:147,195)
+    __syncthreads();
+    if (tid == 64) {
+        int n = 0;
+        for (int k = 0; k < P; ++k) n += cs[k * 8 + 6] < 0.0;      // thr < 0 marks a nulled (exact-path) peak
+        part[67] = (double)n;
+    }
+    for (int r = tid; r < NRP; r += nthreads) {
+        double C[kFarTerms];
+#pragma unroll
+        for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
+        unsigned any_far = 0;
+        unsigned* mk = mask + (size_t)r * (MW + 1);
+        double sn = 0.0, cn = 1.0;
+        if (r < NR) {
+            const int ir = r * 32 * R;
+            const double w_c = fma(0.5 * (32 * R - 1), h, sw[ir]);
+            for (int wd = 0; wd < MW; ++wd) {
+                unsigned m = 0;
+                const int kend = min(P, wd * 32 + 32);
+                for (int k = wd * 32; k < kend; ++k) {
+                    const double* o = cs + k * 8;
+                    SpanCoef c;
+                    c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
+                    if (c.thr < 0.0) continue;             // exact-path peak: neither near nor far
+                    if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
+                    else m |= 1u << (k & 31);
+                }
+                mk[wd] = m;
+            }
+            sincos(p0 + (p1 * (double)ir) / (double)N, &sn, &cn);
+        } else {
+            for (int wd = 0; wd < MW; ++wd) mk[wd] = 0u;
+        }
+        mk[MW] = any_far;
+        double* fc = far + (size_t)r * kFarTerms;
+#pragma unroll
+        for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
+        anchor[r * 2] = cn;
+        anchor[r * 2 + 1] = sn;
+    }
+}
+
+// One warp, one particle, one region: sum over the warp's 32*R points of (weights * (V_data - V_fit))^2, identical
+// in every lane on return.  cf [P][8], pt [kPartDoubles], mk [MW+1], fc [kFarTerms] (16-byte aligned) and ew are the
+// particle's constants for this region; the thread's R points sit at suv_t[j*stride], swt_t[j*stride];
+// w_first is the abscissa of its first point and xi0 that point's position inside the region.  The exact path
+// (peaks too narrow for the recurrences) reads the particle's parameters xs and the stored abscissae sw_first[0..n_valid).
+template <int R, int TB>
+__device__ __forceinline__ double eval_region(const double* __restrict__ cf, const double* __restrict__ pt,
+                                              const unsigned* __restrict__ mk, const double* __restrict__ fc,
+                                              const double2 ew, int MW, int P, int lane, double w_first, double xi0,
+                                              const double2* __restrict__ suv_t, const double* __restrict__ swt_t,
+                                              int stride, const double* __restrict__ tab,
+                                              const double* __restrict__ xs, const double* __restrict__ sw_first,
+                                              int n_valid, double h, double w_ulp) {
+    constexpr double H = 16.0 * R;                         // half a region, in points
+    double acc[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[j] = 0.0;
+    for (int wd = 0; wd < MW; ++wd)
+    for (unsigned m = mk[wd]; m; m &= m - 1) {             // peaks near this warp's region
+        const int k = wd * 32 + __ffs(m) - 1;
+        const double2 c01 = *reinterpret_cast<const double2*>(cf + k * 8);
+        const double2 c23 = *reinterpret_cast<const double2*>(cf + k * 8 + 2);
+        const double2 c45 = *reinterpret_cast<const double2*>(cf + k * 8 + 4);
+        const double2 c67 = *reinterpret_cast<const double2*>(cf + k * 8 + 6);
+        SpanCoef c;
+        c.loc = c01.x; c.kL = c01.y; c.kG = c23.x; c.aL = c23.y;
+        c.aG = c45.x; c.dT = c45.y; c.thr = c67.x; c.c2 = c67.y;
+        peak_span<R, TB>(w_first - c.loc, c, tab, acc);
+    }
+    if (mk[MW]) {                                          // all far peaks at once
+        double C[kFarTerms];
+#pragma unroll
+        for (int n = 0; n < kFarTerms; n += 2) {
+            const double2 t = *reinterpret_cast<const double2*>(fc + n);
+            C[n] = t.x; C[n + 1] = t.y;
+        }
+        far_eval<R>(C, xi0, 1.0 / H, acc);
+    }
+    if (pt[67] != 0.0) {                                   // rare: peaks too narrow for the uniform-axis shortcuts
+        for (int k = 0; k < P; ++k) {
+            if (!(cf[k * 8 + 6] < 0.0)) continue;
+            const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+            peak_exact<R, TB>(sw_first, n_valid, w_first, h, c, tab, acc);
+        }
+    }
+    // residual against the phase-rotated data; the rotation advances by p1/N per point
+    const double2 el = *reinterpret_cast<const double2*>(pt + 2 * lane);
+    const double cd = pt[64], sd = pt[65], py = pt[66];
+    double cr = fma(ew.x, el.x, -(ew.y * el.y));
+    double ci = fma(ew.y, el.x, ew.x * el.y);
+    double ss = 0.0;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const double2 uv = suv_t[j * stride];
+        const double wt = swt_t[j * stride];
+        const double vd = fma(uv.x, cr, -fma(uv.y, ci, py));     // V_data - P*yoff
+        const double res = wt * (vd - acc[j]);
+        ss = fma(res, res, ss);
+        if (j + 1 < R) {
+            const double c2 = fma(cr, cd, -(ci * sd));
+            ci = fma(ci, cd, cr * sd);
+            cr = c2;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    return ss;
+}
+
+}  // namespace nmrfit

@@ -40,6 +40,16 @@ def _fit_im_mode(fit_im):
     return f(fit_im)
 
 
+def _fused_mode(fused):
+    """'auto' (default): small swarms run their generations in one cooperative launch (csrc/swarm_fused.cu);
+    'off': always one set of launches per generation; 'require': fail when the fused kernel cannot run."""
+    modes = {'auto': _cabi.FUSED_AUTO, None: _cabi.FUSED_AUTO, 'off': _cabi.FUSED_OFF, False: _cabi.FUSED_OFF,
+             'require': _cabi.FUSED_REQUIRE, True: _cabi.FUSED_AUTO}
+    if fused not in modes:
+        raise ValueError("fused must be 'auto', 'off' or 'require'")
+    return modes[fused]
+
+
 def _check_bounds(lower, upper):
     lb = np.array(lower, dtype=np.float64)
     ub = np.array(upper, dtype=np.float64)
@@ -72,7 +82,7 @@ def _draw_generations(rnd, n, S, D):
 
 def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxiter=100, omega=0.5, phip=0.5,
                phig=0.5, minstep=1e-8, minfunc=1e-8, rng='host', seed=0, precision='fp64', chunk=16, device=None,
-               quiet=False, trace=None, tuning=None):
+               quiet=False, trace=None, tuning=None, fused='auto'):
     """Minimise the nmrfit objective for one spectrum.  Returns (x_best, f_best, info).
 
     rng='host' consumes ``np.random`` exactly as pyswarm does (rand(S,D) for the
@@ -88,9 +98,10 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
     host = rng == 'host'
     if rng not in ('host', 'device'):
         raise ValueError("rng must be 'host' or 'device'")
-    with _cabi.Context(1, w.size, (D - 4) // 3, device=device, precision=_precision(precision)) as ctx:
+    with _cabi.pooled_context(1, w.size, (D - 4) // 3, device=device, precision=_precision(precision)) as ctx:
         if tuning:
             ctx.set_tuning(**tuning)
+        ctx.set_fused(_fused_mode(fused))
         ctx.set_spectrum(0, w, u, v, weights)
         opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed)
         r_pos = np.random.rand(S, D) if host else None
@@ -133,7 +144,7 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
 
 def pso_batch(spectra, lowers, uppers, fit_im=False, swarmsize=100, maxiter=100, omega=0.5, phip=0.5, phig=0.5,
               minstep=1e-8, minfunc=1e-8, rng='device', seeds=None, seed=0, precision='fp64', chunk=16, device=None,
-              tuning=None):
+              tuning=None, fused='auto'):
     """B independent fits in one context.  ``spectra``: sequence of (w, u, v, weights),
     all of one length; ``lowers``/``uppers``: [B][D].
 
@@ -155,9 +166,10 @@ def pso_batch(spectra, lowers, uppers, fit_im=False, swarmsize=100, maxiter=100,
         if seeds is None or len(seeds) != B:
             raise ValueError("rng='host' needs one seed per spectrum")
         streams = [np.random.RandomState(int(s)) for s in seeds]
-    with _cabi.Context(B, N, (D - 4) // 3, device=device, precision=_precision(precision)) as ctx:
+    with _cabi.pooled_context(B, N, (D - 4) // 3, device=device, precision=_precision(precision)) as ctx:
         if tuning:
             ctx.set_tuning(**tuning)
+        ctx.set_fused(_fused_mode(fused))
         for b, (w, u, v, wt) in enumerate(spectra):
             ctx.set_spectrum(b, w, u, v, wt)
         opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed)
@@ -252,7 +264,7 @@ def pso_sharded(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, max
     torch.cuda.set_device(dev)
     stream = torch.cuda.current_stream().cuda_stream
     w = _cabi.as_f64(w)
-    with _cabi.Context(1, w.size, (D - 4) // 3, device=dev, precision=_precision(precision)) as ctx:
+    with _cabi.pooled_context(1, w.size, (D - 4) // 3, device=dev, precision=_precision(precision)) as ctx:
         if tuning:
             ctx.set_tuning(**tuning)
         ctx.set_spectrum(0, w, u, v, weights)

@@ -78,6 +78,8 @@ class FitUtility:
       ``minstep``, ``minfunc``   pyswarm's stop tolerances (1e-8).
       ``precision`` 'fp64' (default) or 'fp32'.
       ``chunk``     generations queued between host checks of the stop flag.
+      ``fused``     'auto' (default) | 'off' | 'require': run the generations of a small swarm in one
+                    cooperative launch (bit-identical to the per-step kernels).
       ``device``    CUDA device index.
     ``processes`` is accepted and ignored (the GPU evaluates every particle at once).
     """
@@ -108,7 +110,7 @@ class FitUtility:
             omega=opt.get('omega', -0.2134), phip=opt.get('phip', -0.3344), phig=opt.get('phig', 2.3259),
             minstep=opt.get('minstep', 1e-8), minfunc=opt.get('minfunc', 1e-8),
             rng=opt.get('rng', 'host'), seed=opt.get('seed', 0), precision=opt.get('precision', 'fp64'),
-            chunk=opt.get('chunk', 16), device=opt.get('device', None))
+            chunk=opt.get('chunk', 16), device=opt.get('device', None), fused=opt.get('fused', 'auto'))
 
         self.params = xopt
         self.error = fopt
