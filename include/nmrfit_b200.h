@@ -76,6 +76,20 @@ void nmrfit_ctx_destroy(nmrfit_ctx* ctx);
 int nmrfit_ctx_set_spectrum(nmrfit_ctx* ctx, int b, const double* w, const double* u, const double* v,
                             const double* weights);
 
+/* Bulk form of nmrfit_ctx_set_spectrum: spectra b0 .. b0+count-1 from four [count][n_points] arrays (host or
+ * device).  weights may be NULL when nmrfit_ctx_compute_weights follows. */
+int nmrfit_ctx_set_spectra(nmrfit_ctx* ctx, int b0, int count, const double* w, const double* u, const double* v,
+                           const double* weights);
+
+/* FitUtility._compute_weights (utils.py:191-224) + equations.laplace1d (equations.py:215-238) for every spectrum of
+ * the context at once, written into the context's weights plane: windows [argmin|w-b0|, argmin|w-b1|] per peak,
+ * later peaks overwriting earlier ones, then `sweeps` Jacobi sweeps with pinned ends (reference: 10, omega
+ * 0.33333333).  peak_bounds [n_spectra][n_windows][2] = Peak.bounds; peak_values [n_spectra][n_windows] =
+ * (max|height| / |height_k|)**expon, computed by the caller.  weights_out: optional [n_spectra][n_points] copy
+ * (host or device).  Bit-identical to the reference's numpy result. */
+int nmrfit_ctx_compute_weights(nmrfit_ctx* ctx, const double* peak_bounds, const double* peak_values, int n_windows,
+                               int sweeps, double omega, double* weights_out, void* stream);
+
 /* Which objective kernel runs (default NMRFIT_ALGO_AUTO), and which one a launch with this fit_im would use.
  * Both kernels evaluate equations.objective (equations.py:152-212); the uniform-axis one exploits
  * w_i = w_0 + i*h (what core.load builds, core.py:58-60) to replace most exponentials by a recurrence. */

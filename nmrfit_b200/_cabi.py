@@ -48,6 +48,8 @@ SIGNATURES = {
     'nmrfit_ctx_create': (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i]),
     'nmrfit_ctx_destroy': (None, [_vp]),
     'nmrfit_ctx_set_spectrum': (_i, [_vp, _i, _vp, _vp, _vp, _vp]),
+    'nmrfit_ctx_set_spectra': (_i, [_vp, _i, _i, _vp, _vp, _vp, _vp]),
+    'nmrfit_ctx_compute_weights': (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp]),
     'nmrfit_ctx_set_algorithm': (_i, [_vp, _i]),
     'nmrfit_ctx_get_algorithm': (_i, [_vp, _i, c_int_p]),
     'nmrfit_ctx_set_tuning': (_i, [_vp, _i, _i, _i, _i]),
@@ -167,6 +169,27 @@ class Context:
             if a.shape != (self.N,):
                 raise ValueError('spectrum arrays must have shape (%d,), got %s' % (self.N, a.shape))
         check(lib().nmrfit_ctx_set_spectrum(self._h, int(b), *[ptr(a) for a in arrs]))
+
+    def set_spectra(self, w, u, v, weights=None, b0=0):
+        """Bulk upload: ``w, u, v`` (and optionally ``weights``) are [count, N] arrays for spectra b0..b0+count-1."""
+        arrs = [as_f64(a) for a in (w, u, v)]
+        count = arrs[0].shape[0]
+        wts = None if weights is None else as_f64(weights)
+        for a in arrs + ([wts] if wts is not None else []):
+            if a.shape != (count, self.N):
+                raise ValueError('spectra arrays must have shape (%d, %d), got %s' % (count, self.N, a.shape))
+        check(lib().nmrfit_ctx_set_spectra(self._h, int(b0), count, *[ptr(a) for a in arrs], ptr(wts)))
+
+    def compute_weights(self, peak_bounds, peak_values, sweeps=10, omega=0.33333333, want_host=True, stream=None):
+        """Residual weights of every spectrum on the device (utils.py:191-224).  ``peak_bounds`` [B, K, 2],
+        ``peak_values`` [B, K].  Returns the [B, N] weights when ``want_host``."""
+        pb, pv = as_f64(peak_bounds), as_f64(peak_values)
+        if pb.ndim != 3 or pb.shape[0] != self.B or pb.shape[2] != 2 or pv.shape != pb.shape[:2]:
+            raise ValueError('peak_bounds must be [%d, K, 2] and peak_values [%d, K]' % (self.B, self.B))
+        out = np.empty((self.B, self.N)) if want_host else None
+        check(lib().nmrfit_ctx_compute_weights(self._h, ptr(pb), ptr(pv), pb.shape[1], int(sweeps), float(omega),
+                                               ptr(out), ptr(stream)))
+        return out
 
     def set_algorithm(self, algorithm=ALGO_AUTO):
         """ALGO_AUTO (default), ALGO_GENERAL (any axis) or ALGO_UNIFORM (require the uniform-axis kernel)."""

@@ -88,6 +88,7 @@ struct nmrfit_ctx {
     DevBuf<int> sstop, sit;
     DevBuf<double> frec_f, frec_x;     // fused swarm kernel: published records
     DevBuf<unsigned> fbarrier;
+    DevBuf<double> wscratch, wbounds;  // batched weights: sweep scratch [B][N], windows + values
     int fused_mode = NMRFIT_FUSED_AUTO;
     long long fused_launches = 0;
     int* h_flags = nullptr;            // pinned [2*B]
@@ -98,6 +99,23 @@ struct nmrfit_ctx {
 };
 
 namespace {
+
+// Is the axis uniform?  h = (w_last - w_0)/(N-1); every stored w_i within 4 ulp of w_0 + i*h.
+// grid[0] = h, grid[1] = 2^-52 * max|w|.
+bool axis_is_uniform(const double* hw, int N, double* grid) {
+    double h = 0.0, big = 0.0;
+    bool uni = N >= 2;
+    if (uni) {
+        h = (hw[N - 1] - hw[0]) / (double)(N - 1);
+        big = std::max(std::fabs(hw[0]), std::fabs(hw[N - 1]));
+        const double tol = 4.0 * 2.220446049250313e-16 * big;
+        uni = std::isfinite(h) && h != 0.0 && std::isfinite(big);
+        for (int i = 0; uni && i < N; ++i) uni = std::fabs(hw[i] - std::fma((double)i, h, hw[0])) <= tol;
+    }
+    grid[0] = h;
+    grid[1] = 2.220446049250313e-16 * big;
+    return uni;
+}
 
 // Which objective kernel a launch uses: the uniform-axis kernels (FP64 or FP32) need every spectrum of the
 // batch on a uniform axis and the real-only fit; anything else runs the general kernel of that precision.
@@ -303,6 +321,8 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->frec_f.release();
     c->frec_x.release();
     c->fbarrier.release();
+    c->wscratch.release();
+    c->wbounds.release();
     if (c->h_flags) cudaFreeHost(c->h_flags);
     for (cudaEvent_t ev : c->prof_events) cudaEventDestroy(ev);
     delete c;
@@ -318,22 +338,72 @@ int nmrfit_ctx_set_spectrum(nmrfit_ctx* c, int b, const double* w, const double*
     const double* src[4] = {w, u, v, weights};
     for (int k = 0; k < 4; ++k)
         CK(cudaMemcpy(dst + (size_t)k * c->N, src[k], sizeof(double) * c->N, cudaMemcpyDefault));
-    // Is the axis uniform?  h = (w_last - w_0)/(N-1); every stored w_i within 4 ulp of w_0 + i*h.
-    std::vector<double> hw(c->N);
-    CK(cudaMemcpy(hw.data(), dst, sizeof(double) * c->N, cudaMemcpyDeviceToHost));
-    double h = 0.0, big = 0.0;
-    bool uni = c->N >= 2;
-    if (uni) {
-        h = (hw[c->N - 1] - hw[0]) / (double)(c->N - 1);
-        big = std::max(std::fabs(hw[0]), std::fabs(hw[c->N - 1]));
-        const double tol = 4.0 * 2.220446049250313e-16 * big;
-        uni = std::isfinite(h) && h != 0.0 && std::isfinite(big);
-        for (int i = 0; uni && i < c->N; ++i) uni = std::fabs(hw[i] - std::fma((double)i, h, hw[0])) <= tol;
+    std::vector<double> hw;
+    const double* wh = w;                                  // checked on the host: the caller's memory if it is host memory
+    if (is_device_pointer(w)) {
+        hw.resize(c->N);
+        CK(cudaMemcpy(hw.data(), dst, sizeof(double) * c->N, cudaMemcpyDeviceToHost));
+        wh = hw.data();
     }
-    c->uniform[b] = uni ? 1 : 0;
-    const double grid[2] = {h, 2.220446049250313e-16 * big};
+    double grid[2];
+    c->uniform[b] = axis_is_uniform(wh, c->N, grid) ? 1 : 0;
     CK(cudaMemcpy(c->grid_h.ptr + 2 * (size_t)b, grid, sizeof(grid), cudaMemcpyHostToDevice));
     c->spec_set[b] = 1;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_set_spectra(nmrfit_ctx* c, int b0, int count, const double* w, const double* u, const double* v,
+                           const double* weights) {
+    if (int r = check_ctx(c)) return r;
+    if (b0 < 0 || count < 1 || b0 + count > c->B) return fail(NMRFIT_ERR_ARG, "spectrum range out of bounds");
+    if (!w || !u || !v) return fail(NMRFIT_ERR_ARG, "w, u, v must be non-NULL");
+    CK(cudaSetDevice(c->device));
+    const size_t N = (size_t)c->N, row = sizeof(double) * N;
+    double* dst = c->spec.ptr + (size_t)b0 * 4 * N;
+    const double* src[4] = {w, u, v, weights};
+    for (int k = 0; k < 4; ++k) {
+        if (!src[k]) continue;                             // weights may follow from nmrfit_ctx_compute_weights
+        CK(cudaMemcpy2D(dst + k * N, 4 * row, src[k], row, row, count, cudaMemcpyDefault));
+    }
+    // uniformity of every axis, on the host: straight from the caller's memory when that is host memory
+    std::vector<double> hw;
+    const double* wh = w;
+    if (is_device_pointer(w)) {
+        hw.resize((size_t)count * N);
+        CK(cudaMemcpy(hw.data(), w, row * count, cudaMemcpyDeviceToHost));
+        wh = hw.data();
+    }
+    std::vector<double> grid(2 * (size_t)count);
+    for (int i = 0; i < count; ++i) {
+        c->uniform[b0 + i] = axis_is_uniform(wh + (size_t)i * N, c->N, &grid[2 * (size_t)i]) ? 1 : 0;
+        c->spec_set[b0 + i] = 1;
+    }
+    CK(cudaMemcpy(c->grid_h.ptr + 2 * (size_t)b0, grid.data(), sizeof(double) * grid.size(), cudaMemcpyHostToDevice));
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_compute_weights(nmrfit_ctx* c, const double* peak_bounds, const double* peak_values, int n_windows,
+                               int sweeps, double omega, double* weights_out, void* stream) {
+    if (int r = check_ctx(c)) return r;
+    if (!peak_bounds || !peak_values) return fail(NMRFIT_ERR_ARG, "peak_bounds and peak_values must be non-NULL");
+    if (n_windows < 1 || n_windows > 4096) return fail(NMRFIT_ERR_ARG, "n_windows must be 1..4096");
+    if (sweeps < 0) return fail(NMRFIT_ERR_ARG, "sweeps must be >= 0");
+    for (char f : c->spec_set)
+        if (!f) return fail(NMRFIT_ERR_STATE, "every spectrum must be set before its weights are computed");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t B = (size_t)c->B, N = (size_t)c->N, nb = B * 2 * n_windows, nv = B * n_windows;
+    CK(c->wscratch.reserve(B * N));
+    CK(c->wbounds.reserve(nb + nv));
+    CK(cudaMemcpyAsync(c->wbounds.ptr, peak_bounds, sizeof(double) * nb, cudaMemcpyDefault, st));
+    CK(cudaMemcpyAsync(c->wbounds.ptr + nb, peak_values, sizeof(double) * nv, cudaMemcpyDefault, st));
+    cudaError_t e = launch_weights(c->spec.ptr, c->wscratch.ptr, c->wbounds.ptr, c->wbounds.ptr + nb, c->B, c->N,
+                                   n_windows, sweeps, omega, st);
+    if (e != cudaSuccess) return fail_cuda(e, "weights launch");
+    if (weights_out)
+        CK(cudaMemcpy2DAsync(weights_out, sizeof(double) * N, c->spec.ptr + 3 * N, sizeof(double) * 4 * N,
+                             sizeof(double) * N, B, cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));                         // the staged bounds may be pageable host memory
     return NMRFIT_OK;
 }
 

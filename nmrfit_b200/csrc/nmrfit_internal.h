@@ -108,6 +108,10 @@ struct FusedPlan {
 cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjTune& t, int device, FusedPlan* plan);
 cudaError_t launch_swarm_fused(FusedArgs a, const FusedPlan& plan, int B, int S, cudaStream_t st);
 
+// ---- K8 residual weights of a batch (weights.cu) -----------------------------------
+cudaError_t launch_weights(double* spec, double* scratch, const double* bounds_dev, const double* values_dev, int B,
+                           int N, int n_windows, int sweeps, double omega, cudaStream_t st);
+
 // ---- K4/K5 curves -------------------------------------------------------------
 cudaError_t launch_ps2(const double* u, const double* v, int n, double p0, double p1, int inv, double* re, double* im,
                        cudaStream_t st);

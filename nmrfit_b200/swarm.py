@@ -144,59 +144,69 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
 
 def pso_batch(spectra, lowers, uppers, fit_im=False, swarmsize=100, maxiter=100, omega=0.5, phip=0.5, phig=0.5,
               minstep=1e-8, minfunc=1e-8, rng='device', seeds=None, seed=0, precision='fp64', chunk=16, device=None,
-              tuning=None, fused='auto'):
+              tuning=None, fused='auto', ctx=None):
     """B independent fits in one context.  ``spectra``: sequence of (w, u, v, weights),
-    all of one length; ``lowers``/``uppers``: [B][D].
+    all of one length; ``lowers``/``uppers``: [B][D].  With ``ctx`` (a context that already
+    holds the B spectra) ``spectra`` is ignored.
 
     rng='host' gives spectrum b its own legacy stream ``RandomState(seeds[b])``, drawn
     in pyswarm's order - i.e. the result equals running the reference fit b after
     ``np.random.seed(seeds[b])``.  rng='device' uses Philox keyed by ``seed``.
     Returns (x_best [B][D], f_best [B], generations [B], stop [B]).
     """
-    B = len(spectra)
     lb = np.array(lowers, dtype=np.float64)
     ub = np.array(uppers, dtype=np.float64)
+    B = lb.shape[0] if ctx is not None else len(spectra)
     assert lb.shape == ub.shape and lb.ndim == 2 and lb.shape[0] == B, 'bounds must be [B][D]'
     assert np.all(ub > lb), 'All upper-bound values must be greater than lower-bound values'
     D = lb.shape[1]
+    if ctx is not None:
+        return _pso_batch_run(ctx, lb, ub, fit_im, swarmsize, maxiter, omega, phip, phig, minstep, minfunc, rng,
+                              seeds, seed, chunk, tuning, fused)
     N = len(spectra[0][0])
+    with _cabi.pooled_context(B, N, (D - 4) // 3, device=device, precision=_precision(precision)) as own:
+        own.set_spectra(*[np.stack([sp[k] for sp in spectra]) for k in range(4)])
+        return _pso_batch_run(own, lb, ub, fit_im, swarmsize, maxiter, omega, phip, phig, minstep, minfunc, rng,
+                              seeds, seed, chunk, tuning, fused)
+
+
+def _pso_batch_run(ctx, lb, ub, fit_im, swarmsize, maxiter, omega, phip, phig, minstep, minfunc, rng, seeds, seed,
+                   chunk, tuning, fused):
+    B, D = lb.shape
     S = int(swarmsize)
     host = rng == 'host'
     if host:
         if seeds is None or len(seeds) != B:
             raise ValueError("rng='host' needs one seed per spectrum")
         streams = [np.random.RandomState(int(s)) for s in seeds]
-    with _cabi.pooled_context(B, N, (D - 4) // 3, device=device, precision=_precision(precision)) as ctx:
-        if tuning:
-            ctx.set_tuning(**tuning)
-        ctx.set_fused(_fused_mode(fused))
-        for b, (w, u, v, wt) in enumerate(spectra):
-            ctx.set_spectrum(b, w, u, v, wt)
-        opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed)
-        r_pos = r_vel = None
+    if tuning:
+        ctx.set_tuning(**tuning)
+    ctx.set_fused(_fused_mode(fused))
+    opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed)
+    r_pos = r_vel = None
+    if host:
+        r_pos = np.empty((B, S, D))
+        r_vel = np.empty((B, S, D))
+        for b, st in enumerate(streams):
+            r_pos[b] = st.rand(S, D)
+            r_vel[b] = st.rand(S, D)
+    ctx.pso_begin(lb, ub, opts, r_pos, r_vel)
+    ctx.pso_commit()
+    done = 0
+    while done < maxiter:
+        n = min(max(1, int(chunk)), maxiter - done)
+        rp = rg = None
         if host:
-            r_pos = np.empty((B, S, D))
-            r_vel = np.empty((B, S, D))
+            rp = np.empty((n, B, S, D))
+            rg = np.empty((n, B, S, D))
             for b, st in enumerate(streams):
-                r_pos[b] = st.rand(S, D)
-                r_vel[b] = st.rand(S, D)
-        ctx.pso_begin(lb, ub, opts, r_pos, r_vel)
-        ctx.pso_commit()
-        done = 0
-        while done < maxiter:
-            n = min(max(1, int(chunk)), maxiter - done)
-            rp = rg = None
-            if host:
-                rp = np.empty((n, B, S, D))
-                rg = np.empty((n, B, S, D))
-                for b, st in enumerate(streams):
-                    for k in range(n):
-                        rp[k, b] = st.uniform(size=(S, D))
-                        rg[k, b] = st.uniform(size=(S, D))
-            if ctx.pso_run(n, rp, rg) == 0:
-                break
-            done += n
-        return ctx.pso_best()
+                for k in range(n):
+                    rp[k, b] = st.uniform(size=(S, D))
+                    rg[k, b] = st.uniform(size=(S, D))
+        if ctx.pso_run(n, rp, rg) == 0:
+            break
+        done += n
+    return ctx.pso_best()
 
 
 # ---- particle sharding over torch.distributed ------------------------------------------------------

@@ -61,6 +61,22 @@ def compute_weights(w, peaks, expon=0.5):
     return equations.laplace1d(weights)
 
 
+def peak_windows(peaks_list, expon=0.5):
+    """Inputs of the device weights kernel for a batch: ``bounds`` [B, K, 2] (``Peak.bounds``) and ``values``
+    [B, K] = (tallest/|height|)**expon per spectrum (utils.py:206-221) - the only host arithmetic left."""
+    B, K = len(peaks_list), len(peaks_list[0])
+    bounds = np.empty((B, K, 2))
+    mag = np.empty((B, K))
+    for b, peaks in enumerate(peaks_list):
+        if len(peaks) != K:
+            raise ValueError('every spectrum of a batch must have the same number of peaks')
+        for k, pk in enumerate(peaks):
+            bounds[b, k, 0], bounds[b, k, 1] = pk.bounds[0], pk.bounds[1]
+            mag[b, k] = np.abs(pk.height)
+    values = np.power(np.amax(mag, axis=1, keepdims=True) / mag, expon)
+    return bounds, values
+
+
 class FitUtility:
     """Interface used to perform a fit of the data (drop-in for utils.py:96-339).
 
