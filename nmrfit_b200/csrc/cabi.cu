@@ -88,6 +88,8 @@ struct nmrfit_ctx {
     DevBuf<int> sstop, sit;
     DevBuf<double> frec_f, frec_x;     // fused swarm kernel: published records
     DevBuf<unsigned> fbarrier;
+    DevBuf<double> fin_scratch;        // finish kernel: per-CTA candidates
+    DevBuf<unsigned> fin_tickets;
     DevBuf<double> wscratch, wbounds;  // batched weights: sweep scratch [B][N], windows + values
     int fused_mode = NMRFIT_FUSED_AUTO;
     long long fused_launches = 0;
@@ -167,7 +169,7 @@ int check_ctx(const nmrfit_ctx* c) {
 }
 
 int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double* f_dev, const int* frozen,
-                  cudaStream_t st) {
+                  cudaStream_t st, const MoveArgs* mv = nullptr, int* tiles_out = nullptr, int* nsum_out = nullptr) {
     for (int b = 0; b < c->B; ++b)
         if (!c->spec_set[b]) return fail(NMRFIT_ERR_STATE, "spectrum " + std::to_string(b) + " was never set");
     if (fit_im < 0 || fit_im > 2) return fail(NMRFIT_ERR_ARG, "fit_im must be 0, 1 or 2");
@@ -216,9 +218,15 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
         ev1 = c->prof_events[c->prof_used + 1];
         c->prof_used += 2;
     }
-    cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, uni, st, ev0, ev1)
-                    : uni                       ? launch_objective_uniform(a, t, c->B, f_dev, st, ev0, ev1)
-                                                : launch_objective(a, t, c->B, f_dev, st, ev0, ev1);
+    const bool move_in_prepare = mv && uni && c->precision == NMRFIT_FP64;
+    if (mv && !move_in_prepare) {                          // paths without a prepare pass move the swarm on their own
+        cudaError_t em = launch_swarm_move(mv->s, mv->rp, mv->rg, mv->generation, st);
+        if (em != cudaSuccess) return fail_cuda(em, "swarm move");
+    }
+    if (nsum_out) *nsum_out = (c->precision == NMRFIT_FP32 || uni) ? 1 : (fit_im ? 2 : 1);
+    cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, uni, st, ev0, ev1, tiles_out)
+                    : uni ? launch_objective_uniform(a, t, c->B, f_dev, st, ev0, ev1, move_in_prepare ? mv : nullptr, tiles_out)
+                          : launch_objective(a, t, c->B, f_dev, st, ev0, ev1, tiles_out);
     if (e != cudaSuccess) return fail_cuda(e, "objective launch");
     return NMRFIT_OK;
 }
@@ -253,7 +261,7 @@ int fused_setup(nmrfit_ctx* c, int n_gen, const double* rp_d, const double* rg_d
     a->n_gen = n_gen;
     a->gen0 = c->generation + 1;
     a->maxiter = c->maxiter;
-    cudaError_t e = swarm_fused_plan(*a, c->D, s.B, s.S, t, c->device, plan);
+    cudaError_t e = swarm_fused_plan(*a, c->D, s.B, s.S, t, c->device, c->fused_mode == NMRFIT_FUSED_REQUIRE, plan);
     if (e != cudaSuccess) return fail_cuda(e, "fused swarm plan");
     if (!plan->ok) return NMRFIT_OK;
     CK(c->frec_f.reserve(2 * (size_t)s.B * s.S));
@@ -262,6 +270,21 @@ int fused_setup(nmrfit_ctx* c, int n_gen, const double* rp_d, const double* rg_d
     a->rec_f = c->frec_f.ptr;
     a->rec_x = c->frec_x.ptr;
     a->barrier = c->fbarrier.ptr;
+    return NMRFIT_OK;
+}
+
+// One generation of the per-step path in three launches: [move + per-particle constants], [objective tiles],
+// [tile sums + personal bests + local best record (+ swarm-best commit)].  generation 0 (`move` false) evaluates
+// the freshly initialised swarm.
+int swarm_generation(nmrfit_ctx* c, bool move, const double* rp_d, const double* rg_d, int commit, cudaStream_t st) {
+    SwarmState& s = c->sw;
+    MoveArgs mv{s, rp_d, rg_d, c->generation};
+    int n_tiles = 0, nsum = 1;
+    if (int rc = run_objective(c, s.x, s.S, c->kk, nullptr, move ? s.stop : nullptr, st, move ? &mv : nullptr, &n_tiles, &nsum))
+        return rc;
+    cudaError_t e = launch_swarm_finish(s, c->partials.ptr, n_tiles, nsum, c->N, s.rec, c->fin_scratch.ptr,
+                                        c->fin_tickets.ptr, commit, c->maxiter, st);
+    if (e != cudaSuccess) return fail_cuda(e, "swarm finish");
     return NMRFIT_OK;
 }
 
@@ -322,6 +345,8 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->frec_x.release();
     c->fbarrier.release();
     c->wscratch.release();
+    c->fin_scratch.release();
+    c->fin_tickets.release();
     c->wbounds.release();
     if (c->h_flags) cudaFreeHost(c->h_flags);
     for (cudaEvent_t ev : c->prof_events) cudaEventDestroy(ev);
@@ -528,6 +553,9 @@ int nmrfit_pso_begin(nmrfit_ctx* c, const double* lb, const double* ub, const nm
     CK(c->sg.reserve((size_t)B * D)); CK(c->sfg.reserve(B)); CK(c->sbx.reserve((size_t)B * D)); CK(c->sbf.reserve(B));
     CK(c->slb.reserve((size_t)B * D)); CK(c->sub.reserve((size_t)B * D)); CK(c->srec.reserve((size_t)B * (D + 2)));
     CK(c->sstop.reserve(B)); CK(c->sit.reserve(B));
+    CK(c->fin_scratch.reserve(swarm_finish_scratch_doubles(B, S)));
+    CK(c->fin_tickets.reserve(B));
+    CK(cudaMemsetAsync(c->fin_tickets.ptr, 0, sizeof(unsigned) * B, (cudaStream_t)stream));
     std::vector<double> hl((size_t)B * D), hu((size_t)B * D);
     for (int b = 0; b < B; ++b)
         for (int d = 0; d < D; ++d) {
@@ -554,10 +582,7 @@ int nmrfit_pso_begin(nmrfit_ctx* c, const double* lb, const double* ub, const nm
     cudaError_t e = launch_swarm_init(s, rp_d, nullptr, st);
     if (e == cudaSuccess) e = launch_swarm_init_velocity(s, rv_d, st);
     if (e != cudaSuccess) return fail_cuda(e, "swarm init");
-    if (int rc = run_objective(c, s.x, S, c->kk, s.fx, nullptr, st)) return rc;
-    e = launch_swarm_local_best(s, s.rec, st);
-    if (e != cudaSuccess) return fail_cuda(e, "swarm local best");
-    return NMRFIT_OK;
+    return swarm_generation(c, false, nullptr, nullptr, 0, st);
 }
 
 int nmrfit_pso_advance(nmrfit_ctx* c, const double* rp, const double* rg, void* stream) {
@@ -572,12 +597,7 @@ int nmrfit_pso_advance(nmrfit_ctx* c, const double* rp, const double* rg, void* 
     if (int rc = stage(rp, nsd, c->rnd_a, st, &rp_d)) return rc;
     if (int rc = stage(rg, nsd, c->rnd_b, st, &rg_d)) return rc;
     c->generation += 1;
-    cudaError_t e = launch_swarm_move(s, rp_d, rg_d, c->generation, st);
-    if (e != cudaSuccess) return fail_cuda(e, "swarm move");
-    if (int rc = run_objective(c, s.x, s.S, c->kk, s.fx, s.stop, st)) return rc;
-    e = launch_swarm_local_best(s, s.rec, st);
-    if (e != cudaSuccess) return fail_cuda(e, "swarm local best");
-    return NMRFIT_OK;
+    return swarm_generation(c, true, rp_d, rg_d, 0, st);
 }
 
 int nmrfit_pso_record(nmrfit_ctx* c, double** rec_dev, int* n_doubles) {
@@ -630,13 +650,8 @@ int nmrfit_pso_run(nmrfit_ctx* c, int n_generations, const double* rp_all, const
     }
     for (int k = 0; k < n_generations; ++k) {
         c->generation += 1;
-        cudaError_t e = launch_swarm_move(s, rp_d ? rp_d + nsd * k : nullptr, rg_d ? rg_d + nsd * k : nullptr,
-                                          c->generation, st);
-        if (e != cudaSuccess) return fail_cuda(e, "swarm move");
-        if (int rc = run_objective(c, s.x, s.S, c->kk, s.fx, s.stop, st)) return rc;
-        e = launch_swarm_local_best(s, s.rec, st);
-        if (e == cudaSuccess) e = launch_swarm_commit(s, s.rec, 1, 0, c->maxiter, st);
-        if (e != cudaSuccess) return fail_cuda(e, "swarm best");
+        if (int rc = swarm_generation(c, true, rp_d ? rp_d + nsd * k : nullptr, rg_d ? rg_d + nsd * k : nullptr, 1, st))
+            return rc;
     }
     CK(cudaMemcpyAsync(c->h_flags, s.stop, sizeof(int) * s.B, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
@@ -706,13 +721,7 @@ int nmrfit_generate_result(const double* params, int P, const double* w, int n, 
     if (!params || P < 1 || n < 0) return fail(NMRFIT_ERR_ARG, "bad generate_result arguments");
     if (n > 0 && (!w || !real || !imag || !V || !I || !u || !v)) return fail(NMRFIT_ERR_ARG, "NULL output buffer");
     if (n == 0) return NMRFIT_OK;
-    cudaStream_t st = (cudaStream_t)stream;
-    double* pd = nullptr;
-    const int D = 4 + 3 * P;
-    CK(cudaMallocAsync(&pd, sizeof(double) * D, st));
-    CK(cudaMemcpyAsync(pd, params, sizeof(double) * D, cudaMemcpyHostToDevice, st));
-    cudaError_t e = launch_generate_result(pd, P, w, n, real, imag, V, I, u, v, st);
-    cudaFreeAsync(pd, st);
+    cudaError_t e = launch_generate_result(params, P, w, n, real, imag, V, I, u, v, (cudaStream_t)stream);
     if (e != cudaSuccess) return fail_cuda(e, "generate_result launch");
     return NMRFIT_OK;
 }

@@ -59,14 +59,21 @@ __global__ void kk_kernel(const double* __restrict__ w, int n, double r, double 
     out[i] = body_imag(c, iw, iw * kSqrtLn2, w[i]);
 }
 
-// one thread per grid point, all peaks; every store is coalesced along the grid
+// one thread per grid point, all peaks; every store is coalesced along the grid.  The D parameters travel as
+// a kernel argument when they fit (up to kGenInlinePeaks peaks: no allocation, no copy, nothing to wait for
+// on the host); larger fits read them from `params_dev`.
 constexpr int kGenThreads = 256;
 constexpr int kGenMaxPeaks = 256;
+constexpr int kGenInlinePeaks = 64;
+struct GenParams { double v[4 + 3 * kGenInlinePeaks]; };
+
+template <bool INLINE>
 __global__ void __launch_bounds__(kGenThreads)
-generate_result_kernel(const double* __restrict__ params, int P, const double* __restrict__ w, int n,
-                       double* __restrict__ real, double* __restrict__ imag, double* __restrict__ V,
+generate_result_kernel(const GenParams gp, const double* __restrict__ params_dev, int P, const double* __restrict__ w,
+                       int n, double* __restrict__ real, double* __restrict__ imag, double* __restrict__ V,
                        double* __restrict__ I, double* __restrict__ u, double* __restrict__ v) {
     extern __shared__ __align__(16) double sm[];   // [P][8]
+    const double* params = INLINE ? gp.v : params_dev;
     const double p0 = params[0], p1 = params[1], r = params[2], yoff = params[3];
     for (int k = threadIdx.x; k < P; k += kGenThreads) {
         double width = params[4 + 3 * k], loc = params[5 + 3 * k], a = params[6 + 3 * k];
@@ -123,14 +130,32 @@ cudaError_t launch_kk(const double* w, int n, double r, double width, double loc
     return cudaGetLastError();
 }
 
-cudaError_t launch_generate_result(const double* params_dev, int P, const double* w, int n, double* real,
+// params_host: the D = 4 + 3P fitted parameters in host memory
+cudaError_t launch_generate_result(const double* params_host, int P, const double* w, int n, double* real,
                                    double* imag, double* V, double* I, double* u, double* v, cudaStream_t st) {
     if (n <= 0) return cudaSuccess;
     if (P > kGenMaxPeaks) return cudaErrorInvalidValue;
     count_launches(1);
-    generate_result_kernel<<<(n + kGenThreads - 1) / kGenThreads, kGenThreads, (size_t)P * 8 * sizeof(double), st>>>(
-        params_dev, P, w, n, real, imag, V, I, u, v);
-    return cudaGetLastError();
+    const int D = 4 + 3 * P;
+    const unsigned grid = (n + kGenThreads - 1) / kGenThreads;
+    const size_t smem = (size_t)P * 8 * sizeof(double);
+    if (P <= kGenInlinePeaks) {
+        GenParams gp;
+        for (int d = 0; d < D; ++d) gp.v[d] = params_host[d];
+        generate_result_kernel<true><<<grid, kGenThreads, smem, st>>>(gp, nullptr, P, w, n, real, imag, V, I, u, v);
+        return cudaGetLastError();
+    }
+    double* pd = nullptr;
+    cudaError_t e = cudaMallocAsync(&pd, sizeof(double) * D, st);
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(pd, params_host, sizeof(double) * D, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) {
+        GenParams gp{};
+        generate_result_kernel<false><<<grid, kGenThreads, smem, st>>>(gp, pd, P, w, n, real, imag, V, I, u, v);
+        e = cudaGetLastError();
+    }
+    cudaFreeAsync(pd, st);
+    return e;
 }
 
 }  // namespace nmrfit

@@ -38,8 +38,9 @@ struct ObjTune {
 int objective_tiles(int N, const ObjTune& t);
 size_t objective_smem_bytes(int P, const ObjTune& t, int kk);
 // ev0/ev1 (nullable) are recorded immediately before/after the main kernel on `st`
+// f == nullptr skips the finalize pass; tiles_out receives the number of partial sums per particle
 cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0 = nullptr,
-                             cudaEvent_t ev1 = nullptr);
+                             cudaEvent_t ev1 = nullptr, int* tiles_out = nullptr);
 
 // fixed-order sum over point tiles + sqrt(mean) (shared by the objective kernels)
 cudaError_t launch_objective_finalize(const double* partials, int n_tiles, int nsum, int N, int S, int B,
@@ -50,15 +51,20 @@ size_t objective_uniform_smem_bytes(int P, const ObjTune& t);
 // per-particle sizes (in doubles / 32-bit words) of the prepare pass's outputs
 void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, size_t* coef, size_t* part, size_t* far, size_t* anchor,
                                   size_t* mask_words, int* pad_particles);
+struct SwarmState;
+struct MoveArgs;
+// f == nullptr skips the finalize pass (the swarm's finish kernel sums the tiles itself); mv != nullptr moves the
+// swarm (pso.cu's update) inside the prepare pass, one launch fewer per generation
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st,
-                                     cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+                                     cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, const MoveArgs* mv = nullptr,
+                                     int* tiles_out = nullptr);
 
-cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaStream_t st);
+cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaStream_t st, const MoveArgs* mv = nullptr);
 
 // opt-in FP32 objective: uniform-axis kernel when `uniform`, else a plain FP32 kernel for any axis (real-only fit)
 size_t objective_f32_smem_bytes(int P, const ObjTune& t);
 cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, bool uniform, cudaStream_t st,
-                                 cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr);
+                                 cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, int* tiles_out = nullptr);
 
 // ---- K2/K3 swarm --------------------------------------------------------------
 struct SwarmState {
@@ -74,6 +80,18 @@ struct SwarmState {
     unsigned long long seed;
     long long index0;       // global index of local particle 0 (particle sharding)
 };
+
+struct MoveArgs {
+    SwarmState s;
+    const double* rp;       // [B][S][D] host-stream uniforms of this generation, or null for device Philox
+    const double* rg;
+    int generation;
+};
+// finalize + personal bests + local best record (+ swarm-best commit when `commit`) in one launch:
+// partials [B][S][n_tiles][nsum] -> fx, fp, p, rec; `scratch` holds [B][ceil(S/8)][2] doubles, `tickets` [B] zeroed once
+cudaError_t launch_swarm_finish(const SwarmState& s, const double* partials, int n_tiles, int nsum, int N, double* rec,
+                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st);
+size_t swarm_finish_scratch_doubles(int B, int S);
 
 cudaError_t launch_swarm_init(const SwarmState& s, const double* r_pos, const double* r_vel, cudaStream_t st);
 cudaError_t launch_swarm_init_velocity(const SwarmState& s, const double* r_vel, cudaStream_t st);
@@ -105,7 +123,9 @@ struct FusedPlan {
     size_t smem;
 };
 // can B*S CTAs be co-resident for this shape?  plan->ok says so; never launches
-cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjTune& t, int device, FusedPlan* plan);
+// `force`: ignore the size heuristic (NMRFIT_FUSED_REQUIRE)
+cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjTune& t, int device, bool force,
+                             FusedPlan* plan);
 cudaError_t launch_swarm_fused(FusedArgs a, const FusedPlan& plan, int B, int S, cudaStream_t st);
 
 // ---- K8 residual weights of a batch (weights.cu) -----------------------------------
@@ -119,7 +139,7 @@ cudaError_t launch_voigt(const double* w, int n, double r, double yoff, double w
                          cudaStream_t st);
 cudaError_t launch_kk(const double* w, int n, double r, double width, double loc, double a, double* out,
                       cudaStream_t st);
-cudaError_t launch_generate_result(const double* params_dev, int P, const double* w, int n, double* real,
+cudaError_t launch_generate_result(const double* params_host, int P, const double* w, int n, double* real,
                                    double* imag, double* V, double* I, double* u, double* v, cudaStream_t st);
 
 // ---- probes -------------------------------------------------------------------

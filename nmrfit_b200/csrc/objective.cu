@@ -266,9 +266,10 @@ size_t objective_smem_bytes(int P, const ObjTune& t, int kk) {
 }
 
 cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0,
-                             cudaEvent_t ev1) {
+                             cudaEvent_t ev1, int* tiles_out) {
     a.sp = t.sp;
     const int n_tiles = objective_tiles(a.N, t);
+    if (tiles_out) *tiles_out = n_tiles;
     dim3 grid((a.S + t.sp - 1) / t.sp, n_tiles, B);
     cudaError_t e = cudaErrorInvalidValue;
     if (ev0) cudaEventRecord(ev0, st);
@@ -280,8 +281,8 @@ cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cuda
     else if (t.threads == 256 && t.r == 8) e = launch_tb<256, 8>(a, t.tb, grid, st);
     if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) return e;
-    e = launch_objective_finalize(a.partials, n_tiles, a.kk ? 2 : 1, a.N, a.S, B, a.frozen, f, st);
-    count_launches(2);
+    if (f) e = launch_objective_finalize(a.partials, n_tiles, a.kk ? 2 : 1, a.N, a.S, B, a.frozen, f, st);
+    count_launches(f ? 2 : 1);
     return e;
 }
 

@@ -330,7 +330,7 @@ static cudaError_t launch_uniform_f32(const ObjArgs& a, int B, cudaStream_t st) 
 }
 
 cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, bool uniform, cudaStream_t st,
-                                 cudaEvent_t ev0, cudaEvent_t ev1) {
+                                 cudaEvent_t ev0, cudaEvent_t ev1, int* tiles_out) {
     if (a.kk != 0) return cudaErrorNotSupported;           // fit_im needs the FP64 general kernel
     cudaError_t e;
     int n_tiles;
@@ -363,8 +363,9 @@ cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, 
     }
     if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) return e;
-    e = launch_objective_finalize(a.partials, n_tiles, 1, a.N, a.S, B, a.frozen, f, st);
-    count_launches(2);
+    if (tiles_out) *tiles_out = n_tiles;
+    if (f) e = launch_objective_finalize(a.partials, n_tiles, 1, a.N, a.S, B, a.frozen, f, st);
+    count_launches(f ? 2 : 1);
     return e;
 }
 

@@ -44,6 +44,7 @@
 #include "nmrfit_math.cuh"
 #include "uniform_common.cuh"
 #include "uniform_eval.cuh"
+#include "swarm_common.cuh"
 
 namespace nmrfit {
 
@@ -69,6 +70,42 @@ objective_prepare_kernel(ObjArgs a) {
                         128, cs, a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles,
                         a.prep_far + ps * NRP * kFarTerms, a.prep_anchor + ps * NRP * 2,
                         a.prep_mask + ps * NRP * (MW + 1));
+}
+
+// pass 1 with the swarm's move in front (pso.cu's swarm_move_kernel for this particle): one launch fewer
+template <int R>
+__global__ void __launch_bounds__(128)
+objective_move_prepare_kernel(ObjArgs a, MoveArgs mv) {
+    extern __shared__ __align__(16) double cs[];           // [P][8] then the moved particle [D]
+    const int b = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
+    const SwarmState& s = mv.s;
+    if (s.stop[b]) return;
+    const int P = a.P, N = a.N, D = 4 + 3 * P, MW = (P + 31) / 32;
+    const int NR = (N + 32 * R - 1) / (32 * R), NRP = a.n_tiles * a.nw;
+    const size_t ps = (size_t)b * a.S + sl;
+    double* xs = cs + P * 8;
+    for (int d = tid; d < D; d += 128) {
+        const size_t idx = ps * D + d;
+        double rp, rg;
+        if (mv.rp) {
+            rp = mv.rp[idx];
+            rg = mv.rg[idx];
+        } else {
+            const Philox2 u = philox_uniform2(s.seed, elem_counter(s, b, sl, d), (unsigned long long)mv.generation);
+            rp = u.a;
+            rg = u.b;
+        }
+        double x = s.x[idx], v = s.v[idx];
+        move_element(s.omega, s.phip, s.phig, rp, rg, s.p[idx], s.g[(size_t)b * D + d], s.lb[(size_t)b * D + d],
+                     s.ub[(size_t)b * D + d], x, v);
+        s.v[idx] = v;
+        s.x[idx] = x;
+        xs[d] = x;
+    }
+    __syncthreads();
+    prepare_particle<R>(xs, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid, 128, cs,
+                        a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles, a.prep_far + ps * NRP * kFarTerms,
+                        a.prep_anchor + ps * NRP * 2, a.prep_mask + ps * NRP * (MW + 1));
 }
 
 // ---- pass 2: evaluation ------------------------------------------------------------------------------
@@ -221,13 +258,21 @@ size_t objective_uniform_smem_bytes(int P, const ObjTune& t) {
 }
 
 // pass 1 (shared with the FP32 evaluation kernel); fills a.sp / a.n_tiles / a.nw
-cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaStream_t st) {
+cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaStream_t st, const MoveArgs* mv) {
     if (t.sp > kPadParticles) return cudaErrorInvalidValue;
     a.sp = t.sp;
     a.n_tiles = objective_tiles(a.N, t);
     a.nw = t.threads / 32;
     dim3 pgrid(a.S, B);
     const size_t pbytes = (size_t)a.P * 8 * sizeof(double);
+    if (mv) {
+        const size_t mbytes = pbytes + (size_t)(4 + 3 * a.P) * sizeof(double);
+        if (t.r == 4) objective_move_prepare_kernel<4><<<pgrid, 128, mbytes, st>>>(a, *mv);
+        else if (t.r == 8) objective_move_prepare_kernel<8><<<pgrid, 128, mbytes, st>>>(a, *mv);
+        else if (t.r == 16) objective_move_prepare_kernel<16><<<pgrid, 128, mbytes, st>>>(a, *mv);
+        else return cudaErrorInvalidValue;
+        return cudaGetLastError();
+    }
     if (t.r == 4) objective_prepare_kernel<4><<<pgrid, 128, pbytes, st>>>(a);
     else if (t.r == 8) objective_prepare_kernel<8><<<pgrid, 128, pbytes, st>>>(a);
     else if (t.r == 16) objective_prepare_kernel<16><<<pgrid, 128, pbytes, st>>>(a);
@@ -236,9 +281,9 @@ cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaSt
 }
 
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0,
-                                     cudaEvent_t ev1) {
+                                     cudaEvent_t ev1, const MoveArgs* mv, int* tiles_out) {
     if (ev0) cudaEventRecord(ev0, st);
-    cudaError_t e = launch_objective_prepare(a, t, B, st);
+    cudaError_t e = launch_objective_prepare(a, t, B, st, mv);
     if (e != cudaSuccess) return e;
     e = cudaErrorInvalidValue;
     if (t.threads == 128 && t.r == 4) e = launch_tb<128, 4>(a, t.tb, B, st);
@@ -249,8 +294,9 @@ cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double*
     else if (t.threads == 256 && t.r == 16) e = launch_tb<256, 16>(a, t.tb, B, st);
     if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) return e;
-    e = launch_objective_finalize(a.partials, a.n_tiles, 1, a.N, a.S, B, a.frozen, f, st);
-    count_launches(3);
+    if (tiles_out) *tiles_out = a.n_tiles;
+    if (f) e = launch_objective_finalize(a.partials, a.n_tiles, 1, a.N, a.S, B, a.frozen, f, st);
+    count_launches(f ? 3 : 2);
     return e;
 }
 

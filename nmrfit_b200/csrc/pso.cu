@@ -112,13 +112,11 @@ __global__ void __launch_bounds__(256) swarm_local_best_kernel(SwarmState s, dou
     for (int d = tid; d < s.D; d += 256) r[2 + d] = src[((size_t)b * s.S + best) * s.D + d];
 }
 
-// swarm-best update and the minfunc/minstep stop tests.  `recs` holds one record
-// per rank ([n_ranks][B][D+2]); every rank runs this redundantly on identical
-// input, so g/fg stay bit-identical everywhere.
-__global__ void __launch_bounds__(128) swarm_commit_kernel(SwarmState s, const double* __restrict__ recs, int n_ranks,
-                                                           int initial, int maxiter) {
-    const int b = blockIdx.x, tid = threadIdx.x;
-    if (s.stop[b]) return;
+// swarm-best update and the minfunc/minstep stop tests for spectrum b, by one CTA of `nthreads` threads.
+// `recs` holds one record per rank ([n_ranks][B][D+2]); every rank runs this redundantly on identical input,
+// so g/fg stay bit-identical everywhere.
+__device__ __forceinline__ void commit_spectrum(const SwarmState& s, const double* recs, int n_ranks,
+                                                int initial, int maxiter, int b, int tid, int nthreads) {
     const int W = s.D + 2;
     __shared__ int s_win;
     __shared__ double s_step;
@@ -138,7 +136,7 @@ __global__ void __launch_bounds__(128) swarm_commit_kernel(SwarmState s, const d
     double* g = s.g + (size_t)b * s.D;
     if (initial) {
         // pyswarm: fg = fp[i_min]; g = p[i_min] (else g = x[0] when nothing is finite)
-        for (int d = tid; d < s.D; d += 128) { g[d] = q[2 + d]; s.best_x[(size_t)b * s.D + d] = q[2 + d]; }
+        for (int d = tid; d < s.D; d += nthreads) { g[d] = q[2 + d]; s.best_x[(size_t)b * s.D + d] = q[2 + d]; }
         if (tid == 0) { s.fg[b] = fmin; s.best_f[b] = fmin; s.it[b] = 0; }
         return;
     }
@@ -164,7 +162,7 @@ __global__ void __launch_bounds__(128) swarm_commit_kernel(SwarmState s, const d
     }
     __syncthreads();
     if (s_action == 0) return;
-    for (int d = tid; d < s.D; d += 128) {
+    for (int d = tid; d < s.D; d += nthreads) {
         s.best_x[(size_t)b * s.D + d] = q[2 + d];
         if (s_action == 1) g[d] = q[2 + d];
     }
@@ -172,6 +170,109 @@ __global__ void __launch_bounds__(128) swarm_commit_kernel(SwarmState s, const d
         s.best_f[b] = fmin;
         if (s_action == 1) s.fg[b] = fmin;
     }
+}
+
+__global__ void __launch_bounds__(128) swarm_commit_kernel(SwarmState s, const double* __restrict__ recs, int n_ranks,
+                                                           int initial, int maxiter) {
+    const int b = blockIdx.x;
+    if (s.stop[b]) return;
+    commit_spectrum(s, recs, n_ranks, initial, maxiter, b, threadIdx.x, 128);
+}
+
+// ---- finish: everything after the objective's tile sums, in ONE launch --------------------------------------
+// Per particle (one warp each): fixed-order sum of its tile partials -> fx = sqrt(mean) (equations.py:202,
+// 205-209), personal-best update (value and position), and a candidate (fp, index) for the swarm's argmin.
+// The CTAs of a spectrum combine their candidates through a ticket: the last one to finish reduces them
+// (argmin with the lowest-index tie-break is order-independent, so this is deterministic), writes the local
+// best record and - when `commit` - applies pyswarm's swarm-best update and stop tests right there.
+constexpr int kFinWarps = 8;
+
+__global__ void __launch_bounds__(kFinWarps * 32)
+swarm_finish_kernel(SwarmState s, const double* __restrict__ partials, int n_tiles, int nsum, int N,
+                    double* rec, double* __restrict__ scratch, unsigned* __restrict__ tickets, int commit,
+                    int maxiter) {
+    const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
+    if (s.stop[b]) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int i = blk * kFinWarps + warp;                  // this warp's particle
+    __shared__ double sf[kFinWarps];
+    __shared__ int si[kFinWarps];
+    __shared__ int s_last;
+    double cf = CUDART_INF;
+    int ci = 0x7fffffff;
+    if (i < s.S) {
+        const size_t bs = (size_t)b * s.S + i;
+        const double* p = partials + bs * n_tiles * nsum;
+        double sv = 0.0, sim = 0.0;
+        for (int t0 = 0; t0 < n_tiles; t0 += 32) {         // coalesced load, then the same sequential order as
+            const int t = t0 + lane;                       // objective_finalize_kernel (every lane sums all of them)
+            const double a0 = t < n_tiles ? p[t * nsum] : 0.0;
+            const double a1 = (nsum == 2 && t < n_tiles) ? p[t * nsum + 1] : 0.0;
+            const int cnt = min(32, n_tiles - t0);
+            for (int k = 0; k < cnt; ++k) {
+                sv += __shfl_sync(0xffffffffu, a0, k);
+                if (nsum == 2) sim += __shfl_sync(0xffffffffu, a1, k);
+            }
+        }
+        double fx = sqrt(sv / (double)N);
+        if (nsum == 2) fx = (fx + sqrt(sim / (double)N)) / 2.0;
+        double fp = s.fp[bs];
+        if (fx < fp) {
+            fp = fx;
+            for (int d = lane; d < s.D; d += 32) s.p[bs * s.D + d] = s.x[bs * s.D + d];
+        }
+        if (lane == 0) { s.fx[bs] = fx; s.fp[bs] = fp; }
+        cf = fp;
+        ci = i;
+    }
+    if (lane == 0) { sf[warp] = cf; si[warp] = ci; }
+    __syncthreads();
+    if (tid == 0) {
+        double bf = CUDART_INF;
+        int bi = 0x7fffffff;
+        for (int k = 0; k < kFinWarps; ++k)
+            if (sf[k] < bf || (sf[k] == bf && si[k] < bi)) { bf = sf[k]; bi = si[k]; }
+        double* sc = scratch + ((size_t)b * nblk + blk) * 2;
+        sc[0] = bf;
+        sc[1] = (double)bi;
+        __threadfence();                                   // candidate and the p rows above are visible before the ticket
+        const unsigned t = atomicAdd(tickets + b, 1u);
+        s_last = t == (unsigned)nblk - 1u;
+        if (s_last) tickets[b] = 0u;                       // ready for the next launch
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // the last CTA of this spectrum: argmin over the CTA candidates, first index wins (np.argmin)
+    double bf = CUDART_INF;
+    int bi = 0x7fffffff;
+    for (int k = tid; k < nblk; k += kFinWarps * 32) {
+        const double* sc = scratch + ((size_t)b * nblk + k) * 2;
+        const double of = __ldcg(sc);
+        const int oi = (int)__ldcg(sc + 1);
+        if (of < bf || (of == bf && oi < bi)) { bf = of; bi = oi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const double of = __shfl_xor_sync(0xffffffffu, bf, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (of < bf || (of == bf && oi < bi)) { bf = of; bi = oi; }
+    }
+    __syncthreads();                                       // sf/si are reused
+    if (lane == 0) { sf[warp] = bf; si[warp] = bi; }
+    __syncthreads();
+    bf = sf[0]; bi = si[0];
+    for (int k = 1; k < kFinWarps; ++k)
+        if (sf[k] < bf || (sf[k] == bf && si[k] < bi)) { bf = sf[k]; bi = si[k]; }
+    int best = bi;
+    const double* src = s.p;
+    if (best == 0x7fffffff) { best = 0; src = s.x; }       // nothing finite yet: pyswarm falls back to x[0]
+    double* r = rec + (size_t)b * (s.D + 2);
+    if (tid == 0) { r[0] = bf; r[1] = (double)(s.index0 + best); }
+    for (int d = tid; d < s.D; d += kFinWarps * 32) r[2 + d] = __ldcg(src + ((size_t)b * s.S + best) * s.D + d);
+    if (!commit) return;
+    __syncthreads();                                       // the record is complete (same CTA wrote it)
+    commit_spectrum(s, rec, 1, 0, maxiter, b, tid, kFinWarps * 32);
 }
 
 static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }
@@ -203,6 +304,16 @@ cudaError_t launch_swarm_local_best(const SwarmState& s, double* rec, cudaStream
     swarm_pbest_kernel<<<blocks_for(total, 256), 256, 0, st>>>(s);
     swarm_local_best_kernel<<<s.B, 256, 0, st>>>(s, rec);
     count_launches(2);
+    return cudaGetLastError();
+}
+
+size_t swarm_finish_scratch_doubles(int B, int S) { return (size_t)B * ((S + kFinWarps - 1) / kFinWarps) * 2; }
+
+cudaError_t launch_swarm_finish(const SwarmState& s, const double* partials, int n_tiles, int nsum, int N, double* rec,
+                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st) {
+    dim3 grid((s.S + kFinWarps - 1) / kFinWarps, s.B);
+    swarm_finish_kernel<<<grid, kFinWarps * 32, 0, st>>>(s, partials, n_tiles, nsum, N, rec, scratch, tickets, commit, maxiter);
+    count_launches(1);
     return cudaGetLastError();
 }
 

@@ -351,11 +351,15 @@ static cudaError_t plan_one(const FusedArgs& a, int D, int grid, int device, Fus
     return cudaSuccess;
 }
 
-cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjTune& t, int device, FusedPlan* plan) {
+cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjTune& t, int device, bool force,
+                             FusedPlan* plan) {
     plan->ok = false;
     if (t.tb != 6 || (t.r != 4 && t.r != 8) || (t.threads != 128 && t.threads != 256)) return cudaSuccess;
     const long long grid = (long long)B * S;
     if (grid > 4096) return cudaSuccess;
+    // One CTA walks its particle's whole axis: past ~8k points (32 regions) the three-launch per-step path, which
+    // spreads the tiles of a particle over many CTAs, is faster (measured: profiles/r01k_fused_probe.json)
+    if (!force && a.n_vtiles * a.vw > 32) return cudaSuccess;
     int sms = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
