@@ -176,6 +176,9 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip()))
 
+    def count(self, t0, t1):
+        return sum(1 for t, _ in list(self.rows) if t0 <= t <= t1)
+
     def stop(self, t0, t1):
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
@@ -299,7 +302,19 @@ def run_b200(args):
     launches = _cabi.launch_count() - launches0
     kernel_ms, kernel_launches = ctx.profile_read()
     ctx.profile(False)
-    clocks = sampler.stop(t0, t1)
+    # nvidia-smi samples every 50 ms; a short timed region can fall between two samples.  Then the same steps keep
+    # running (untimed) until a few samples exist, and the clocks line says so.
+    extended = 0.0
+    if sampler.count(t0, t1) < 3:
+        while time.perf_counter() - t1 < 0.5 and sampler.count(t0, time.perf_counter()) < 4:
+            for _ in range(8):
+                step()
+            torch.cuda.synchronize()
+        extended = time.perf_counter() - t1
+    clocks = sampler.stop(t0, t1 + extended)
+    if extended:
+        clocks['note'] = ('timed region %.0f ms is shorter than the sampling period allows: the same steps ran on, '
+                          'untimed, for %.0f ms more while sampling' % (1e3 * (t1 - t0), 1e3 * extended))
     step_ms = np.array([a.elapsed_time(b) for a, b in ev])
     total_ms = torch.tensor([float(step_ms.sum())], dtype=torch.float64, device='cuda')
     if world > 1:

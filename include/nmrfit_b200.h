@@ -190,6 +190,20 @@ int nmrfit_generate_result_host(int device, const double* params, int n_peaks, c
                                 double* imag, double* V, double* I, double* u, double* v);
 
 /* ---- measurement ------------------------------------------------------------------------------ */
+/* ---- phase estimation before the fit: Data.shift_phase(method='brute' | 'auto') (containers.py:51-78) for a batch
+ * of spectra.  The handle keeps device copies of u, v ([n_spectra][n_points], host or device source). */
+typedef struct nmrfit_phase nmrfit_phase;
+int nmrfit_phase_create(nmrfit_phase** out, int device, int n_spectra, int n_points, const double* u, const double* v);
+void nmrfit_phase_destroy(nmrfit_phase* h);
+/* Data._brute_phase (containers.py:98-110): p0_candidates [K] = np.arange(-pi, pi, step); best_p0 [n_spectra] (0 when
+ * no candidate points upwards, as in the reference); optional best_err [n_spectra], err [n_spectra][K], ok
+ * [n_spectra][K].  All host pointers. */
+int nmrfit_phase_brute(nmrfit_phase* h, const double* p0_candidates, int K, double* best_p0, double* best_err,
+                       double* err, int* ok);
+/* _ps_acme_score (proc_autophase.py:142-187) for K candidates ph [K][2] = (p0, p1) in RADIANS (the reference's ps()
+ * converts its degree arguments first, proc_autophase.py:60-62) -> score [n_spectra][K].  Host pointers. */
+int nmrfit_phase_acme(nmrfit_phase* h, const double* ph, int K, double* score);
+
 /* DFMA throughput of the device (TFLOP/s): best single launch and back-to-back average. */
 int nmrfit_fp64_peak(int device, int iters, int repeats, double* burst_tflops, double* sustained_tflops);
 /* Kernels launched by this library in this process since load (for bench.py's gpu_launches). */

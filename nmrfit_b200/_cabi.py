@@ -75,6 +75,10 @@ SIGNATURES = {
     'nmrfit_kk_host': (_i, [_i, _vp, _i, _d, _d, _d, _d, _d, _vp]),
     'nmrfit_generate_result': (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     'nmrfit_generate_result_host': (_i, [_i, _vp, _i, _vp, _i, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'nmrfit_phase_create': (_i, [ctypes.POINTER(_vp), _i, _i, _i, _vp, _vp]),
+    'nmrfit_phase_destroy': (None, [_vp]),
+    'nmrfit_phase_brute': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    'nmrfit_phase_acme': (_i, [_vp, _vp, _i, _vp]),
     'nmrfit_fp64_peak': (_i, [_i, _i, _i, c_double_p, c_double_p]),
     'nmrfit_launch_count': (ctypes.c_longlong, []),
 }
@@ -306,6 +310,50 @@ class Context:
                    fx=np.empty((self.B, S)), fp=np.empty((self.B, S)))
         check(lib().nmrfit_pso_get_state(self._h, *[ptr(out[k]) for k in ('x', 'v', 'p', 'fx', 'fp')]))
         return out
+
+
+class PhaseScorer:
+    """Device copies of a batch of spectra (u, v: [B, N] or [N]) for phase estimation (csrc/phase.cu)."""
+
+    def __init__(self, u, v, device=None):
+        u, v = as_f64(np.atleast_2d(u)), as_f64(np.atleast_2d(v))
+        if u.shape != v.shape or u.ndim != 2:
+            raise ValueError('u and v must have the same [B, N] shape')
+        self.B, self.N = u.shape
+        self._h = ctypes.c_void_p()
+        dev = default_device() if device is None else int(device)
+        check(lib().nmrfit_phase_create(ctypes.byref(self._h), dev, self.B, self.N, ptr(u), ptr(v)))
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            lib().nmrfit_phase_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def brute(self, candidates, details=False):
+        """First smallest baseline error among the upward candidates, per spectrum (containers.py:98-110)."""
+        c = as_f64(candidates)
+        best, berr = np.empty(self.B), np.empty(self.B)
+        err = np.empty((self.B, c.size)) if details else None
+        ok = np.empty((self.B, c.size), dtype=np.int32) if details else None
+        check(lib().nmrfit_phase_brute(self._h, ptr(c), c.size, ptr(best), ptr(berr), ptr(err), ptr(ok)))
+        return (best, berr, err, ok.astype(bool)) if details else best
+
+    def acme(self, ph_radians):
+        """ACME score [B, K] for candidates [(p0, p1), ...] in radians (proc_autophase.py:142-187)."""
+        ph = as_f64(np.atleast_2d(ph_radians))
+        if ph.shape[1] != 2:
+            raise ValueError('ph must be [K, 2]')
+        score = np.empty((self.B, ph.shape[0]))
+        check(lib().nmrfit_phase_acme(self._h, ptr(ph), ph.shape[0], ptr(score)))
+        return score
 
 
 # ---- context pool ---------------------------------------------------------------------------------

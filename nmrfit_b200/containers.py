@@ -3,11 +3,10 @@ that the fit path consumes (containers.py:8-252): ``w, u, v, V, I, p0, p1, peaks
 roibounds``; ``shift_phase(method='manual', p0=, p1=)``; ``select_bounds(low, high)``;
 ``generate_solution_bounds``; ``approximate_areas``; ``approximate_area_fraction``.
 
-The reference's preprocessing heuristics that run once per spectrum before the fit -
-automatic/brute-force phase estimation (containers.py:71-74, 98-110) and interactive
-or automatic peak picking (containers.py:132-173) - are outside the accelerated path
-(SURVEY.md section 2, rows 6-8); they raise NotImplementedError here and peaks are attached
-with ``set_peaks``.
+Phase estimation (``shift_phase(method='auto'|'brute')``, containers.py:71-74, 98-110) runs on
+the GPU (csrc/phase.cu).  Interactive or automatic peak picking (containers.py:132-173) is
+outside the accelerated path: it raises NotImplementedError
+here and peaks are attached with ``set_peaks``.
 """
 import numpy as np
 
@@ -27,13 +26,19 @@ class Data:
         if method.lower() == 'manual':
             self.p0 = p0
             self.p1 = p1
-        elif method.lower() in ('auto', 'brute'):
-            raise NotImplementedError(
-                "shift_phase(method=%r) is one-shot preprocessing outside the accelerated path; "
-                "estimate the phase with the reference package and pass method='manual'" % method)
+        elif method.lower() == 'auto':
+            self.p0, self.p1 = proc_autophase.approximate_phase(self.u + 1j * self.v, 'acme')
+        elif method.lower() == 'brute':
+            self.p0, self.p1 = self._brute_phase(step=step)
         else:
             raise ValueError("Method must be 'auto', 'brute', or 'manual'.")
         self.V, self.I = proc_autophase.ps2(self.u, self.v, self.p0, self.p1)
+
+    def _brute_phase(self, step=np.pi / 360):
+        """Exhaustive zero-order scan (containers.py:98-110), every candidate in one launch.  Like the
+        reference it leaves ``V, I`` phased by the LAST candidate until ``shift_phase`` recomputes them."""
+        p0 = float(proc_autophase.brute_phase_batch(self.u[None], self.v[None], step)[0])
+        return p0, 0.0
 
     def select_bounds(self, low=None, high=None):
         """Keep the points with low < w < high (strict, as utils.py:433)."""

@@ -100,6 +100,12 @@ struct nmrfit_ctx {
     size_t prof_used = 0;
 };
 
+struct nmrfit_phase {
+    int device = 0, B = 0, N = 0;
+    DevBuf<double> u, v, cands, out;   // spectra [B][N] x 2; candidates; err/score [B][K] + best [2][B]
+    DevBuf<int> ok;
+};
+
 namespace {
 
 // Is the axis uniform?  h = (w_last - w_0)/(N-1); every stored w_i within 4 ulp of w_0 + i*h.
@@ -802,6 +808,74 @@ int nmrfit_generate_result_host(int device, const double* params, int P, const d
     CK(cudaMemcpy(I, dI, sizeof(double) * n, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(u, du, sizeof(double) * n, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(v, dv, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
+}
+
+// ---- phase estimation ----------------------------------------------------------------------------
+
+int nmrfit_phase_create(nmrfit_phase** out, int device, int n_spectra, int n_points, const double* u, const double* v) {
+    if (!out) return fail(NMRFIT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_spectra < 1 || n_points < 2 || !u || !v) return fail(NMRFIT_ERR_ARG, "bad phase arguments");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(NMRFIT_ERR_ARG, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    nmrfit_phase* h = new (std::nothrow) nmrfit_phase();
+    if (!h) return fail(NMRFIT_ERR_NOMEM, "out of host memory");
+    h->device = device; h->B = n_spectra; h->N = n_points;
+    const size_t n = (size_t)n_spectra * n_points;
+    cudaError_t e = h->u.reserve(n);
+    if (e == cudaSuccess) e = h->v.reserve(n);
+    if (e == cudaSuccess) e = cudaMemcpy(h->u.ptr, u, sizeof(double) * n, cudaMemcpyDefault);
+    if (e == cudaSuccess) e = cudaMemcpy(h->v.ptr, v, sizeof(double) * n, cudaMemcpyDefault);
+    if (e != cudaSuccess) {
+        nmrfit_phase_destroy(h);
+        return fail_cuda(e, "phase allocation");
+    }
+    *out = h;
+    return NMRFIT_OK;
+}
+
+void nmrfit_phase_destroy(nmrfit_phase* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    h->u.release(); h->v.release(); h->cands.release(); h->out.release(); h->ok.release();
+    delete h;
+}
+
+int nmrfit_phase_brute(nmrfit_phase* h, const double* p0_candidates, int K, double* best_p0, double* best_err,
+                       double* err, int* ok) {
+    if (!h) return fail(NMRFIT_ERR_ARG, "handle is NULL");
+    if (!p0_candidates || K < 1 || !best_p0) return fail(NMRFIT_ERR_ARG, "bad brute-phase arguments");
+    CK(cudaSetDevice(h->device));
+    const size_t BK = (size_t)h->B * K;
+    CK(h->cands.reserve(K));
+    CK(h->out.reserve(BK + 2 * (size_t)h->B));
+    CK(h->ok.reserve(BK));
+    CK(cudaMemcpy(h->cands.ptr, p0_candidates, sizeof(double) * K, cudaMemcpyDefault));
+    double* d_best = h->out.ptr + BK;
+    cudaError_t e = launch_phase_brute(h->u.ptr, h->v.ptr, h->B, h->N, h->cands.ptr, K, h->out.ptr, h->ok.ptr, d_best,
+                                       d_best + h->B, nullptr);
+    if (e != cudaSuccess) return fail_cuda(e, "brute phase launch");
+    CK(cudaMemcpy(best_p0, d_best, sizeof(double) * h->B, cudaMemcpyDeviceToHost));
+    if (best_err) CK(cudaMemcpy(best_err, d_best + h->B, sizeof(double) * h->B, cudaMemcpyDeviceToHost));
+    if (err) CK(cudaMemcpy(err, h->out.ptr, sizeof(double) * BK, cudaMemcpyDeviceToHost));
+    if (ok) CK(cudaMemcpy(ok, h->ok.ptr, sizeof(int) * BK, cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
+}
+
+int nmrfit_phase_acme(nmrfit_phase* h, const double* ph, int K, double* score) {
+    if (!h) return fail(NMRFIT_ERR_ARG, "handle is NULL");
+    if (!ph || K < 1 || !score) return fail(NMRFIT_ERR_ARG, "bad ACME arguments");
+    CK(cudaSetDevice(h->device));
+    const size_t BK = (size_t)h->B * K;
+    CK(h->cands.reserve(2 * (size_t)K));
+    CK(h->out.reserve(BK));
+    CK(cudaMemcpy(h->cands.ptr, ph, sizeof(double) * 2 * K, cudaMemcpyDefault));
+    cudaError_t e = launch_phase_acme(h->u.ptr, h->v.ptr, h->B, h->N, h->cands.ptr, K, h->out.ptr, nullptr);
+    if (e != cudaSuccess) return fail_cuda(e, "ACME launch");
+    CK(cudaMemcpy(score, h->out.ptr, sizeof(double) * BK, cudaMemcpyDeviceToHost));
     return NMRFIT_OK;
 }
 

@@ -132,6 +132,12 @@ cudaError_t launch_swarm_fused(FusedArgs a, const FusedPlan& plan, int B, int S,
 cudaError_t launch_weights(double* spec, double* scratch, const double* bounds_dev, const double* values_dev, int B,
                            int N, int n_windows, int sweeps, double omega, cudaStream_t st);
 
+// ---- K9 phase estimation (phase.cu) --------------------------------------------------
+cudaError_t launch_phase_brute(const double* u, const double* v, int B, int N, const double* cands_dev, int K,
+                               double* err, int* ok, double* best_p0, double* best_err, cudaStream_t st);
+cudaError_t launch_phase_acme(const double* u, const double* v, int B, int N, const double* ph_dev, int K, double* score,
+                              cudaStream_t st);
+
 // ---- K4/K5 curves -------------------------------------------------------------
 cudaError_t launch_ps2(const double* u, const double* v, int n, double p0, double p1, int inv, double* re, double* im,
                        cudaStream_t st);

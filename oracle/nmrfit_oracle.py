@@ -39,6 +39,77 @@ def ps2(u, v, p0=0.0, p1=0.0, inv=False):
     return z.real, z.imag
 
 
+def ps(data, p0=0.0, p1=0.0, inv=False):
+    """Phase rotation of a complex spectrum with (p0, p1) in DEGREES (proc_autophase.py:39-68)."""
+    pi = np.pi
+    p0 = p0 * pi / 180.
+    p1 = p1 * pi / 180.
+    size = data.shape[-1]
+    apod = np.exp(1.0j * (p0 + (p1 * np.arange(size) / size))).astype(data.dtype)
+    if inv:
+        apod = 1 / apod
+    return apod * data
+
+
+# --------------------------------------------------------------------------
+# phase estimation before the fit  (SURVEY 8(f) row 3)
+# --------------------------------------------------------------------------
+def brute_phase(u, v, step=np.pi / 360):
+    """Zero-order phase by exhaustive scan (containers.py:98-110): the candidate whose phased real part has the
+    most level baseline (first-n mean vs last-n mean) among those that point upwards.  Returns (p0, 0.0)."""
+    p0_best = 0
+    best = np.inf
+    n = max(1, int(len(u) / 5000))
+    for p0 in np.arange(-np.pi, np.pi, step):
+        V, _ = ps2(u, v, p0, 0.0)
+        error = np.sqrt((V[:n].mean() - V[-n:].mean())**2)
+        if error < best and np.max(V) > abs(np.min(V)):
+            best = error
+            p0_best = p0
+    return p0_best, 0.0
+
+
+def brute_phase_errors(u, v, step=np.pi / 360):
+    """The scan's per-candidate (p0, error, upward) triples - what the device kernel is compared with."""
+    n = max(1, int(len(u) / 5000))
+    cands = np.arange(-np.pi, np.pi, step)
+    err = np.empty(cands.size)
+    ok = np.empty(cands.size, dtype=bool)
+    for k, p0 in enumerate(cands):
+        V, _ = ps2(u, v, p0, 0.0)
+        err[k] = np.sqrt((V[:n].mean() - V[-n:].mean())**2)
+        ok[k] = np.max(V) > abs(np.min(V))
+    return cands, err, ok
+
+
+def acme_score(ph, data):
+    """ACME phase score, (p0, p1) in degrees (proc_autophase.py:142-187): entropy of the normalised first
+    derivative of the phased real part + 1000 x the squared negative excursions."""
+    stepsize = 1
+    phc0, phc1 = ph
+    s0 = ps(data, p0=phc0, p1=phc1)
+    data = np.real(s0)
+    ds1 = np.abs((data[1:] - data[:-1]) / (stepsize * 2))
+    p1 = ds1 / np.sum(ds1)
+    p1[p1 == 0] = 1
+    h1 = -p1 * np.log(p1)
+    h1s = np.sum(h1)
+    pfun = 0.0
+    as_ = data - np.abs(data)
+    sumas = np.sum(as_)
+    if sumas < 0:
+        pfun = pfun + np.sum((as_ / 2) ** 2)
+    p = 1000 * pfun
+    return h1s + p
+
+
+def approximate_phase(data, score=acme_score, p0=0.0, p1=0.0):
+    """Nelder-Mead on the phase score, result converted degrees -> radians (proc_autophase.py:107-139)."""
+    import scipy.optimize
+    opt = scipy.optimize.fmin(score, x0=[p0, p1], args=(data, ), disp=False)
+    return opt[0] * np.pi / 180, opt[1] * np.pi / 180
+
+
 # --------------------------------------------------------------------------
 # lineshape  (reference: nmrfit/equations.py:115-149, ``voigt``)
 # --------------------------------------------------------------------------

@@ -169,6 +169,26 @@ def main():
     out['generate_result_40x6']['area_fraction_true'] = fu.calculate_area_fraction()
     out['generate_result_40x6']['areas_true'] = fu.get_areas()
 
+    # ---- phase estimation before the fit: brute scan and ACME score / Nelder-Mead (reference Data.shift_phase) ----
+    ph_cases = {}
+    for tag, N, P, seed, p0t, p1t in (('a', 4096, 6, 41, 0.25, 0.05), ('b', 1500, 6, 42, -1.3, 0.0), ('c', 12000, 12, 43, 2.9, -0.2)):
+        data, true = synth.multiplet(N, P, seed=seed)
+        # move the spectrum's phase from synth's (0.25, 0.05) to (p0t, p1t)
+        data.u, data.v = orc.ps2(data.u, data.v, p0t - true[0], p1t - true[1], inv=True)
+        rd = ref.containers.Data(data.w.copy(), data.u.copy(), data.v.copy())
+        p0b, p1b = rd._brute_phase()
+        note('brute_phase', orc.brute_phase(data.u, data.v)[0], p0b)
+        z = data.u + 1j * data.v
+        phs = np.array([(0.0, 0.0), (p0t * 180 / np.pi, p1t * 180 / np.pi), (35.0, -10.0), (-120.0, 60.0), (179.0, 2.5)])
+        sc = np.array([pa._ps_acme_score(ph_, z) for ph_ in phs])
+        note('acme_score', [orc.acme_score(ph_, z) for ph_ in phs], sc)
+        auto = pa.approximate_phase(z, 'acme')
+        note('approximate_phase', orc.approximate_phase(z), auto)
+        ph_cases.update({'u_' + tag: data.u, 'v_' + tag: data.v, 'brute_' + tag: np.array([p0b, p1b]),
+                         'acme_ph_' + tag: phs, 'acme_score_' + tag: sc, 'auto_' + tag: np.array(auto),
+                         'true_' + tag: np.array([p0t, p1t])})
+    out['phase'] = ph_cases
+
     # ---- end-to-end fits through reference core.fit + restated pso, legacy RNG seeded -------------
     for name, N, P, S, maxiter, seed in (('fit_lite_1024x6', 1024, 6, 24, 12, 0), ('fit_c1_4096x6', 4096, 6, 100, 100, 0),
                                          ('fit_default_2048x6', 2048, 6, 204, 2000, 4)):

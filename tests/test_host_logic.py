@@ -71,8 +71,6 @@ def test_data_contract():
     n0 = d.w.size
     d.select_bounds(3.3, 3.5)
     assert d.w.min() > 3.3 and d.w.max() < 3.5 and d.w.size < n0 and d.u.size == d.w.size
-    with pytest.raises(NotImplementedError):
-        d.shift_phase('auto')
     with pytest.raises(ValueError):
         d.shift_phase('nonsense')
     with pytest.raises(NotImplementedError):

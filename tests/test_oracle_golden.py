@@ -143,3 +143,15 @@ def test_pso_argument_checks_and_stops():
     x, f, info = pso_oracle.pso(lambda x: float(np.sum(x * x)), [-1, -1], [1, 1], swarmsize=30, maxiter=500,
                                 omega=0.5, phip=0.5, phig=0.5, rng=rng, quiet=True)
     assert info['stop'] in (pso_oracle.STOP_MINFUNC, pso_oracle.STOP_MINSTEP) and info['it'] < 500
+
+
+@pytest.mark.parametrize('tag', 'abc')
+def test_phase_estimation_oracle_matches_reference(tag):
+    """brute scan, ACME score and the Nelder-Mead phase against the reference's outputs (phase.npz)."""
+    g = load_golden('phase')
+    u, v = g['u_' + tag], g['v_' + tag]
+    assert orc.brute_phase(u, v)[0] == g['brute_' + tag][0]
+    z = u + 1j * v
+    assert np.array_equal([orc.acme_score(ph, z) for ph in g['acme_ph_' + tag]], g['acme_score_' + tag])
+    assert np.array_equal(orc.approximate_phase(z), g['auto_' + tag])
+    assert abs(g['brute_' + tag][0] - g['true_' + tag][0]) < 0.15     # and the estimate is near the truth
