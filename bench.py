@@ -304,12 +304,17 @@ def run_b200(args):
     ctx.profile(False)
     # nvidia-smi samples every 50 ms; a short timed region can fall between two samples.  Then the same steps keep
     # running (untimed) until a few samples exist, and the clocks line says so.
-    extended = 0.0
-    if sampler.count(t0, t1) < 3:
-        while time.perf_counter() - t1 < 0.5 and sampler.count(t0, time.perf_counter()) < 4:
-            for _ in range(8):
-                step()
-            torch.cuda.synchronize()
+    extended, extra_steps = 0.0, 0
+    plan = torch.tensor([0], dtype=torch.int64, device='cuda')
+    if rank == 0 and sampler.count(t0, t1) < 2:            # rank 0 decides, every rank runs the same number of steps
+        plan[0] = int(min(4000, max(8, 0.35 * args.steps / max(t1 - t0, 1e-6))))
+    if world > 1:
+        dist.broadcast(plan, 0)
+    extra_steps = int(plan.item())
+    if extra_steps:
+        for _ in range(extra_steps):
+            step()
+        sync_all()
         extended = time.perf_counter() - t1
     clocks = sampler.stop(t0, t1 + extended)
     if extended:
@@ -323,7 +328,7 @@ def run_b200(args):
     value = S * B * world * args.steps / (total_ms * 1e-3)
 
     x, f, it, stop = ctx.pso_best()
-    assert np.all(it == args.warmup + args.steps) and np.all(np.isfinite(f)) and np.all(stop == 0)
+    assert np.all(it == args.warmup + args.steps + extra_steps) and np.all(np.isfinite(f)) and np.all(stop == 0)
 
     # ---- end to end through the public host-buffer API
     from nmrfit_b200 import synth

@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, 'csrc', 'libnmrfit_b200.so')
+LIB_PATH = os.environ.get('NMRFIT_B200_LIB') or os.path.join(_HERE, 'csrc', 'libnmrfit_b200.so')
 
 OK = 0
 FP64, FP32 = 0, 1

@@ -111,7 +111,7 @@ objective_move_prepare_kernel(ObjArgs a, MoveArgs mv) {
 // ---- pass 2: evaluation ------------------------------------------------------------------------------
 // shared-memory carve-up (in doubles), shared by kernel and launcher; every offset is even (16-byte alignment)
 struct UniSmem {
-    int tab, uv, wt, bar, wpart, coef, part, far, anchor, mask, mw, total;
+    int tab, uv, wt, wf, bar, wpart, coef, part, far, anchor, mask, mw, total;
     __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB) {
         const int nw = threads / 32;
         mw = (P + 31) / 32;                               // near-peak mask words per region, + 1 has-far word
@@ -119,6 +119,7 @@ struct UniSmem {
         tab = o;    o += TB ? (1 << TB) : 0;
         uv = o;     o += threads * R * 2;
         wt = o;     o += threads * R;
+        wf = o;     o += threads;                         // abscissa of every thread's first point
         bar = o;    o += 2;                               // one mbarrier
         wpart = o;  o += sp * nw;
         coef = o;   o += sp * P * 8;
@@ -145,6 +146,7 @@ objective_uniform_kernel(ObjArgs a) {
     double* tab = smem + L.tab;
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
     double* swt = smem + L.wt;
+    double* swf = smem + L.wf;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
     double* wpart = smem + L.wpart;
     const double* coef = smem + L.coef;
@@ -178,16 +180,18 @@ objective_uniform_kernel(ObjArgs a) {
         }
     }
 
-    // ---- meanwhile stage the tile: coalesced reads, [j][thread] placement (point tile0 + t*R + j -> slot j*THREADS + t)
+    // ---- meanwhile stage the tile: coalesced reads, swizzled [j][thread] placement (uniform_eval.cuh)
     for (int e = tid; e < THREADS * R; e += THREADS) {
         const int i = tile0 + e;
         const bool ok = i < N;
-        const int slot = (e % R) * THREADS + e / R;
-        suv[slot] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
-        swt[slot] = ok ? sw[3 * N + i] : 0.0;              // zero weight: padding contributes nothing
+        const int t = e / R, j = e % R;
+        suv[stage_slot_uv(t, j, THREADS)] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
+        swt[stage_slot_wt(t, j, THREADS)] = ok ? sw[3 * N + i] : 0.0;      // zero weight: padding contributes nothing
     }
-    const int i_first = tile0 + tid * R;                   // this thread's first point
-    const double w_first = i_first < N ? sw[i_first] : fma((double)i_first, h, sw[0]);
+    {
+        const int i_first = tile0 + tid * R;               // first point of thread slot `tid`
+        swf[tid] = i_first < N ? sw[i_first] : fma((double)i_first, h, sw[0]);
+    }
     if (TB) {
         const double* src = ExpTabU<TB>::src();
         for (int i = tid; i < (1 << TB); i += THREADS) tab[i] = src[i];
@@ -196,12 +200,18 @@ objective_uniform_kernel(ObjArgs a) {
     __syncthreads();                                       // tile, table and the mbarrier initialisation are visible
     mbar_wait(bar, 0);                                     // the constants have landed
 
+    // A region's cost depends on how many peaks are near it - the same regions for every particle - so each warp
+    // walks the tile's regions round robin, one particle each, instead of owning one: the warps of a CTA finish
+    // together (ncu before: 8 % of the stall samples sat at the final barrier / EXIT).
     for (int sp = 0; sp < nsp; ++sp) {
+        const int rw = (warp + sp) & (NW - 1);             // the region this warp evaluates for particle sp
+        const int t = rw * 32 + lane;
+        const int i_first = tile0 + t * R;
         const double ss = eval_region<R, TB>(
-            coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + warp) * (MW + 1),
-            farc + (size_t)(sp * NW + warp) * kFarTerms, anchor[sp * NW + warp], MW, P, lane, w_first, xi0, suv + tid,
-            swt + tid, THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp);
-        if (lane == 0) wpart[sp * NW + warp] = ss;
+            coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + rw) * (MW + 1),
+            farc + (size_t)(sp * NW + rw) * kFarTerms, anchor[sp * NW + rw], MW, P, lane, swf[t], xi0, suv, swt, t,
+            THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp);
+        if (lane == 0) wpart[sp * NW + rw] = ss;
     }
     __syncthreads();
     if (tid < nsp) {

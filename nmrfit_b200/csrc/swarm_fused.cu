@@ -141,9 +141,9 @@ swarm_fused_kernel(FusedArgs a) {
         for (int e = tid; e < THREADS * R; e += THREADS) {
             const int i = base + e;
             const bool ok = i < N;
-            const int o = slot * THREADS * R + (e % R) * THREADS + e / R;
-            suv[o] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
-            swt[o] = ok ? sw[3 * N + i] : 0.0;             // zero weight: padding contributes nothing
+            const int t = e / R, j = e % R, o = slot * THREADS * R;
+            suv[o + stage_slot_uv(t, j, THREADS)] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
+            swt[o + stage_slot_wt(t, j, THREADS)] = ok ? sw[3 * N + i] : 0.0;      // zero weight: padding adds nothing
         }
     };
     if (resident)
@@ -187,8 +187,8 @@ swarm_fused_kernel(FusedArgs a) {
                 const double w_first = i_first < N ? __ldg(sw + i_first) : fma((double)i_first, h, __ldg(sw));
                 const double2 ew = *reinterpret_cast<const double2*>(anchor + 2 * rgn);
                 const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rgn * (MW + 1), farc + (size_t)rgn * kFarTerms,
-                                                     ew, MW, P, lane, w_first, xi0, suv + slot * THREADS * R + tid,
-                                                     swt + slot * THREADS * R + tid, THREADS, tab, xs, sw + i_first,
+                                                     ew, MW, P, lane, w_first, xi0, suv + slot * THREADS * R,
+                                                     swt + slot * THREADS * R, tid, THREADS, tab, xs, sw + i_first,
                                                      N - i_first, h, w_ulp);
                 if (lane == 0) wpart[rgn] = ss;
             }

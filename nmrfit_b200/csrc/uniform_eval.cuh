@@ -90,16 +90,24 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
     }
 }
 
+// Shared-memory placement of a tile's staged points.  Point e of the tile (thread t = e / R, j = e % R) lives in
+// row j at column t ^ j (double2 (u, v) array) resp. t ^ 2j (weights array): the evaluation reads row j with
+// consecutive t (a permutation inside each aligned group of 16 columns: conflict-free), and the staging loop,
+// whose consecutive lanes hold consecutive e - eight different rows of the same column - spreads over eight
+// different banks instead of colliding 8-way (ncu before: 18.3 M of 66.6 M shared wavefronts were such conflicts).
+__device__ __forceinline__ int stage_slot_uv(int t, int j, int stride) { return j * stride + (t ^ j); }
+__device__ __forceinline__ int stage_slot_wt(int t, int j, int stride) { return j * stride + (t ^ (2 * j)); }
+
 // One warp, one particle, one region: sum over the warp's 32*R points of (weights * (V_data - V_fit))^2, identical
 // in every lane on return.  cf [P][8], pt [kPartDoubles], mk [MW+1], fc [kFarTerms] (16-byte aligned) and ew are the
-// particle's constants for this region; the thread's R points sit at suv_t[j*stride], swt_t[j*stride];
-// w_first is the abscissa of its first point and xi0 that point's position inside the region.  The exact path
+// particle's constants for this region; the R points of thread t of the tile sit at stage_slot_uv/wt(t, j, stride) of
+// suv / swt; w_first is the abscissa of its first point and xi0 that point's position inside the region.  The exact path
 // (peaks too narrow for the recurrences) reads the particle's parameters xs and the stored abscissae sw_first[0..n_valid).
 template <int R, int TB>
 __device__ __forceinline__ double eval_region(const double* __restrict__ cf, const double* __restrict__ pt,
                                               const unsigned* __restrict__ mk, const double* __restrict__ fc,
                                               const double2 ew, int MW, int P, int lane, double w_first, double xi0,
-                                              const double2* __restrict__ suv_t, const double* __restrict__ swt_t,
+                                              const double2* __restrict__ suv, const double* __restrict__ swt, int t,
                                               int stride, const double* __restrict__ tab,
                                               const double* __restrict__ xs, const double* __restrict__ sw_first,
                                               int n_valid, double h, double w_ulp) {
@@ -143,8 +151,8 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
     double ss = 0.0;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        const double2 uv = suv_t[j * stride];
-        const double wt = swt_t[j * stride];
+        const double2 uv = suv[stage_slot_uv(t, j, stride)];
+        const double wt = swt[stage_slot_wt(t, j, stride)];
         const double vd = fma(uv.x, cr, -fma(uv.y, ci, py));     // V_data - P*yoff
         const double res = wt * (vd - acc[j]);
         ss = fma(res, res, ss);
