@@ -115,6 +115,8 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
         chunk = max(1, int(chunk)) if trace is None else 1
         while done < maxiter:
             n = min(chunk, maxiter - done)
+            if not host and trace is None:
+                chunk = min(2 * chunk, 256)                # device RNG: nothing to rewind, so poll the stop flag less and less often
             if host:
                 state = np.random.get_state()
                 rp, rg = _draw_generations(np.random, n, S, D)
@@ -193,8 +195,11 @@ def _pso_batch_run(ctx, lb, ub, fit_im, swarmsize, maxiter, omega, phip, phig, m
     ctx.pso_begin(lb, ub, opts, r_pos, r_vel)
     ctx.pso_commit()
     done = 0
+    chunk = max(1, int(chunk))
     while done < maxiter:
-        n = min(max(1, int(chunk)), maxiter - done)
+        n = min(chunk, maxiter - done)
+        if not host:
+            chunk = min(2 * chunk, 256)                    # device RNG: poll the stop flags less and less often
         rp = rg = None
         if host:
             rp = np.empty((n, B, S, D))

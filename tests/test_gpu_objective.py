@@ -170,3 +170,25 @@ def test_argument_errors():
             ctx.set_tuning(threads=100)
     with pytest.raises(ValueError):
         equations.objective_batch(np.zeros((3, 5)), np.zeros(8), np.zeros(8), np.zeros(8), np.zeros(8))
+
+
+def test_unchanged_spectrum_is_not_resent_but_a_changed_one_is():
+    """The host shadow of a small context's spectrum: same arrays -> same values; an array modified IN PLACE between
+    two calls must be noticed (byte comparison, not identity)."""
+    data, true = synth.multiplet(1500, 6, seed=8)
+    lo, up = data.generate_solution_bounds()
+    xs = synth.particles(lo, up, 9)
+    wts = utils.compute_weights(data.w, data.peaks)
+    a = equations.objective_batch(xs, data.w, data.u, data.v, wts)
+    b = equations.objective_batch(xs, data.w, data.u, data.v, wts)
+    assert np.array_equal(a, b)
+    u2 = data.u.copy()
+    u2[700] += 0.25
+    c = equations.objective_batch(xs, data.w, u2, data.v, wts)
+    assert relerr(c, orc.objective_swarm(xs, data.w, u2, data.v, wts)) < 1e-11 and not np.array_equal(a, c)
+    u2[700] -= 0.25                                        # same buffer, original content again
+    d = equations.objective_batch(xs, data.w, u2, data.v, wts)
+    assert np.array_equal(a, d)
+    wts[10:20] *= 3.0                                      # in place
+    e = equations.objective_batch(xs, data.w, u2, data.v, wts)
+    assert relerr(e, orc.objective_swarm(xs, data.w, u2, data.v, wts)) < 1e-11
