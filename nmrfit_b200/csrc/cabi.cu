@@ -131,7 +131,9 @@ bool axis_is_uniform(const double* hw, int N, double* grid) {
 // Which objective kernel a launch uses: the uniform-axis kernels (FP64 or FP32) need every spectrum of the
 // batch on a uniform axis and the real-only fit; anything else runs the general kernel of that precision.
 bool use_uniform(const nmrfit_ctx* c, int fit_im) {
-    if (c->algorithm == NMRFIT_ALGO_GENERAL || fit_im != NMRFIT_REAL_ONLY) return false;
+    if (c->algorithm == NMRFIT_ALGO_GENERAL) return false;
+    // real-only fit in both precisions; fit_im with the reference's semantics (last peak's counterpart) in FP64
+    if (fit_im == NMRFIT_IM_SUM || (fit_im == NMRFIT_IM_REFERENCE && c->precision != NMRFIT_FP64)) return false;
     for (char u : c->uniform)
         if (!u) return false;
     return true;
@@ -232,7 +234,7 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
         cudaError_t em = launch_swarm_move(mv->s, mv->rp, mv->rg, mv->generation, st);
         if (em != cudaSuccess) return fail_cuda(em, "swarm move");
     }
-    if (nsum_out) *nsum_out = (c->precision == NMRFIT_FP32 || uni) ? 1 : (fit_im ? 2 : 1);
+    if (nsum_out) *nsum_out = c->precision == NMRFIT_FP32 ? 1 : (fit_im ? 2 : 1);
     cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, uni, st, ev0, ev1, tiles_out)
                     : uni ? launch_objective_uniform(a, t, c->B, f_dev, st, ev0, ev1, move_in_prepare ? mv : nullptr, tiles_out)
                           : launch_objective(a, t, c->B, f_dev, st, ev0, ev1, tiles_out);

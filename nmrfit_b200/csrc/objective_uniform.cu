@@ -121,7 +121,7 @@ struct UniSmem {
         wt = o;     o += threads * R;
         wf = o;     o += threads;                         // abscissa of every thread's first point
         bar = o;    o += 2;                               // one mbarrier
-        wpart = o;  o += sp * nw;
+        wpart = o;  o += sp * nw * 2;                      // x2: the imaginary sums of fit_im
         coef = o;   o += sp * P * 8;
         part = o;   o += sp * kPartDoubles;
         far = o;    o += sp * nw * kFarTerms;             // far-field polynomial per (particle, warp region)
@@ -131,9 +131,10 @@ struct UniSmem {
     }
 };
 
-template <int THREADS, int R, int TB>
+template <int THREADS, int R, int TB, int KK>
 __global__ void __launch_bounds__(THREADS, (R <= 8 ? 768 : 512) / THREADS)    // 24 (16 for R = 16) resident warps per SM
 objective_uniform_kernel(ObjArgs a) {
+    constexpr int NSUM = KK ? 2 : 1;
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) double smem[];
     const int b = blockIdx.z;
@@ -207,23 +208,28 @@ objective_uniform_kernel(ObjArgs a) {
         const int rw = (warp + sp) & (NW - 1);             // the region this warp evaluates for particle sp
         const int t = rw * 32 + lane;
         const int i_first = tile0 + t * R;
-        const double ss = eval_region<R, TB>(
+        double ssi = 0.0;
+        const double ss = eval_region<R, TB, KK>(
             coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + rw) * (MW + 1),
             farc + (size_t)(sp * NW + rw) * kFarTerms, anchor[sp * NW + rw], MW, P, lane, swf[t], xi0, suv, swt, t,
-            THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp);
-        if (lane == 0) wpart[sp * NW + rw] = ss;
+            THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
+        if (lane == 0) {
+            wpart[(sp * NW + rw) * NSUM] = ss;
+            if (KK) wpart[(sp * NW + rw) * NSUM + 1] = ssi;
+        }
     }
     __syncthreads();
-    if (tid < nsp) {
+    for (int idx = tid; idx < nsp * NSUM; idx += THREADS) {
+        const int sp = idx / NSUM, c = idx - sp * NSUM;
         double t = 0.0;
 #pragma unroll
-        for (int wi = 0; wi < NW; ++wi) t += wpart[tid * NW + wi];
-        a.partials[(q0 + tid) * n_tiles + tile] = t;
+        for (int wi = 0; wi < NW; ++wi) t += wpart[(sp * NW + wi) * NSUM + c];
+        a.partials[((q0 + sp) * n_tiles + tile) * NSUM + c] = t;
     }
 }
 
 // ---- launcher -----------------------------------------------------------------
-template <int THREADS, int R, int TB>
+template <int THREADS, int R, int TB, int KK>
 static cudaError_t launch_one(const ObjArgs& a, int B, cudaStream_t st) {
     static bool attr_set[NMRFIT_MAX_DEVICES] = {};
     UniSmem L(a.sp, a.P, THREADS, R, TB);
@@ -231,23 +237,23 @@ static cudaError_t launch_one(const ObjArgs& a, int B, cudaStream_t st) {
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev % NMRFIT_MAX_DEVICES]) {
-        cudaError_t e = cudaFuncSetAttribute(objective_uniform_kernel<THREADS, R, TB>,
+        cudaError_t e = cudaFuncSetAttribute(objective_uniform_kernel<THREADS, R, TB, KK>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev % NMRFIT_MAX_DEVICES] = true;
     }
     dim3 grid((a.S + a.sp - 1) / a.sp, a.n_tiles, B);
-    objective_uniform_kernel<THREADS, R, TB><<<grid, THREADS, bytes, st>>>(a);
+    objective_uniform_kernel<THREADS, R, TB, KK><<<grid, THREADS, bytes, st>>>(a);
     return cudaGetLastError();
 }
 
 template <int THREADS, int R>
 static cudaError_t launch_tb(const ObjArgs& a, int tb, int B, cudaStream_t st) {
     switch (tb) {
-        case 0: return launch_one<THREADS, R, 0>(a, B, st);
-        case 6: return launch_one<THREADS, R, 6>(a, B, st);
-        case 8: return launch_one<THREADS, R, 8>(a, B, st);
-        case 10: return launch_one<THREADS, R, 10>(a, B, st);
+        case 0: return a.kk ? launch_one<THREADS, R, 0, 1>(a, B, st) : launch_one<THREADS, R, 0, 0>(a, B, st);
+        case 6: return a.kk ? launch_one<THREADS, R, 6, 1>(a, B, st) : launch_one<THREADS, R, 6, 0>(a, B, st);
+        case 8: return a.kk ? launch_one<THREADS, R, 8, 1>(a, B, st) : launch_one<THREADS, R, 8, 0>(a, B, st);
+        case 10: return a.kk ? launch_one<THREADS, R, 10, 1>(a, B, st) : launch_one<THREADS, R, 10, 0>(a, B, st);
         default: return cudaErrorInvalidValue;
     }
 }
@@ -305,7 +311,7 @@ cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double*
     if (ev1) cudaEventRecord(ev1, st);
     if (e != cudaSuccess) return e;
     if (tiles_out) *tiles_out = a.n_tiles;
-    if (f) e = launch_objective_finalize(a.partials, a.n_tiles, 1, a.N, a.S, B, a.frozen, f, st);
+    if (f) e = launch_objective_finalize(a.partials, a.n_tiles, a.kk ? 2 : 1, a.N, a.S, B, a.frozen, f, st);
     count_launches(f ? 3 : 2);
     return e;
 }

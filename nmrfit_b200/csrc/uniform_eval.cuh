@@ -48,6 +48,14 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
         part[2 * e + 1] = sn;
     }
     if (tid == 64) part[66] = (double)P * xs[3];           // yoff is added once per peak (equations.py:147,195)
+    if (tid == 96) {
+        // fit_im is True: I_fit is OVERWRITTEN peak by peak (equations.py:198-199), so only the last peak's
+        // Kramers-Kronig curve is ever compared with the data
+        const int k = P - 1;
+        const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+        part[68] = c.loc; part[69] = c.kL; part[70] = c.kG; part[71] = c.aL; part[72] = c.aG * kTwoOverSqrtPi;
+        part[73] = c.exact ? 1.0 : 0.0;
+    }
     __syncthreads();
     if (tid == 64) {
         int n = 0;
@@ -103,14 +111,16 @@ __device__ __forceinline__ int stage_slot_wt(int t, int j, int stride) { return 
 // particle's constants for this region; the R points of thread t of the tile sit at stage_slot_uv/wt(t, j, stride) of
 // suv / swt; w_first is the abscissa of its first point and xi0 that point's position inside the region.  The exact path
 // (peaks too narrow for the recurrences) reads the particle's parameters xs and the stored abscissae sw_first[0..n_valid).
-template <int R, int TB>
+// KK = 1 (fit_im, reference semantics) also returns through *ss_im the same sum for the imaginary parts:
+// I_data = u sin(phi) + v cos(phi) against the last peak's Kramers-Kronig counterpart (closed form, nmrfit_math.cuh).
+template <int R, int TB, int KK = 0>
 __device__ __forceinline__ double eval_region(const double* __restrict__ cf, const double* __restrict__ pt,
                                               const unsigned* __restrict__ mk, const double* __restrict__ fc,
                                               const double2 ew, int MW, int P, int lane, double w_first, double xi0,
                                               const double2* __restrict__ suv, const double* __restrict__ swt, int t,
                                               int stride, const double* __restrict__ tab,
                                               const double* __restrict__ xs, const double* __restrict__ sw_first,
-                                              int n_valid, double h, double w_ulp) {
+                                              int n_valid, double h, double w_ulp, double* ss_im = nullptr) {
     constexpr double H = 16.0 * R;                         // half a region, in points
     double acc[R];
 #pragma unroll
@@ -148,7 +158,10 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
     const double cd = pt[64], sd = pt[65], py = pt[66];
     double cr = fma(ew.x, el.x, -(ew.y * el.y));
     double ci = fma(ew.y, el.x, ew.x * el.y);
-    double ss = 0.0;
+    double ss = 0.0, ssi = 0.0;
+    const double kloc = KK ? pt[68] : 0.0, kkL = KK ? pt[69] : 0.0, kkG = KK ? pt[70] : 0.0;
+    const double kaL = KK ? pt[71] : 0.0, kaG = KK ? pt[72] : 0.0;
+    const bool kexact = KK ? pt[73] != 0.0 : false;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const double2 uv = suv[stage_slot_uv(t, j, stride)];
@@ -156,6 +169,18 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
         const double vd = fma(uv.x, cr, -fma(uv.y, ci, py));     // V_data - P*yoff
         const double res = wt * (vd - acc[j]);
         ss = fma(res, res, ss);
+        if (KK) {
+            const double idat = fma(uv.x, ci, uv.y * cr);
+            // abscissa: w_first + j*h on the uniform axis; the stored value when the peak is too narrow for that
+            const double wj = (kexact && j < n_valid) ? sw_first[j] : (j == 0 ? w_first : fma((double)j, h, w_first));
+            const double d = wj - kloc;
+            const double tt = d * kkL;
+            const double rq = rcp_pos(fma(tt, tt, 1.0));
+            const double daw = dawson(d * kkG, NMRFIT_DAW_TAB, NMRFIT_DAW_TAIL);
+            const double ifit = fma(kaL * tt, rq, kaG * daw);
+            const double ri = wt * (idat - ifit);
+            ssi = fma(ri, ri, ssi);
+        }
         if (j + 1 < R) {
             const double c2 = fma(cr, cd, -(ci * sd));
             ci = fma(ci, cd, cr * sd);
@@ -163,7 +188,11 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
         }
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+    for (int o = 16; o > 0; o >>= 1) {
+        ss += __shfl_xor_sync(0xffffffffu, ss, o);
+        if (KK) ssi += __shfl_xor_sync(0xffffffffu, ssi, o);
+    }
+    if (KK) *ss_im = ssi;
     return ss;
 }
 

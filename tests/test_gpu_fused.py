@@ -64,6 +64,8 @@ def _assert_identical(a, b):
     (1000, 6, 31, 20),         # ragged axis, 4 points per thread
     (16384, 6, 64, 6),         # spectrum too large for shared memory: restaged tile by tile
     (3000, 12, 40, 10),        # ragged, 12 peaks
+    (2500, 36, 12, 5),         # more than 32 peaks: two near-peak mask words per region
+    (300, 6, 1, 4),            # a swarm of one
 ])
 def test_fused_equals_per_step_kernels_bitwise(N, P, S, iters):
     sp, lo, up = _spectrum(N, P, seed=11)

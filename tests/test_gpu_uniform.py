@@ -26,7 +26,8 @@ def test_golden_axes_select_the_uniform_kernel_and_match(case):
     n_peaks = (g['xs'].shape[1] - 4) // 3
     with _ctx(g, n_peaks, _cabi.ALGO_AUTO) as ctx:
         assert ctx.get_algorithm() == _cabi.ALGO_UNIFORM              # np.linspace axes
-        assert ctx.get_algorithm(_cabi.IM_REFERENCE) == _cabi.ALGO_GENERAL   # fit_im stays on the general kernel
+        assert ctx.get_algorithm(_cabi.IM_REFERENCE) == _cabi.ALGO_UNIFORM   # fit_im (reference semantics) too
+        assert ctx.get_algorithm(_cabi.IM_SUM) == _cabi.ALGO_GENERAL         # the summed variant stays general
         f_uni = ctx.objective_host(g['xs'])
         assert relerr(f_uni, g['f']) < TOL
         ctx.set_algorithm(_cabi.ALGO_GENERAL)
@@ -165,3 +166,59 @@ def test_full_size_c2_uniform_against_general_and_oracle():
         ctx.set_algorithm(_cabi.ALGO_UNIFORM)
         perm = np.random.default_rng(0).permutation(S)
         assert np.array_equal(ctx.objective_host(xs[perm]), f[perm])
+
+
+@pytest.mark.parametrize('n_peaks', [36, 66])
+def test_more_than_32_peaks_uses_several_mask_words(n_peaks):
+    """The near-peak mask of a region is one 32-bit word per 32 peaks: 36 peaks -> 2 words, 66 -> 3."""
+    data, true = synth.multiplet(3000, n_peaks, seed=n_peaks)
+    wts = utils.compute_weights(data.w, data.peaks)
+    lo, up = data.generate_solution_bounds()
+    xs = synth.particles(lo, up, 6, seed=2)
+    xs[0] = true
+    want = orc.objective_swarm(xs, data.w, data.u, data.v, wts)
+    with _cabi.Context(1, 3000, n_peaks) as ctx:
+        ctx.set_spectrum(0, data.w, data.u, data.v, wts)
+        assert ctx.get_algorithm() == _cabi.ALGO_UNIFORM
+        assert relerr(ctx.objective_host(xs), want) < TOL
+        ctx.set_algorithm(_cabi.ALGO_GENERAL)
+        assert relerr(ctx.objective_host(xs), want) < TOL
+
+
+@pytest.mark.parametrize('n_points,n_peaks', [(96, 6), (1000, 6), (4096, 12), (2500, 36)])
+def test_fit_im_reference_semantics_on_the_uniform_kernel(n_points, n_peaks):
+    """fit_im is True (equations.py:198-209): the imaginary residual against the LAST peak's Kramers-Kronig curve.
+    Uniform-axis kernel vs general kernel vs the oracle (closed form; the golden test pins it to the reference's quad)."""
+    data, true = synth.multiplet(max(n_points, 600), n_peaks, seed=31)
+    w, u, v = data.w[:n_points], data.u[:n_points], data.v[:n_points]
+    wts = utils.compute_weights(data.w, data.peaks)[:n_points]
+    lo, up = data.generate_solution_bounds()
+    xs = synth.particles(lo, up, 7, seed=5)
+    xs[0] = true
+    xs[1, -3] = 2e-5                                     # a last peak narrower than a grid step: stored abscissae
+    want = np.array([orc.objective(x, w, u, v, wts, True) for x in xs])
+    with _cabi.Context(1, n_points, n_peaks) as ctx:
+        ctx.set_spectrum(0, w, u, v, wts)
+        assert ctx.get_algorithm(_cabi.IM_REFERENCE) == _cabi.ALGO_UNIFORM
+        assert ctx.get_algorithm(_cabi.IM_SUM) == _cabi.ALGO_GENERAL
+        got = ctx.objective_host(xs, _cabi.IM_REFERENCE)
+        assert relerr(got, want) < TOL
+        ctx.set_algorithm(_cabi.ALGO_GENERAL)
+        assert relerr(ctx.objective_host(xs, _cabi.IM_REFERENCE), got) < TOL
+
+
+def test_fit_with_fit_im_true_follows_the_oracle_loop():
+    import io, contextlib
+    import nmrfit_b200
+    from oracle import pso_oracle
+    data, true = synth.multiplet(1200, 6, seed=17)
+    lo, up = data.generate_solution_bounds()
+    wts = utils.compute_weights(data.w, data.peaks)
+    PSO = dict(omega=-0.2134, phip=-0.3344, phig=2.3259)
+    np.random.seed(3)
+    x_ref, f_ref, info = pso_oracle.pso(orc.objective, lo, up, args=(data.w, data.u, data.v, wts, True), swarmsize=20,
+                                        maxiter=15, quiet=True, **PSO)
+    np.random.seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        fit = nmrfit_b200.fit(data, lo, up, fit_im=True, summary=False, options={'swarmsize': 20, 'maxiter': 15})
+    assert np.array_equal(fit.params, x_ref) and abs(fit.error / f_ref - 1) < 1e-10
