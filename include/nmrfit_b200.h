@@ -114,6 +114,10 @@ int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* p
 #define NMRFIT_FUSED_REQUIRE 2
 int nmrfit_ctx_set_fused(nmrfit_ctx* ctx, int mode);
 int nmrfit_ctx_fused_launches(nmrfit_ctx* ctx, long long* launches);
+/* Measurement hook: when enabled, CTA 0 of the fused kernel adds up the SM clock cycles of each phase of a generation
+ * (move, constants, objective, tile sums, publish, barrier, argmin, commit).  cycles (nullable): read the 8 counters
+ * accumulated so far before they are reset. */
+int nmrfit_ctx_fused_timing(nmrfit_ctx* ctx, int enable, long long* cycles);
 
 /* Per-launch timing of the objective kernel with CUDA events on the launching stream (for bench.py's
  * roofline: enable, run, then read the summed duration and the launch count; read resets). */

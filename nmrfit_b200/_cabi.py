@@ -56,6 +56,7 @@ SIGNATURES = {
     'nmrfit_ctx_get_tuning': (_i, [_vp, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     'nmrfit_ctx_set_fused': (_i, [_vp, _i]),
     'nmrfit_ctx_fused_launches': (_i, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
+    'nmrfit_ctx_fused_timing': (_i, [_vp, _i, _vp]),
     'nmrfit_ctx_profile': (_i, [_vp, _i]),
     'nmrfit_ctx_profile_read': (_i, [_vp, c_double_p, ctypes.POINTER(ctypes.c_longlong)]),
     'nmrfit_objective_batch': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
@@ -218,6 +219,13 @@ class Context:
         """FUSED_AUTO: ``pso_run`` uses the one-launch fused swarm kernel whenever the shape allows;
         FUSED_OFF: always the per-step kernels; FUSED_REQUIRE: fail if the fused kernel cannot run."""
         check(lib().nmrfit_ctx_set_fused(self._h, int(mode)))
+
+    def fused_timing(self, enable=True, read=False):
+        """Per-phase cycle counters of the fused swarm kernel (CTA 0): move, constants, objective, tile sums,
+        publish, barrier, argmin, commit.  ``read`` returns what accumulated since they were enabled."""
+        out = np.zeros(8, dtype=np.int64) if read else None
+        check(lib().nmrfit_ctx_fused_timing(self._h, int(bool(enable)), ptr(out)))
+        return out
 
     def fused_launches(self):
         n = ctypes.c_longlong(0)

@@ -95,6 +95,8 @@ struct nmrfit_ctx {
     DevBuf<unsigned> fin_tickets;
     DevBuf<double> wscratch, wbounds;  // batched weights: sweep scratch [B][N], windows + values
     int fused_mode = NMRFIT_FUSED_AUTO;
+    DevBuf<long long> ftiming;         // optional per-phase cycle counters of the fused kernel
+    bool fused_timing = false;
     long long fused_launches = 0;
     int* h_flags = nullptr;            // pinned [2*B]
     // optional per-launch timing of the objective kernel (nmrfit_ctx_profile)
@@ -281,6 +283,7 @@ int fused_setup(nmrfit_ctx* c, int n_gen, const double* rp_d, const double* rg_d
     a->rec_f = c->frec_f.ptr;
     a->rec_x = c->frec_x.ptr;
     a->barrier = c->fbarrier.ptr;
+    a->timing = c->fused_timing ? c->ftiming.ptr : nullptr;
     return NMRFIT_OK;
 }
 
@@ -355,6 +358,7 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->frec_f.release();
     c->frec_x.release();
     c->fbarrier.release();
+    c->ftiming.release();
     c->wscratch.release();
     c->fin_scratch.release();
     c->fin_tickets.release();
@@ -507,6 +511,22 @@ int nmrfit_ctx_set_fused(nmrfit_ctx* c, int mode) {
     if (mode != NMRFIT_FUSED_AUTO && mode != NMRFIT_FUSED_OFF && mode != NMRFIT_FUSED_REQUIRE)
         return fail(NMRFIT_ERR_ARG, "mode must be NMRFIT_FUSED_AUTO, _OFF or _REQUIRE");
     c->fused_mode = mode;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_fused_timing(nmrfit_ctx* c, int enable, long long* cycles) {
+    if (int rc = check_ctx(c)) return rc;
+    CK(cudaSetDevice(c->device));
+    if (cycles) {
+        if (!c->ftiming.ptr) return fail(NMRFIT_ERR_STATE, "fused timing was not enabled");
+        CK(cudaDeviceSynchronize());
+        CK(cudaMemcpy(cycles, c->ftiming.ptr, sizeof(long long) * 8, cudaMemcpyDeviceToHost));
+    }
+    c->fused_timing = enable != 0;
+    if (c->fused_timing) {
+        CK(c->ftiming.reserve(8));
+        CK(cudaMemset(c->ftiming.ptr, 0, sizeof(long long) * 8));
+    }
     return NMRFIT_OK;
 }
 

@@ -116,6 +116,7 @@ struct FusedArgs {
     int gen0;               // absolute number of the first of them (Philox counter)
     int maxiter;
     int slots;              // supertiles of (u, v, weights) held in shared memory (filled by the launcher)
+    long long* timing;      // optional [8] per-phase cycle counters (null: off)
 };
 struct FusedPlan {
     bool ok;

@@ -331,27 +331,44 @@ constexpr int kFarTerms = 12;
 constexpr double kFarRhoInv2 = 256.0;
 
 // Classify one peak for a region whose centre sits Dc = w_c - loc from the peak's centre; H = half the
-// region's point count.  Far: adds the peak's expansion to C and returns true.  Near: returns false.
-NMRFIT_HD bool far_accumulate(double Dc, const SpanCoef& c, double H, double (&C)[kFarTerms]) {
+// region's point count.  Returns kFarNear (evaluate it with peak_span), kFarSeries (v[n] = Im[u^(n+1)]/A filled:
+// the peak adds (-1)^n aL v[n] to the region's coefficient n) or kFarNothing (infinitely far: adds nothing).
+enum { kFarNear = 0, kFarSeries = 1, kFarNothing = 2 };
+NMRFIT_HD int far_terms(double Dc, const SpanCoef& c, double H, double (&v)[kFarTerms]) {
     const double A = H * c.dT;
     const double tc = Dc * c.kL;
     const double qc = NMRFIT_FMA(tc, tc, 1.0);
     const double sc = Dc * c.kG;
     const double reach = NMRFIT_FMA(H * kSqrtLn2, NMRFIT_ABS(c.dT), kGaussCut);   // 6.5 + H*|hG|
-    if (NMRFIT_ABS(sc) <= reach) return false;                // the Gaussian reaches the region
-    if (!(kFarRhoInv2 * (A * A) <= qc)) return false;         // too close for the series (or NaN)
-    if (!(qc <= 1e300)) return true;                          // infinitely far: contributes nothing
+    if (NMRFIT_ABS(sc) <= reach) return kFarNear;             // the Gaussian reaches the region
+    if (!(kFarRhoInv2 * (A * A) <= qc)) return kFarNear;      // too close for the series (or NaN)
+    if (!(qc <= 1e300)) return kFarNothing;                   // infinitely far: contributes nothing
     const double iq = rcp_pos(qc);
     const double two_p = 2.0 * (A * tc) * iq;                 // 2 Re(u)
     const double rho2 = (A * A) * iq;                         // |u|^2
-    double vm = 0.0, v = iq;
+    double vm = 0.0, vc = iq;
 #pragma unroll
     for (int n = 0; n < kFarTerms; ++n) {
-        C[n] = NMRFIT_FMA((n & 1) ? -c.aL : c.aL, v, C[n]);
-        const double vn = NMRFIT_FMA(two_p, v, -(rho2 * vm));
-        vm = v;
-        v = vn;
+        v[n] = vc;
+        const double vn = NMRFIT_FMA(two_p, vc, -(rho2 * vm));
+        vm = vc;
+        vc = vn;
     }
+    return kFarSeries;
+}
+
+// C[n] += (-1)^n aL v[n]: one peak's series into the region's polynomial (peaks are added in index order)
+NMRFIT_HD void far_add(double aL, const double (&v)[kFarTerms], double (&C)[kFarTerms]) {
+#pragma unroll
+    for (int n = 0; n < kFarTerms; ++n) C[n] = NMRFIT_FMA((n & 1) ? -aL : aL, v[n], C[n]);
+}
+
+// Far: adds the peak's expansion to C and returns true.  Near: returns false.
+NMRFIT_HD bool far_accumulate(double Dc, const SpanCoef& c, double H, double (&C)[kFarTerms]) {
+    double v[kFarTerms];
+    const int kind = far_terms(Dc, c, H, v);
+    if (kind == kFarNear) return false;
+    if (kind == kFarSeries) far_add(c.aL, v, C);
     return true;
 }
 

@@ -36,7 +36,7 @@ namespace {
 
 // shared-memory carve-up in doubles; every offset is even (16-byte alignment)
 struct FusedSmem {
-    int tab, uv, wt, cs, part, far, anchor, mask, wpart, state, red, misc, total;
+    int tab, uv, wt, cs, part, far, anchor, mask, wpart, state, red, misc, pairs, total;
     __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP) {
         const int mw = (P + 31) / 32;
         const int De = (D + 1) & ~1;
@@ -53,6 +53,9 @@ struct FusedSmem {
         state = o;  o += 9 * De;         // x, v, p, g, lb, ub, best_x, p_min, spare
         red = o;    o += 64;             // per-warp argmin values and indices
         misc = o;   o += 8;
+        // (region, peak) series scratch of the pair-parallel prepare, when one thread per pair (+ anchors) is available
+        pairs = NRP * P + NRP <= threads ? o : -1;
+        if (pairs >= 0) o += ((NRP * P * kPairDoubles + 1) & ~1);
         total = o;
     }
 };
@@ -72,6 +75,17 @@ __device__ __forceinline__ void take_min(double& bf, int& bi, double f, int i) {
 }
 
 }  // namespace
+
+// Optional phase timing (FusedArgs::timing != null): CTA 0's thread 0 adds the SM clock cycles each phase of a
+// generation took - move, constants, objective, tile sums, publish, barrier, argmin, commit.
+#define FUSED_MARK(slot)                                                        \
+    do {                                                                        \
+        if (a.timing && blockIdx.x == 0 && tid == 0) {                          \
+            const long long now_ = clock64();                                   \
+            a.timing[slot] += now_ - tmark;                                     \
+            tmark = now_;                                                       \
+        }                                                                       \
+    } while (0)
 
 template <int THREADS, int R, int TB>
 __global__ void __launch_bounds__(THREADS, 512 / THREADS)
@@ -109,6 +123,7 @@ swarm_fused_kernel(FusedArgs a) {
     double* redf = smem + L.red;
     int* redi = reinterpret_cast<int*>(smem + L.red + 32);
     double* misc = smem + L.misc;                          // 0 fx, 1 fp, 2 fg, 3 best_f, 4 improved, 5 action, 6 fmin
+    double* pairs = L.pairs >= 0 ? smem + L.pairs : nullptr;
 
     const double* sw = a.spec + (size_t)b * 4 * N;
     const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
@@ -150,6 +165,7 @@ swarm_fused_kernel(FusedArgs a) {
         for (int st = 0; st < n_super; ++st) stage(st, st);
     __syncthreads();
 
+    long long tmark = clock64();
     for (int k = 0; k < a.n_gen && !stop; ++k) {
         const int par = k & 1;
         // ---- move (pyswarm: v = omega v + phip rp (p - x) + phig rg (g - x); x += v; clamp)
@@ -170,10 +186,12 @@ swarm_fused_kernel(FusedArgs a) {
             vs[d] = v;
         }
         __syncthreads();
+        FUSED_MARK(0);
 
         // ---- objective (equations.py:152-212) of the moved particle
-        prepare_particle<R>(xs, sw, h, w_ulp, N, P, NR, NRP, tid, THREADS, cs, nullptr, part, farc, anchor, mask);
+        prepare_particle<R>(xs, sw, h, w_ulp, N, P, NR, NRP, tid, THREADS, cs, nullptr, part, farc, anchor, mask, pairs);
         __syncthreads();
+        FUSED_MARK(1);
         for (int st = 0; st < n_super; ++st) {
             if (!resident) {
                 __syncthreads();
@@ -194,6 +212,7 @@ swarm_fused_kernel(FusedArgs a) {
             }
         }
         __syncthreads();
+        FUSED_MARK(2);
         if (tid == 0) {
             // same order as the per-step path: the warps of a point tile, then the tiles, then sqrt(mean)
             double total = 0.0;
@@ -210,6 +229,7 @@ swarm_fused_kernel(FusedArgs a) {
             a.rec_f[((size_t)par * s.B + b) * S + sl] = misc[1];
         }
         __syncthreads();
+        FUSED_MARK(3);
         {
             const bool better = misc[4] != 0.0;
             double* rx = a.rec_x + (((size_t)par * s.B + b) * S + sl) * D;
@@ -221,6 +241,7 @@ swarm_fused_kernel(FusedArgs a) {
 
         // ---- barrier among the S CTAs of this spectrum
         __syncthreads();
+        FUSED_MARK(4);
         if (tid == 0) {
             // release: this CTA's record (ordered before by the bar.sync above) is visible to whoever acquires the count
             red_release_add(a.barrier + b, 1u);
@@ -228,6 +249,7 @@ swarm_fused_kernel(FusedArgs a) {
             while (ld_acquire(a.barrier + b) < target) { }
         }
         __syncthreads();
+        FUSED_MARK(5);
 
         // ---- swarm best: argmin over the personal bests, first index wins (np.argmin)
         {
@@ -254,9 +276,15 @@ swarm_fused_kernel(FusedArgs a) {
                 take_min(bf, bi, of, oi);
             }
             const int win = bi == 0x7fffffff ? 0 : bi;
+            double* sq = pm + De;                          // (g - p_min)^2, element by element
             if (bf < misc[2]) {                            // only a new swarm best needs its position
                 const double* rx = a.rec_x + (((size_t)par * s.B + b) * S + win) * D;
-                for (int d = lane; d < D; d += 32) pm[d] = __ldcg(rx + d);
+                for (int d = lane; d < D; d += 32) {
+                    const double pd = __ldcg(rx + d);
+                    const double df = __dsub_rn(gs[d], pd);
+                    pm[d] = pd;
+                    sq[d] = __dmul_rn(df, df);
+                }
             }
             __syncwarp();
             if (lane == 0) {
@@ -264,11 +292,8 @@ swarm_fused_kernel(FusedArgs a) {
                 const double fmin = bf, fg = misc[2];
                 int action = 0;
                 if (fmin < fg) {
-                    double acc = 0.0;
-                    for (int d = 0; d < D; ++d) {
-                        const double df = __dsub_rn(gs[d], pm[d]);
-                        acc = __dadd_rn(acc, __dmul_rn(df, df));
-                    }
+                    double acc = 0.0;                      // summed in index order, as the per-step commit does
+                    for (int d = 0; d < D; ++d) acc = __dadd_rn(acc, sq[d]);
                     const double step = sqrt(acc);
                     if (fabs(__dsub_rn(fg, fmin)) <= s.minfunc) action = 2 + kStopMinFunc;
                     else if (step <= s.minstep) action = 2 + kStopMinStep;
@@ -279,6 +304,7 @@ swarm_fused_kernel(FusedArgs a) {
             }
         }
         __syncthreads();
+        FUSED_MARK(6);
         {
             const int action = (int)misc[5];
             it += 1;
@@ -296,6 +322,7 @@ swarm_fused_kernel(FusedArgs a) {
             }
         }
         __syncthreads();
+        FUSED_MARK(7);
     }
 
     // ---- write the state back for the host (and for further generations by either path)

@@ -18,13 +18,18 @@ namespace nmrfit {
 // xs: the particle's D parameters; sw: its spectrum's w plane (N points); cs: shared [P][8] scratch that ends up
 // holding the span coefficients; coef_out: optional second copy of them; part [kPartDoubles]; far [NRP][kFarTerms];
 // anchor [NRP][2]; mask [NRP][MW+1].  NR regions cover the axis, NRP >= NR slots are filled (the rest neutral).
-// Called by all `nthreads` (>= 128) threads of a CTA; contains one __syncthreads().
+// Called by all `nthreads` (>= 128) threads of a CTA; contains __syncthreads().
+// `pairs` (optional shared scratch of NRP*P*kPairDoubles doubles, only when NRP*P + NRP <= nthreads): the
+// (region, peak) series are computed one pair per thread instead of one region per thread - same values, same order
+// of accumulation, but P times shorter on the critical path (the fused swarm kernel has one CTA per particle).
+constexpr int kPairDoubles = kFarTerms + 1;
 template <int R>
 __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, const double* __restrict__ sw, double h,
                                                  double w_ulp, int N, int P, int NR, int NRP, int tid, int nthreads,
                                                  double* __restrict__ cs, double* __restrict__ coef_out,
                                                  double* __restrict__ part, double* __restrict__ far,
-                                                 double* __restrict__ anchor, unsigned* __restrict__ mask) {
+                                                 double* __restrict__ anchor, unsigned* __restrict__ mask,
+                                                 double* __restrict__ pairs = nullptr) {
     const int MW = (P + 31) / 32;
     const double p0 = xs[0], p1 = xs[1];
     constexpr double H = 16.0 * R;
@@ -61,6 +66,66 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
         int n = 0;
         for (int k = 0; k < P; ++k) n += cs[k * 8 + 6] < 0.0;      // thr < 0 marks a nulled (exact-path) peak
         part[67] = (double)n;
+    }
+    if (pairs) {
+        // one (region, peak) pair per thread; the region anchors by the threads at the other end
+        if (tid < NRP * P) {
+            const int r = tid / P, k = tid - r * P;
+            double* pr = pairs + (size_t)tid * kPairDoubles;
+            double kind = -1.0;                            // -1: padding region or exact-path peak (neither near nor far)
+            if (r < NR) {
+                const double* o = cs + k * 8;
+                SpanCoef c;
+                c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
+                if (!(c.thr < 0.0)) {
+                    const double w_c = fma(0.5 * (32 * R - 1), h, sw[r * 32 * R]);
+                    double v[kFarTerms];
+                    kind = (double)far_terms(w_c - c.loc, c, H, v);
+#pragma unroll
+                    for (int n = 0; n < kFarTerms; ++n) pr[1 + n] = v[n];
+                }
+            }
+            pr[0] = kind;
+        }
+        const int ra = nthreads - 1 - tid;
+        if (ra < NRP) {
+            double sn = 0.0, cn = 1.0;
+            if (ra < NR) sincos(p0 + (p1 * (double)(ra * 32 * R)) / (double)N, &sn, &cn);
+            anchor[ra * 2] = cn;
+            anchor[ra * 2 + 1] = sn;
+        }
+        __syncthreads();
+        if (tid < NRP) {
+            const int r = tid;
+            double C[kFarTerms];
+#pragma unroll
+            for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
+            unsigned any_far = 0;
+            unsigned* mk = mask + (size_t)r * (MW + 1);
+            for (int wd = 0; wd < MW; ++wd) {
+                unsigned m = 0;
+                const int kend = min(P, wd * 32 + 32);
+                for (int k = wd * 32; k < kend; ++k) {
+                    const double* pr = pairs + (size_t)(r * P + k) * kPairDoubles;
+                    const int kind = (int)pr[0];
+                    if (kind < 0) continue;
+                    if (kind == kFarNear) { m |= 1u << (k & 31); continue; }
+                    any_far = 1u;
+                    if (kind == kFarSeries) {
+                        double v[kFarTerms];
+#pragma unroll
+                        for (int n = 0; n < kFarTerms; ++n) v[n] = pr[1 + n];
+                        far_add(cs[k * 8 + 3], v, C);
+                    }
+                }
+                mk[wd] = m;
+            }
+            mk[MW] = any_far;
+            double* fc = far + (size_t)r * kFarTerms;
+#pragma unroll
+            for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
+        }
+        return;
     }
     for (int r = tid; r < NRP; r += nthreads) {
         double C[kFarTerms];

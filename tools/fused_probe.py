@@ -51,6 +51,18 @@ def main():
             t0 = time.perf_counter()
             ctx.pso_best()
             row[tag + '_best_ms'] = 1e3 * (time.perf_counter() - t0)
+        # phase breakdown of the fused kernel (CTA 0), cycles per generation
+        ctx.set_fused(_cabi.FUSED_AUTO)
+        ctx.pso_begin(lo, up, swarm._make_opts(S, 10 ** 9, PSO['omega'], PSO['phip'], PSO['phig'], -1.0, -1.0, False, 7))
+        ctx.pso_commit()
+        ctx.pso_run(8)
+        before = ctx.fused_launches()
+        ctx.fused_timing(True)
+        ctx.pso_run(256)
+        cyc = ctx.fused_timing(False, read=True)
+        if ctx.fused_launches() > before:
+            names = ('move', 'constants', 'objective', 'tile_sums', 'publish', 'barrier', 'argmin', 'commit')
+            row['fused_phase_cycles_per_gen'] = {n: float(c) / 256 for n, c in zip(names, cyc)}
         row['fused_launches'] = ctx.fused_launches()
         t0 = time.perf_counter()
         ctx.close()
