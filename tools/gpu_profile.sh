@@ -14,3 +14,6 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --c
 timeout 300 python bench.py --steps 20 --warmup 3 --quick > gpurun_out/${TAG}_bench_short2.log 2>&1 &&
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:${KREGEX} -s 5 -c 2 -o gpurun_out/${TAG}_prof python bench.py --steps 20 --warmup 3 --quick > gpurun_out/${TAG}_ncu_full.log 2>&1
 for f in smoke pytest_gpu bench bench_reference; do tail -n 3 gpurun_out/${TAG}_$f.log; done
+# extra captures: the fused swarm kernel (single-fit path) and the finish kernel
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:swarm_fused_kernel -s 2 -c 1 -o gpurun_out/${TAG}_prof_fused python tools/fit_latency.py > gpurun_out/${TAG}_ncu_fused.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:swarm_finish_kernel -s 5 -c 1 -o gpurun_out/${TAG}_prof_finish python bench.py --steps 20 --warmup 3 --quick > gpurun_out/${TAG}_ncu_finish.log 2>&1
