@@ -168,11 +168,13 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
     if (c->user_tune.sp > 0) sp = std::min(c->user_tune.sp, std::max(1, S));
     t.sp = sp;
     // per-particle coefficients live in shared memory: keep the CTA under the 200 KB opt-in limit
-    while (t.sp > 1 && (uni ? objective_uniform_smem_bytes(c->P, t) : objective_smem_bytes(c->P, t, 2)) > 200 * 1024)
+    const bool f32 = c->precision == NMRFIT_FP32;
+    auto uni_bytes = [&]() { return f32 ? objective_f32_smem_bytes(c->P, t) : objective_uniform_smem_bytes(c->P, t); };
+    while (t.sp > 1 && (uni ? uni_bytes() : objective_smem_bytes(c->P, t, 2)) > 200 * 1024)
         t.sp /= 2;
-    // uniform-axis kernel: three CTAs per SM if a smaller particle tile achieves it (227 KB / 3)
+    // uniform-axis kernels: three CTAs per SM if a smaller particle tile achieves it (227 KB / 3)
     if (uni && c->user_tune.sp <= 0)
-        while (t.sp > 4 && objective_uniform_smem_bytes(c->P, t) > 74 * 1024) t.sp -= 1;
+        while (t.sp > 4 && uni_bytes() > 74 * 1024) t.sp -= 1;
     return t;
 }
 

@@ -72,7 +72,7 @@ __device__ __forceinline__ void peak_span_f32(float t0, float s0, float dT, floa
 
 // shared-memory carve-up (in doubles): as UniSmem without the exp table
 struct F32Smem {
-    int uv, wt, bar, wpart, coef, part, far, anchor, mask, mw, total;
+    int uv, wt, bar, wpart, coef, part, far, anchor, mask, coef32, far32, mw, total;
     __host__ __device__ F32Smem(int sp, int P, int threads, int R) {
         const int nw = threads / 32;
         mw = (P + 31) / 32;
@@ -86,6 +86,11 @@ struct F32Smem {
         far = o;    o += sp * nw * kFarTerms;
         anchor = o; o += sp * nw * 2;
         mask = o;   o += ((sp * nw * (mw + 1) + 3) / 4) * 2;
+        // single-precision copies made once per CTA (a double -> float conversion costs four FP64 issue slots: doing
+        // it per thread and particle was 30 conversions per 8 points, now 1.5 + the 8 of the residual)
+        coef32 = o; o += sp * P * 4;                       // 8 floats per peak: kL, kG, dT, aL, aG, c2, thr, -
+        far32 = o;  o += (sp * nw * kFarTerms + 1) / 2;
+        o = (o + 1) & ~1;
         total = o;
     }
 };
@@ -112,6 +117,8 @@ objective_uniform_f32_kernel(ObjArgs a) {
     const double2* anchor = reinterpret_cast<const double2*>(smem + L.anchor);
     const unsigned* mask = reinterpret_cast<const unsigned*>(smem + L.mask);
     const int MW = L.mw;
+    float* coef32 = reinterpret_cast<float*>(smem + L.coef32);
+    float* far32 = reinterpret_cast<float*>(smem + L.far32);
     constexpr float H = 16.f * R;
 
     const int tile0 = tile * (THREADS * R);
@@ -146,6 +153,14 @@ objective_uniform_f32_kernel(ObjArgs a) {
     const float xi0 = ((float)(lane * R) - 0.5f * (32 * R - 1)) / H;
     __syncthreads();
     mbar_wait(bar, 0);
+    for (int e = tid; e < SP * P; e += THREADS) {          // kL, kG, dT, aL, aG, c2, thr of every (particle, peak)
+        const double* c = coef + (size_t)e * 8;
+        float* o = coef32 + (size_t)e * 8;
+        o[0] = (float)c[1]; o[1] = (float)c[2]; o[2] = (float)c[5]; o[3] = (float)c[3];
+        o[4] = (float)c[4]; o[5] = (float)c[7]; o[6] = (float)c[6]; o[7] = 0.f;
+    }
+    for (int e = tid; e < SP * NW * kFarTerms; e += THREADS) far32[e] = (float)farc[e];
+    __syncthreads();
 
     for (int sp = 0; sp < nsp; ++sp) {
         float acc[R];
@@ -157,21 +172,18 @@ objective_uniform_f32_kernel(ObjArgs a) {
         for (int wd = 0; wd < MW; ++wd)
         for (unsigned m = mk[wd]; m; m &= m - 1) {
             const int k = wd * 32 + __ffs(m) - 1;
-            const double2 c01 = *reinterpret_cast<const double2*>(cf + k * 8);         // loc, kL
-            const double2 c23 = *reinterpret_cast<const double2*>(cf + k * 8 + 2);     // kG, aL
-            const double2 c45 = *reinterpret_cast<const double2*>(cf + k * 8 + 4);     // aG, dT
-            const double2 c67 = *reinterpret_cast<const double2*>(cf + k * 8 + 6);     // thr, c2
-            const double d0 = w_first - c01.x;
-            peak_span_f32<R>((float)(d0 * c01.y), (float)(d0 * c23.x), (float)c45.y, (float)c23.y, (float)c45.x,
-                             (float)c67.y, (float)c67.x, acc);
+            const float4 f0 = *reinterpret_cast<const float4*>(coef32 + ((size_t)sp * P + k) * 8);       // kL, kG, dT, aL
+            const float4 f1 = *reinterpret_cast<const float4*>(coef32 + ((size_t)sp * P + k) * 8 + 4);   // aG, c2, thr, -
+            const float d0 = (float)(w_first - cf[k * 8]);       // the subtraction in FP64, one conversion
+            peak_span_f32<R>(d0 * f0.x, d0 * f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, acc);
         }
         if (mk[MW]) {
-            const double* fc = farc + (size_t)(sp * NW + warp) * kFarTerms;
+            const float* fc = far32 + (size_t)(sp * NW + warp) * kFarTerms;
             float C[kFarTerms];
 #pragma unroll
-            for (int n = 0; n < kFarTerms; n += 2) {
-                const double2 t = *reinterpret_cast<const double2*>(fc + n);
-                C[n] = (float)t.x; C[n + 1] = (float)t.y;
+            for (int n = 0; n < kFarTerms; n += 4) {
+                const float4 t = *reinterpret_cast<const float4*>(fc + n);
+                C[n] = t.x; C[n + 1] = t.y; C[n + 2] = t.z; C[n + 3] = t.w;
             }
 #pragma unroll
             for (int j = 0; j < R; ++j) {

@@ -111,17 +111,16 @@ objective_move_prepare_kernel(ObjArgs a, MoveArgs mv) {
 // ---- pass 2: evaluation ------------------------------------------------------------------------------
 // shared-memory carve-up (in doubles), shared by kernel and launcher; every offset is even (16-byte alignment)
 struct UniSmem {
-    int tab, uv, wt, wf, bar, wpart, coef, part, far, anchor, mask, mw, total;
-    __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB) {
+    int tab, uv, wt, bar, wpart, coef, part, far, anchor, mask, mw, total;
+    __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB, int nsum = 1) {
         const int nw = threads / 32;
         mw = (P + 31) / 32;                               // near-peak mask words per region, + 1 has-far word
         int o = 0;
         tab = o;    o += TB ? (1 << TB) : 0;
         uv = o;     o += threads * R * 2;
         wt = o;     o += threads * R;
-        wf = o;     o += threads;                         // abscissa of every thread's first point
         bar = o;    o += 2;                               // one mbarrier
-        wpart = o;  o += sp * nw * 2;                      // x2: the imaginary sums of fit_im
+        wpart = o;  o += sp * nw * nsum;                   // nsum = 2: real and imaginary sums of fit_im
         coef = o;   o += sp * P * 8;
         part = o;   o += sp * kPartDoubles;
         far = o;    o += sp * nw * kFarTerms;             // far-field polynomial per (particle, warp region)
@@ -143,11 +142,10 @@ objective_uniform_kernel(ObjArgs a) {
     const int P = a.P, N = a.N, D = 4 + 3 * P, SP = a.sp;
     const int n_tiles = a.n_tiles, tile = blockIdx.y, NRP = n_tiles * NW;
     const int s0 = blockIdx.x * SP, nsp = min(SP, a.S - s0);
-    const UniSmem L(SP, P, THREADS, R, TB);
+    const UniSmem L(SP, P, THREADS, R, TB, NSUM);
     double* tab = smem + L.tab;
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
     double* swt = smem + L.wt;
-    double* swf = smem + L.wf;
     uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
     double* wpart = smem + L.wpart;
     const double* coef = smem + L.coef;
@@ -189,10 +187,8 @@ objective_uniform_kernel(ObjArgs a) {
         suv[stage_slot_uv(t, j, THREADS)] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
         swt[stage_slot_wt(t, j, THREADS)] = ok ? sw[3 * N + i] : 0.0;      // zero weight: padding contributes nothing
     }
-    {
-        const int i_first = tile0 + tid * R;               // first point of thread slot `tid`
-        swf[tid] = i_first < N ? sw[i_first] : fma((double)i_first, h, sw[0]);
-    }
+    const int i_first = tile0 + tid * R;                   // this thread's first point
+    const double w_first = i_first < N ? sw[i_first] : fma((double)i_first, h, sw[0]);
     if (TB) {
         const double* src = ExpTabU<TB>::src();
         for (int i = tid; i < (1 << TB); i += THREADS) tab[i] = src[i];
@@ -201,21 +197,17 @@ objective_uniform_kernel(ObjArgs a) {
     __syncthreads();                                       // tile, table and the mbarrier initialisation are visible
     mbar_wait(bar, 0);                                     // the constants have landed
 
-    // A region's cost depends on how many peaks are near it - the same regions for every particle - so each warp
-    // walks the tile's regions round robin, one particle each, instead of owning one: the warps of a CTA finish
-    // together (ncu before: 8 % of the stall samples sat at the final barrier / EXIT).
+    // (Assigning the tile's regions to the warps round robin, one particle each, to even out the regions' different
+    // costs was measured: no gain - the SM's other CTAs already fill the gaps - and it cost 2 KB of shared memory.)
     for (int sp = 0; sp < nsp; ++sp) {
-        const int rw = (warp + sp) & (NW - 1);             // the region this warp evaluates for particle sp
-        const int t = rw * 32 + lane;
-        const int i_first = tile0 + t * R;
         double ssi = 0.0;
         const double ss = eval_region<R, TB, KK>(
-            coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + rw) * (MW + 1),
-            farc + (size_t)(sp * NW + rw) * kFarTerms, anchor[sp * NW + rw], MW, P, lane, swf[t], xi0, suv, swt, t,
+            coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + warp) * (MW + 1),
+            farc + (size_t)(sp * NW + warp) * kFarTerms, anchor[sp * NW + warp], MW, P, lane, w_first, xi0, suv, swt, tid,
             THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
         if (lane == 0) {
-            wpart[(sp * NW + rw) * NSUM] = ss;
-            if (KK) wpart[(sp * NW + rw) * NSUM + 1] = ssi;
+            wpart[(sp * NW + warp) * NSUM] = ss;
+            if (KK) wpart[(sp * NW + warp) * NSUM + 1] = ssi;
         }
     }
     __syncthreads();
@@ -232,7 +224,7 @@ objective_uniform_kernel(ObjArgs a) {
 template <int THREADS, int R, int TB, int KK>
 static cudaError_t launch_one(const ObjArgs& a, int B, cudaStream_t st) {
     static bool attr_set[NMRFIT_MAX_DEVICES] = {};
-    UniSmem L(a.sp, a.P, THREADS, R, TB);
+    UniSmem L(a.sp, a.P, THREADS, R, TB, KK ? 2 : 1);
     const size_t bytes = (size_t)L.total * sizeof(double);
     int dev = 0;
     cudaGetDevice(&dev);

@@ -5,9 +5,7 @@
 
 namespace nmrfit {
 
-// per particle: e^{i p1 lane R/N} for 32 lanes (64), cos/sin(p1/N), P*yoff, #exact peaks, then the LAST peak's
-// Kramers-Kronig constants for fit_im (loc, kL, kG, aL, aG*2/sqrt(pi), exact flag): equations.py:198-199 keeps only it
-constexpr int kPartDoubles = 74;
+constexpr int kPartDoubles = 68;   // per particle: e^{i p1 lane R/N} for 32 lanes (64), cos/sin(p1/N), P*yoff, #exact peaks
 constexpr int kPadParticles = 64;  // slack at the end of the prepare buffers: the last group is copied whole
 
 // TMA bulk copy (global -> shared, 1-D) completing on an mbarrier, and the barrier's own operations.

@@ -53,14 +53,6 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
         part[2 * e + 1] = sn;
     }
     if (tid == 64) part[66] = (double)P * xs[3];           // yoff is added once per peak (equations.py:147,195)
-    if (tid == 96) {
-        // fit_im is True: I_fit is OVERWRITTEN peak by peak (equations.py:198-199), so only the last peak's
-        // Kramers-Kronig curve is ever compared with the data
-        const int k = P - 1;
-        const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
-        part[68] = c.loc; part[69] = c.kL; part[70] = c.kG; part[71] = c.aL; part[72] = c.aG * kTwoOverSqrtPi;
-        part[73] = c.exact ? 1.0 : 0.0;
-    }
     __syncthreads();
     if (tid == 64) {
         int n = 0;
@@ -224,9 +216,22 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
     double cr = fma(ew.x, el.x, -(ew.y * el.y));
     double ci = fma(ew.y, el.x, ew.x * el.y);
     double ss = 0.0, ssi = 0.0;
-    const double kloc = KK ? pt[68] : 0.0, kkL = KK ? pt[69] : 0.0, kkG = KK ? pt[70] : 0.0;
-    const double kaL = KK ? pt[71] : 0.0, kaG = KK ? pt[72] : 0.0;
-    const bool kexact = KK ? pt[73] != 0.0 : false;
+    // fit_im is True: I_fit is OVERWRITTEN peak by peak (equations.py:198-199), so only the LAST peak's Kramers-Kronig
+    // curve is ever compared with the data.  Its constants are its span coefficients - rebuilt from the parameters
+    // when the peak is on the exact path (the shared copy is nulled then).
+    double kloc = 0.0, kkL = 0.0, kkG = 0.0, kaL = 0.0, kaG = 0.0;
+    bool kexact = false;
+    if (KK) {
+        const double* cl = cf + (P - 1) * 8;
+        kexact = cl[6] < 0.0;
+        if (kexact) {
+            const int k = P - 1;
+            const SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+            kloc = c.loc; kkL = c.kL; kkG = c.kG; kaL = c.aL; kaG = c.aG * kTwoOverSqrtPi;
+        } else {
+            kloc = cl[0]; kkL = cl[1]; kkG = cl[2]; kaL = cl[3]; kaG = cl[4] * kTwoOverSqrtPi;
+        }
+    }
 #pragma unroll
     for (int j = 0; j < R; ++j) {
         const double2 uv = suv[stage_slot_uv(t, j, stride)];
