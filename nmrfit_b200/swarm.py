@@ -71,13 +71,11 @@ def _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed, of
 
 
 def _draw_generations(rnd, n, S, D):
-    """rp then rg per generation, from the legacy stream - pyswarm's order."""
-    rp = np.empty((n, S, D))
-    rg = np.empty((n, S, D))
-    for k in range(n):
-        rp[k] = rnd.uniform(size=(S, D))
-        rg[k] = rnd.uniform(size=(S, D))
-    return rp, rg
+    """rp then rg per generation, from the legacy stream - pyswarm's order.  One call for the whole chunk: the
+    legacy generator fills an array sequentially, so uniform(size=(n, 2, S, D)) consumes the stream exactly as
+    n x (uniform(size=(S, D)), uniform(size=(S, D))) would."""
+    r = rnd.uniform(size=(n, 2, S, D))
+    return np.ascontiguousarray(r[:, 0]), np.ascontiguousarray(r[:, 1])
 
 
 def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxiter=100, omega=0.5, phip=0.5,
@@ -115,8 +113,10 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
         chunk = max(1, int(chunk)) if trace is None else 1
         while done < maxiter:
             n = min(chunk, maxiter - done)
-            if not host and trace is None:
-                chunk = min(2 * chunk, 256)                # device RNG: nothing to rewind, so poll the stop flag less and less often
+            if trace is None:
+                # poll the stop flag less and less often; with host numbers an early stop rewinds the stream and
+                # redraws what was used, so the chunks stay moderate there
+                chunk = min(2 * chunk, 256 if not host else 64)
             if host:
                 state = np.random.get_state()
                 rp, rg = _draw_generations(np.random, n, S, D)
@@ -205,9 +205,7 @@ def _pso_batch_run(ctx, lb, ub, fit_im, swarmsize, maxiter, omega, phip, phig, m
             rp = np.empty((n, B, S, D))
             rg = np.empty((n, B, S, D))
             for b, st in enumerate(streams):
-                for k in range(n):
-                    rp[k, b] = st.uniform(size=(S, D))
-                    rg[k, b] = st.uniform(size=(S, D))
+                rp[:, b], rg[:, b] = _draw_generations(st, n, S, D)
         if ctx.pso_run(n, rp, rg) == 0:
             break
         done += n
