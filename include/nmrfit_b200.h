@@ -8,7 +8,7 @@
  *     equations.objective / voigt / kk_relation*            equations.py:152-212, 115-149, 52-112, 242
  *     proc_autophase.ps2                                    proc_autophase.py:9-36
  * Each entry point below names the reference interface it stands in for.  The
- * Python mirror of that surface (nmrfit_b200/*.py) binds these symbols with ctypes;
+ * Python mirror of that surface (the nmrfit_b200 package) binds these symbols with ctypes;
  * INTEGRATION.md shows the stub a maintainer of the reference would add.
  *
  * Conventions

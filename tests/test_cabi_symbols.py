@@ -55,3 +55,23 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
     monkeypatch.setattr(_cabi, 'LIB_PATH', str(tmp_path / 'nope.so'))
     with pytest.raises(ImportError, match='no CPU fallback'):
         _cabi.lib()
+
+
+def test_c_consumer_compiles_against_the_header(tmp_path):
+    """examples/c_abi_demo.c is plain C99 using only include/nmrfit_b200.h (no Python, no torch)."""
+    import subprocess
+    exe = str(tmp_path / 'c_abi_demo')
+    subprocess.run(['gcc', '-std=c99', '-Wall', '-Werror', '-O2', '-I', os.path.join(ROOT, 'include'),
+                    os.path.join(ROOT, 'examples', 'c_abi_demo.c'), '-o', exe, '-ldl', '-lm'], check=True)
+
+
+@pytest.mark.gpu
+def test_c_consumer_runs_on_the_gpu(tmp_path):
+    import subprocess
+    exe = str(tmp_path / 'c_abi_demo')
+    subprocess.run(['gcc', '-std=c99', '-O2', '-I', os.path.join(ROOT, 'include'),
+                    os.path.join(ROOT, 'examples', 'c_abi_demo.c'), '-o', exe, '-ldl', '-lm'], check=True)
+    out = subprocess.run([exe, os.path.join(ROOT, 'nmrfit_b200', 'csrc', 'libnmrfit_b200.so')], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert 'swarm:' in out.stdout
