@@ -116,11 +116,12 @@ struct FusedArgs {
     int gen0;               // absolute number of the first of them (Philox counter)
     int maxiter;
     int slots;              // supertiles of (u, v, weights) held in shared memory (filled by the launcher)
+    int cluster;            // CTAs (one thread-block cluster) per particle (filled by the launcher)
     long long* timing;      // optional [8] per-phase cycle counters (null: off)
 };
 struct FusedPlan {
     bool ok;
-    int threads, r, slots;
+    int threads, r, slots, cluster;
     size_t smem;
 };
 // can B*S CTAs be co-resident for this shape?  plan->ok says so; never launches

@@ -18,8 +18,17 @@
 // summed in the same order (warp tree, then the warps of a point tile, then the tiles), so a fused run is
 // bit-identical to the same generations stepped kernel by kernel (tests/test_gpu_fused.py).
 //
-// Requires every CTA of the grid to be co-resident: launched with cudaLaunchCooperativeKernel, and the host
-// falls back to the per-step kernels when n_spectra * swarmsize exceeds what the device can hold.
+// Longer axes (more than 16 regions of 256 points): a THREAD-BLOCK CLUSTER of up to 8 CTAs owns a particle.  Each
+// CTA keeps its contiguous run of the spectrum in its own shared memory, evaluates its regions, and the regions'
+// sums are all-gathered through DISTRIBUTED SHARED MEMORY (every CTA stores its sums into every peer's array,
+// cluster.sync()), after which all CTAs of the cluster continue redundantly exactly as the single CTA does - same
+// summation order, so still bit-identical to the per-step kernels.  (3 CTAs per SM for the cluster variant was
+// measured: the 80-register build spills and gains nothing on balance.)
+//
+// Requires every CTA of the grid to be co-resident: launched cooperatively (cudaLaunchKernelEx with the cooperative
+// attribute, plus the cluster dimension), and the host falls back to the per-step kernels when the device cannot
+// hold n_spectra * swarmsize * cluster CTAs or a CTA's run of the axis would exceed 32 regions.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <math_constants.h>
 #include <algorithm>
@@ -37,7 +46,8 @@ namespace {
 // shared-memory carve-up in doubles; every offset is even (16-byte alignment)
 struct FusedSmem {
     int tab, uv, wt, cs, part, far, anchor, mask, wpart, state, red, misc, pairs, total;
-    __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP) {
+    // NRP: region slots of the whole axis (tile sums of every region end up in every CTA); NRL: regions this CTA owns
+    __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP, int NRL) {
         const int mw = (P + 31) / 32;
         const int De = (D + 1) & ~1;
         int o = 0;
@@ -46,16 +56,16 @@ struct FusedSmem {
         wt = o;     o += slots * threads * R;
         cs = o;     o += P * 8;
         part = o;   o += kPartDoubles;
-        far = o;    o += NRP * kFarTerms;
-        anchor = o; o += NRP * 2;
-        mask = o;   o += ((NRP * (mw + 1) + 3) / 4) * 2;
+        far = o;    o += NRL * kFarTerms;
+        anchor = o; o += NRL * 2;
+        mask = o;   o += ((NRL * (mw + 1) + 3) / 4) * 2;
         wpart = o;  o += (NRP + 1) & ~1;
         state = o;  o += 9 * De;         // x, v, p, g, lb, ub, best_x, p_min, spare
         red = o;    o += 64;             // per-warp argmin values and indices
         misc = o;   o += 8;
         // (region, peak) series scratch of the pair-parallel prepare, when one thread per pair (+ anchors) is available
-        pairs = NRP * P + NRP <= threads ? o : -1;
-        if (pairs >= 0) o += ((NRP * P * kPairDoubles + 1) & ~1);
+        pairs = NRL * P + NRL <= threads ? o : -1;
+        if (pairs >= 0) o += ((NRL * P * kPairDoubles + 1) & ~1);
         total = o;
     }
 };
@@ -87,22 +97,28 @@ __device__ __forceinline__ void take_min(double& bf, int& bi, double f, int i) {
         }                                                                       \
     } while (0)
 
-template <int THREADS, int R, int TB>
+template <int THREADS, int R, int TB, bool CL>
 __global__ void __launch_bounds__(THREADS, 512 / THREADS)
 swarm_fused_kernel(FusedArgs a) {
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) double smem[];
     const SwarmState& s = a.s;
     const int S = s.S, D = s.D, De = (D + 1) & ~1;
-    const int b = blockIdx.x / S, sl = blockIdx.x % S;
-    if (s.stop[b]) return;                                 // this spectrum's swarm has already stopped
+    // a.cluster CTAs (one thread-block cluster) share a particle: each owns a contiguous run of supertiles
+    const int G = CL ? a.cluster : 1, crank = CL ? (int)(blockIdx.x % G) : 0;
+    const int pidx = blockIdx.x / G;
+    const int b = pidx / S, sl = pidx % S;
+    if (s.stop[b]) return;                                 // this spectrum's swarm has already stopped (whole cluster)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.P, N = a.N, MW = (P + 31) / 32;
     const int VW = a.vw, NRP = a.n_vtiles * VW;            // warps per point tile of the per-step kernels; region slots
     const int NR = (N + 32 * R - 1) / (32 * R);
     const int n_super = (NRP + NW - 1) / NW;
-    const bool resident = a.slots >= n_super;
-    const FusedSmem L(P, D, THREADS, R, a.slots, NRP);
+    const int per = (n_super + G - 1) / G;                 // supertiles per CTA
+    const int st_lo = min(crank * per, n_super), st_hi = min(st_lo + per, n_super);
+    const int r_lo = st_lo * NW, r_hi = min(st_hi * NW, NRP);
+    const bool resident = a.slots >= per;
+    const FusedSmem L(P, D, THREADS, R, a.slots, NRP, per * NW);
     double* tab = smem + L.tab;
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
     double* swt = smem + L.wt;
@@ -162,7 +178,7 @@ swarm_fused_kernel(FusedArgs a) {
         }
     };
     if (resident)
-        for (int st = 0; st < n_super; ++st) stage(st, st);
+        for (int st = st_lo; st < st_hi; ++st) stage(st, st - st_lo);
     __syncthreads();
 
     long long tmark = clock64();
@@ -189,10 +205,11 @@ swarm_fused_kernel(FusedArgs a) {
         FUSED_MARK(0);
 
         // ---- objective (equations.py:152-212) of the moved particle
-        prepare_particle<R>(xs, sw, h, w_ulp, N, P, NR, NRP, tid, THREADS, cs, nullptr, part, farc, anchor, mask, pairs);
+        prepare_particle<R>(xs, sw, h, w_ulp, N, P, NR, NRP, tid, THREADS, cs, nullptr, part, farc, anchor, mask, pairs, r_lo,
+                            r_hi);
         __syncthreads();
         FUSED_MARK(1);
-        for (int st = 0; st < n_super; ++st) {
+        for (int st = st_lo; st < st_hi; ++st) {
             if (!resident) {
                 __syncthreads();
                 stage(st, 0);
@@ -200,18 +217,25 @@ swarm_fused_kernel(FusedArgs a) {
             }
             const int rgn = st * NW + warp;
             if (rgn < NRP) {
-                const int slot = resident ? st : 0;
+                const int slot = resident ? st - st_lo : 0;
+                const int rl = rgn - r_lo;                 // index into this CTA's region constants
                 const int i_first = (st * THREADS + tid) * R;
                 const double w_first = i_first < N ? __ldg(sw + i_first) : fma((double)i_first, h, __ldg(sw));
-                const double2 ew = *reinterpret_cast<const double2*>(anchor + 2 * rgn);
-                const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rgn * (MW + 1), farc + (size_t)rgn * kFarTerms,
+                const double2 ew = *reinterpret_cast<const double2*>(anchor + 2 * rl);
+                const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rl * (MW + 1), farc + (size_t)rl * kFarTerms,
                                                      ew, MW, P, lane, w_first, xi0, suv + slot * THREADS * R,
                                                      swt + slot * THREADS * R, tid, THREADS, tab, xs, sw + i_first,
                                                      N - i_first, h, w_ulp);
-                if (lane == 0) wpart[rgn] = ss;
+                if (!CL) {
+                    if (lane == 0) wpart[rgn] = ss;
+                } else if (lane < G) {
+                    // all-gather through distributed shared memory: lane q stores into CTA q of the cluster
+                    cooperative_groups::this_cluster().map_shared_rank(wpart, lane)[rgn] = ss;
+                }
             }
         }
-        __syncthreads();
+        if (!CL) __syncthreads();
+        else cooperative_groups::this_cluster().sync();    // every CTA of the particle now holds every region's sum
         FUSED_MARK(2);
         if (tid == 0) {
             // same order as the per-step path: the warps of a point tile, then the tiles, then sqrt(mean)
@@ -226,7 +250,7 @@ swarm_fused_kernel(FusedArgs a) {
             misc[0] = fx;
             if (better) misc[1] = fx;
             misc[4] = better ? 1.0 : 0.0;
-            a.rec_f[((size_t)par * s.B + b) * S + sl] = misc[1];
+            if (crank == 0) a.rec_f[((size_t)par * s.B + b) * S + sl] = misc[1];
         }
         __syncthreads();
         FUSED_MARK(3);
@@ -235,7 +259,7 @@ swarm_fused_kernel(FusedArgs a) {
             double* rx = a.rec_x + (((size_t)par * s.B + b) * S + sl) * D;
             for (int d = tid; d < D; d += THREADS) {
                 if (better) ps[d] = xs[d];
-                rx[d] = ps[d];
+                if (crank == 0) rx[d] = ps[d];
             }
         }
 
@@ -245,7 +269,7 @@ swarm_fused_kernel(FusedArgs a) {
         if (tid == 0) {
             // release: this CTA's record (ordered before by the bar.sync above) is visible to whoever acquires the count
             red_release_add(a.barrier + b, 1u);
-            const unsigned target = (unsigned)S * (unsigned)(k + 1);
+            const unsigned target = (unsigned)(S * G) * (unsigned)(k + 1);
             while (ld_acquire(a.barrier + b) < target) { }
         }
         __syncthreads();
@@ -326,6 +350,7 @@ swarm_fused_kernel(FusedArgs a) {
     }
 
     // ---- write the state back for the host (and for further generations by either path)
+    if (crank != 0) return;                                // the cluster's CTAs hold identical state: one writes it back
     for (int d = tid; d < D; d += THREADS) {
         s.x[bs * D + d] = xs[d];
         s.v[bs * D + d] = vs[d];
@@ -349,29 +374,73 @@ swarm_fused_kernel(FusedArgs a) {
 
 // ---- host side ------------------------------------------------------------------------------------------
 
-template <int THREADS, int R>
-static cudaError_t plan_one(const FusedArgs& a, int D, int grid, int device, FusedPlan* plan) {
-    auto kern = swarm_fused_kernel<THREADS, R, 6>;
-    static bool attr_set[NMRFIT_MAX_DEVICES] = {};
-    if (!attr_set[device % NMRFIT_MAX_DEVICES]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set[device % NMRFIT_MAX_DEVICES] = true;
+static const void* fused_kernel(int threads, int r, int cluster) {
+    if (cluster > 1) {
+        if (threads == 256 && r == 8) return (const void*)swarm_fused_kernel<256, 8, 6, true>;
+        if (threads == 256 && r == 4) return (const void*)swarm_fused_kernel<256, 4, 6, true>;
+        return nullptr;
     }
-    int sms = 0;
-    cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (threads == 512 && r == 8) return (const void*)swarm_fused_kernel<512, 8, 6, false>;
+    if (threads == 512 && r == 4) return (const void*)swarm_fused_kernel<512, 4, 6, false>;
+    if (threads == 256 && r == 8) return (const void*)swarm_fused_kernel<256, 8, 6, false>;
+    if (threads == 256 && r == 4) return (const void*)swarm_fused_kernel<256, 4, 6, false>;
+    return nullptr;
+}
+
+static void fill_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int grid, int threads, size_t smem, int cluster,
+                        cudaStream_t st) {
+    *cfg = cudaLaunchConfig_t{};
+    cfg->gridDim = dim3((unsigned)grid);
+    cfg->blockDim = dim3((unsigned)threads);
+    cfg->dynamicSmemBytes = smem;
+    cfg->stream = st;
+    at[0].id = cudaLaunchAttributeCooperative;             // every CTA co-resident, or the launch fails
+    at[0].val.cooperative = 1;
+    at[1].id = cudaLaunchAttributeClusterDimension;
+    at[1].val.clusterDim.x = (unsigned)cluster;
+    at[1].val.clusterDim.y = 1;
+    at[1].val.clusterDim.z = 1;
+    cfg->attrs = at;
+    cfg->numAttrs = cluster > 1 ? 2 : 1;
+}
+
+// Can `particles * cluster` CTAs of `threads` threads be co-resident?  Tries the whole share of the spectrum resident
+// in shared memory first, then one supertile at a time.
+static cudaError_t plan_one(const FusedArgs& a, int D, int particles, int threads, int r, int cluster, int device,
+                            FusedPlan* plan) {
+    const void* kern = fused_kernel(threads, r, cluster);
+    if (!kern) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    const int NRP = a.n_vtiles * a.vw, n_super = (NRP + THREADS / 32 - 1) / (THREADS / 32);
-    // the whole spectrum stays in shared memory when that still leaves room for enough CTAs; else one supertile
-    for (int slots : {n_super, 1}) {
-        const size_t bytes = (size_t)FusedSmem(a.P, D, THREADS, R, slots, NRP).total * sizeof(double);
-        if (bytes > 200 * 1024) continue;
-        int per_sm = 0;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, THREADS, bytes);
-        if (e != cudaSuccess) return e;
-        if ((long long)per_sm * sms >= grid) {
-            plan->ok = true; plan->threads = THREADS; plan->r = R; plan->slots = slots; plan->smem = bytes;
-            return cudaSuccess;
+    int sms = 0;
+    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    if (e != cudaSuccess) return e;
+    const int NW = threads / 32, NRP = a.n_vtiles * a.vw, n_super = (NRP + NW - 1) / NW;
+    const int per = (n_super + cluster - 1) / cluster;
+    const int grid = particles * cluster;
+    for (int slots : {per, 1}) {
+        const size_t bytes = (size_t)FusedSmem(a.P, D, threads, r, slots, NRP, per * NW).total * sizeof(double);
+        if (bytes <= 200 * 1024) {
+            long long capacity = 0;
+            if (cluster > 1) {
+                cudaLaunchConfig_t cfg;
+                cudaLaunchAttribute at[2];
+                fill_config(&cfg, at, grid, threads, bytes, cluster, nullptr);
+                int clusters = 0;
+                e = cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg);
+                if (e != cudaSuccess) { cudaGetLastError(); clusters = 0; }
+                capacity = (long long)clusters * cluster;
+            } else {
+                int per_sm = 0;
+                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, bytes);
+                if (e != cudaSuccess) return e;
+                capacity = (long long)per_sm * sms;
+            }
+            if (capacity >= grid) {
+                plan->ok = true; plan->threads = threads; plan->r = r; plan->slots = slots; plan->cluster = cluster;
+                plan->smem = bytes;
+                return cudaSuccess;
+            }
         }
         if (slots == 1) break;
     }
@@ -382,36 +451,48 @@ cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjT
                              FusedPlan* plan) {
     plan->ok = false;
     if (t.tb != 6 || (t.r != 4 && t.r != 8) || (t.threads != 128 && t.threads != 256)) return cudaSuccess;
-    const long long grid = (long long)B * S;
-    if (grid > 4096) return cudaSuccess;
-    // One CTA walks its particle's whole axis: past ~8k points (32 regions) the three-launch per-step path, which
-    // spreads the tiles of a particle over many CTAs, is faster (measured: profiles/r01k_fused_probe.json)
-    if (!force && a.n_vtiles * a.vw > 32) return cudaSuccess;
+    const long long particles = (long long)B * S;
+    if (particles > 4096) return cudaSuccess;
     int sms = 0;
     cudaError_t e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (e != cudaSuccess) return e;
-    // one CTA per SM can afford 16 warps; more CTAs than SMs share an SM two (or more) at a time with 8 warps each
-    const bool wide = grid <= sms && a.n_vtiles * a.vw > 8;
-    if (wide) {
-        e = t.r == 8 ? plan_one<512, 8>(a, D, (int)grid, device, plan) : plan_one<512, 4>(a, D, (int)grid, device, plan);
+    const int NRP = a.n_vtiles * a.vw;
+    // Short axes (<= 16 regions): one CTA per particle - 16 warps when every particle has an SM to itself.
+    if (NRP <= 16) {
+        // (a cluster of two 8-warp CTAs instead of one 16-warp CTA was measured here: no gain - the phase is bound by
+        // each warp's own dependent chain, not by the SM's FP64 rate)
+        if (particles <= sms && NRP > 8) {
+            e = plan_one(a, D, (int)particles, 512, t.r, 1, device, plan);
+            if (e != cudaSuccess || plan->ok) return e;
+        }
+        return plan_one(a, D, (int)particles, 256, t.r, 1, device, plan);
+    }
+    // Longer axes: a thread-block cluster per particle, as many CTAs as stay co-resident (<= 8, the portable limit),
+    // each with its run of supertiles; past ~32 regions per CTA the three-launch per-step path, which spreads a
+    // particle's tiles over many CTAs, is faster (profiles/r01k_fused_probe.json).
+    const int n_super = (NRP + 7) / 8;
+    for (int cluster = 8; cluster >= 1; cluster /= 2) {
+        if (cluster > n_super) continue;
+        const int per = (n_super + cluster - 1) / cluster;
+        if (!force && per * 8 > 32) break;                 // smaller clusters only get longer runs
+        e = plan_one(a, D, (int)particles, 256, t.r, cluster, device, plan);
         if (e != cudaSuccess || plan->ok) return e;
     }
-    return t.r == 8 ? plan_one<256, 8>(a, D, (int)grid, device, plan) : plan_one<256, 4>(a, D, (int)grid, device, plan);
+    return cudaSuccess;
 }
 
 cudaError_t launch_swarm_fused(FusedArgs a, const FusedPlan& plan, int B, int S, cudaStream_t st) {
     a.slots = plan.slots;
-    void* args[] = {&a};
-    dim3 grid((unsigned)(B * S)), block((unsigned)plan.threads);
-    const void* kern = nullptr;
-    if (plan.threads == 512 && plan.r == 8) kern = (const void*)swarm_fused_kernel<512, 8, 6>;
-    else if (plan.threads == 512 && plan.r == 4) kern = (const void*)swarm_fused_kernel<512, 4, 6>;
-    else if (plan.threads == 256 && plan.r == 8) kern = (const void*)swarm_fused_kernel<256, 8, 6>;
-    else if (plan.threads == 256 && plan.r == 4) kern = (const void*)swarm_fused_kernel<256, 4, 6>;
-    else return cudaErrorInvalidValue;
+    a.cluster = plan.cluster;
+    const void* kern = fused_kernel(plan.threads, plan.r, plan.cluster);
+    if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(a.barrier, 0, sizeof(unsigned) * B, st);
     if (e != cudaSuccess) return e;
-    e = cudaLaunchCooperativeKernel(kern, grid, block, args, plan.smem, st);
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[2];
+    fill_config(&cfg, at, B * S * plan.cluster, plan.threads, plan.smem, plan.cluster, st);
+    void* args[] = {&a};
+    e = cudaLaunchKernelExC(&cfg, kern, args);
     count_launches(1);
     return e;
 }

@@ -29,7 +29,10 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
                                                  double* __restrict__ cs, double* __restrict__ coef_out,
                                                  double* __restrict__ part, double* __restrict__ far,
                                                  double* __restrict__ anchor, unsigned* __restrict__ mask,
-                                                 double* __restrict__ pairs = nullptr) {
+                                                 double* __restrict__ pairs = nullptr, int r_lo = 0, int r_hi = -1) {
+    // regions [r_lo, r_hi) are filled, at index r - r_lo of far / anchor / mask (default: all NRP slots)
+    if (r_hi < 0) r_hi = NRP;
+    const int nr = r_hi - r_lo;
     const int MW = (P + 31) / 32;
     const double p0 = xs[0], p1 = xs[1];
     constexpr double H = 16.0 * R;
@@ -61,8 +64,8 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
     }
     if (pairs) {
         // one (region, peak) pair per thread; the region anchors by the threads at the other end
-        if (tid < NRP * P) {
-            const int r = tid / P, k = tid - r * P;
+        if (tid < nr * P) {
+            const int rl = tid / P, k = tid - rl * P, r = r_lo + rl;
             double* pr = pairs + (size_t)tid * kPairDoubles;
             double kind = -1.0;                            // -1: padding region or exact-path peak (neither near nor far)
             if (r < NR) {
@@ -79,16 +82,17 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
             }
             pr[0] = kind;
         }
-        const int ra = nthreads - 1 - tid;
-        if (ra < NRP) {
+        const int ral = nthreads - 1 - tid;
+        if (ral < nr) {
+            const int ra = r_lo + ral;
             double sn = 0.0, cn = 1.0;
             if (ra < NR) sincos(p0 + (p1 * (double)(ra * 32 * R)) / (double)N, &sn, &cn);
-            anchor[ra * 2] = cn;
-            anchor[ra * 2 + 1] = sn;
+            anchor[ral * 2] = cn;
+            anchor[ral * 2 + 1] = sn;
         }
         __syncthreads();
-        if (tid < NRP) {
-            const int r = tid;
+        if (tid < nr) {
+            const int r = tid;                             // local index
             double C[kFarTerms];
 #pragma unroll
             for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
@@ -119,12 +123,13 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
         }
         return;
     }
-    for (int r = tid; r < NRP; r += nthreads) {
+    for (int rl = tid; rl < nr; rl += nthreads) {
+        const int r = r_lo + rl;
         double C[kFarTerms];
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
         unsigned any_far = 0;
-        unsigned* mk = mask + (size_t)r * (MW + 1);
+        unsigned* mk = mask + (size_t)rl * (MW + 1);
         double sn = 0.0, cn = 1.0;
         if (r < NR) {
             const int ir = r * 32 * R;
@@ -147,11 +152,11 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
             for (int wd = 0; wd < MW; ++wd) mk[wd] = 0u;
         }
         mk[MW] = any_far;
-        double* fc = far + (size_t)r * kFarTerms;
+        double* fc = far + (size_t)rl * kFarTerms;
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
-        anchor[r * 2] = cn;
-        anchor[r * 2 + 1] = sn;
+        anchor[rl * 2] = cn;
+        anchor[rl * 2 + 1] = sn;
     }
 }
 

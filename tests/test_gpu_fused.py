@@ -62,7 +62,11 @@ def _assert_identical(a, b):
     (4096, 6, 100, 30),        # BASELINE configs[0]: whole spectrum resident in shared memory, 16-warp CTAs
     (4096, 6, 204, 12),        # the reference's default swarm: more CTAs than SMs, two per SM
     (1000, 6, 31, 20),         # ragged axis, 4 points per thread
-    (16384, 6, 64, 6),         # spectrum too large for shared memory: restaged tile by tile
+    (16384, 6, 64, 6),         # a cluster of 4 CTAs per particle, two resident supertiles each
+    (8192, 6, 30, 8),          # cluster of 4, one supertile each
+    (32768, 12, 10, 4),        # cluster of 8, two supertiles each
+    (16384, 6, 204, 5),        # cluster of 2: four supertiles each, restaged tile by tile
+    (5000, 6, 20, 6),          # ragged: the last CTA of the cluster owns a partial run
     (3000, 12, 40, 10),        # ragged, 12 peaks
     (2500, 36, 12, 5),         # more than 32 peaks: two near-peak mask words per region
     (300, 6, 1, 4),            # a swarm of one

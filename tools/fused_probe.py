@@ -18,8 +18,8 @@ PSO = dict(omega=-0.2134, phip=-0.3344, phig=2.3259)
 def main():
     import torch
     out = {}
-    shapes = [(4096, 6, 100), (4096, 6, 148), (4096, 6, 204), (4096, 6, 296), (16384, 6, 204), (32768, 12, 148),
-              (2048, 6, 100)]
+    shapes = [(4096, 6, 100), (4096, 6, 148), (4096, 6, 204), (4096, 6, 296), (2048, 6, 100), (8192, 6, 100),
+              (8192, 6, 148), (8192, 6, 204), (16384, 6, 100), (16384, 6, 204), (32768, 12, 36), (32768, 12, 148)]
     for N, P, S in shapes:
         data, _ = synth.multiplet(N, P, seed=1000)
         lo, up = (np.array(a) for a in data.generate_solution_bounds())
