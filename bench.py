@@ -522,7 +522,7 @@ def extra_measurements(device):
     fits['single_fits_per_s'] = 1e3 / fits['single_fit_ms_rng_device']
     fits['note'] = ('configs[0]: 6 peaks, 4,096 points, swarmsize 100, maxiter 100, wall clock through the public API '
                     'incl. weights, uploads and result readback; rng=host replays numpy\'s legacy stream (parity mode); single fits run '
-                    'the fused swarm kernel (one cooperative launch per 16 generations), *_per_step_kernels = 7 launches '
+                    'the fused swarm kernel (one cooperative launch per chunk of generations), *_per_step_kernels = 3 launches '
                     'per generation; default_fit = swarmsize 204, maxiter 2000, pyswarm stop rules')
     out['fits'] = fits
     return out

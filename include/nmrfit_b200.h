@@ -105,7 +105,7 @@ int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* p
                           int* particles_per_cta, int* n_point_tiles);
 
 /* Small swarms: nmrfit_pso_run executes its generations in ONE cooperative launch (one CTA per particle,
- * one barrier per generation) instead of seven launches per generation - the loop pyswarm.pso runs on the host
+ * one barrier per generation) instead of three launches per generation - the loop pyswarm.pso runs on the host
  * (call site utils.py:176-182).  Bit-identical to the per-step kernels.  AUTO uses it whenever it can run
  * (FP64, uniform axis, real-only fit, n_spectra * swarmsize CTAs co-resident); REQUIRE makes nmrfit_pso_run
  * fail with NMRFIT_ERR_STATE otherwise. */

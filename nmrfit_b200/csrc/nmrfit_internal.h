@@ -96,7 +96,6 @@ size_t swarm_finish_scratch_doubles(int B, int S);
 cudaError_t launch_swarm_init(const SwarmState& s, const double* r_pos, const double* r_vel, cudaStream_t st);
 cudaError_t launch_swarm_init_velocity(const SwarmState& s, const double* r_vel, cudaStream_t st);
 cudaError_t launch_swarm_move(const SwarmState& s, const double* rp, const double* rg, int generation, cudaStream_t st);
-cudaError_t launch_swarm_local_best(const SwarmState& s, double* rec, cudaStream_t st);
 cudaError_t launch_swarm_commit(const SwarmState& s, const double* recs, int n_ranks, int initial, int maxiter,
                                 cudaStream_t st);
 

@@ -70,48 +70,6 @@ __global__ void swarm_move_kernel(SwarmState s, const double* __restrict__ rp_in
     s.x[idx] = x;
 }
 
-// personal best positions (elementwise; fp itself is updated by the reduction kernel that follows)
-__global__ void swarm_pbest_kernel(SwarmState s) {
-    size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    size_t total = (size_t)s.B * s.S * s.D;
-    if (idx >= total) return;
-    size_t bs = idx / s.D;
-    int b = bs / s.S;
-    if (s.stop[b]) return;
-    if (s.fx[bs] < s.fp[bs]) s.p[idx] = s.x[idx];
-}
-
-// fp update + argmin(fp) with first-index tie-break (np.argmin semantics) -> record
-__global__ void __launch_bounds__(256) swarm_local_best_kernel(SwarmState s, double* __restrict__ rec) {
-    const int b = blockIdx.x, tid = threadIdx.x;
-    if (s.stop[b]) return;
-    __shared__ double sf[256];
-    __shared__ int si[256];
-    double bf = CUDART_INF;
-    int bi = 0x7fffffff;
-    for (int i = tid; i < s.S; i += 256) {
-        size_t bs = (size_t)b * s.S + i;
-        double fx = s.fx[bs], fp = s.fp[bs];
-        if (fx < fp) { fp = fx; s.fp[bs] = fx; }
-        if (fp < bf || (fp == bf && i < bi)) { bf = fp; bi = i; }
-    }
-    sf[tid] = bf; si[tid] = bi;
-    __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
-        if (tid < o) {
-            double of = sf[tid + o]; int oi = si[tid + o];
-            if (of < sf[tid] || (of == sf[tid] && oi < si[tid])) { sf[tid] = of; si[tid] = oi; }
-        }
-        __syncthreads();
-    }
-    int best = si[0];
-    const double* src = s.p;
-    if (best == 0x7fffffff) { best = 0; src = s.x; }   // nothing finite yet: pyswarm falls back to x[0]
-    double* r = rec + (size_t)b * (s.D + 2);
-    if (tid == 0) { r[0] = sf[0]; r[1] = (double)(s.index0 + best); }
-    for (int d = tid; d < s.D; d += 256) r[2 + d] = src[((size_t)b * s.S + best) * s.D + d];
-}
-
 // swarm-best update and the minfunc/minstep stop tests for spectrum b, by one CTA of `nthreads` threads.
 // `recs` holds one record per rank ([n_ranks][B][D+2]); every rank runs this redundantly on identical input,
 // so g/fg stay bit-identical everywhere.
@@ -296,14 +254,6 @@ cudaError_t launch_swarm_move(const SwarmState& s, const double* rp, const doubl
     size_t total = (size_t)s.B * s.S * s.D;
     swarm_move_kernel<<<blocks_for(total, 256), 256, 0, st>>>(s, rp, rg, generation);
     count_launches(1);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_swarm_local_best(const SwarmState& s, double* rec, cudaStream_t st) {
-    size_t total = (size_t)s.B * s.S * s.D;
-    swarm_pbest_kernel<<<blocks_for(total, 256), 256, 0, st>>>(s);
-    swarm_local_best_kernel<<<s.B, 256, 0, st>>>(s, rec);
-    count_launches(2);
     return cudaGetLastError();
 }
 

@@ -3,8 +3,8 @@
 // pyswarm.pso (called from the reference at utils.py:176-182) is a host loop: move every particle, call the
 // objective once per particle, update personal and swarm bests, test for convergence, repeat.  The per-step
 // kernels (pso.cu + objective_uniform.cu) already keep that loop on the device, but a generation is still
-// seven launches, and for the swarm sizes a single nmrfit.fit uses (100-204 particles, 4k-16k points) every one
-// of them is shorter than its own launch latency: ~40 us per generation for ~1 us of arithmetic.
+// three launches, and for the swarm sizes a single nmrfit.fit uses (100-204 particles, 4k-16k points) every one
+// of them is shorter than its own launch latency: ~25 us per generation for ~1 us of arithmetic.
 //
 // Here one CTA owns one particle for the whole run of generations.  Its state (x, v, p, fp, and replicas of the
 // swarm best g, fg and of the box) lives in shared memory; when the spectrum fits it is staged in shared memory
