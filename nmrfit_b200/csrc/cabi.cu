@@ -146,8 +146,9 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
     // The point tiling fixes the summation order of the residual, so it may depend on
     // N alone (never on how many particles or spectra a rank happens to hold).
     if (uni) {
-        if (c->N >= 8192) { t.threads = 256; t.r = 8; }          // 2,048-point tiles
-        else if (c->N >= 2048) { t.threads = 128; t.r = 8; }
+        // 2,048-point tiles from 2,048 points up (measured 9 % faster than 1,024-point tiles at 2,048 and 4,096
+        // points, 6 peaks: tools/tune_probe.py)
+        if (c->N >= 2048) { t.threads = 256; t.r = 8; }
         else { t.threads = 128; t.r = 4; }
     } else {
         if (c->N >= 8192) { t.threads = 256; t.r = 4; }
