@@ -19,3 +19,13 @@ def test_random_shapes(seed):
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
     rep = json.loads(out.stdout)
     assert rep['failures'] == [] and rep['worst']['objective_rel'] < 1e-10
+
+
+def test_adversarial_parameters():
+    """tools/fuzz_wild.py: widths over seven decades (incl. the recurrence / exact-path switch), centres at the edges
+    and outside the window, pure Lorentzian / Gaussian, large phases - both kernels, real-only and fit_im, 1e-9."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, 'tools', 'fuzz_wild.py'), '5'], capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-2000:]
+    rep = json.loads(out.stdout)
+    assert rep['n_bad'] == 0 and max(rep['worst'].values()) < 1e-9
