@@ -116,10 +116,11 @@ struct FusedArgs {
     int maxiter;
     int slots;              // supertiles of (u, v, weights) held in shared memory (filled by the launcher)
     int cluster;            // CTAs (one thread-block cluster) per particle (filled by the launcher)
+    int pairs;              // pair-parallel constants pass (needs its scratch in shared memory; filled by the launcher)
     long long* timing;      // optional [8] per-phase cycle counters (null: off)
 };
 struct FusedPlan {
-    bool ok;
+    bool ok, dense, pairs;
     int threads, r, slots, cluster;
     size_t smem;
 };

@@ -22,8 +22,8 @@
 // CTA keeps its contiguous run of the spectrum in its own shared memory, evaluates its regions, and the regions'
 // sums are all-gathered through DISTRIBUTED SHARED MEMORY (every CTA stores its sums into every peer's array,
 // cluster.sync()), after which all CTAs of the cluster continue redundantly exactly as the single CTA does - same
-// summation order, so still bit-identical to the per-step kernels.  (3 CTAs per SM for the cluster variant was
-// measured: the 80-register build spills and gains nothing on balance.)
+// summation order, so still bit-identical to the per-step kernels.  An 80-register build of the cluster variant
+// (3 CTAs per SM, a few spills) is used only when the 2-per-SM build cannot make the clusters co-resident.
 //
 // Requires every CTA of the grid to be co-resident: launched cooperatively (cudaLaunchKernelEx with the cooperative
 // attribute, plus the cluster dimension), and the host falls back to the per-step kernels when the device cannot
@@ -47,7 +47,7 @@ namespace {
 struct FusedSmem {
     int tab, uv, wt, cs, part, far, anchor, mask, wpart, state, red, misc, pairs, total;
     // NRP: region slots of the whole axis (tile sums of every region end up in every CTA); NRL: regions this CTA owns
-    __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP, int NRL) {
+    __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP, int NRL, bool want_pairs) {
         const int mw = (P + 31) / 32;
         const int De = (D + 1) & ~1;
         int o = 0;
@@ -64,7 +64,7 @@ struct FusedSmem {
         red = o;    o += 64;             // per-warp argmin values and indices
         misc = o;   o += 8;
         // (region, peak) series scratch of the pair-parallel prepare, when one thread per pair (+ anchors) is available
-        pairs = NRL * P + NRL <= threads ? o : -1;
+        pairs = want_pairs && NRL * P + NRL <= threads ? o : -1;
         if (pairs >= 0) o += ((NRL * P * kPairDoubles + 1) & ~1);
         total = o;
     }
@@ -97,8 +97,8 @@ __device__ __forceinline__ void take_min(double& bf, int& bi, double f, int i) {
         }                                                                       \
     } while (0)
 
-template <int THREADS, int R, int TB, bool CL>
-__global__ void __launch_bounds__(THREADS, 512 / THREADS)
+template <int THREADS, int R, int TB, bool CL, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB)
 swarm_fused_kernel(FusedArgs a) {
     constexpr int NW = THREADS / 32;
     extern __shared__ __align__(16) double smem[];
@@ -118,7 +118,7 @@ swarm_fused_kernel(FusedArgs a) {
     const int st_lo = min(crank * per, n_super), st_hi = min(st_lo + per, n_super);
     const int r_lo = st_lo * NW, r_hi = min(st_hi * NW, NRP);
     const bool resident = a.slots >= per;
-    const FusedSmem L(P, D, THREADS, R, a.slots, NRP, per * NW);
+    const FusedSmem L(P, D, THREADS, R, a.slots, NRP, per * NW, a.pairs != 0);
     double* tab = smem + L.tab;
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
     double* swt = smem + L.wt;
@@ -374,16 +374,18 @@ swarm_fused_kernel(FusedArgs a) {
 
 // ---- host side ------------------------------------------------------------------------------------------
 
-static const void* fused_kernel(int threads, int r, int cluster) {
+// dense = 3 CTAs of 256 threads per SM (80 registers, a few spills) instead of 2: only when that is what makes the
+// clusters co-resident
+static const void* fused_kernel(int threads, int r, int cluster, bool dense) {
     if (cluster > 1) {
-        if (threads == 256 && r == 8) return (const void*)swarm_fused_kernel<256, 8, 6, true>;
-        if (threads == 256 && r == 4) return (const void*)swarm_fused_kernel<256, 4, 6, true>;
-        return nullptr;
+        if (threads != 256) return nullptr;
+        if (dense) return r == 8 ? (const void*)swarm_fused_kernel<256, 8, 6, true, 3> : r == 4 ? (const void*)swarm_fused_kernel<256, 4, 6, true, 3> : nullptr;
+        return r == 8 ? (const void*)swarm_fused_kernel<256, 8, 6, true, 2> : r == 4 ? (const void*)swarm_fused_kernel<256, 4, 6, true, 2> : nullptr;
     }
-    if (threads == 512 && r == 8) return (const void*)swarm_fused_kernel<512, 8, 6, false>;
-    if (threads == 512 && r == 4) return (const void*)swarm_fused_kernel<512, 4, 6, false>;
-    if (threads == 256 && r == 8) return (const void*)swarm_fused_kernel<256, 8, 6, false>;
-    if (threads == 256 && r == 4) return (const void*)swarm_fused_kernel<256, 4, 6, false>;
+    if (threads == 512 && r == 8) return (const void*)swarm_fused_kernel<512, 8, 6, false, 1>;
+    if (threads == 512 && r == 4) return (const void*)swarm_fused_kernel<512, 4, 6, false, 1>;
+    if (threads == 256 && r == 8) return (const void*)swarm_fused_kernel<256, 8, 6, false, 2>;
+    if (threads == 256 && r == 4) return (const void*)swarm_fused_kernel<256, 4, 6, false, 2>;
     return nullptr;
 }
 
@@ -405,10 +407,10 @@ static void fill_config(cudaLaunchConfig_t* cfg, cudaLaunchAttribute* at, int gr
 }
 
 // Can `particles * cluster` CTAs of `threads` threads be co-resident?  Tries the whole share of the spectrum resident
-// in shared memory first, then one supertile at a time.
-static cudaError_t plan_one(const FusedArgs& a, int D, int particles, int threads, int r, int cluster, int device,
-                            FusedPlan* plan) {
-    const void* kern = fused_kernel(threads, r, cluster);
+// in shared memory first, then one supertile at a time; with the pair-parallel constants pass, then without its scratch.
+static cudaError_t plan_one(const FusedArgs& a, int D, int particles, int threads, int r, int cluster, bool dense,
+                            int device, FusedPlan* plan) {
+    const void* kern = fused_kernel(threads, r, cluster, dense);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
@@ -418,31 +420,32 @@ static cudaError_t plan_one(const FusedArgs& a, int D, int particles, int thread
     const int NW = threads / 32, NRP = a.n_vtiles * a.vw, n_super = (NRP + NW - 1) / NW;
     const int per = (n_super + cluster - 1) / cluster;
     const int grid = particles * cluster;
-    for (int slots : {per, 1}) {
-        const size_t bytes = (size_t)FusedSmem(a.P, D, threads, r, slots, NRP, per * NW).total * sizeof(double);
-        if (bytes <= 200 * 1024) {
-            long long capacity = 0;
-            if (cluster > 1) {
-                cudaLaunchConfig_t cfg;
-                cudaLaunchAttribute at[2];
-                fill_config(&cfg, at, grid, threads, bytes, cluster, nullptr);
-                int clusters = 0;
-                e = cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg);
-                if (e != cudaSuccess) { cudaGetLastError(); clusters = 0; }
-                capacity = (long long)clusters * cluster;
-            } else {
-                int per_sm = 0;
-                e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, bytes);
-                if (e != cudaSuccess) return e;
-                capacity = (long long)per_sm * sms;
-            }
-            if (capacity >= grid) {
-                plan->ok = true; plan->threads = threads; plan->r = r; plan->slots = slots; plan->cluster = cluster;
-                plan->smem = bytes;
-                return cudaSuccess;
-            }
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        const int slots = (attempt & 1) ? 1 : per;
+        const bool pairs = attempt < 2;
+        if ((attempt & 1) && per == 1) continue;
+        const size_t bytes = (size_t)FusedSmem(a.P, D, threads, r, slots, NRP, per * NW, pairs).total * sizeof(double);
+        if (bytes > 200 * 1024) continue;
+        long long capacity = 0;
+        if (cluster > 1) {
+            cudaLaunchConfig_t cfg;
+            cudaLaunchAttribute at[2];
+            fill_config(&cfg, at, grid, threads, bytes, cluster, nullptr);
+            int clusters = 0;
+            e = cudaOccupancyMaxActiveClusters(&clusters, kern, &cfg);
+            if (e != cudaSuccess) { cudaGetLastError(); clusters = 0; }
+            capacity = (long long)clusters * cluster;
+        } else {
+            int per_sm = 0;
+            e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, threads, bytes);
+            if (e != cudaSuccess) return e;
+            capacity = (long long)per_sm * sms;
         }
-        if (slots == 1) break;
+        if (capacity >= grid) {
+            plan->ok = true; plan->threads = threads; plan->r = r; plan->slots = slots; plan->cluster = cluster;
+            plan->dense = dense; plan->pairs = pairs; plan->smem = bytes;
+            return cudaSuccess;
+        }
     }
     return cudaSuccess;
 }
@@ -462,10 +465,10 @@ cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjT
         // (a cluster of two 8-warp CTAs instead of one 16-warp CTA was measured here: no gain - the phase is bound by
         // each warp's own dependent chain, not by the SM's FP64 rate)
         if (particles <= sms && NRP > 8) {
-            e = plan_one(a, D, (int)particles, 512, t.r, 1, device, plan);
+            e = plan_one(a, D, (int)particles, 512, t.r, 1, false, device, plan);
             if (e != cudaSuccess || plan->ok) return e;
         }
-        return plan_one(a, D, (int)particles, 256, t.r, 1, device, plan);
+        return plan_one(a, D, (int)particles, 256, t.r, 1, false, device, plan);
     }
     // Longer axes: a thread-block cluster per particle, as many CTAs as stay co-resident (<= 8, the portable limit),
     // each with its run of supertiles; past ~32 regions per CTA the three-launch per-step path, which spreads a
@@ -475,8 +478,11 @@ cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjT
         if (cluster > n_super) continue;
         const int per = (n_super + cluster - 1) / cluster;
         if (!force && per * 8 > 32) break;                 // smaller clusters only get longer runs
-        e = plan_one(a, D, (int)particles, 256, t.r, cluster, device, plan);
-        if (e != cudaSuccess || plan->ok) return e;
+        for (bool dense : {false, true}) {
+            if (dense && cluster == 1) continue;
+            e = plan_one(a, D, (int)particles, 256, t.r, cluster, dense, device, plan);
+            if (e != cudaSuccess || plan->ok) return e;
+        }
     }
     return cudaSuccess;
 }
@@ -484,7 +490,8 @@ cudaError_t swarm_fused_plan(const FusedArgs& a, int D, int B, int S, const ObjT
 cudaError_t launch_swarm_fused(FusedArgs a, const FusedPlan& plan, int B, int S, cudaStream_t st) {
     a.slots = plan.slots;
     a.cluster = plan.cluster;
-    const void* kern = fused_kernel(plan.threads, plan.r, plan.cluster);
+    a.pairs = plan.pairs ? 1 : 0;
+    const void* kern = fused_kernel(plan.threads, plan.r, plan.cluster, plan.dense);
     if (!kern) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(a.barrier, 0, sizeof(unsigned) * B, st);
     if (e != cudaSuccess) return e;
