@@ -95,6 +95,7 @@ int main(int argc, char** argv) {
     nmrfit_pso_opts o;
     o.swarmsize = 64; o.maxiter = 150; o.omega = -0.2134; o.phip = -0.3344; o.phig = 2.3259;
     o.minstep = 1e-8; o.minfunc = 1e-8; o.fit_im = NMRFIT_REAL_ONLY; o.bounds_per_spectrum = 0; o.seed = 5; o.particle_offset = 0;
+    o.spectrum_offset = 0;
     double x0[ND], f0, x1[ND], f1;
     int gens = 0, stop = 0, running = 1;
     if (p_nmrfit_pso_begin(ctx, lb, ub, &o, NULL, NULL, NULL) || p_nmrfit_pso_commit(ctx, NULL, 1, NULL) ||

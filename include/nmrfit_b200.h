@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define NMRFIT_ABI_VERSION 1
+#define NMRFIT_ABI_VERSION 2
 
 #define NMRFIT_OK 0
 #define NMRFIT_ERR_ARG (-1)    /* bad argument */
@@ -143,6 +143,8 @@ typedef struct nmrfit_pso_opts {
     int bounds_per_spectrum;     /* 0: lb/ub are [D] shared by all spectra; 1: [n_spectra][D] */
     unsigned long long seed;     /* device Philox stream, used wherever a random array is NULL */
     long long particle_offset;   /* global index of local particle 0 (particle sharding; else 0) */
+    long long spectrum_offset;   /* global index of local spectrum 0 (spectra sharding; else 0): with both offsets the
+                                    device random stream does not depend on how the work is split over ranks */
 } nmrfit_pso_opts;
 
 /* Initial swarm: x = lb + r_pos*(ub-lb), v = vlow + r_vel*(vhigh-vlow), evaluate, personal bests,

@@ -36,7 +36,8 @@ class PsoOpts(ctypes.Structure):
                 ('omega', ctypes.c_double), ('phip', ctypes.c_double), ('phig', ctypes.c_double),
                 ('minstep', ctypes.c_double), ('minfunc', ctypes.c_double),
                 ('fit_im', ctypes.c_int), ('bounds_per_spectrum', ctypes.c_int),
-                ('seed', ctypes.c_ulonglong), ('particle_offset', ctypes.c_longlong)]
+                ('seed', ctypes.c_ulonglong), ('particle_offset', ctypes.c_longlong),
+                ('spectrum_offset', ctypes.c_longlong)]
 
 
 # name -> (restype, argtypes); every symbol include/nmrfit_b200.h declares
@@ -101,7 +102,7 @@ def lib():
             fn = getattr(handle, name)       # AttributeError here = header and library disagree
             fn.restype = res
             fn.argtypes = args
-        if handle.nmrfit_abi_version() != 1:
+        if handle.nmrfit_abi_version() != 2:
             raise ImportError('libnmrfit_b200.so ABI version mismatch')
         _lib = handle
     return _lib

@@ -628,7 +628,7 @@ int nmrfit_pso_begin(nmrfit_ctx* c, const double* lb, const double* ub, const nm
     s.g = c->sg.ptr; s.fg = c->sfg.ptr; s.best_x = c->sbx.ptr; s.best_f = c->sbf.ptr;
     s.lb = c->slb.ptr; s.ub = c->sub.ptr; s.rec = c->srec.ptr; s.stop = c->sstop.ptr; s.it = c->sit.ptr;
     s.omega = o->omega; s.phip = o->phip; s.phig = o->phig; s.minstep = o->minstep; s.minfunc = o->minfunc;
-    s.seed = o->seed; s.index0 = o->particle_offset;
+    s.seed = o->seed; s.index0 = o->particle_offset; s.spec0 = o->spectrum_offset;
     c->maxiter = o->maxiter; c->kk = o->fit_im; c->generation = 0; c->swarm = true;
 
     const double *rp_d = nullptr, *rv_d = nullptr;

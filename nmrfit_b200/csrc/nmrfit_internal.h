@@ -79,6 +79,7 @@ struct SwarmState {
     double omega, phip, phig, minstep, minfunc;
     unsigned long long seed;
     long long index0;       // global index of local particle 0 (particle sharding)
+    long long spec0;        // global index of local spectrum 0 (spectra sharding)
 };
 
 struct MoveArgs {

@@ -11,7 +11,7 @@ enum { kStopRunning = 0, kStopMinFunc = 1, kStopMinStep = 2, kStopMaxIter = 3 };
 
 __device__ __forceinline__ unsigned long long elem_counter(const SwarmState& s, int b, int sl, int d) {
     // global (sharding-independent) element number
-    return ((unsigned long long)b << 40) ^ ((unsigned long long)(s.index0 + sl) * (unsigned long long)s.D + d);
+    return ((unsigned long long)(s.spec0 + b) << 40) ^ ((unsigned long long)(s.index0 + sl) * (unsigned long long)s.D + d);
 }
 
 // pyswarm's update in numpy's evaluation order, every operation rounded on its own (no FMA contraction):

@@ -59,7 +59,7 @@ def _check_bounds(lower, upper):
     return lb, ub
 
 
-def _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed, offset=0):
+def _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed, offset=0, spectrum_offset=0):
     o = _cabi.PsoOpts()
     o.swarmsize, o.maxiter = int(S), int(maxiter)
     o.omega, o.phip, o.phig = float(omega), float(phip), float(phig)
@@ -67,6 +67,7 @@ def _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed, of
     o.fit_im = _fit_im_mode(fit_im)
     o.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     o.particle_offset = int(offset)
+    o.spectrum_offset = int(spectrum_offset)
     return o
 
 
@@ -146,7 +147,7 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
 
 def pso_batch(spectra, lowers, uppers, fit_im=False, swarmsize=100, maxiter=100, omega=0.5, phip=0.5, phig=0.5,
               minstep=1e-8, minfunc=1e-8, rng='device', seeds=None, seed=0, precision='fp64', chunk=16, device=None,
-              tuning=None, fused='auto', ctx=None):
+              tuning=None, fused='auto', ctx=None, spectrum_offset=0):
     """B independent fits in one context.  ``spectra``: sequence of (w, u, v, weights),
     all of one length; ``lowers``/``uppers``: [B][D].  With ``ctx`` (a context that already
     holds the B spectra) ``spectra`` is ignored.
@@ -164,16 +165,16 @@ def pso_batch(spectra, lowers, uppers, fit_im=False, swarmsize=100, maxiter=100,
     D = lb.shape[1]
     if ctx is not None:
         return _pso_batch_run(ctx, lb, ub, fit_im, swarmsize, maxiter, omega, phip, phig, minstep, minfunc, rng,
-                              seeds, seed, chunk, tuning, fused)
+                              seeds, seed, chunk, tuning, fused, spectrum_offset)
     N = len(spectra[0][0])
     with _cabi.pooled_context(B, N, (D - 4) // 3, device=device, precision=_precision(precision)) as own:
         own.set_spectra(*[np.stack([sp[k] for sp in spectra]) for k in range(4)])
         return _pso_batch_run(own, lb, ub, fit_im, swarmsize, maxiter, omega, phip, phig, minstep, minfunc, rng,
-                              seeds, seed, chunk, tuning, fused)
+                              seeds, seed, chunk, tuning, fused, spectrum_offset)
 
 
 def _pso_batch_run(ctx, lb, ub, fit_im, swarmsize, maxiter, omega, phip, phig, minstep, minfunc, rng, seeds, seed,
-                   chunk, tuning, fused):
+                   chunk, tuning, fused, spectrum_offset=0):
     B, D = lb.shape
     S = int(swarmsize)
     host = rng == 'host'
@@ -184,7 +185,7 @@ def _pso_batch_run(ctx, lb, ub, fit_im, swarmsize, maxiter, omega, phip, phig, m
     if tuning:
         ctx.set_tuning(**tuning)
     ctx.set_fused(_fused_mode(fused))
-    opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed)
+    opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed, spectrum_offset=spectrum_offset)
     r_pos = r_vel = None
     if host:
         r_pos = np.empty((B, S, D))

@@ -36,17 +36,18 @@ def test_exports_match_header(built):
 def test_abi_version_and_error_string(built):
     from nmrfit_b200 import _cabi
     lib = _cabi.lib()
-    assert lib.nmrfit_abi_version() == 1
+    assert lib.nmrfit_abi_version() == 2
     assert isinstance(lib.nmrfit_last_error(), bytes)
     assert _cabi.launch_count() >= 0
 
 
 def test_pso_opts_layout_matches_header():
     from nmrfit_b200 import _cabi
-    # struct nmrfit_pso_opts: 2 int, 5 double, 2 int, u64, i64  -> 72 bytes with natural alignment
-    assert ctypes.sizeof(_cabi.PsoOpts) == 72
+    # struct nmrfit_pso_opts: 2 int, 5 double, 2 int, u64, 2 x i64  -> 80 bytes with natural alignment
+    assert ctypes.sizeof(_cabi.PsoOpts) == 80
     assert _cabi.PsoOpts.omega.offset == 8 and _cabi.PsoOpts.fit_im.offset == 48
     assert _cabi.PsoOpts.seed.offset == 56 and _cabi.PsoOpts.particle_offset.offset == 64
+    assert _cabi.PsoOpts.spectrum_offset.offset == 72
 
 
 def test_missing_library_fails_loudly(monkeypatch, tmp_path):

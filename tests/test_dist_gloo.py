@@ -117,3 +117,54 @@ def test_sharded_protocol_equals_unsharded(world):
         for r in range(world):
             x, f, it = out[r]
             assert np.array_equal(x, ref_x) and f == ref_f and it == info['it']
+
+
+def _sharded_batch_worker(rank, world, port, B, D, out):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from nmrfit_b200 import core
+
+    class Fake:
+        pass
+
+    def fake_fit_batch(datas, lowers, uppers, expon, dynamic_weighting, fit_im, summary, options):
+        fits = []
+        for k, d in enumerate(datas):
+            f = Fake()
+            f.params = np.full(D, float(d)) + np.arange(D) * 1e-3       # recognisable per spectrum
+            f.error = float(d) * 10.0
+            f.fit_info = dict(generations=int(d) + 1, stop=int(d) % 3, seed=options['seed'], seeds=options.get('seeds'))
+            fits.append(f)
+        out.put((rank, len(datas), options['spectrum_offset'], options.get('seeds')))
+        return fits
+
+    datas = list(range(100, 100 + B))                     # the "spectra" are just tags here
+    lo = [[0.0] * D] * B
+    x, f, it, stop = core.fit_batch_sharded(datas, lo, lo, options={'seed': 7, 'seeds': list(range(B))}, fit_fn=fake_fit_batch)
+    assert x.shape == (B, D) and np.array_equal(x[:, 0], np.arange(100, 100 + B, dtype=float))
+    assert np.array_equal(f, 10.0 * np.arange(100, 100 + B)) and np.array_equal(it, np.arange(101, 101 + B))
+    assert np.array_equal(stop, np.arange(100, 100 + B) % 3)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('B', [5, 2, 1])
+def test_fit_batch_sharded_splits_and_gathers(B):
+    """Spectra-sharded batch fit: contiguous blocks per rank (uneven and even empty), per-rank seed offsets, one final
+    all-gather that hands every rank every result in spectrum order."""
+    world, D = 2, 7
+    ctx = mp.get_context('spawn')
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sharded_batch_worker, args=(r, world, port, B, D, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    seen = sorted(out.get(timeout=5) for _ in range(min(world, B)))
+    counts = [s[1] for s in seen]
+    assert sum(counts) == B and max(counts) - min(counts) <= 1 if B >= world else counts == [1]
+    assert seen[0][2] == 0 and seen[0][3] == list(range(counts[0]))      # rank 0: spectrum offset 0, its slice of seeds
+    if len(seen) > 1:
+        assert seen[1][2] == counts[0] and seen[1][3] == list(range(counts[0], B))
