@@ -2,7 +2,7 @@
 arithmetic on the GPU.
 
 Same names, argument order and meaning as the reference:
-``voigt`` (equations.py:115-149), ``kk_relation`` / ``kk_relation_vectorized`` /
+``voigt`` (equations.py:115-149), ``kk_equation`` (:9-49), ``kk_relation`` / ``kk_relation_vectorized`` /
 ``kk_relation_parallel`` (:52-112, :242), ``objective`` (:152-212), ``laplace1d``
 (:215-238).  ``objective_batch`` is the addition that makes the path fast: one
 call evaluates a whole swarm generation.
@@ -41,6 +41,17 @@ def kk_relation_vectorized(w, r, yoff, width, loc, a):
     _cabi.check(_cabi.lib().nmrfit_kk_host(_cabi.default_device(), _cabi.ptr(w), w.size, float(r), float(yoff),
                                            float(width), float(loc), float(a), _cabi.ptr(out)))
     return out
+
+
+def kk_equation(x, r, yoff, width, loc, a, w):
+    """The integrand of the reference's Kramers-Kronig quadrature, [V(w - x) - V(w + x)] / x (equations.py:9-49).
+    Kept importable for callers that integrate it themselves; ``kk_relation`` here does not need it (closed form).
+    ``x`` may be an array; the two Voigt evaluations run on the GPU."""
+    x = _cabi.as_f64(np.atleast_1d(x))
+    v1 = voigt(x + w, r, yoff, width, loc, a)
+    v2 = voigt(-x + w, r, yoff, width, loc, a)
+    out = 1 / x * (v2 - v1)
+    return out if out.size > 1 else float(out[0])
 
 
 def kk_relation(w, r, yoff, width, loc, a):

@@ -86,3 +86,18 @@ def test_generate_result_config5_shape():
     # the fitted curve, re-phased on its own grid, returns to (V, I)
     V2, I2 = orc.ps2(f.u, f.v, true[0], true[1])
     assert np.allclose(V2, f.V, atol=1e-13) and np.allclose(I2, f.I, atol=1e-13)
+
+
+def test_kk_equation_integrand_matches_reference_form():
+    """equations.kk_equation (equations.py:9-49) stays importable: the integrand [V(w-x) - V(w+x)]/x, and integrating
+    it the reference's way reproduces our closed-form kk_relation."""
+    import scipy.integrate
+    from nmrfit_b200 import equations
+    pars = (0.6, 0.003, 0.004, 3.40, 0.02)
+    w0 = 3.4013
+    x = np.array([1e-4, 2e-3, 0.05, 1.0])
+    want = 1 / x * (orc.voigt(-x + w0, *pars) - orc.voigt(x + w0, *pars))
+    got = equations.kk_equation(x, *pars, w0)
+    assert np.max(np.abs(got - want)) < 1e-9 * np.max(np.abs(want))
+    quad = scipy.integrate.quad(lambda t: equations.kk_equation(t, *pars, w0), 0, np.inf)[0] / np.pi
+    assert abs(quad - equations.kk_relation(w0, *pars)) < 2e-8 * abs(quad)
