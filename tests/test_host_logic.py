@@ -119,3 +119,15 @@ def test_draw_order_matches_pyswarm():
     rs = np.random.RandomState(5)
     rp, rg = swarm._draw_generations(rs, 2, 3, 2)
     assert np.array_equal(rp[0], a) and np.array_equal(rg[0], b) and np.array_equal(rp[1], c)
+
+
+def test_pyswarm_compat_refuses_what_it_cannot_accelerate():
+    from nmrfit_b200 import pyswarm_compat
+    with pytest.raises(NotImplementedError, match='nmrfit objective'):
+        pyswarm_compat.pso(lambda x: float(np.sum(x ** 2)), [0, 0], [1, 1])
+    from nmrfit_b200 import equations
+    assert pyswarm_compat._is_nmrfit_objective(equations.objective)
+    with pytest.raises(NotImplementedError, match='constraints'):
+        pyswarm_compat.pso(equations.objective, [0] * 7, [1] * 7, ieqcons=[lambda x: 1.0], args=(None,) * 5)
+    with pytest.raises(ValueError, match='args'):
+        pyswarm_compat.pso(equations.objective, [0] * 7, [1] * 7, args=(1, 2))
