@@ -781,15 +781,43 @@ int nmrfit_generate_result(const double* params, int P, const double* w, int n, 
     return NMRFIT_OK;
 }
 
-// host-staged variants: allocate, copy in, run, copy out, free
+// host-staged variants: copy in, run, copy out.  Their device staging comes from a per-thread, per-device arena that is
+// kept between calls (a cudaMalloc/cudaFree pair costs more than these kernels run); requests beyond kArenaKeep are
+// served by a temporary allocation instead, so one large call does not pin device memory for good.
 namespace {
+constexpr size_t kArenaKeep = (size_t)8 << 20;             // doubles (64 MB)
+struct Arena {
+    double* ptr = nullptr;
+    size_t cap = 0;
+};
+thread_local Arena t_arena[NMRFIT_MAX_DEVICES];
+
 struct Scratch {
-    std::vector<double*> ptrs;
-    ~Scratch() { for (double* p : ptrs) cudaFree(p); }
-    cudaError_t get(size_t n, double** out) {
-        cudaError_t e = cudaMalloc(out, std::max<size_t>(n, 1) * sizeof(double));
-        if (e == cudaSuccess) ptrs.push_back(*out);
-        return e;
+    double* base = nullptr;
+    double* temp = nullptr;                                // temporary allocation of an oversized request
+    size_t used = 0, total = 0;
+    cudaError_t err = cudaSuccess;
+    Scratch(int device, size_t total_doubles) : total(std::max<size_t>(total_doubles, 1)) {
+        if (total > kArenaKeep || device < 0 || device >= NMRFIT_MAX_DEVICES) {
+            err = cudaMalloc(&temp, total * sizeof(double));
+            base = temp;
+            return;
+        }
+        Arena& a = t_arena[device];
+        if (a.cap < total) {
+            if (a.ptr) cudaFree(a.ptr);
+            a.ptr = nullptr;
+            a.cap = 0;
+            err = cudaMalloc(&a.ptr, total * sizeof(double));
+            if (err == cudaSuccess) a.cap = total;
+        }
+        base = a.ptr;
+    }
+    ~Scratch() { if (temp) cudaFree(temp); }
+    double* take(size_t n) {
+        double* p = base + used;
+        used += std::max<size_t>(n, 1);
+        return p;
     }
 };
 }  // namespace
@@ -799,9 +827,9 @@ int nmrfit_ps2_host(int device, const double* u, const double* v, int n, double 
     if (n < 0 || (n > 0 && (!u || !v || !re || !im))) return fail(NMRFIT_ERR_ARG, "bad ps2 arguments");
     if (n == 0) return NMRFIT_OK;
     CK(cudaSetDevice(device));
-    Scratch s;
-    double *du, *dv, *dr, *di;
-    CK(s.get(n, &du)); CK(s.get(n, &dv)); CK(s.get(n, &dr)); CK(s.get(n, &di));
+    Scratch s(device, 4 * (size_t)n);
+    CK(s.err);
+    double *du = s.take(n), *dv = s.take(n), *dr = s.take(n), *di = s.take(n);
     CK(cudaMemcpy(du, u, sizeof(double) * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dv, v, sizeof(double) * n, cudaMemcpyHostToDevice));
     if (int rc = nmrfit_ps2(du, dv, n, p0, p1, inv, dr, di, nullptr)) return rc;
@@ -815,9 +843,9 @@ int nmrfit_voigt_host(int device, const double* w, int n, double r, double yoff,
     if (n < 0 || (n > 0 && (!w || !out))) return fail(NMRFIT_ERR_ARG, "bad voigt arguments");
     if (n == 0) return NMRFIT_OK;
     CK(cudaSetDevice(device));
-    Scratch s;
-    double *dw, *dout;
-    CK(s.get(n, &dw)); CK(s.get(n, &dout));
+    Scratch s(device, 2 * (size_t)n);
+    CK(s.err);
+    double *dw = s.take(n), *dout = s.take(n);
     CK(cudaMemcpy(dw, w, sizeof(double) * n, cudaMemcpyHostToDevice));
     if (int rc = nmrfit_voigt(dw, n, r, yoff, width, loc, a, dout, nullptr)) return rc;
     CK(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
@@ -829,9 +857,9 @@ int nmrfit_kk_host(int device, const double* w, int n, double r, double yoff, do
     if (n < 0 || (n > 0 && (!w || !out))) return fail(NMRFIT_ERR_ARG, "bad kk arguments");
     if (n == 0) return NMRFIT_OK;
     CK(cudaSetDevice(device));
-    Scratch s;
-    double *dw, *dout;
-    CK(s.get(n, &dw)); CK(s.get(n, &dout));
+    Scratch s(device, 2 * (size_t)n);
+    CK(s.err);
+    double *dw = s.take(n), *dout = s.take(n);
     CK(cudaMemcpy(dw, w, sizeof(double) * n, cudaMemcpyHostToDevice));
     if (int rc = nmrfit_kk(dw, n, r, yoff, width, loc, a, dout, nullptr)) return rc;
     CK(cudaMemcpy(out, dout, sizeof(double) * n, cudaMemcpyDeviceToHost));
@@ -844,11 +872,11 @@ int nmrfit_generate_result_host(int device, const double* params, int P, const d
     if (n > 0 && (!w || !real || !imag || !V || !I || !u || !v)) return fail(NMRFIT_ERR_ARG, "NULL output buffer");
     if (n == 0) return NMRFIT_OK;
     CK(cudaSetDevice(device));
-    Scratch s;
-    double *dw, *dreal, *dimag, *dV, *dI, *du, *dv;
     size_t pn = (size_t)P * n;
-    CK(s.get(n, &dw)); CK(s.get(pn, &dreal)); CK(s.get(pn, &dimag));
-    CK(s.get(n, &dV)); CK(s.get(n, &dI)); CK(s.get(n, &du)); CK(s.get(n, &dv));
+    Scratch s(device, 2 * pn + 5 * (size_t)n);
+    CK(s.err);
+    double *dw = s.take(n), *dreal = s.take(pn), *dimag = s.take(pn);
+    double *dV = s.take(n), *dI = s.take(n), *du = s.take(n), *dv = s.take(n);
     CK(cudaMemcpy(dw, w, sizeof(double) * n, cudaMemcpyHostToDevice));
     if (int rc = nmrfit_generate_result(params, P, dw, n, dreal, dimag, dV, dI, du, dv, nullptr)) return rc;
     CK(cudaMemcpy(real, dreal, sizeof(double) * pn, cudaMemcpyDeviceToHost));
