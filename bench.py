@@ -268,8 +268,11 @@ def run_b200(args):
             ctx.pso_commit(stream=stream)
 
     def step():
-        ctx.pso_advance(stream=stream)
-        commit()
+        if world > 1 and not batched:
+            ctx.pso_advance(stream=stream)                 # particle-sharded: advance, exchange the best records, commit
+            commit()
+        else:
+            ctx.pso_step(stream=stream)                    # the swarm lives in this context: one call, three launches
 
     commit()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device='cuda')

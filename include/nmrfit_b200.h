@@ -155,6 +155,9 @@ int nmrfit_pso_begin(nmrfit_ctx* ctx, const double* lb, const double* ub, const 
 /* One generation: velocity/position update with rp, rg (host, device, or NULL = Philox), clamp to the
  * box, evaluate, personal bests, local best record. */
 int nmrfit_pso_advance(nmrfit_ctx* ctx, const double* rp, const double* rg, void* stream);
+/* One whole generation of a swarm held by ONE context (no rank exchange): advance + commit, asynchronous on `stream` -
+ * what nmrfit_pso_run does per generation, without its final synchronisation.  Three launches. */
+int nmrfit_pso_step(nmrfit_ctx* ctx, const double* rp, const double* rg, void* stream);
 /* Device pointer and length (doubles) of the local best record, [n_spectra][D+2] = (f, global index, x[D]). */
 int nmrfit_pso_record(nmrfit_ctx* ctx, double** rec_dev, int* n_doubles);
 /* Swarm-best update and the minfunc/minstep/maxiter tests.  recs_dev = [n_ranks][n_spectra][D+2]

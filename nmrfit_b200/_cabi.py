@@ -64,6 +64,7 @@ SIGNATURES = {
     'nmrfit_objective_batch_host': (_i, [_vp, _vp, _i, _i, _vp]),
     'nmrfit_pso_begin': (_i, [_vp, _vp, _vp, ctypes.POINTER(PsoOpts), _vp, _vp, _vp]),
     'nmrfit_pso_advance': (_i, [_vp, _vp, _vp, _vp]),
+    'nmrfit_pso_step': (_i, [_vp, _vp, _vp, _vp]),
     'nmrfit_pso_record': (_i, [_vp, ctypes.POINTER(_vp), c_int_p]),
     'nmrfit_pso_commit': (_i, [_vp, _vp, _i, _vp]),
     'nmrfit_pso_run': (_i, [_vp, _i, _vp, _vp, c_int_p, _vp]),
@@ -288,6 +289,11 @@ class Context:
     def pso_advance(self, rp=None, rg=None, stream=None):
         rp, rg = self._rand(rp, self._swarmsize), self._rand(rg, self._swarmsize)
         check(lib().nmrfit_pso_advance(self._h, ptr(rp), ptr(rg), ptr(stream)))
+
+    def pso_step(self, rp=None, rg=None, stream=None):
+        """One whole single-context generation (advance + commit), asynchronous."""
+        rp, rg = self._rand(rp, self._swarmsize), self._rand(rg, self._swarmsize)
+        check(lib().nmrfit_pso_step(self._h, ptr(rp), ptr(rg), ptr(stream)))
 
     def pso_record(self):
         p, n = ctypes.c_void_p(), ctypes.c_int(0)

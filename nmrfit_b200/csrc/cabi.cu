@@ -655,6 +655,21 @@ int nmrfit_pso_advance(nmrfit_ctx* c, const double* rp, const double* rg, void* 
     return swarm_generation(c, true, rp_d, rg_d, 0, st);
 }
 
+int nmrfit_pso_step(nmrfit_ctx* c, const double* rp, const double* rg, void* stream) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    if ((rp == nullptr) != (rg == nullptr)) return fail(NMRFIT_ERR_ARG, "rp and rg must both be given or both be NULL");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SwarmState& s = c->sw;
+    size_t nsd = (size_t)s.B * s.S * s.D;
+    const double *rp_d = nullptr, *rg_d = nullptr;
+    if (int rc = stage(rp, nsd, c->rnd_a, st, &rp_d)) return rc;
+    if (int rc = stage(rg, nsd, c->rnd_b, st, &rg_d)) return rc;
+    c->generation += 1;
+    return swarm_generation(c, true, rp_d, rg_d, 1, st);
+}
+
 int nmrfit_pso_record(nmrfit_ctx* c, double** rec_dev, int* n_doubles) {
     if (int rc = check_ctx(c)) return rc;
     if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");

@@ -243,3 +243,27 @@ def test_pso_argument_errors():
         with pytest.raises(_cabi.NmrfitError, match='pso_begin'):
             ctx._swarmsize = 4
             ctx.pso_advance()
+
+
+def test_pso_step_equals_advance_plus_commit():
+    g = load_golden('fit_lite_1024x6')
+    S, D, iters = 17, 22, 6
+    rs = np.random.RandomState(9)
+    r_pos, r_vel = rs.rand(S, D), rs.rand(S, D)
+    rp, rg = rs.rand(iters, S, D), rs.rand(iters, S, D)
+    outs = []
+    for use_step in (True, False):
+        with _cabi.Context(1, g['w'].size, 6) as ctx:
+            ctx.set_spectrum(0, g['w'], g['u'], g['v'], g['weights'])
+            ctx.pso_begin(g['lower'], g['upper'], swarm._make_opts(S, 100, PSO['omega'], PSO['phip'], PSO['phig'], 1e-8, 1e-8, False, 0), r_pos, r_vel)
+            ctx.pso_commit()
+            for k in range(iters):
+                if use_step:
+                    ctx.pso_step(rp[k], rg[k])
+                else:
+                    ctx.pso_advance(rp[k], rg[k])
+                    ctx.pso_commit()
+            outs.append((ctx.pso_best(), ctx.pso_state()))
+    (ba, sa), (bb, sb) = outs
+    assert all(np.array_equal(x, y) for x, y in zip(ba, bb))
+    assert all(np.array_equal(sa[k], sb[k]) for k in ('x', 'v', 'p', 'fx', 'fp'))
