@@ -397,6 +397,11 @@ def run_b200(args):
             'spectra_generations_per_s': (B * world * args.steps / (total_ms * 1e-3)) if batched else None,
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s',
                          'frac': achieved / sustained, 'traffic': traffic,
+                         'traffic_note': 'DRAM bytes of the evaluation kernel under ncu (cold L2): almost all of it is the '
+                                         'per-particle constants the prepare pass wrote (coefficients, far-field polynomial '
+                                         'and phase anchor per 256-point region), read ONCE by TMA bulk copies - a memory-for-'
+                                         'recompute trade at < 3 % of the HBM peak, not re-reads of the spectrum (32 B/point, '
+                                         'algorithmic_bytes_per_launch below)',
                          'kernel': 'objective_prepare_kernel + objective_uniform_kernel (one CUDA-event bracket around both)'
                                    if ctx.get_algorithm() == _cabi.ALGO_UNIFORM else 'objective_kernel',
                          'kernel_ms_per_launch': per_launch_ms,
