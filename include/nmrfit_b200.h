@@ -213,6 +213,11 @@ int nmrfit_phase_brute(nmrfit_phase* h, const double* p0_candidates, int K, doub
  * converts its degree arguments first, proc_autophase.py:60-62) -> score [n_spectra][K].  Host pointers. */
 int nmrfit_phase_acme(nmrfit_phase* h, const double* ph, int K, double* score);
 
+/* Page-locked host memory for result buffers: device-to-host copies into it run at PCIe speed and skip the page
+ * faults of freshly allocated pageable memory (generate_result at scale 16 writes 109 MB).  The Python layer pools these. */
+int nmrfit_host_alloc(size_t bytes, void** out);
+int nmrfit_host_free(void* p);
+
 /* DFMA throughput of the device (TFLOP/s): best single launch and back-to-back average. */
 int nmrfit_fp64_peak(int device, int iters, int repeats, double* burst_tflops, double* sustained_tflops);
 /* Kernels launched by this library in this process since load (for bench.py's gpu_launches). */

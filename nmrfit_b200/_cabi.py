@@ -82,6 +82,8 @@ SIGNATURES = {
     'nmrfit_phase_destroy': (None, [_vp]),
     'nmrfit_phase_brute': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     'nmrfit_phase_acme': (_i, [_vp, _vp, _i, _vp]),
+    'nmrfit_host_alloc': (_i, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
+    'nmrfit_host_free': (_i, [_vp]),
     'nmrfit_fp64_peak': (_i, [_i, _i, _i, c_double_p, c_double_p]),
     'nmrfit_launch_count': (ctypes.c_longlong, []),
 }
@@ -369,6 +371,58 @@ class PhaseScorer:
         score = np.empty((self.B, ph.shape[0]))
         check(lib().nmrfit_phase_acme(self._h, ptr(ph), ph.shape[0], ptr(score)))
         return score
+
+
+# ---- pinned result buffers --------------------------------------------------------------------------
+# Large results (generate_result at scale 16: 109 MB) are written into page-locked host memory taken from a small
+# pool: the device-to-host copy runs at PCIe speed and there are no first-touch page faults.  A block goes back to the
+# pool when the last numpy view of it is garbage collected.
+import weakref
+
+_PINNED_MIN = 4 << 20          # smaller results use ordinary numpy memory
+_PINNED_KEEP = 512 << 20       # bytes kept in the pool; blocks beyond that are freed
+_pinned_idle = {}              # block size -> [address, ...]
+_pinned_bytes = 0
+
+
+class _PinnedBlock:
+    """Owner of one pinned allocation; numpy arrays made from it keep it alive through ``.base``."""
+
+    def __init__(self, address, nbytes, count):
+        self.address, self.nbytes = address, nbytes
+        self.__array_interface__ = {'shape': (count,), 'typestr': '<f8', 'data': (address, False), 'version': 3}
+
+
+def _pinned_release(address, nbytes):
+    global _pinned_bytes
+    if _pinned_bytes + nbytes <= _PINNED_KEEP:
+        _pinned_idle.setdefault(nbytes, []).append(address)
+        _pinned_bytes += nbytes
+    else:
+        try:
+            lib().nmrfit_host_free(ctypes.c_void_p(address))
+        except Exception:      # interpreter shutdown
+            pass
+
+
+def result_empty(count):
+    """1-D float64 array of ``count`` elements for results: pinned and pooled when large, else ``np.empty``."""
+    global _pinned_bytes
+    nbytes = int(count) * 8
+    if nbytes < _PINNED_MIN:
+        return np.empty(int(count))
+    size = (nbytes + (1 << 21) - 1) & ~((1 << 21) - 1)     # 2 MB buckets so that blocks are reusable
+    idle = _pinned_idle.get(size)
+    if idle:
+        address = idle.pop()
+        _pinned_bytes -= size
+    else:
+        p = ctypes.c_void_p()
+        check(lib().nmrfit_host_alloc(size, ctypes.byref(p)))
+        address = p.value
+    block = _PinnedBlock(address, size, int(count))
+    weakref.finalize(block, _pinned_release, address, size)
+    return np.asarray(block)
 
 
 # ---- context pool ---------------------------------------------------------------------------------

@@ -971,6 +971,19 @@ int nmrfit_phase_acme(nmrfit_phase* h, const double* ph, int K, double* score) {
     return NMRFIT_OK;
 }
 
+int nmrfit_host_alloc(size_t bytes, void** out) {
+    if (!out || bytes == 0) return fail(NMRFIT_ERR_ARG, "bad host_alloc arguments");
+    *out = nullptr;
+    CK(cudaHostAlloc(out, bytes, cudaHostAllocPortable));
+    return NMRFIT_OK;
+}
+
+int nmrfit_host_free(void* p) {
+    if (!p) return NMRFIT_OK;
+    CK(cudaFreeHost(p));
+    return NMRFIT_OK;
+}
+
 int nmrfit_fp64_peak(int device, int iters, int repeats, double* burst, double* sustained) {
     if (!burst || !sustained || iters < 1 || repeats < 1) return fail(NMRFIT_ERR_ARG, "bad probe arguments");
     CK(cudaSetDevice(device));

@@ -153,9 +153,11 @@ class FitUtility:
         n_peaks = (params.size - 4) // 3
         w = _cabi.as_f64(w)
         n = w.size
-        real = np.empty((n_peaks, n))
-        imag = np.empty((n_peaks, n))
-        V, I, u, v = (np.empty(n) for _ in range(4))
+        # one result block (pinned and pooled when large: _cabi.result_empty), carved into the six outputs
+        block = _cabi.result_empty((2 * n_peaks + 4) * n)
+        real = block[:n_peaks * n].reshape(n_peaks, n)
+        imag = block[n_peaks * n:2 * n_peaks * n].reshape(n_peaks, n)
+        V, I, u, v = (block[(2 * n_peaks + k) * n:(2 * n_peaks + k + 1) * n] for k in range(4))
         dev = self.options.get('device', None)
         _cabi.check(_cabi.lib().nmrfit_generate_result_host(
             _cabi.default_device() if dev is None else int(dev), _cabi.ptr(params), n_peaks, _cabi.ptr(w), n,
