@@ -195,7 +195,7 @@ class Context:
         pb, pv = as_f64(peak_bounds), as_f64(peak_values)
         if pb.ndim != 3 or pb.shape[0] != self.B or pb.shape[2] != 2 or pv.shape != pb.shape[:2]:
             raise ValueError('peak_bounds must be [%d, K, 2] and peak_values [%d, K]' % (self.B, self.B))
-        out = np.empty((self.B, self.N)) if want_host else None
+        out = result_empty(self.B * self.N).reshape(self.B, self.N) if want_host else None
         check(lib().nmrfit_ctx_compute_weights(self._h, ptr(pb), ptr(pv), pb.shape[1], int(sweeps), float(omega),
                                                ptr(out), ptr(stream)))
         return out
