@@ -1,9 +1,11 @@
 """CPU oracle for the nmrfit objective-evaluation hot path.
 
 TEST INFRASTRUCTURE ONLY.  Nothing under ``nmrfit_b200/`` may import this
-package; the only permitted importers are ``tests/``, ``__graft_entry__.smoke()``
-and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py``, and there
-only as the checker or as the CPU arm being timed, never as the product path.
+package; the only permitted importers are ``tests/`` (including its fuzz drivers
+``tests/fuzz_*.py``), ``__graft_entry__.smoke()`` and the CPU legs of the benchmarks
+(``cpu_baseline`` / ``--impl reference`` in ``bench.py``; the quadrature timing in
+``tools/bench_curves.py``, config 5's counterpart), and there only as the checker or
+as the CPU arm being timed, never as the product path.
 
 Parity status
 -------------

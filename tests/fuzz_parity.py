@@ -2,7 +2,7 @@
 """Randomised differential test on the GPU: random shapes (points, peaks, particles, spectra), objective against
 the CPU oracle, fused swarm kernel against the per-step kernels (bitwise), device weights against the oracle.
 
-    python tools/fuzz_parity.py [--cases 40] [--seed 0]
+    python tests/fuzz_parity.py [--cases 40] [--seed 0]
 """
 import argparse
 import json
