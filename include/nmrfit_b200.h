@@ -104,8 +104,9 @@ int nmrfit_ctx_set_tuning(nmrfit_ctx* ctx, int threads, int points_per_thread, i
 int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* points_per_thread, int* exp_table_bits,
                           int* particles_per_cta, int* n_point_tiles);
 
-/* Small swarms: nmrfit_pso_run executes its generations in ONE cooperative launch (one CTA per particle,
- * one barrier per generation) instead of three launches per generation - the loop pyswarm.pso runs on the host
+/* Small swarms: nmrfit_pso_run executes its generations in ONE cooperative launch (one CTA - on longer axes one
+ * thread-block cluster of up to 8 CTAs exchanging through distributed shared memory - per particle, one barrier per
+ * generation) instead of three launches per generation - the loop pyswarm.pso runs on the host
  * (call site utils.py:176-182).  Bit-identical to the per-step kernels.  AUTO uses it whenever it can run
  * (FP64, uniform axis, real-only fit, n_spectra * swarmsize CTAs co-resident); REQUIRE makes nmrfit_pso_run
  * fail with NMRFIT_ERR_STATE otherwise. */
