@@ -134,7 +134,7 @@ def run_reference(args):
     return 0
 
 
-def workload_config(name, gpus):
+def workload_config(name, gpus, exchange='nccl'):
     P, N, S, _ = WORKLOADS[name]
     if name == 'c3':
         return {'workload': 'BASELINE config[2] C3: %d independent spectra (6 peaks, 16,384 points), one swarm of 204 '
@@ -146,7 +146,8 @@ def workload_config(name, gpus):
     return {'workload': 'BASELINE config[1] C2: single fit, 12 peaks, 32,768-point window, swarmsize 4,096 per GPU, '
                         'FP64 objective' if name == 'c2' else 'workload %s' % name,
             'n_peaks': P, 'n_points': N, 'particles_per_gpu': S, 'swarm_total': S * gpus,
-            'parallelism': 'particles sharded over %d GPU(s), one best-record all-gather per generation' % gpus,
+            'parallelism': 'particles sharded over %d GPU(s), one best-record %s per generation'
+                           % (gpus, 'exchange over peer memory (NVLink stores)' if exchange == 'p2p' else 'all-gather'),
             'l2': 'flushed between timed steps (256 MiB fill outside the per-step event brackets)'}
 
 
@@ -255,20 +256,31 @@ def run_b200(args):
     opts = swarm._make_opts(S, 10 ** 9, PSO['omega'], PSO['phip'], PSO['phig'], 0.0, 0.0, False, 1234, offset=off)
     opts.minstep = -1.0      # never stop early: every timed step does the full generation's work
     opts.minfunc = -1.0
+    p2p = world > 1 and not batched and args.exchange == 'p2p'
+    if p2p:
+        handle, _ = ctx.peer_export(world, rank)
+        handles = [None] * world
+        dist.all_gather_object(handles, handle)
+        ctx.peer_open(ipc_handles=handles)
+        dist.barrier()
     ctx.pso_begin(lo, up, opts, stream=stream)
     rec = None
-    if world > 1 and not batched:
+    if world > 1 and not batched and not p2p:
         ptr, nrec = ctx.pso_record()
         rec = torch.as_tensor(swarm._DeviceArray(ptr, nrec), device='cuda:%d' % local)
 
     def commit():
-        if world > 1 and not batched:
+        if p2p:
+            ctx.pso_commit_peers(stream=stream)
+        elif world > 1 and not batched:
             ctx.pso_commit(swarm.gather_records(rec), world, stream=stream)
         else:
             ctx.pso_commit(stream=stream)
 
     def step():
-        if world > 1 and not batched:
+        if p2p:
+            ctx.pso_step_peers(stream=stream)              # particle-sharded, records exchanged over peer memory
+        elif world > 1 and not batched:
             ctx.pso_advance(stream=stream)                 # particle-sharded: advance, exchange the best records, commit
             commit()
         else:
@@ -392,7 +404,7 @@ def run_b200(args):
             'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if batched else 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': dict(workload_config(args.workload, world), kernel=tune),
+            'config': dict(workload_config(args.workload, world, args.exchange), kernel=tune),
             'peak_points_per_s': value * N * P,
             'spectra_generations_per_s': (B * world * args.steps / (total_ms * 1e-3)) if batched else None,
             'roofline': {'bound': 'fp64', 'achieved': achieved, 'peak': sustained, 'unit': 'TFLOP/s',
@@ -430,6 +442,8 @@ def run_b200(args):
         if extras:
             line.update(extras)
         print(json.dumps(line))
+    if world > 1:
+        dist.barrier()                                     # nobody unmaps a window a peer may still store into
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
@@ -543,6 +557,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='c2', choices=sorted(WORKLOADS))
+    ap.add_argument('--exchange', default='nccl', choices=['nccl', 'p2p'],
+                    help='particle sharding (N > 1): best-record all-gather over NCCL, or the exchange + commit kernel '
+                         'over peer memory (CUDA IPC windows, NVLink stores)')
     ap.add_argument('--tune', default='', help='threads,points_per_thread,exp_table_bits,particles_per_cta')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--quick', action='store_true', help='main measurement only (no CPU baseline, no extra shapes / fits)')

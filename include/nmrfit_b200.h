@@ -159,6 +159,21 @@ int nmrfit_pso_advance(nmrfit_ctx* ctx, const double* rp, const double* rg, void
 /* One whole generation of a swarm held by ONE context (no rank exchange): advance + commit, asynchronous on `stream` -
  * what nmrfit_pso_run does per generation, without its final synchronisation.  Three launches. */
 int nmrfit_pso_step(nmrfit_ctx* ctx, const double* rp, const double* rg, void* stream);
+/* ---- particle sharding without a collective call: the record exchange over peer memory (NVLink stores) -----------
+ * Each rank's context owns a window of records and generation tokens; every rank maps every window (CUDA IPC between
+ * processes, plain pointers between contexts of one process).  nmrfit_pso_commit_peers replaces "all-gather the records,
+ * nmrfit_pso_commit": one kernel stores this rank's record into every peer's window, publishes the generation token,
+ * waits (bounded) for all ranks' tokens and commits.  nmrfit_pso_step_peers = nmrfit_pso_advance + that: a generation
+ * in four launches with no NCCL call.  Same results as the all-gather path, bit for bit.
+ *   export: allocate the window for n_ranks; ipc_handle_out (64 bytes, nullable) for other processes, base_out
+ *           (nullable) for other contexts of this process.
+ *   open:   ipc_handles [n_ranks][64] and/or local_bases [n_ranks] (entry `rank` is ignored).
+ *   error:  1 when a wait expired (a peer never arrived); the swarm state is then undefined. */
+int nmrfit_pso_peer_export(nmrfit_ctx* ctx, int n_ranks, int rank, void* ipc_handle_out, void** base_out);
+int nmrfit_pso_peer_open(nmrfit_ctx* ctx, const void* ipc_handles, void* const* local_bases);
+int nmrfit_pso_commit_peers(nmrfit_ctx* ctx, void* stream);
+int nmrfit_pso_step_peers(nmrfit_ctx* ctx, const double* rp, const double* rg, void* stream);
+int nmrfit_pso_peer_error(nmrfit_ctx* ctx, int* timed_out);
 /* Device pointer and length (doubles) of the local best record, [n_spectra][D+2] = (f, global index, x[D]). */
 int nmrfit_pso_record(nmrfit_ctx* ctx, double** rec_dev, int* n_doubles);
 /* Swarm-best update and the minfunc/minstep/maxiter tests.  recs_dev = [n_ranks][n_spectra][D+2]

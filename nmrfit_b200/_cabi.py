@@ -65,6 +65,11 @@ SIGNATURES = {
     'nmrfit_pso_begin': (_i, [_vp, _vp, _vp, ctypes.POINTER(PsoOpts), _vp, _vp, _vp]),
     'nmrfit_pso_advance': (_i, [_vp, _vp, _vp, _vp]),
     'nmrfit_pso_step': (_i, [_vp, _vp, _vp, _vp]),
+    'nmrfit_pso_peer_export': (_i, [_vp, _i, _i, _vp, ctypes.POINTER(_vp)]),
+    'nmrfit_pso_peer_open': (_i, [_vp, _vp, _vp]),
+    'nmrfit_pso_commit_peers': (_i, [_vp, _vp]),
+    'nmrfit_pso_step_peers': (_i, [_vp, _vp, _vp, _vp]),
+    'nmrfit_pso_peer_error': (_i, [_vp, c_int_p]),
     'nmrfit_pso_record': (_i, [_vp, ctypes.POINTER(_vp), c_int_p]),
     'nmrfit_pso_commit': (_i, [_vp, _vp, _i, _vp]),
     'nmrfit_pso_run': (_i, [_vp, _i, _vp, _vp, c_int_p, _vp]),
@@ -296,6 +301,39 @@ class Context:
         """One whole single-context generation (advance + commit), asynchronous."""
         rp, rg = self._rand(rp, self._swarmsize), self._rand(rg, self._swarmsize)
         check(lib().nmrfit_pso_step(self._h, ptr(rp), ptr(rg), ptr(stream)))
+
+    # -- record exchange over peer memory
+    def peer_export(self, n_ranks, rank):
+        """Allocate this context's exchange window; returns (ipc_handle bytes[64], base address)."""
+        handle = ctypes.create_string_buffer(64)
+        base = ctypes.c_void_p()
+        check(lib().nmrfit_pso_peer_export(self._h, int(n_ranks), int(rank), handle, ctypes.byref(base)))
+        self._peer_ranks = int(n_ranks)
+        return handle.raw, base.value
+
+    def peer_open(self, ipc_handles=None, local_bases=None):
+        """ipc_handles: list of 64-byte handles (one per rank) from other processes; local_bases: list of base
+        addresses of other contexts of THIS process (None entries fall back to the handle)."""
+        R = self._peer_ranks
+        hbuf = None
+        if ipc_handles is not None:
+            hbuf = ctypes.create_string_buffer(b''.join(bytes(h) for h in ipc_handles), 64 * R)
+        lb = None
+        if local_bases is not None:
+            lb = (ctypes.c_void_p * R)(*[ctypes.c_void_p(b) if b else None for b in local_bases])
+        check(lib().nmrfit_pso_peer_open(self._h, hbuf, lb))
+
+    def pso_commit_peers(self, stream=None):
+        check(lib().nmrfit_pso_commit_peers(self._h, ptr(stream)))
+
+    def pso_step_peers(self, rp=None, rg=None, stream=None):
+        rp, rg = self._rand(rp, self._swarmsize), self._rand(rg, self._swarmsize)
+        check(lib().nmrfit_pso_step_peers(self._h, ptr(rp), ptr(rg), ptr(stream)))
+
+    def peer_error(self):
+        e = ctypes.c_int(0)
+        check(lib().nmrfit_pso_peer_error(self._h, ctypes.byref(e)))
+        return e.value
 
     def pso_record(self):
         p, n = ctypes.c_void_p(), ctypes.c_int(0)

@@ -93,6 +93,16 @@ struct nmrfit_ctx {
     DevBuf<unsigned> fbarrier;
     DevBuf<double> fin_scratch;        // finish kernel: per-CTA candidates
     DevBuf<unsigned> fin_tickets;
+    // record exchange over peer memory (particle sharding without a collective call)
+    void* peer_win = nullptr;          // this context's window: records [2][R][B][D+2], then tokens [R][B]
+    size_t peer_rec_bytes = 0;
+    int peer_ranks = 0, peer_rank = 0;
+    bool peers_ready = false;
+    std::vector<void*> peer_opened;    // windows of other processes opened through CUDA IPC
+    DevBuf<double*> peer_recs_dev;
+    DevBuf<long long*> peer_tok_dev;
+    DevBuf<int> peer_err;
+    long long epoch = 0;               // fits begun on this context: part of the exchange token
     DevBuf<double> wscratch, wbounds;  // batched weights: sweep scratch [B][N], windows + values
     int fused_mode = NMRFIT_FUSED_AUTO;
     DevBuf<long long> ftiming;         // optional per-phase cycle counters of the fused kernel
@@ -362,6 +372,11 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->frec_x.release();
     c->fbarrier.release();
     c->ftiming.release();
+    for (void* p : c->peer_opened) cudaIpcCloseMemHandle(p);
+    if (c->peer_win) cudaFree(c->peer_win);
+    c->peer_recs_dev.release();
+    c->peer_tok_dev.release();
+    c->peer_err.release();
     c->wscratch.release();
     c->fin_scratch.release();
     c->fin_tickets.release();
@@ -630,6 +645,7 @@ int nmrfit_pso_begin(nmrfit_ctx* c, const double* lb, const double* ub, const nm
     s.omega = o->omega; s.phip = o->phip; s.phig = o->phig; s.minstep = o->minstep; s.minfunc = o->minfunc;
     s.seed = o->seed; s.index0 = o->particle_offset; s.spec0 = o->spectrum_offset;
     c->maxiter = o->maxiter; c->kk = o->fit_im; c->generation = 0; c->swarm = true;
+    c->epoch += 1;
 
     const double *rp_d = nullptr, *rv_d = nullptr;
     if (int rc = stage(r_pos, nsd, c->rnd_a, st, &rp_d)) return rc;
@@ -668,6 +684,103 @@ int nmrfit_pso_step(nmrfit_ctx* c, const double* rp, const double* rg, void* str
     if (int rc = stage(rg, nsd, c->rnd_b, st, &rg_d)) return rc;
     c->generation += 1;
     return swarm_generation(c, true, rp_d, rg_d, 1, st);
+}
+
+// ---- record exchange over peer memory -------------------------------------------------------------
+
+int nmrfit_pso_peer_export(nmrfit_ctx* c, int n_ranks, int rank, void* ipc_handle_out, void** base_out) {
+    if (int rc = check_ctx(c)) return rc;
+    if (n_ranks < 1 || n_ranks > 64 || rank < 0 || rank >= n_ranks) return fail(NMRFIT_ERR_ARG, "bad rank / n_ranks");
+    if (c->peer_win) return fail(NMRFIT_ERR_STATE, "the exchange window of this context already exists");
+    CK(cudaSetDevice(c->device));
+    const size_t W = (size_t)c->D + 2;
+    c->peer_rec_bytes = (2 * (size_t)n_ranks * c->B * W * sizeof(double) + 15) & ~(size_t)15;
+    const size_t bytes = c->peer_rec_bytes + (size_t)n_ranks * c->B * sizeof(long long);
+    CK(cudaMalloc(&c->peer_win, bytes));
+    CK(cudaMemset(c->peer_win, 0, bytes));                 // tokens start at 0; the first real token is (1 << 32)
+    CK(cudaDeviceSynchronize());
+    c->peer_ranks = n_ranks;
+    c->peer_rank = rank;
+    if (ipc_handle_out) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handles are 64 bytes");
+        cudaIpcMemHandle_t h;
+        CK(cudaIpcGetMemHandle(&h, c->peer_win));
+        std::memcpy(ipc_handle_out, &h, sizeof(h));
+    }
+    if (base_out) *base_out = c->peer_win;
+    return NMRFIT_OK;
+}
+
+int nmrfit_pso_peer_open(nmrfit_ctx* c, const void* ipc_handles, void* const* local_bases) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->peer_win) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_peer_export has not been called");
+    if (!ipc_handles && !local_bases) return fail(NMRFIT_ERR_ARG, "ipc_handles or local_bases must be given");
+    CK(cudaSetDevice(c->device));
+    const int R = c->peer_ranks;
+    std::vector<double*> recs(R);
+    std::vector<long long*> toks(R);
+    for (int q = 0; q < R; ++q) {
+        void* base = nullptr;
+        if (q == c->peer_rank) {
+            base = c->peer_win;
+        } else if (local_bases && local_bases[q]) {
+            base = local_bases[q];                          // another context of this process
+        } else {
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, (const char*)ipc_handles + (size_t)q * sizeof(h), sizeof(h));
+            CK(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+            c->peer_opened.push_back(base);
+        }
+        recs[q] = (double*)base;
+        toks[q] = (long long*)((char*)base + c->peer_rec_bytes);
+    }
+    CK(c->peer_recs_dev.reserve(R));
+    CK(c->peer_tok_dev.reserve(R));
+    CK(c->peer_err.reserve(1));
+    CK(cudaMemcpy(c->peer_recs_dev.ptr, recs.data(), sizeof(double*) * R, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->peer_tok_dev.ptr, toks.data(), sizeof(long long*) * R, cudaMemcpyHostToDevice));
+    CK(cudaMemset(c->peer_err.ptr, 0, sizeof(int)));
+    c->peers_ready = true;
+    return NMRFIT_OK;
+}
+
+namespace {
+int exchange_commit(nmrfit_ctx* c, cudaStream_t st) {
+    if (!c->peers_ready) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_peer_open has not been called");
+    PeerArgs pa{};
+    pa.recs = c->peer_recs_dev.ptr;
+    pa.tokens = c->peer_tok_dev.ptr;
+    pa.n_ranks = c->peer_ranks;
+    pa.rank = c->peer_rank;
+    pa.token = (c->epoch << 32) | (long long)c->generation;
+    pa.max_spins = 1LL << 23;                              // a few seconds of polling, then the error flag
+    pa.error = c->peer_err.ptr;
+    cudaError_t e = launch_swarm_exchange_commit(c->sw, pa, c->generation == 0, c->maxiter, st);
+    if (e != cudaSuccess) return fail_cuda(e, "exchange + commit launch");
+    return NMRFIT_OK;
+}
+}  // namespace
+
+int nmrfit_pso_commit_peers(nmrfit_ctx* c, void* stream) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    CK(cudaSetDevice(c->device));
+    return exchange_commit(c, (cudaStream_t)stream);
+}
+
+int nmrfit_pso_step_peers(nmrfit_ctx* c, const double* rp, const double* rg, void* stream) {
+    if (int rc = nmrfit_pso_advance(c, rp, rg, stream)) return rc;
+    return exchange_commit(c, (cudaStream_t)stream);
+}
+
+int nmrfit_pso_peer_error(nmrfit_ctx* c, int* timed_out) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!timed_out) return fail(NMRFIT_ERR_ARG, "timed_out is NULL");
+    *timed_out = 0;
+    if (!c->peers_ready) return NMRFIT_OK;
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpy(timed_out, c->peer_err.ptr, sizeof(int), cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
 }
 
 int nmrfit_pso_record(nmrfit_ctx* c, double** rec_dev, int* n_doubles) {

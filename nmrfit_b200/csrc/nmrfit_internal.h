@@ -94,6 +94,18 @@ cudaError_t launch_swarm_finish(const SwarmState& s, const double* partials, int
                                 double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st);
 size_t swarm_finish_scratch_doubles(int B, int S);
 
+// record exchange over peer memory (pso.cu): device arrays of per-rank window pointers
+struct PeerArgs {
+    double* const* recs;        // [n_ranks] -> that rank's record window [2][n_ranks][B][D+2]
+    long long* const* tokens;   // [n_ranks] -> that rank's token array [n_ranks][B]
+    int n_ranks, rank;
+    long long token;            // (fit epoch << 32) | generation: monotonic over the life of the windows
+    long long max_spins;        // bound of the wait
+    int* error;                 // set to 1 when the wait expired
+};
+cudaError_t launch_swarm_exchange_commit(const SwarmState& s, const PeerArgs& pa, int initial, int maxiter,
+                                         cudaStream_t st);
+
 cudaError_t launch_swarm_init(const SwarmState& s, const double* r_pos, const double* r_vel, cudaStream_t st);
 cudaError_t launch_swarm_init_velocity(const SwarmState& s, const double* r_vel, cudaStream_t st);
 cudaError_t launch_swarm_move(const SwarmState& s, const double* rp, const double* rg, int generation, cudaStream_t st);

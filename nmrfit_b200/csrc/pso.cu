@@ -73,23 +73,27 @@ __global__ void swarm_move_kernel(SwarmState s, const double* __restrict__ rp_in
 // swarm-best update and the minfunc/minstep stop tests for spectrum b, by one CTA of `nthreads` threads.
 // `recs` holds one record per rank ([n_ranks][B][D+2]); every rank runs this redundantly on identical input,
 // so g/fg stay bit-identical everywhere.
+// Record of rank r for this spectrum: recs + r * rank_stride + b_offset (global [n_ranks][B][D+2] layout:
+// rank_stride = B * (D+2), b_offset = b * (D+2); a per-spectrum shared-memory copy: D+2 and 0).
 __device__ __forceinline__ void commit_spectrum(const SwarmState& s, const double* recs, int n_ranks,
-                                                int initial, int maxiter, int b, int tid, int nthreads) {
+                                                int initial, int maxiter, int b, int tid, int nthreads,
+                                                size_t rank_stride, size_t b_offset) {
     const int W = s.D + 2;
+    (void)W;
     __shared__ int s_win;
     __shared__ double s_step;
     __shared__ int s_action;   // 0 nothing, 1 adopt as g, 2 stop (return p_min)
     if (tid == 0) {
         int win = 0;
-        double wf = recs[(size_t)b * W], wi = recs[(size_t)b * W + 1];
+        double wf = recs[b_offset], wi = recs[b_offset + 1];
         for (int r = 1; r < n_ranks; ++r) {
-            const double* q = recs + ((size_t)r * s.B + b) * W;
+            const double* q = recs + (size_t)r * rank_stride + b_offset;
             if (q[0] < wf || (q[0] == wf && q[1] < wi)) { wf = q[0]; wi = q[1]; win = r; }
         }
         s_win = win;
     }
     __syncthreads();
-    const double* q = recs + ((size_t)s_win * s.B + b) * W;
+    const double* q = recs + (size_t)s_win * rank_stride + b_offset;
     const double fmin = q[0];
     double* g = s.g + (size_t)b * s.D;
     if (initial) {
@@ -134,7 +138,7 @@ __global__ void __launch_bounds__(128) swarm_commit_kernel(SwarmState s, const d
                                                            int initial, int maxiter) {
     const int b = blockIdx.x;
     if (s.stop[b]) return;
-    commit_spectrum(s, recs, n_ranks, initial, maxiter, b, threadIdx.x, 128);
+    commit_spectrum(s, recs, n_ranks, initial, maxiter, b, threadIdx.x, 128, (size_t)s.B * (s.D + 2), (size_t)b * (s.D + 2));
 }
 
 // ---- finish: everything after the objective's tile sums, in ONE launch --------------------------------------
@@ -230,7 +234,72 @@ swarm_finish_kernel(SwarmState s, const double* __restrict__ partials, int n_til
     for (int d = tid; d < s.D; d += kFinWarps * 32) r[2 + d] = __ldcg(src + ((size_t)b * s.S + best) * s.D + d);
     if (!commit) return;
     __syncthreads();                                       // the record is complete (same CTA wrote it)
-    commit_spectrum(s, rec, 1, 0, maxiter, b, tid, kFinWarps * 32);
+    commit_spectrum(s, rec, 1, 0, maxiter, b, tid, kFinWarps * 32, (size_t)s.B * (s.D + 2), (size_t)b * (s.D + 2));
+}
+
+// ---- record exchange over peer memory (particle sharding without a collective call) -------------------------
+// Every rank's context owns a window [2 parities][n_ranks][B][D+2] of records plus [n_ranks][B] 64-bit tokens,
+// mapped into every peer (CUDA IPC between processes; plain pointers between contexts of one process).  One CTA per
+// spectrum stores this rank's local best record into slot `rank` of EVERY peer's window (NVLink stores), fences at
+// system scope, stores the generation token into every peer's token array, waits until the tokens of all ranks have
+// arrived in its own window, and applies the same commit as every other rank on the same n_ranks records - the
+// all-gather + commit of the NCCL path in one kernel.  Windows are double-buffered by generation parity: a rank cannot
+// be two generations ahead, because its next commit needs the slowest rank's next token.  The wait is bounded: on
+// expiry the kernel raises *error and returns without committing.
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__global__ void __launch_bounds__(128)
+swarm_exchange_commit_kernel(SwarmState s, PeerArgs pa, int initial, int maxiter) {
+    extern __shared__ __align__(16) double srec[];         // [n_ranks][D+2] of this spectrum
+    const int b = blockIdx.x, tid = threadIdx.x;
+    if (s.stop[b]) return;                                 // identical on every rank
+    const int W = s.D + 2, R = pa.n_ranks;
+    const int par = (int)(pa.token & 1);
+    const double* mine = s.rec + (size_t)b * W;
+    for (int q = 0; q < R; ++q) {
+        double* dst = pa.recs[q] + (((size_t)par * R + pa.rank) * s.B + b) * W;
+        for (int d = tid; d < W; d += 128) dst[d] = mine[d];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < R) st_release_sys(pa.tokens[tid] + (size_t)pa.rank * s.B + b, pa.token);
+    __shared__ int s_timeout;
+    if (tid == 0) s_timeout = 0;
+    __syncthreads();
+    if (tid < R) {
+        const long long* mytok = pa.tokens[pa.rank] + (size_t)tid * s.B + b;
+        long long spins = 0;
+        while (ld_acquire_sys(mytok) < pa.token) {
+            if (++spins > pa.max_spins) { s_timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (s_timeout) {
+        if (tid == 0) atomicExch(pa.error, 1);
+        return;
+    }
+    const double* win = pa.recs[pa.rank] + ((size_t)par * R * s.B + b) * W;
+    for (int i = tid; i < R * W; i += 128) {
+        const int q = i / W, d = i - q * W;
+        srec[i] = __ldcv(win + (size_t)q * s.B * W + d);   // written by peers: never from a stale L1 line
+    }
+    __syncthreads();
+    commit_spectrum(s, srec, R, initial, maxiter, b, tid, 128, (size_t)W, 0);
+}
+
+cudaError_t launch_swarm_exchange_commit(const SwarmState& s, const PeerArgs& pa, int initial, int maxiter,
+                                         cudaStream_t st) {
+    const size_t smem = (size_t)pa.n_ranks * (s.D + 2) * sizeof(double);
+    swarm_exchange_commit_kernel<<<s.B, 128, smem, st>>>(s, pa, initial, maxiter);
+    count_launches(1);
+    return cudaGetLastError();
 }
 
 static inline unsigned blocks_for(size_t n, int t) { return (unsigned)((n + t - 1) / t); }

@@ -257,15 +257,20 @@ def select_record(recs):
 
 def pso_sharded(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxiter=100, omega=0.5, phip=0.5,
                 phig=0.5, minstep=1e-8, minfunc=1e-8, seed=0, precision='fp64', check_every=8, device=None,
-                group=None, host_random=None, tuning=None):
+                group=None, host_random=None, tuning=None, exchange='nccl'):
     """One swarm of ``swarmsize`` particles sharded over the ranks of ``group``.
 
     Every rank holds the spectrum and a contiguous block of particles.  Random numbers
     come from device Philox keyed by the GLOBAL particle index, so the trajectory does
     not depend on the number of ranks; ``host_random`` (dict with 'pos', 'vel' [S,D] and a
     callable 'gen'(k) -> (rp, rg) [S,D]) substitutes host numbers for lock-step tests.
+    ``exchange``: 'nccl' - one ``all_gather`` of the best records per generation, then the commit kernel;
+    'p2p' - the exchange + commit kernel stores the records straight into every peer's window over NVLink (CUDA
+    IPC handles are exchanged once through the group) and no collective runs per generation.  Same result, bit for bit.
     Returns (x_best, f_best, info) - identical on every rank.
     """
+    if exchange not in ('nccl', 'p2p'):
+        raise ValueError("exchange must be 'nccl' or 'p2p'")
     import torch
     import torch.distributed as dist
     rank, world = dist.get_rank(group), dist.get_world_size(group)
@@ -278,35 +283,53 @@ def pso_sharded(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, max
     torch.cuda.set_device(dev)
     stream = torch.cuda.current_stream().cuda_stream
     w = _cabi.as_f64(w)
-    with _cabi.pooled_context(1, w.size, (D - 4) // 3, device=dev, precision=_precision(precision)) as ctx:
+    p2p = exchange == 'p2p'
+    # a context with an exchange window is wired to its peers: it does not come from (or go back to) the pool
+    manager = _cabi.Context(1, w.size, (D - 4) // 3, device=dev, precision=_precision(precision)) if p2p else \
+        _cabi.pooled_context(1, w.size, (D - 4) // 3, device=dev, precision=_precision(precision))
+    with manager as ctx:
         if tuning:
             ctx.set_tuning(**tuning)
         ctx.set_spectrum(0, w, u, v, weights)
+        if p2p:
+            handle, _ = ctx.peer_export(world, rank)
+            handles = [None] * world
+            dist.all_gather_object(handles, handle, group=group)
+            ctx.peer_open(ipc_handles=handles)
+            dist.barrier(group)                            # every window is mapped before anyone stores into it
         opts = _make_opts(cnt, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed, offset=off)
         sl = slice(off, off + cnt)
         r_pos = host_random['pos'][sl] if host_random else None
         r_vel = host_random['vel'][sl] if host_random else None
         ctx.pso_begin(lb, ub, opts, r_pos, r_vel, stream=stream)
-        ptr, n = ctx.pso_record()
-        rec = torch.as_tensor(_DeviceArray(ptr, n), device='cuda:%d' % dev)
-        recs = gather_records(rec, group)
-        ctx.pso_commit(recs, world, stream=stream)
+        if p2p:
+            ctx.pso_commit_peers(stream=stream)
+        else:
+            ptr, n = ctx.pso_record()
+            rec = torch.as_tensor(_DeviceArray(ptr, n), device='cuda:%d' % dev)
+            recs = gather_records(rec, group)
+            ctx.pso_commit(recs, world, stream=stream)
         gen = 0
         stop = np.zeros(1, dtype=np.int32)
         while gen < maxiter:
             for _ in range(min(check_every, maxiter - gen)):
                 gen += 1
-                if host_random:
-                    rp, rg = host_random['gen'](gen)
-                    ctx.pso_advance(rp[sl], rg[sl], stream=stream)
+                rp, rg = host_random['gen'](gen) if host_random else (None, None)
+                rp, rg = (rp[sl], rg[sl]) if host_random else (None, None)
+                if p2p:
+                    ctx.pso_step_peers(rp, rg, stream=stream)
                 else:
-                    ctx.pso_advance(stream=stream)
-                recs = gather_records(rec, group)
-                ctx.pso_commit(recs, world, stream=stream)
+                    ctx.pso_advance(rp, rg, stream=stream)
+                    recs = gather_records(rec, group)
+                    ctx.pso_commit(recs, world, stream=stream)
             x, f, it, stop = ctx.pso_best()
+            if p2p and ctx.peer_error():
+                raise _cabi.NmrfitError(-3, 'record exchange over peer memory: a peer never arrived (wait expired)')
             if stop[0] != _cabi.RUNNING:
                 break
         x, f, it, stop = ctx.pso_best()
+        if p2p:
+            dist.barrier(group)                            # nobody unmaps a window a peer may still store into
     info = dict(generations=int(it[0]), stop=int(stop[0]), evaluations=int(swarmsize) * (int(it[0]) + 1),
                 world=world, local_particles=cnt)
     return x[0].copy(), float(f[0]), info

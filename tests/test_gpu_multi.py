@@ -16,13 +16,16 @@ def _gpus():
     return _cabi.device_count()
 
 
+@pytest.mark.parametrize('exchange', ['nccl', 'p2p'])
 @pytest.mark.parametrize('world', [2, 4, 8])
-def test_sharded_swarm_over_nccl_is_bit_identical(world):
+def test_sharded_swarm_over_nccl_is_bit_identical(world, exchange):
+    """exchange='nccl': one all-gather of best records per generation; 'p2p': the exchange + commit kernel over peer
+    memory (CUDA IPC windows, NVLink stores), no collective per generation."""
     if _gpus() < world:
         pytest.skip('needs %d GPUs' % world)
     cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(world),
-           '--master-addr', '127.0.0.1', '--master-port', str(29520 + world), os.path.join(ROOT, 'tools', 'dist_check.py'),
-           '--shape', 'c1', '--swarm', '250', '--maxiter', '30']
+           '--master-addr', '127.0.0.1', '--master-port', str(29520 + world + (10 if exchange == 'p2p' else 0)), os.path.join(ROOT, 'tools', 'dist_check.py'),
+           '--shape', 'c1', '--swarm', '250', '--maxiter', '30', '--exchange', exchange]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     line = json.loads([l for l in out.stdout.splitlines() if l.startswith('{')][-1])

@@ -267,3 +267,60 @@ def test_pso_step_equals_advance_plus_commit():
     (ba, sa), (bb, sb) = outs
     assert all(np.array_equal(x, y) for x, y in zip(ba, bb))
     assert all(np.array_equal(sa[k], sb[k]) for k in ('x', 'v', 'p', 'fx', 'fp'))
+
+
+@pytest.mark.parametrize('ranks', [2, 3])
+def test_record_exchange_over_peer_memory_equals_unsharded(ranks):
+    """Particle sharding with the exchange + commit kernel (records and generation tokens stored straight into every
+    peer's window; here the peers are contexts of one process on one GPU, each on its own stream): same trajectory,
+    bit for bit, as the unsharded swarm - and as the all-gather path, which the test above pins the same way."""
+    import torch
+    g = load_golden('fit_c1_4096x6')
+    S, D, iters = 45, 22, 9
+    rs = np.random.RandomState(4)
+    r_pos, r_vel = rs.rand(S, D), rs.rand(S, D)
+    rp, rg = rs.rand(iters, S, D), rs.rand(iters, S, D)
+    lb, ub = g['lower'], g['upper']
+
+    def opts(cnt, off):
+        return swarm._make_opts(cnt, iters, PSO['omega'], PSO['phip'], PSO['phig'], 1e-8, 1e-8, False, 0, offset=off)
+
+    with _cabi.Context(1, g['w'].size, 6) as ctx:
+        ctx.set_spectrum(0, g['w'], g['u'], g['v'], g['weights'])
+        ctx.pso_begin(lb, ub, opts(S, 0), r_pos, r_vel)
+        ctx.pso_commit()
+        ctx.pso_run(iters, rp, rg)
+        want = ctx.pso_best()
+        want_x = ctx.pso_state()['x'][0]
+
+    ctxs = [_cabi.Context(1, g['w'].size, 6) for _ in range(ranks)]
+    streams = [torch.cuda.Stream() for _ in range(ranks)]
+    try:
+        shards = [swarm.shard_range(S, r, ranks) for r in range(ranks)]
+        bases = []
+        for r, c in enumerate(ctxs):
+            c.set_spectrum(0, g['w'], g['u'], g['v'], g['weights'])
+            c.set_fused(_cabi.FUSED_OFF)
+            bases.append(c.peer_export(ranks, r)[1])
+        for c in ctxs:
+            c.peer_open(local_bases=bases)
+        for r, c in enumerate(ctxs):
+            off, cnt = shards[r]
+            c.pso_begin(lb, ub, opts(cnt, off), r_pos[off:off + cnt], r_vel[off:off + cnt], stream=streams[r].cuda_stream)
+        for r, c in enumerate(ctxs):
+            c.pso_commit_peers(stream=streams[r].cuda_stream)
+        for k in range(iters):
+            for r, c in enumerate(ctxs):
+                off, cnt = shards[r]
+                c.pso_step_peers(np.ascontiguousarray(rp[k, off:off + cnt]), np.ascontiguousarray(rg[k, off:off + cnt]),
+                                 stream=streams[r].cuda_stream)
+        torch.cuda.synchronize()
+        assert all(c.peer_error() == 0 for c in ctxs)
+        outs = [c.pso_best() for c in ctxs]
+        for o in outs:
+            assert all(np.array_equal(a, b) for a, b in zip(o, want))
+        got_x = np.concatenate([c.pso_state()['x'][0] for c in ctxs])
+        assert np.array_equal(got_x, want_x)
+    finally:
+        for c in ctxs:
+            c.close()

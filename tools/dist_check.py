@@ -29,6 +29,7 @@ def main():
     ap.add_argument('--swarm', type=int, default=0)
     ap.add_argument('--maxiter', type=int, default=40)
     ap.add_argument('--mode', default='particles', choices=['particles', 'spectra'])
+    ap.add_argument('--exchange', default='nccl', choices=['nccl', 'p2p'])
     args = ap.parse_args()
     P, N, S, seed = {'c1': (6, 4096, 256, 1000), 'c2': (12, 32768, 4096, 2000), 'c4': (24, 65536, 8192, 4000)}[args.shape]
     S = args.swarm or S
@@ -45,7 +46,7 @@ def main():
     torch.cuda.synchronize()
     dist.barrier()
     t0 = time.perf_counter()
-    x, f, info = swarm.pso_sharded(data.w, data.u, data.v, wts, lo, up, device=local, **kw)
+    x, f, info = swarm.pso_sharded(data.w, data.u, data.v, wts, lo, up, device=local, exchange=args.exchange, **kw)
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     # identical on every rank
@@ -54,7 +55,7 @@ def main():
     dist.all_gather(gathered, blob)
     same_on_all = all(torch.equal(g, gathered[0]) for g in gathered)
     ok = same_on_all
-    line = dict(world=world, shape=args.shape, swarmsize=S, generations=info['generations'], stop=info['stop'], f=f,
+    line = dict(world=world, shape=args.shape, exchange=args.exchange, swarmsize=S, generations=info['generations'], stop=info['stop'], f=f,
                 seconds=dt, evals_per_s=S * (info['generations'] + 1) / dt, identical_on_all_ranks=same_on_all)
     if rank == 0:
         x1, f1, info1 = swarm.pso_single(data.w, data.u, data.v, wts, lo, up, rng='device', quiet=True, device=local, **kw)
