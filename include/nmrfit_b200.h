@@ -124,6 +124,10 @@ int nmrfit_ctx_fused_timing(nmrfit_ctx* ctx, int enable, long long* cycles);
  * roofline: enable, run, then read the summed duration and the launch count; read resets). */
 int nmrfit_ctx_profile(nmrfit_ctx* ctx, int enable);
 int nmrfit_ctx_profile_read(nmrfit_ctx* ctx, double* total_ms, long long* launches);
+/* The same, split at the event recorded between the two passes of the uniform-axis path: per-particle constants
+ * (prepare kernel, with the swarm's move when it is folded in) and the evaluation kernel proper - the roofline's
+ * dominant kernel.  Paths without a prepare pass report 0 for it. */
+int nmrfit_ctx_profile_read_split(nmrfit_ctx* ctx, double* prepare_ms, double* evaluate_ms, long long* launches);
 
 /* ---- objective: equations.objective (equations.py:152-212) for a whole swarm generation -------
  * x [n_spectra][n_particles][D] -> f [n_spectra][n_particles].  One call replaces the

@@ -60,6 +60,7 @@ SIGNATURES = {
     'nmrfit_ctx_fused_timing': (_i, [_vp, _i, _vp]),
     'nmrfit_ctx_profile': (_i, [_vp, _i]),
     'nmrfit_ctx_profile_read': (_i, [_vp, c_double_p, ctypes.POINTER(ctypes.c_longlong)]),
+    'nmrfit_ctx_profile_read_split': (_i, [_vp, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_longlong)]),
     'nmrfit_objective_batch': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'nmrfit_objective_batch_host': (_i, [_vp, _vp, _i, _i, _vp]),
     'nmrfit_pso_begin': (_i, [_vp, _vp, _vp, ctypes.POINTER(PsoOpts), _vp, _vp, _vp]),
@@ -249,6 +250,12 @@ class Context:
         ms, n = ctypes.c_double(0), ctypes.c_longlong(0)
         check(lib().nmrfit_ctx_profile_read(self._h, ctypes.byref(ms), ctypes.byref(n)))
         return ms.value, n.value
+
+    def profile_read_split(self):
+        """(prepare-pass ms, evaluation-kernel ms, launches) since the last read."""
+        a, b, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_longlong(0)
+        check(lib().nmrfit_ctx_profile_read_split(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(n)))
+        return a.value, b.value, n.value
 
     # -- objective
     def objective_host(self, x, fit_im=REAL_ONLY):

@@ -231,18 +231,26 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     a.frozen = frozen;
     a.grid_h = c->grid_h.ptr;
     a.N = c->N; a.P = c->P; a.S = S; a.kk = fit_im; a.sp = t.sp;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // profiling: three events per launch - before the prepare pass, between it and the evaluation kernel, after
+    cudaEvent_t ev0 = nullptr, evm = nullptr, ev1 = nullptr;
     if (c->profiling) {
-        if (c->prof_used + 2 > c->prof_events.size()) {
-            for (int k = 0; k < 2; ++k) {
+        if (c->prof_used + 3 > c->prof_events.size()) {
+            for (int k = 0; k < 3; ++k) {
                 cudaEvent_t ev;
                 CK(cudaEventCreate(&ev));
                 c->prof_events.push_back(ev);
             }
         }
         ev0 = c->prof_events[c->prof_used];
-        ev1 = c->prof_events[c->prof_used + 1];
-        c->prof_used += 2;
+        evm = c->prof_events[c->prof_used + 1];
+        ev1 = c->prof_events[c->prof_used + 2];
+        c->prof_used += 3;
+    }
+    const bool two_pass = uni && c->precision == NMRFIT_FP64;
+    if (evm && !two_pass) {                                // no separate prepare pass on this path: zero-length first leg
+        CK(cudaEventRecord(ev0, st));
+        CK(cudaEventRecord(evm, st));
+        ev0 = nullptr;
     }
     const bool move_in_prepare = mv && uni && c->precision == NMRFIT_FP64;
     if (mv && !move_in_prepare) {                          // paths without a prepare pass move the swarm on their own
@@ -251,7 +259,7 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     }
     if (nsum_out) *nsum_out = c->precision == NMRFIT_FP32 ? 1 : (fit_im ? 2 : 1);
     cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, uni, st, ev0, ev1, tiles_out)
-                    : uni ? launch_objective_uniform(a, t, c->B, f_dev, st, ev0, ev1, move_in_prepare ? mv : nullptr, tiles_out)
+                    : uni ? launch_objective_uniform(a, t, c->B, f_dev, st, ev0, ev1, move_in_prepare ? mv : nullptr, tiles_out, evm)
                           : launch_objective(a, t, c->B, f_dev, st, ev0, ev1, tiles_out);
     if (e != cudaSuccess) return fail_cuda(e, "objective launch");
     return NMRFIT_OK;
@@ -562,19 +570,29 @@ int nmrfit_ctx_profile(nmrfit_ctx* c, int enable) {
     return NMRFIT_OK;
 }
 
-int nmrfit_ctx_profile_read(nmrfit_ctx* c, double* total_ms, long long* launches) {
+int nmrfit_ctx_profile_read_split(nmrfit_ctx* c, double* prepare_ms, double* evaluate_ms, long long* launches) {
     if (int rc = check_ctx(c)) return rc;
     CK(cudaSetDevice(c->device));
-    double sum = 0.0;
-    for (size_t i = 0; i + 1 < c->prof_used; i += 2) {
-        CK(cudaEventSynchronize(c->prof_events[i + 1]));
-        float ms = 0.f;
-        CK(cudaEventElapsedTime(&ms, c->prof_events[i], c->prof_events[i + 1]));
-        sum += ms;
+    double prep = 0.0, eval = 0.0;
+    for (size_t i = 0; i + 2 < c->prof_used; i += 3) {
+        CK(cudaEventSynchronize(c->prof_events[i + 2]));
+        float a = 0.f, b = 0.f;
+        CK(cudaEventElapsedTime(&a, c->prof_events[i], c->prof_events[i + 1]));
+        CK(cudaEventElapsedTime(&b, c->prof_events[i + 1], c->prof_events[i + 2]));
+        prep += a;
+        eval += b;
     }
-    if (total_ms) *total_ms = sum;
-    if (launches) *launches = (long long)(c->prof_used / 2);
+    if (prepare_ms) *prepare_ms = prep;
+    if (evaluate_ms) *evaluate_ms = eval;
+    if (launches) *launches = (long long)(c->prof_used / 3);
     c->prof_used = 0;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_profile_read(nmrfit_ctx* c, double* total_ms, long long* launches) {
+    double prep = 0.0, eval = 0.0;
+    if (int rc = nmrfit_ctx_profile_read_split(c, &prep, &eval, launches)) return rc;
+    if (total_ms) *total_ms = prep + eval;
     return NMRFIT_OK;
 }
 

@@ -57,7 +57,7 @@ struct MoveArgs;
 // swarm (pso.cu's update) inside the prepare pass, one launch fewer per generation
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st,
                                      cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, const MoveArgs* mv = nullptr,
-                                     int* tiles_out = nullptr);
+                                     int* tiles_out = nullptr, cudaEvent_t evm = nullptr);
 
 cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaStream_t st, const MoveArgs* mv = nullptr);
 

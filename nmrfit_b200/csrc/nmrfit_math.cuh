@@ -385,6 +385,46 @@ NMRFIT_HD void far_eval(const double (&C)[kFarTerms], double xi0, double dxi, do
     }
 }
 
+// ---- numpy's summation order ---------------------------------------------------------------------------
+// pyswarm's stop test is stepsize = np.sqrt(np.sum((g - p_min)**2)); np.sum over a contiguous float64
+// vector is numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src, pairwise_sum): fewer
+// than 8 elements sequentially; up to 128 elements in eight interleaved accumulators r[j] += a[i + j]
+// combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)) with the tail added sequentially; longer vectors split
+// at n/2 rounded down to a multiple of 8.  Reproduced operation by operation, so that the comparison
+// `stepsize <= minstep` sees the very value the CPU run sees.  `sq[i]` holds the rounded squares.
+// LEVELS bounds the recursion: 128 << LEVELS elements (3 -> 1,024 >= 4 + 3*256 parameters).
+#ifdef NMRFIT_HOST_MATH
+#define NMRFIT_ADD_RN(a, b) ((a) + (b))
+#else
+#define NMRFIT_ADD_RN(a, b) __dadd_rn((a), (b))
+#endif
+template <int LEVELS>
+NMRFIT_HD double numpy_pairwise_sum(const double* sq, int n) {
+    if (n < 8) {
+        double res = 0.0;
+        for (int i = 0; i < n; ++i) res = NMRFIT_ADD_RN(res, sq[i]);
+        return res;
+    }
+    if (LEVELS == 0 || n <= 128) {
+        double r[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) r[j] = sq[j];
+        int i = 8;
+        for (; i < n - (n % 8); i += 8) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) r[j] = NMRFIT_ADD_RN(r[j], sq[i + j]);
+        }
+        double res = NMRFIT_ADD_RN(NMRFIT_ADD_RN(NMRFIT_ADD_RN(r[0], r[1]), NMRFIT_ADD_RN(r[2], r[3])),
+                                   NMRFIT_ADD_RN(NMRFIT_ADD_RN(r[4], r[5]), NMRFIT_ADD_RN(r[6], r[7])));
+        for (; i < n; ++i) res = NMRFIT_ADD_RN(res, sq[i]);
+        return res;
+    }
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    return NMRFIT_ADD_RN(numpy_pairwise_sum<(LEVELS > 0 ? LEVELS - 1 : 0)>(sq, n2),
+                         numpy_pairwise_sum<(LEVELS > 0 ? LEVELS - 1 : 0)>(sq + n2, n - n2));
+}
+
 // Philox4x32-10 (Salmon et al., SC'11) -> two uniform doubles in [0, 1) with 53
 // random bits each, built as MT19937's genrand_res53 builds them:
 // (a >> 5) * 2^26 + (b >> 6), scaled by 2^-53.

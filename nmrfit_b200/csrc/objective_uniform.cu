@@ -289,10 +289,11 @@ cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaSt
 }
 
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0,
-                                     cudaEvent_t ev1, const MoveArgs* mv, int* tiles_out) {
+                                     cudaEvent_t ev1, const MoveArgs* mv, int* tiles_out, cudaEvent_t evm) {
     if (ev0) cudaEventRecord(ev0, st);
     cudaError_t e = launch_objective_prepare(a, t, B, st, mv);
     if (e != cudaSuccess) return e;
+    if (evm) cudaEventRecord(evm, st);
     e = cudaErrorInvalidValue;
     if (t.threads == 128 && t.r == 4) e = launch_tb<128, 4>(a, t.tb, B, st);
     else if (t.threads == 128 && t.r == 8) e = launch_tb<128, 8>(a, t.tb, B, st);

@@ -103,15 +103,18 @@ __device__ __forceinline__ void commit_spectrum(const SwarmState& s, const doubl
         return;
     }
     const double fg = s.fg[b];
+    // stepsize = np.sqrt(np.sum((g - p_min)**2)): the squares element by element, then numpy's pairwise order
+    __shared__ double s_sq[kMaxParams];
+    if (fmin < fg)
+        for (int d = tid; d < s.D; d += nthreads) {
+            const double df = __dsub_rn(g[d], q[2 + d]);
+            s_sq[d] = __dmul_rn(df, df);
+        }
+    __syncthreads();
     if (tid == 0) {
         int action = 0;
         if (fmin < fg) {
-            double acc = 0.0;
-            for (int d = 0; d < s.D; ++d) {
-                double df = __dsub_rn(g[d], q[2 + d]);
-                acc = __dadd_rn(acc, __dmul_rn(df, df));
-            }
-            s_step = sqrt(acc);
+            s_step = sqrt(numpy_pairwise_sum<3>(s_sq, s.D));
             if (fabs(__dsub_rn(fg, fmin)) <= s.minfunc) { action = 2; s.stop[b] = kStopMinFunc; }
             else if (s_step <= s.minstep) { action = 2; s.stop[b] = kStopMinStep; }
             else action = 1;

@@ -316,9 +316,7 @@ swarm_fused_kernel(FusedArgs a) {
                 const double fmin = bf, fg = misc[2];
                 int action = 0;
                 if (fmin < fg) {
-                    double acc = 0.0;                      // summed in index order, as the per-step commit does
-                    for (int d = 0; d < D; ++d) acc = __dadd_rn(acc, sq[d]);
-                    const double step = sqrt(acc);
+                    const double step = sqrt(numpy_pairwise_sum<3>(sq, D));   // np.sum's order, as the per-step commit
                     if (fabs(__dsub_rn(fg, fmin)) <= s.minfunc) action = 2 + kStopMinFunc;
                     else if (step <= s.minstep) action = 2 + kStopMinStep;
                     else action = 1;

@@ -72,6 +72,8 @@ def ref_data(ref, data):
 
 
 worst = {}
+# `python tests/golden/make_golden.py --only objective_c4` regenerates only the fixtures whose name starts with that
+ONLY = sys.argv[sys.argv.index('--only') + 1] if '--only' in sys.argv else ''
 
 
 def note(name, got, want):
@@ -88,8 +90,13 @@ def main():
 
     # ---- objective on random particles inside the solution bounds ------------------------------
     cases = [('c1_4096x6', 4096, 6, 48, 0), ('ragged_1000x6', 1000, 6, 16, 3), ('p12_2048', 2048, 12, 16, 5),
-             ('tiny_257x6', 257, 6, 8, 7), ('p24_1536', 1536, 24, 8, 9)]
+             ('tiny_257x6', 257, 6, 8, 7), ('p24_1536', 1536, 24, 8, 9),
+             # the full BASELINE shapes (synth seeds of bench.py's workloads): the reference itself pins the far-field
+             # path at 64 / 128 / 256 regions of 256 points
+             ('c3_16384x6', 16384, 6, 15, 3000), ('c2_32768x12', 32768, 12, 15, 2000), ('c4_65536x24', 65536, 24, 7, 4000)]
     for name, N, P, S, seed in cases:
+        if ONLY and not ('objective_' + name).startswith(ONLY):
+            continue
         data, true = synth.multiplet(N, P, seed=seed)
         rd = ref_data(ref, data)
         lo, up = rd.generate_solution_bounds()
@@ -212,6 +219,8 @@ def main():
         print(name, 'generations', info['it'], 'stop', info['stop'], 'error', fobj.error)
 
     for name, d in out.items():
+        if ONLY and not name.startswith(ONLY):
+            continue
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **{k: np.asarray(v) for k, v in d.items()})
     print('worst relative disagreement oracle vs reference:')
     for k, v in worst.items():

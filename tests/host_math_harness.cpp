@@ -117,6 +117,8 @@ void h_span_fit(const double* w, int n, double h, const double* x, int P, int R,
     }
 }
 
+double h_numpy_sum(const double* sq, int n) { return nmrfit::numpy_pairwise_sum<3>(sq, n); }
+
 void h_philox(unsigned long long seed, unsigned long long lo, unsigned long long hi, double* out2) {
     nmrfit::Philox2 p = nmrfit::philox_uniform2(seed, lo, hi);
     out2[0] = p.a; out2[1] = p.b;

@@ -10,7 +10,8 @@ from oracle import nmrfit_oracle as orc
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
-OBJ_CASES = ['c1_4096x6', 'ragged_1000x6', 'p12_2048', 'tiny_257x6', 'p24_1536']
+OBJ_CASES = ['c1_4096x6', 'ragged_1000x6', 'p12_2048', 'tiny_257x6', 'p24_1536',
+             'c3_16384x6', 'c2_32768x12', 'c4_65536x24']      # the last three: full BASELINE shapes
 
 
 @pytest.mark.parametrize('case', OBJ_CASES)
@@ -144,7 +145,7 @@ def test_full_size_properties_c2():
         assert f.shape == (S,) and np.all(np.isfinite(f)) and np.all(f > 0)
         floor = 1e-4 * np.sqrt(np.mean(wts ** 2))             # weighted noise floor (sigma = 1e-4)
         assert f[0] == f.min() and 0.8 * floor < f[0] < 1.2 * floor   # generating parameters sit on it
-        idx = [0, 1, 2, S // 2, S - 1]
+        idx = np.r_[0, 1, 2, S // 2, S - 1, np.random.default_rng(5).choice(S, 251, replace=False)]   # 256 particles
         assert relerr(f[idx], orc.objective_swarm(xs[idx], data.w, data.u, data.v, wts)) < TOL
         # permutation of particles permutes the result bitwise
         perm = np.random.default_rng(0).permutation(S)

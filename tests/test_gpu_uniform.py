@@ -10,7 +10,8 @@ from oracle import nmrfit_oracle as orc
 
 pytestmark = pytest.mark.gpu
 TOL = 1e-11
-OBJ_CASES = ['c1_4096x6', 'ragged_1000x6', 'p12_2048', 'tiny_257x6', 'p24_1536']
+OBJ_CASES = ['c1_4096x6', 'ragged_1000x6', 'p12_2048', 'tiny_257x6', 'p24_1536',
+             'c3_16384x6', 'c2_32768x12', 'c4_65536x24']      # the last three: full BASELINE shapes
 
 
 def _ctx(g, n_peaks, algo):
@@ -161,7 +162,7 @@ def test_full_size_c2_uniform_against_general_and_oracle():
         ctx.set_algorithm(_cabi.ALGO_GENERAL)
         fg = ctx.objective_host(xs)
         assert relerr(f, fg) < 1e-11
-        idx = [0, 1, 2, S // 2, S - 1]
+        idx = np.r_[0, 1, 2, S // 2, S - 1, np.random.default_rng(5).choice(S, 251, replace=False)]   # 256 particles
         assert relerr(f[idx], orc.objective_swarm(xs[idx], data.w, data.u, data.v, wts)) < TOL
         ctx.set_algorithm(_cabi.ALGO_UNIFORM)
         perm = np.random.default_rng(0).permutation(S)

@@ -196,3 +196,25 @@ def test_far_field_extremes(hm):
             hm.h_region_fit(P(w), N, h, P(x), n_peaks, R, P(got))
             assert np.all(np.isfinite(got))
             assert np.abs(got - want).max() < 2e-12 * np.abs(want).max(), R
+
+
+def test_stepsize_sum_reproduces_numpys_pairwise_order(hm):
+    """pyswarm: stepsize = np.sqrt(np.sum((g - p_min)**2)).  The device commit sums the rounded squares in numpy's
+    pairwise order (eight interleaved accumulators up to 128 elements, halves rounded to multiples of 8 beyond), so the
+    `stepsize <= minstep` comparison sees the same double as the CPU run - for every parameter count 4 + 3P, P <= 256."""
+    hm.h_numpy_sum.restype = ctypes.c_double
+    rng = np.random.default_rng(11)
+    sizes = sorted({4 + 3 * p for p in (1, 2, 6, 12, 24, 36, 41, 42, 43, 66, 85, 86, 170, 171, 256)} | set(range(1, 40)) |
+                   {127, 128, 129, 255, 256, 257, 264, 511, 512, 513, 772})
+    seq_differs = 0
+    for n in sizes:
+        for rep in range(20):
+            d = rng.normal(size=n) * 10.0 ** rng.uniform(-9, 0, n)
+            sq = d ** 2
+            got = hm.h_numpy_sum(P(sq), n)
+            assert got == np.sum(sq), (n, rep)
+            seq = 0.0
+            for v in sq:
+                seq += v
+            seq_differs += seq != got
+    assert seq_differs > 100          # the order matters at the last ulp: a sequential sum is NOT what numpy computes

@@ -8,7 +8,8 @@ from conftest import load_golden, peaks_from_golden, relerr
 from oracle import nmrfit_oracle as orc
 from oracle import pso_oracle
 
-OBJ_CASES = ['c1_4096x6', 'ragged_1000x6', 'p12_2048', 'tiny_257x6', 'p24_1536']
+OBJ_CASES = ['c1_4096x6', 'ragged_1000x6', 'p12_2048', 'tiny_257x6', 'p24_1536',
+             'c3_16384x6', 'c2_32768x12', 'c4_65536x24']      # the last three: full BASELINE shapes
 
 
 @pytest.mark.parametrize('case', OBJ_CASES)

@@ -104,8 +104,10 @@ def objective_json(src, dst, workload='c2', peak_points=4096 * 32768 * 12):
     def to_bytes(name):
         v, u = g(name), units[hdr.index(name)]
         return v * {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}[u]
+    peak_points = float(peak_points)
     cycles = g('sm__cycles_elapsed.avg')
-    fp64 = sum(g('smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed' % k) for k in ('dfma', 'dmul', 'dadd')) * cycles
+    per_op = {k: g('smsp__sass_thread_inst_executed_op_%s_pred_on.sum.per_cycle_elapsed' % k) * cycles for k in ('dfma', 'dmul', 'dadd')}
+    fp64 = sum(per_op.values())
     d = {
         'kernel': r[hdr.index('Kernel Name')], 'source': src,
         'duration_ms_under_ncu': g('gpu__time_duration.sum') * {'ms': 1, 'us': 1e-3, 'ns': 1e-6, 'usecond': 1e-3, 'msecond': 1}[units[hdr.index('gpu__time_duration.sum')]],
@@ -114,6 +116,8 @@ def objective_json(src, dst, workload='c2', peak_points=4096 * 32768 * 12):
         'issue_slots_busy_pct': g('smsp__issue_active.avg.pct_of_peak_sustained_active'),
         'warp_inst_per_peak_point': g('smsp__inst_executed.sum') * 32 / peak_points,
         'fp64_arith_inst_per_peak_point': fp64 / peak_points,
+        'fp64_flop_per_peak_point': (2 * per_op['dfma'] + per_op['dmul'] + per_op['dadd']) / peak_points,
+        'peak_points_per_launch': peak_points,
         'registers_per_thread': g('launch__registers_per_thread'),
         'warps_active_pct': g('sm__warps_active.avg.pct_of_peak_sustained_active'),
     }
@@ -126,4 +130,5 @@ def objective_json(src, dst, workload='c2', peak_points=4096 * 32768 * 12):
 
 
 if __name__ == '__main__':
-    {'launches': launches, 'full': full, 'objective_json': objective_json}[sys.argv[1]](*sys.argv[2:4])
+    # objective_json <report> <dst.json> <workload> <peak-points per launch>
+    {'launches': launches, 'full': full, 'objective_json': objective_json}[sys.argv[1]](*sys.argv[2:6])
