@@ -103,6 +103,12 @@ int nmrfit_ctx_set_tuning(nmrfit_ctx* ctx, int threads, int points_per_thread, i
                           int particles_per_cta);
 int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* points_per_thread, int* exp_table_bits,
                           int* particles_per_cta, int* n_point_tiles);
+/* Which FP64 uniform-axis evaluation kernel runs (development / A-B measurement knob; results are bit-identical):
+ * variant -1 the library's choice (the streamed kernel), 0 one particle group per CTA (objective_uniform_kernel),
+ * 1 streamed (objective_stream_kernel: a CTA keeps its point tile and walks many particle groups through a
+ * `stages`-deep ring of TMA-filled shared-memory slots; stages 0 = auto, else 2..4). */
+int nmrfit_ctx_set_variant(nmrfit_ctx* ctx, int variant, int stages);
+int nmrfit_ctx_get_variant(nmrfit_ctx* ctx, int n_particles, int* variant, int* stages);
 
 /* Small swarms: nmrfit_pso_run executes its generations in ONE cooperative launch (one CTA - on longer axes one
  * thread-block cluster of up to 8 CTAs exchanging through distributed shared memory - per particle, one barrier per

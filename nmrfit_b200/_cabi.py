@@ -55,6 +55,8 @@ SIGNATURES = {
     'nmrfit_ctx_get_algorithm': (_i, [_vp, _i, c_int_p]),
     'nmrfit_ctx_set_tuning': (_i, [_vp, _i, _i, _i, _i]),
     'nmrfit_ctx_get_tuning': (_i, [_vp, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
+    'nmrfit_ctx_set_variant': (_i, [_vp, _i, _i]),
+    'nmrfit_ctx_get_variant': (_i, [_vp, _i, c_int_p, c_int_p]),
     'nmrfit_ctx_set_fused': (_i, [_vp, _i]),
     'nmrfit_ctx_fused_launches': (_i, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
     'nmrfit_ctx_fused_timing': (_i, [_vp, _i, _vp]),
@@ -224,6 +226,15 @@ class Context:
         check(lib().nmrfit_ctx_get_tuning(self._h, int(n_particles), *[ctypes.byref(v) for v in vals]))
         keys = ('threads', 'points_per_thread', 'exp_table_bits', 'particles_per_cta', 'n_point_tiles')
         return dict(zip(keys, (v.value for v in vals)))
+
+    def set_variant(self, variant=-1, stages=0):
+        """FP64 uniform-axis evaluation kernel: -1 library's choice, 0 one particle group per CTA, 1 streamed."""
+        check(lib().nmrfit_ctx_set_variant(self._h, int(variant), int(stages)))
+
+    def get_variant(self, n_particles):
+        v, st = ctypes.c_int(0), ctypes.c_int(0)
+        check(lib().nmrfit_ctx_get_variant(self._h, int(n_particles), ctypes.byref(v), ctypes.byref(st)))
+        return v.value, st.value
 
     def set_fused(self, mode=FUSED_AUTO):
         """FUSED_AUTO: ``pso_run`` uses the one-launch fused swarm kernel whenever the shape allows;
@@ -502,6 +513,7 @@ class pooled_context:
             ctx.close()                    # do not reuse a context an error may have left half way
             return
         ctx.set_tuning()
+        ctx.set_variant()
         ctx.set_fused(FUSED_AUTO)
         ctx.set_algorithm(ALGO_AUTO)
         ctx.profile(False)

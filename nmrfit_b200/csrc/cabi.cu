@@ -82,7 +82,7 @@ struct nmrfit_ctx {
     DevBuf<double> partials, x_stage, f_stage;
     DevBuf<double> prep_coef, prep_part, prep_far, prep_anchor;   // uniform-axis kernel, per-particle constants
     DevBuf<unsigned> prep_mask;
-    ObjTune user_tune{0, 0, 0, 0};
+    ObjTune user_tune{0, 0, 0, 0, -1, 0};   // variant -1: the library's choice
     // swarm
     bool swarm = false;
     SwarmState sw{};
@@ -178,6 +178,35 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
     sp = std::min(sp, std::max(1, S));
     if (c->user_tune.sp > 0) sp = std::min(c->user_tune.sp, std::max(1, S));
     t.sp = sp;
+    // FP64 uniform-axis path: the streamed evaluation kernel (objective_stream.cu) unless the caller asked for the
+    // one-group-per-CTA kernel.  Its `sp` is the particles per pipeline stage: as many as leave three CTAs per SM.
+    t.variant = 0;
+    t.stages = 0;
+    if (uni && c->precision == NMRFIT_FP64 && c->user_tune.variant != 0) {
+        t.variant = 1;
+        const size_t budget = 74 * 1024;
+        auto fit_sp = [&](int stg) {
+            t.stages = stg;
+            int spg = 0;
+            for (int cand = 1; cand <= 16; ++cand) {
+                t.sp = cand;
+                if (objective_stream_smem_bytes(c->P, t, 0) <= budget) spg = cand;
+            }
+            return spg;
+        };
+        int stg = c->user_tune.stages > 0 ? c->user_tune.stages : 3;
+        int spg = fit_sp(stg);
+        if (c->user_tune.stages == 0 && spg < 4) {         // many peaks: two deeper stages rather than three shallow ones
+            const int spg2 = fit_sp(2);
+            if (spg2 > spg) { stg = 2; spg = spg2; }
+        }
+        t.stages = stg;
+        t.sp = std::max(1, spg);
+        if (c->user_tune.sp > 0) t.sp = c->user_tune.sp;
+        t.sp = std::min(t.sp, std::max(1, S));
+        while (t.sp > 1 && objective_stream_smem_bytes(c->P, t, 0) > 200 * 1024) t.sp -= 1;
+        return t;
+    }
     // per-particle coefficients live in shared memory: keep the CTA under the 200 KB opt-in limit
     const bool f32 = c->precision == NMRFIT_FP32;
     auto uni_bytes = [&]() { return f32 ? objective_f32_smem_bytes(c->P, t) : objective_uniform_smem_bytes(c->P, t); };
@@ -195,7 +224,8 @@ int check_ctx(const nmrfit_ctx* c) {
 }
 
 int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double* f_dev, const int* frozen,
-                  cudaStream_t st, const MoveArgs* mv = nullptr, int* tiles_out = nullptr, int* nsum_out = nullptr) {
+                  cudaStream_t st, const MoveArgs* mv = nullptr, int* tiles_out = nullptr, int* nsum_out = nullptr,
+                  int* nw_out = nullptr) {
     for (int b = 0; b < c->B; ++b)
         if (!c->spec_set[b]) return fail(NMRFIT_ERR_STATE, "spectrum " + std::to_string(b) + " was never set");
     if (fit_im < 0 || fit_im > 2) return fail(NMRFIT_ERR_ARG, "fit_im must be 0, 1 or 2");
@@ -210,7 +240,7 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
         return fail(NMRFIT_ERR_ARG, uni ? "points_per_thread must be 4, 8 or 16 for the uniform-axis kernel"
                                         : "points_per_thread must be 2, 4 or 8 for the general kernel");
     int n_tiles = objective_tiles(c->N, t);
-    CK(c->partials.reserve((size_t)c->B * S * n_tiles * 2));
+    CK(c->partials.reserve((size_t)c->B * S * n_tiles * 2 * (t.variant == 1 ? t.threads / 32 : 1)));
     ObjArgs a{};
     if (uni) {
         size_t nc, np, nf, na, nm;
@@ -258,8 +288,9 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
         if (em != cudaSuccess) return fail_cuda(em, "swarm move");
     }
     if (nsum_out) *nsum_out = c->precision == NMRFIT_FP32 ? 1 : (fit_im ? 2 : 1);
+    if (nw_out) *nw_out = 1;
     cudaError_t e = c->precision == NMRFIT_FP32 ? launch_objective_f32(a, t, c->B, f_dev, uni, st, ev0, ev1, tiles_out)
-                    : uni ? launch_objective_uniform(a, t, c->B, f_dev, st, ev0, ev1, move_in_prepare ? mv : nullptr, tiles_out, evm)
+                    : uni ? launch_objective_uniform(a, t, c->B, f_dev, st, ev0, ev1, move_in_prepare ? mv : nullptr, tiles_out, evm, nw_out)
                           : launch_objective(a, t, c->B, f_dev, st, ev0, ev1, tiles_out);
     if (e != cudaSuccess) return fail_cuda(e, "objective launch");
     return NMRFIT_OK;
@@ -314,11 +345,12 @@ int fused_setup(nmrfit_ctx* c, int n_gen, const double* rp_d, const double* rg_d
 int swarm_generation(nmrfit_ctx* c, bool move, const double* rp_d, const double* rg_d, int commit, cudaStream_t st) {
     SwarmState& s = c->sw;
     MoveArgs mv{s, rp_d, rg_d, c->generation};
-    int n_tiles = 0, nsum = 1;
-    if (int rc = run_objective(c, s.x, s.S, c->kk, nullptr, move ? s.stop : nullptr, st, move ? &mv : nullptr, &n_tiles, &nsum))
+    int n_tiles = 0, nsum = 1, nw = 1;
+    if (int rc = run_objective(c, s.x, s.S, c->kk, nullptr, move ? s.stop : nullptr, st, move ? &mv : nullptr, &n_tiles, &nsum,
+                               &nw))
         return rc;
     cudaError_t e = launch_swarm_finish(s, c->partials.ptr, n_tiles, nsum, c->N, s.rec, c->fin_scratch.ptr,
-                                        c->fin_tickets.ptr, commit, c->maxiter, st);
+                                        c->fin_tickets.ptr, commit, c->maxiter, st, nw);
     if (e != cudaSuccess) return fail_cuda(e, "swarm finish");
     return NMRFIT_OK;
 }
@@ -517,7 +549,24 @@ int nmrfit_ctx_set_tuning(nmrfit_ctx* c, int threads, int r, int tb, int sp) {
     if (tb != 0 && tb != 6 && tb != 8 && tb != 10 && tb != -1)
         return fail(NMRFIT_ERR_ARG, "exp_table_bits must be 0 (auto), -1 (no table), 6, 8 or 10");
     if (sp < 0 || sp > 64) return fail(NMRFIT_ERR_ARG, "particles_per_cta must be 0..64");
-    c->user_tune = ObjTune{threads, r, tb, sp};
+    c->user_tune.threads = threads; c->user_tune.r = r; c->user_tune.tb = tb; c->user_tune.sp = sp;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_set_variant(nmrfit_ctx* c, int variant, int stages) {
+    if (int rc = check_ctx(c)) return rc;
+    if (variant < -1 || variant > 1) return fail(NMRFIT_ERR_ARG, "variant must be -1 (auto), 0 (one group per CTA) or 1 (streamed)");
+    if (stages != 0 && (stages < 2 || stages > 4)) return fail(NMRFIT_ERR_ARG, "stages must be 0 (auto) or 2..4");
+    c->user_tune.variant = variant;
+    c->user_tune.stages = stages;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_get_variant(nmrfit_ctx* c, int S, int* variant, int* stages) {
+    if (int rc = check_ctx(c)) return rc;
+    ObjTune t = pick_tune(c, S < 1 ? 1 : S, use_uniform(c, NMRFIT_REAL_ONLY));
+    if (variant) *variant = t.variant;
+    if (stages) *stages = t.stages;
     return NMRFIT_OK;
 }
 

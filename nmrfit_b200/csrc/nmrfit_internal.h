@@ -25,14 +25,21 @@ struct ObjArgs {
     int n_tiles, nw;        // point tiles, warps (= regions) per tile (filled by the launcher)
     int N, P, S;
     int kk;                 // 0 real only, 1 reference fit_im (last peak), 2 sum over peaks
-    int sp;                 // particles per CTA (filled by the launcher)
+    int sp;                 // particles per CTA (filled by the launcher); streamed kernel: particles per pipeline stage
+    // streamed uniform-axis kernel (objective_stream.cu): a CTA keeps its point tile and walks `gpc` particle groups
+    // through a `stages`-deep pipeline of bulk copies; its prepare pass stores the per-region constants tile-major,
+    // [B][n_tiles][S][nw][...], so that one tile's regions of a whole group are one contiguous block
+    int tile_major;         // layout of prep_far / prep_anchor / prep_mask (0: [B][S][n_tiles*nw][...])
+    int stages, gpc;
 };
 
 struct ObjTune {
     int threads;            // 128 | 256
     int r;                  // grid points per thread: 2 | 4 | 8 (general kernel), 4 | 8 | 16 (uniform-grid kernel)
     int tb;                 // exp table bits: 0 | 6 | 8 | 10
-    int sp;                 // particles per CTA
+    int sp;                 // particles per CTA (streamed kernel: per pipeline stage)
+    int variant;            // uniform-axis FP64 evaluation kernel: 0 one particle group per CTA, 1 streamed (objective_stream.cu)
+    int stages;             // streamed kernel: pipeline depth
 };
 
 int objective_tiles(int N, const ObjTune& t);
@@ -43,8 +50,9 @@ cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cuda
                              cudaEvent_t ev1 = nullptr, int* tiles_out = nullptr);
 
 // fixed-order sum over point tiles + sqrt(mean) (shared by the objective kernels)
+// `nw` > 1: the partial sums are per REGION, [n_tiles][nw]: the nw regions of a tile are summed first, then the tiles
 cudaError_t launch_objective_finalize(const double* partials, int n_tiles, int nsum, int N, int S, int B,
-                                      const int* frozen, double* f, cudaStream_t st);
+                                      const int* frozen, double* f, cudaStream_t st, int nw = 1);
 
 // uniform-axis objective (objective_uniform.cu): real-only fit, FP64
 size_t objective_uniform_smem_bytes(int P, const ObjTune& t);
@@ -57,9 +65,13 @@ struct MoveArgs;
 // swarm (pso.cu's update) inside the prepare pass, one launch fewer per generation
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st,
                                      cudaEvent_t ev0 = nullptr, cudaEvent_t ev1 = nullptr, const MoveArgs* mv = nullptr,
-                                     int* tiles_out = nullptr, cudaEvent_t evm = nullptr);
+                                     int* tiles_out = nullptr, cudaEvent_t evm = nullptr, int* nw_out = nullptr);
 
 cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaStream_t st, const MoveArgs* mv = nullptr);
+
+// streamed evaluation kernel (objective_stream.cu): shared-memory need and launch; partial sums per region
+size_t objective_stream_smem_bytes(int P, const ObjTune& t, int kk);
+cudaError_t launch_objective_stream(const ObjArgs& a, const ObjTune& t, int B, cudaStream_t st);
 
 // opt-in FP32 objective: uniform-axis kernel when `uniform`, else a plain FP32 kernel for any axis (real-only fit)
 size_t objective_f32_smem_bytes(int P, const ObjTune& t);
@@ -91,7 +103,7 @@ struct MoveArgs {
 // finalize + personal bests + local best record (+ swarm-best commit when `commit`) in one launch:
 // partials [B][S][n_tiles][nsum] -> fx, fp, p, rec; `scratch` holds [B][ceil(S/8)][2] doubles, `tickets` [B] zeroed once
 cudaError_t launch_swarm_finish(const SwarmState& s, const double* partials, int n_tiles, int nsum, int N, double* rec,
-                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st);
+                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st, int nw = 1);
 size_t swarm_finish_scratch_doubles(int B, int S);
 
 // record exchange over peer memory (pso.cu): device arrays of per-rank window pointers

@@ -204,17 +204,28 @@ objective_kernel(ObjArgs a) {
 }
 
 // fixed-order sum over point tiles, then sqrt(mean) (equations.py:202, 205-209)
+// (nw > 1: partials are per region, [n_tiles][nw]: the regions of a tile first, then the tiles)
 __global__ void objective_finalize_kernel(const double* __restrict__ partials, int n_tiles, int nsum,
                                           int N, int S, int B, const int* __restrict__ frozen,
-                                          double* __restrict__ f) {
+                                          double* __restrict__ f, int nw) {
     int idx = blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * S) return;
     if (frozen && frozen[idx / S]) return;
-    const double* p = partials + (size_t)idx * n_tiles * nsum;
+    const double* p = partials + (size_t)idx * n_tiles * nw * nsum;
     double sv = 0.0, si = 0.0;
     for (int t = 0; t < n_tiles; ++t) {
-        sv += p[t * nsum];
-        if (nsum == 2) si += p[t * nsum + 1];
+        if (nw == 1) {
+            sv += p[t * nsum];
+            if (nsum == 2) si += p[t * nsum + 1];
+        } else {
+            double tv = 0.0, ti = 0.0;
+            for (int w = 0; w < nw; ++w) {
+                tv += p[(t * nw + w) * nsum];
+                if (nsum == 2) ti += p[(t * nw + w) * nsum + 1];
+            }
+            sv += tv;
+            si += ti;
+        }
     }
     double rm = sqrt(sv / (double)N);
     if (nsum == 2) rm = (rm + sqrt(si / (double)N)) / 2.0;
@@ -287,9 +298,9 @@ cudaError_t launch_objective(ObjArgs a, const ObjTune& t, int B, double* f, cuda
 }
 
 cudaError_t launch_objective_finalize(const double* partials, int n_tiles, int nsum, int N, int S, int B,
-                                      const int* frozen, double* f, cudaStream_t st) {
+                                      const int* frozen, double* f, cudaStream_t st, int nw) {
     const int total = B * S;
-    objective_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(partials, n_tiles, nsum, N, S, B, frozen, f);
+    objective_finalize_kernel<<<(total + 255) / 256, 256, 0, st>>>(partials, n_tiles, nsum, N, S, B, frozen, f, nw);
     return cudaGetLastError();
 }
 

@@ -54,6 +54,25 @@ template <> struct ExpTabU<8> { static __device__ __forceinline__ const double* 
 template <> struct ExpTabU<10> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB10; } };
 
 
+// Where particle s of spectrum b keeps its per-region constants (in regions; times 12, 2 or MW+1 entries each):
+// particle-major [B][S][n_tiles*nw] for objective_uniform_kernel, tile-major [B][n_tiles][S][nw] for the streamed
+// kernel, whose CTA reads one tile's regions of a whole particle group as ONE contiguous block.
+struct RegionDst {
+    size_t base, slot_stride;
+    int slot_nw;
+    __device__ RegionDst(const ObjArgs& a, int b, int s, int NRP) {
+        if (a.tile_major) {
+            base = ((size_t)b * a.n_tiles * a.S + s) * a.nw;
+            slot_nw = a.nw;
+            slot_stride = (size_t)a.S * a.nw;
+        } else {
+            base = ((size_t)b * a.S + s) * NRP;
+            slot_nw = 1 << 30;
+            slot_stride = 0;
+        }
+    }
+};
+
 // ---- pass 1: per-particle constants, once per swarm generation ------------------------------------
 // Regions (32*R points each) are stored in axis order, padded to a whole number of tiles; the slots of
 // regions past the end of the axis are neutral.
@@ -66,10 +85,11 @@ objective_prepare_kernel(ObjArgs a) {
     const int P = a.P, N = a.N, D = 4 + 3 * P, MW = (P + 31) / 32;
     const int NR = (N + 32 * R - 1) / (32 * R), NRP = a.n_tiles * a.nw;
     const size_t ps = (size_t)b * a.S + s;
+    const RegionDst rd(a, b, s, NRP);
     prepare_particle<R>(a.x + ps * D, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid,
                         128, cs, a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles,
-                        a.prep_far + ps * NRP * kFarTerms, a.prep_anchor + ps * NRP * 2,
-                        a.prep_mask + ps * NRP * (MW + 1));
+                        a.prep_far + rd.base * kFarTerms, a.prep_anchor + rd.base * 2, a.prep_mask + rd.base * (MW + 1),
+                        nullptr, 0, -1, rd.slot_nw, rd.slot_stride);
 }
 
 // pass 1 with the swarm's move in front (pso.cu's swarm_move_kernel for this particle): one launch fewer
@@ -103,9 +123,11 @@ objective_move_prepare_kernel(ObjArgs a, MoveArgs mv) {
         xs[d] = x;
     }
     __syncthreads();
+    const RegionDst rd(a, b, sl, NRP);
     prepare_particle<R>(xs, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid, 128, cs,
-                        a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles, a.prep_far + ps * NRP * kFarTerms,
-                        a.prep_anchor + ps * NRP * 2, a.prep_mask + ps * NRP * (MW + 1));
+                        a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles, a.prep_far + rd.base * kFarTerms,
+                        a.prep_anchor + rd.base * 2, a.prep_mask + rd.base * (MW + 1), nullptr, 0, -1, rd.slot_nw,
+                        rd.slot_stride);
 }
 
 // ---- pass 2: evaluation ------------------------------------------------------------------------------
@@ -288,12 +310,36 @@ cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaSt
     return cudaGetLastError();
 }
 
+// Groups per CTA of the streamed kernel: enough CTAs for ~5 waves of the 3-per-SM residency (the hardware's CTA
+// scheduler evens out the tiles' different costs), few enough that the tile staging is amortised over >= 4 groups.
+static int stream_groups_per_cta(int S, int sp, int n_tiles, int B) {
+    const long long n_groups = (S + sp - 1) / sp;
+    long long gpc = n_groups * n_tiles * B / (148 * 3 * 5);
+    gpc = std::max<long long>(4, std::min<long long>(32, gpc));
+    const long long chunks = (n_groups + gpc - 1) / gpc;
+    return (int)((n_groups + chunks - 1) / chunks);        // equal chunks
+}
+
 cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double* f, cudaStream_t st, cudaEvent_t ev0,
-                                     cudaEvent_t ev1, const MoveArgs* mv, int* tiles_out, cudaEvent_t evm) {
+                                     cudaEvent_t ev1, const MoveArgs* mv, int* tiles_out, cudaEvent_t evm, int* nw_out) {
     if (ev0) cudaEventRecord(ev0, st);
+    a.tile_major = t.variant == 1;
     cudaError_t e = launch_objective_prepare(a, t, B, st, mv);
     if (e != cudaSuccess) return e;
     if (evm) cudaEventRecord(evm, st);
+    if (nw_out) *nw_out = 1;
+    if (t.variant == 1) {
+        a.stages = t.stages;
+        a.gpc = stream_groups_per_cta(a.S, a.sp, a.n_tiles, B);
+        e = launch_objective_stream(a, t, B, st);
+        if (ev1) cudaEventRecord(ev1, st);
+        if (e != cudaSuccess) return e;
+        if (tiles_out) *tiles_out = a.n_tiles;
+        if (nw_out) *nw_out = a.nw;
+        if (f) e = launch_objective_finalize(a.partials, a.n_tiles, a.kk ? 2 : 1, a.N, a.S, B, a.frozen, f, st, a.nw);
+        count_launches(f ? 3 : 2);
+        return e;
+    }
     e = cudaErrorInvalidValue;
     if (t.threads == 128 && t.r == 4) e = launch_tb<128, 4>(a, t.tb, B, st);
     else if (t.threads == 128 && t.r == 8) e = launch_tb<128, 8>(a, t.tb, B, st);

@@ -155,7 +155,7 @@ constexpr int kFinWarps = 8;
 __global__ void __launch_bounds__(kFinWarps * 32)
 swarm_finish_kernel(SwarmState s, const double* __restrict__ partials, int n_tiles, int nsum, int N,
                     double* rec, double* __restrict__ scratch, unsigned* __restrict__ tickets, int commit,
-                    int maxiter) {
+                    int maxiter, int nw) {
     const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
     if (s.stop[b]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -167,16 +167,31 @@ swarm_finish_kernel(SwarmState s, const double* __restrict__ partials, int n_til
     int ci = 0x7fffffff;
     if (i < s.S) {
         const size_t bs = (size_t)b * s.S + i;
-        const double* p = partials + bs * n_tiles * nsum;
+        // partial sums per tile (nw == 1) or per region, [n_tiles][nw] (the streamed kernel; nw = 4 or 8 divides 32):
+        // the regions of a tile are added first, then the tiles
+        const int n_units = n_tiles * nw;
+        const double* p = partials + bs * n_units * nsum;
         double sv = 0.0, sim = 0.0;
-        for (int t0 = 0; t0 < n_tiles; t0 += 32) {         // coalesced load, then the same sequential order as
+        for (int t0 = 0; t0 < n_units; t0 += 32) {         // coalesced load, then the same sequential order as
             const int t = t0 + lane;                       // objective_finalize_kernel (every lane sums all of them)
-            const double a0 = t < n_tiles ? p[t * nsum] : 0.0;
-            const double a1 = (nsum == 2 && t < n_tiles) ? p[t * nsum + 1] : 0.0;
-            const int cnt = min(32, n_tiles - t0);
-            for (int k = 0; k < cnt; ++k) {
-                sv += __shfl_sync(0xffffffffu, a0, k);
-                if (nsum == 2) sim += __shfl_sync(0xffffffffu, a1, k);
+            const double a0 = t < n_units ? p[t * nsum] : 0.0;
+            const double a1 = (nsum == 2 && t < n_units) ? p[t * nsum + 1] : 0.0;
+            const int cnt = min(32, n_units - t0);
+            if (nw == 1) {
+                for (int k = 0; k < cnt; ++k) {
+                    sv += __shfl_sync(0xffffffffu, a0, k);
+                    if (nsum == 2) sim += __shfl_sync(0xffffffffu, a1, k);
+                }
+            } else {
+                for (int k = 0; k < cnt; k += nw) {
+                    double tv = 0.0, ti = 0.0;
+                    for (int w = 0; w < nw; ++w) {
+                        tv += __shfl_sync(0xffffffffu, a0, k + w);
+                        if (nsum == 2) ti += __shfl_sync(0xffffffffu, a1, k + w);
+                    }
+                    sv += tv;
+                    sim += ti;
+                }
             }
         }
         double fx = sqrt(sv / (double)N);
@@ -332,9 +347,10 @@ cudaError_t launch_swarm_move(const SwarmState& s, const double* rp, const doubl
 size_t swarm_finish_scratch_doubles(int B, int S) { return (size_t)B * ((S + kFinWarps - 1) / kFinWarps) * 2; }
 
 cudaError_t launch_swarm_finish(const SwarmState& s, const double* partials, int n_tiles, int nsum, int N, double* rec,
-                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st) {
+                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st, int nw) {
     dim3 grid((s.S + kFinWarps - 1) / kFinWarps, s.B);
-    swarm_finish_kernel<<<grid, kFinWarps * 32, 0, st>>>(s, partials, n_tiles, nsum, N, rec, scratch, tickets, commit, maxiter);
+    swarm_finish_kernel<<<grid, kFinWarps * 32, 0, st>>>(s, partials, n_tiles, nsum, N, rec, scratch, tickets, commit, maxiter,
+                                                         nw);
     count_launches(1);
     return cudaGetLastError();
 }

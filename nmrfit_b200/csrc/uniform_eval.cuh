@@ -29,8 +29,11 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
                                                  double* __restrict__ cs, double* __restrict__ coef_out,
                                                  double* __restrict__ part, double* __restrict__ far,
                                                  double* __restrict__ anchor, unsigned* __restrict__ mask,
-                                                 double* __restrict__ pairs = nullptr, int r_lo = 0, int r_hi = -1) {
-    // regions [r_lo, r_hi) are filled, at index r - r_lo of far / anchor / mask (default: all NRP slots)
+                                                 double* __restrict__ pairs = nullptr, int r_lo = 0, int r_hi = -1,
+                                                 int slot_nw = 1 << 30, size_t slot_stride = 0) {
+    // regions [r_lo, r_hi) are filled, at index r - r_lo of far / anchor / mask (default: all NRP slots).
+    // Tile-major destinations (the streamed evaluation kernel reads one tile's regions of a whole particle group as
+    // one block): local region rl lands at slot (rl / slot_nw) * slot_stride + rl % slot_nw instead of rl.
     if (r_hi < 0) r_hi = NRP;
     const int nr = r_hi - r_lo;
     const int MW = (P + 31) / 32;
@@ -125,11 +128,12 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
     }
     for (int rl = tid; rl < nr; rl += nthreads) {
         const int r = r_lo + rl;
+        const size_t slot = (size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw);
         double C[kFarTerms];
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
         unsigned any_far = 0;
-        unsigned* mk = mask + (size_t)rl * (MW + 1);
+        unsigned* mk = mask + slot * (MW + 1);
         double sn = 0.0, cn = 1.0;
         if (r < NR) {
             const int ir = r * 32 * R;
@@ -152,11 +156,11 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
             for (int wd = 0; wd < MW; ++wd) mk[wd] = 0u;
         }
         mk[MW] = any_far;
-        double* fc = far + (size_t)rl * kFarTerms;
+        double* fc = far + slot * kFarTerms;
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
-        anchor[rl * 2] = cn;
-        anchor[rl * 2 + 1] = sn;
+        anchor[slot * 2] = cn;
+        anchor[slot * 2 + 1] = sn;
     }
 }
 

@@ -223,3 +223,27 @@ def test_fit_with_fit_im_true_follows_the_oracle_loop():
     with contextlib.redirect_stdout(io.StringIO()):
         fit = nmrfit_b200.fit(data, lo, up, fit_im=True, summary=False, options={'swarmsize': 20, 'maxiter': 15})
     assert np.array_equal(fit.params, x_ref) and abs(fit.error / f_ref - 1) < 1e-10
+
+
+@pytest.mark.parametrize('n_points,n_peaks,n_particles', [(4096, 6, 301), (1000, 6, 37), (32768, 12, 64), (2500, 36, 9), (257, 6, 5)])
+@pytest.mark.parametrize('fit_im', [_cabi.REAL_ONLY, _cabi.IM_REFERENCE])
+def test_streamed_and_one_group_kernels_agree_bit_for_bit(n_points, n_peaks, n_particles, fit_im):
+    """objective_stream_kernel (a CTA keeps its tile and walks many particle groups through a TMA ring, warps rotate
+    over the tile's regions) against objective_uniform_kernel (one group per CTA): the same eval_region on the same
+    constants, region sums added in the same order - identical bits, for every pipeline depth and group size."""
+    data, true = synth.multiplet(max(n_points, 600), n_peaks, seed=n_points)
+    w, u, v = data.w[:n_points], data.u[:n_points], data.v[:n_points]
+    wts = utils.compute_weights(data.w, data.peaks)[:n_points]
+    lo, up = data.generate_solution_bounds()
+    xs = synth.particles(lo, up, n_particles, seed=3)
+    xs[0] = true
+    with _cabi.Context(1, n_points, n_peaks) as ctx:
+        ctx.set_spectrum(0, w, u, v, wts)
+        ctx.set_variant(0)
+        assert ctx.get_variant(n_particles)[0] == 0
+        want = ctx.objective_host(xs, fit_im)
+        for stages, sp in ((0, 0), (2, 1), (2, 3), (3, 4), (4, 2), (3, 7)):
+            ctx.set_variant(1, stages)
+            ctx.set_tuning(0, 0, 0, sp)
+            assert ctx.get_variant(n_particles)[0] == 1
+            assert np.array_equal(ctx.objective_host(xs, fit_im), want), (stages, sp)
