@@ -109,6 +109,10 @@ int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* p
  * `stages`-deep ring of TMA-filled shared-memory slots; stages 0 = auto, else 2..4). */
 int nmrfit_ctx_set_variant(nmrfit_ctx* ctx, int variant, int stages);
 int nmrfit_ctx_get_variant(nmrfit_ctx* ctx, int n_particles, int* variant, int* stages);
+/* Far-field cells per region of 32 * points_per_thread points (csrc/uniform_eval.cuh): 0 = the library's rule (a
+ * function of the axis length only: 64-point cells below 8,192 points, 128-point cells below 32,768, else the whole
+ * region), or 1, 2, 4.  Every FP64 uniform-axis kernel of the context follows it; results agree to rounding. */
+int nmrfit_ctx_set_far_cells(nmrfit_ctx* ctx, int cells);
 
 /* Small swarms: nmrfit_pso_run executes its generations in ONE cooperative launch (one CTA - on longer axes one
  * thread-block cluster of up to 8 CTAs exchanging through distributed shared memory - per particle, one barrier per

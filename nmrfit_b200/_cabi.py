@@ -57,6 +57,7 @@ SIGNATURES = {
     'nmrfit_ctx_get_tuning': (_i, [_vp, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
     'nmrfit_ctx_set_variant': (_i, [_vp, _i, _i]),
     'nmrfit_ctx_get_variant': (_i, [_vp, _i, c_int_p, c_int_p]),
+    'nmrfit_ctx_set_far_cells': (_i, [_vp, _i]),
     'nmrfit_ctx_set_fused': (_i, [_vp, _i]),
     'nmrfit_ctx_fused_launches': (_i, [_vp, ctypes.POINTER(ctypes.c_longlong)]),
     'nmrfit_ctx_fused_timing': (_i, [_vp, _i, _vp]),
@@ -230,6 +231,10 @@ class Context:
     def set_variant(self, variant=-1, stages=0):
         """FP64 uniform-axis evaluation kernel: -1 library's choice, 0 one particle group per CTA, 1 streamed."""
         check(lib().nmrfit_ctx_set_variant(self._h, int(variant), int(stages)))
+
+    def set_far_cells(self, cells=0):
+        """Far-field cells per region (0 = by axis length, or 1, 2, 4); applies to every FP64 uniform-axis kernel."""
+        check(lib().nmrfit_ctx_set_far_cells(self._h, int(cells)))
 
     def get_variant(self, n_particles):
         v, st = ctypes.c_int(0), ctypes.c_int(0)
@@ -514,6 +519,7 @@ class pooled_context:
             return
         ctx.set_tuning()
         ctx.set_variant()
+        ctx.set_far_cells()
         ctx.set_fused(FUSED_AUTO)
         ctx.set_algorithm(ALGO_AUTO)
         ctx.profile(False)

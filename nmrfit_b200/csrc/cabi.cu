@@ -104,6 +104,7 @@ struct nmrfit_ctx {
     DevBuf<int> peer_err;
     long long epoch = 0;               // fits begun on this context: part of the exchange token
     DevBuf<double> wscratch, wbounds;  // batched weights: sweep scratch [B][N], windows + values
+    int far_cells = 0;                 // far-field cells per region: 0 = far_cells_per_region(N, R), else 1 | 2 | 4
     int fused_mode = NMRFIT_FUSED_AUTO;
     DevBuf<long long> ftiming;         // optional per-phase cycle counters of the fused kernel
     bool fused_timing = false;
@@ -151,6 +152,9 @@ bool use_uniform(const nmrfit_ctx* c, int fit_im) {
     return true;
 }
 
+// far-field cells per region of the FP64 uniform-axis kernels (every kernel of a context uses the same split)
+int ctx_cells(const nmrfit_ctx* c, int r) { return c->far_cells ? c->far_cells : far_cells_per_region(c->N, r); }
+
 ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
     ObjTune t;
     // The point tiling fixes the summation order of the residual, so it may depend on
@@ -190,7 +194,7 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
             int spg = 0;
             for (int cand = 1; cand <= 16; ++cand) {
                 t.sp = cand;
-                if (objective_stream_smem_bytes(c->P, t, 0) <= budget) spg = cand;
+                if (objective_stream_smem_bytes(c->P, t, ctx_cells(c, t.r)) <= budget) spg = cand;
             }
             return spg;
         };
@@ -204,12 +208,12 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
         t.sp = std::max(1, spg);
         if (c->user_tune.sp > 0) t.sp = c->user_tune.sp;
         t.sp = std::min(t.sp, std::max(1, S));
-        while (t.sp > 1 && objective_stream_smem_bytes(c->P, t, 0) > 200 * 1024) t.sp -= 1;
+        while (t.sp > 1 && objective_stream_smem_bytes(c->P, t, ctx_cells(c, t.r)) > 200 * 1024) t.sp -= 1;
         return t;
     }
     // per-particle coefficients live in shared memory: keep the CTA under the 200 KB opt-in limit
     const bool f32 = c->precision == NMRFIT_FP32;
-    auto uni_bytes = [&]() { return f32 ? objective_f32_smem_bytes(c->P, t) : objective_uniform_smem_bytes(c->P, t); };
+    auto uni_bytes = [&]() { return f32 ? objective_f32_smem_bytes(c->P, t) : objective_uniform_smem_bytes(c->P, t, ctx_cells(c, t.r)); };
     while (t.sp > 1 && (uni ? uni_bytes() : objective_smem_bytes(c->P, t, 2)) > 200 * 1024)
         t.sp /= 2;
     // uniform-axis kernels: three CTAs per SM if a smaller particle tile achieves it (227 KB / 3)
@@ -242,10 +246,11 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     int n_tiles = objective_tiles(c->N, t);
     CK(c->partials.reserve((size_t)c->B * S * n_tiles * 2 * (t.variant == 1 ? t.threads / 32 : 1)));
     ObjArgs a{};
+    const int sub = (uni && c->precision == NMRFIT_FP64) ? ctx_cells(c, t.r) : 1;
     if (uni) {
         size_t nc, np, nf, na, nm;
         int pad = 0;
-        objective_uniform_prep_sizes(c->N, c->P, t, &nc, &np, &nf, &na, &nm, &pad);
+        objective_uniform_prep_sizes(c->N, c->P, t, sub, &nc, &np, &nf, &na, &nm, &pad);
         const size_t slots = (size_t)c->B * S + pad;
         CK(c->prep_coef.reserve(slots * nc));
         CK(c->prep_part.reserve(slots * np));
@@ -260,7 +265,7 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     a.partials = c->partials.ptr;
     a.frozen = frozen;
     a.grid_h = c->grid_h.ptr;
-    a.N = c->N; a.P = c->P; a.S = S; a.kk = fit_im; a.sp = t.sp;
+    a.N = c->N; a.P = c->P; a.S = S; a.kk = fit_im; a.sp = t.sp; a.sub = sub;
     // profiling: three events per launch - before the prepare pass, between it and the evaluation kernel, after
     cudaEvent_t ev0 = nullptr, evm = nullptr, ev1 = nullptr;
     if (c->profiling) {
@@ -323,6 +328,7 @@ int fused_setup(nmrfit_ctx* c, int n_gen, const double* rp_d, const double* rg_d
     a->N = c->N; a->P = c->P;
     a->n_vtiles = objective_tiles(c->N, t);
     a->vw = t.threads / 32;
+    a->sub = ctx_cells(c, t.r);
     a->n_gen = n_gen;
     a->gen0 = c->generation + 1;
     a->maxiter = c->maxiter;
@@ -559,6 +565,13 @@ int nmrfit_ctx_set_variant(nmrfit_ctx* c, int variant, int stages) {
     if (stages != 0 && (stages < 2 || stages > 4)) return fail(NMRFIT_ERR_ARG, "stages must be 0 (auto) or 2..4");
     c->user_tune.variant = variant;
     c->user_tune.stages = stages;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_set_far_cells(nmrfit_ctx* c, int cells) {
+    if (int rc = check_ctx(c)) return rc;
+    if (cells != 0 && cells != 1 && cells != 2 && cells != 4) return fail(NMRFIT_ERR_ARG, "cells must be 0 (auto), 1, 2 or 4");
+    c->far_cells = cells;
     return NMRFIT_OK;
 }
 

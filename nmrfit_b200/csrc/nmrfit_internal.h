@@ -31,7 +31,18 @@ struct ObjArgs {
     // [B][n_tiles][S][nw][...], so that one tile's regions of a whole group are one contiguous block
     int tile_major;         // layout of prep_far / prep_anchor / prep_mask (0: [B][S][n_tiles*nw][...])
     int stages, gpc;
+    int sub;                // far-field cells per region of 32*R points (1, 2 or 4; uniform_eval.cuh); far / mask hold
+                            // `sub` entries per region
 };
+
+// Far-field cells per warp region (uniform_eval.cuh): the shorter the axis, the shorter the cells, down to 64 points.
+// A function of the axis length and the points per thread ONLY, so that every kernel that evaluates a given spectrum
+// (one group per CTA, streamed, fused swarm) splits it the same way and stays bit-identical to the others.
+__host__ __device__ inline int far_cells_per_region(int N, int R) {
+    const int target = N < 8192 ? 64 : (N < 32768 ? 128 : 256);    // cell length aimed at, in points
+    int sub = 32 * R / target;
+    return sub < 1 ? 1 : (sub > 4 ? 4 : sub);
+}
 
 struct ObjTune {
     int threads;            // 128 | 256
@@ -55,10 +66,10 @@ cudaError_t launch_objective_finalize(const double* partials, int n_tiles, int n
                                       const int* frozen, double* f, cudaStream_t st, int nw = 1);
 
 // uniform-axis objective (objective_uniform.cu): real-only fit, FP64
-size_t objective_uniform_smem_bytes(int P, const ObjTune& t);
-// per-particle sizes (in doubles / 32-bit words) of the prepare pass's outputs
-void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, size_t* coef, size_t* part, size_t* far, size_t* anchor,
-                                  size_t* mask_words, int* pad_particles);
+size_t objective_uniform_smem_bytes(int P, const ObjTune& t, int sub = 1);
+// per-particle sizes (in doubles / 32-bit words) of the prepare pass's outputs; `sub` far-field cells per region
+void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, int sub, size_t* coef, size_t* part, size_t* far,
+                                  size_t* anchor, size_t* mask_words, int* pad_particles);
 struct SwarmState;
 struct MoveArgs;
 // f == nullptr skips the finalize pass (the swarm's finish kernel sums the tiles itself); mv != nullptr moves the
@@ -70,7 +81,7 @@ cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double*
 cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaStream_t st, const MoveArgs* mv = nullptr);
 
 // streamed evaluation kernel (objective_stream.cu): shared-memory need and launch; partial sums per region
-size_t objective_stream_smem_bytes(int P, const ObjTune& t, int kk);
+size_t objective_stream_smem_bytes(int P, const ObjTune& t, int sub);
 cudaError_t launch_objective_stream(const ObjArgs& a, const ObjTune& t, int B, cudaStream_t st);
 
 // opt-in FP32 objective: uniform-axis kernel when `uniform`, else a plain FP32 kernel for any axis (real-only fit)
@@ -139,6 +150,7 @@ struct FusedArgs {
     int n_gen;              // generations to run in this launch
     int gen0;               // absolute number of the first of them (Philox counter)
     int maxiter;
+    int sub;                // far-field cells per region (far_cells_per_region, or the context's override)
     int slots;              // supertiles of (u, v, weights) held in shared memory (filled by the launcher)
     int cluster;            // CTAs (one thread-block cluster) per particle (filled by the launcher)
     int pairs;              // pair-parallel constants pass (needs its scratch in shared memory; filled by the launcher)

@@ -385,6 +385,19 @@ NMRFIT_HD void far_eval(const double (&C)[kFarTerms], double xi0, double dxi, do
     }
 }
 
+// acc[j] = sum_n C[n] xi_j^n: the accumulators START from the far field (the near peaks are added on top).
+template <int R>
+NMRFIT_HD void far_init(const double (&C)[kFarTerms], double xi0, double dxi, double (&acc)[R]) {
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+        const double xi = j == 0 ? xi0 : NMRFIT_FMA((double)j, dxi, xi0);
+        double p = C[kFarTerms - 1];
+#pragma unroll
+        for (int n = kFarTerms - 2; n >= 0; --n) p = NMRFIT_FMA(p, xi, C[n]);
+        acc[j] = p;
+    }
+}
+
 // ---- numpy's summation order ---------------------------------------------------------------------------
 // pyswarm's stop test is stepsize = np.sqrt(np.sum((g - p_min)**2)); np.sum over a contiguous float64
 // vector is numpy's pairwise summation (numpy/core/src/umath/loops_utils.h.src, pairwise_sum): fewer

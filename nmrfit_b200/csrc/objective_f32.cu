@@ -348,6 +348,8 @@ cudaError_t launch_objective_f32(ObjArgs a, const ObjTune& t, int B, double* f, 
     int n_tiles;
     if (ev0) cudaEventRecord(ev0, st);
     if (uniform) {
+        a.sub = 1;                                         // the FP32 kernel keeps one far-field cell per region
+        a.tile_major = 0;
         e = launch_objective_prepare(a, t, B, st);
         if (e != cudaSuccess) return e;
         e = cudaErrorInvalidValue;

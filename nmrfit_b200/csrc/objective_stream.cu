@@ -42,7 +42,7 @@ template <> struct ExpTabS<10> { static __device__ __forceinline__ const double*
 // shared-memory carve-up (in doubles); every offset is even (16-byte alignment)
 struct StreamSmem {
     int tab, uv, wt, wfirst, bars, tickets, slot0, slot, coef, part, far, anchor, mask, mw, total;
-    __host__ __device__ StreamSmem(int spg, int stages, int P, int threads, int R, int TB) {
+    __host__ __device__ StreamSmem(int spg, int stages, int P, int threads, int R, int TB, int sub) {
         const int nw = threads / 32;
         mw = (P + 31) / 32;
         int o = 0;
@@ -58,9 +58,9 @@ struct StreamSmem {
         int q = 0;
         coef = q;    q += spg * P * 8;
         part = q;    q += spg * kPartDoubles;
-        far = q;     q += spg * nw * kFarTerms;
+        far = q;     q += spg * nw * sub * kFarTerms;       // per far-field cell (uniform_eval.cuh)
         anchor = q;  q += spg * nw * 2;
-        mask = q;    q += ((spg * nw * (mw + 1) + 3) / 4) * 2;
+        mask = q;    q += ((spg * nw * sub * (mw + 1) + 3) / 4) * 2;
         slot = q;
         total = slot0 + stages * slot;
     }
@@ -79,7 +79,8 @@ objective_stream_kernel(ObjArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.P, N = a.N, D = 4 + 3 * P, SPG = a.sp, ST = a.stages;
     const int n_tiles = a.n_tiles, tile = blockIdx.y, NRP = n_tiles * NW;
-    const StreamSmem L(SPG, ST, P, THREADS, R, TB);
+    const int SUB = a.sub;
+    const StreamSmem L(SPG, ST, P, THREADS, R, TB, SUB);
     const int MW = L.mw;
     double* tab = smem + L.tab;
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
@@ -101,8 +102,8 @@ objective_stream_kernel(ObjArgs a) {
     const size_t pb = (size_t)b * a.S;                     // first particle slot of this spectrum
     const size_t tb_ = ((size_t)b * n_tiles + tile) * a.S; // ... of this (spectrum, tile) in the tile-major arrays
 
-    const uint32_t b_coef = SPG * P * 8 * 8, b_part = SPG * kPartDoubles * 8, b_far = SPG * NW * kFarTerms * 8;
-    const uint32_t b_anchor = SPG * NW * 2 * 8, b_mask = SPG * NW * (MW + 1) * 4;
+    const uint32_t b_coef = SPG * P * 8 * 8, b_part = SPG * kPartDoubles * 8, b_far = SPG * NW * SUB * kFarTerms * 8;
+    const uint32_t b_anchor = SPG * NW * 2 * 8, b_mask = SPG * NW * SUB * (MW + 1) * 4;
     // one thread asks the TMA for group g (relative to g_lo) into slot g % ST.  Whole groups are copied (the
     // prepare buffers are padded); only the particles that exist are evaluated.
     auto fill = [&](int g) {
@@ -113,9 +114,9 @@ objective_stream_kernel(ObjArgs a) {
         mbar_expect_tx(bar, b_coef + b_part + b_far + b_anchor + b_mask);
         bulk_g2s(dst + L.coef, a.prep_coef + (pb + q0) * P * 8, b_coef, bar);
         bulk_g2s(dst + L.part, a.prep_part + (pb + q0) * kPartDoubles, b_part, bar);
-        bulk_g2s(dst + L.far, a.prep_far + (tb_ + q0) * NW * kFarTerms, b_far, bar);
+        bulk_g2s(dst + L.far, a.prep_far + (tb_ + q0) * NW * SUB * kFarTerms, b_far, bar);
         bulk_g2s(dst + L.anchor, a.prep_anchor + (tb_ + q0) * NW * 2, b_anchor, bar);
-        bulk_g2s(dst + L.mask, a.prep_mask + (tb_ + q0) * NW * (MW + 1), b_mask, bar);
+        bulk_g2s(dst + L.mask, a.prep_mask + (tb_ + q0) * NW * SUB * (MW + 1), b_mask, bar);
     };
 
     if (tid == 0) {
@@ -126,13 +127,14 @@ objective_stream_kernel(ObjArgs a) {
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int g = 0; g < min(ST, my_groups); ++g) fill(g);
     }
-    // ---- meanwhile stage the tile: coalesced reads, swizzled [j][thread] placement (uniform_eval.cuh)
+    // ---- meanwhile stage the tile: coalesced reads, plain [j][thread] placement (uniform_eval.cuh: the stores
+    // collide, once per CTA; the evaluation then reads row j of thread t at a compile-time offset from one base)
     for (int e = tid; e < THREADS * R; e += THREADS) {
         const int i = tile0 + e;
         const bool ok = i < N;
         const int t = e / R, j = e % R;
-        suv[stage_slot_uv(t, j, THREADS)] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
-        swt[stage_slot_wt(t, j, THREADS)] = ok ? sw[3 * N + i] : 0.0;      // zero weight: padding contributes nothing
+        suv[j * THREADS + t] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
+        swt[j * THREADS + t] = ok ? sw[3 * N + i] : 0.0;    // zero weight: padding contributes nothing
     }
     {
         const int i_first = tile0 + tid * R;
@@ -143,7 +145,8 @@ objective_stream_kernel(ObjArgs a) {
         for (int i = tid; i < (1 << TB); i += THREADS) tab[i] = src[i];
     }
     constexpr double H = 16.0 * R;                         // half a region, in points
-    const double xi0 = ((double)(lane * R) - 0.5 * (32 * R - 1)) / H;      // first point's position inside its region
+    const double xi0 = cell_xi0<R>(lane, SUB);             // first point's position inside its far-field cell
+    const double inv_H = (double)SUB / H;
     __syncthreads();                                       // the only CTA-wide barrier: tile, table, mbarriers
 
     int n = 0;                                             // particles this CTA has evaluated: drives the rotation
@@ -163,10 +166,10 @@ objective_stream_kernel(ObjArgs a) {
             const int t = rw * 32 + lane;                  // ... and the thread span inside the tile this lane takes
             const int i_first = tile0 + t * R;
             double ssi = 0.0;
-            const double ss = eval_region<R, TB, KK>(
-                coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + rw) * (MW + 1),
-                farc + (size_t)(sp * NW + rw) * kFarTerms, anchor[sp * NW + rw], MW, P, lane, swf[t], xi0, suv, swt, t,
-                THREADS, tab, a.x + (pb + q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
+            const double ss = eval_region<R, TB, KK, false>(
+                coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + rw) * SUB * (MW + 1),
+                farc + (size_t)(sp * NW + rw) * SUB * kFarTerms, anchor[sp * NW + rw], MW, P, lane, SUB, swf[t], xi0, inv_H,
+                suv, swt, t, THREADS, tab, a.x + (pb + q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
             if (lane == 0) {
                 double* out = a.partials + (((pb + q0 + sp) * n_tiles + tile) * NW + rw) * NSUM;
                 out[0] = ss;
@@ -195,7 +198,7 @@ objective_stream_kernel(ObjArgs a) {
 template <int THREADS, int R, int TB, int KK>
 cudaError_t launch_one(const ObjArgs& a, int B, cudaStream_t st) {
     static bool attr_set[NMRFIT_MAX_DEVICES] = {};
-    StreamSmem L(a.sp, a.stages, a.P, THREADS, R, TB);
+    StreamSmem L(a.sp, a.stages, a.P, THREADS, R, TB, a.sub);
     const size_t bytes = (size_t)L.total * sizeof(double);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -224,9 +227,8 @@ cudaError_t launch_tb(const ObjArgs& a, int tb, int B, cudaStream_t st) {
 
 }  // namespace
 
-size_t objective_stream_smem_bytes(int P, const ObjTune& t, int kk) {
-    (void)kk;
-    return (size_t)StreamSmem(t.sp, t.stages, P, t.threads, t.r, t.tb).total * sizeof(double);
+size_t objective_stream_smem_bytes(int P, const ObjTune& t, int sub) {
+    return (size_t)StreamSmem(t.sp, t.stages, P, t.threads, t.r, t.tb, sub).total * sizeof(double);
 }
 
 // a.sp / a.stages / a.gpc / a.n_tiles / a.nw are set by the caller (launch_objective_uniform)

@@ -88,8 +88,8 @@ objective_prepare_kernel(ObjArgs a) {
     const RegionDst rd(a, b, s, NRP);
     prepare_particle<R>(a.x + ps * D, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid,
                         128, cs, a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles,
-                        a.prep_far + rd.base * kFarTerms, a.prep_anchor + rd.base * 2, a.prep_mask + rd.base * (MW + 1),
-                        nullptr, 0, -1, rd.slot_nw, rd.slot_stride);
+                        a.prep_far + rd.base * a.sub * kFarTerms, a.prep_anchor + rd.base * 2,
+                        a.prep_mask + rd.base * a.sub * (MW + 1), nullptr, 0, -1, rd.slot_nw, rd.slot_stride, a.sub);
 }
 
 // pass 1 with the swarm's move in front (pso.cu's swarm_move_kernel for this particle): one launch fewer
@@ -125,16 +125,16 @@ objective_move_prepare_kernel(ObjArgs a, MoveArgs mv) {
     __syncthreads();
     const RegionDst rd(a, b, sl, NRP);
     prepare_particle<R>(xs, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid, 128, cs,
-                        a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles, a.prep_far + rd.base * kFarTerms,
-                        a.prep_anchor + rd.base * 2, a.prep_mask + rd.base * (MW + 1), nullptr, 0, -1, rd.slot_nw,
-                        rd.slot_stride);
+                        a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles, a.prep_far + rd.base * a.sub * kFarTerms,
+                        a.prep_anchor + rd.base * 2, a.prep_mask + rd.base * a.sub * (MW + 1), nullptr, 0, -1, rd.slot_nw,
+                        rd.slot_stride, a.sub);
 }
 
 // ---- pass 2: evaluation ------------------------------------------------------------------------------
 // shared-memory carve-up (in doubles), shared by kernel and launcher; every offset is even (16-byte alignment)
 struct UniSmem {
     int tab, uv, wt, bar, wpart, coef, part, far, anchor, mask, mw, total;
-    __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB, int nsum = 1) {
+    __host__ __device__ UniSmem(int sp, int P, int threads, int R, int TB, int nsum = 1, int sub = 1) {
         const int nw = threads / 32;
         mw = (P + 31) / 32;                               // near-peak mask words per region, + 1 has-far word
         int o = 0;
@@ -145,9 +145,9 @@ struct UniSmem {
         wpart = o;  o += sp * nw * nsum;                   // nsum = 2: real and imaginary sums of fit_im
         coef = o;   o += sp * P * 8;
         part = o;   o += sp * kPartDoubles;
-        far = o;    o += sp * nw * kFarTerms;             // far-field polynomial per (particle, warp region)
+        far = o;    o += sp * nw * sub * kFarTerms;       // far-field polynomial per (particle, cell of a warp region)
         anchor = o; o += sp * nw * 2;                     // phase at the first point of each warp region
-        mask = o;   o += ((sp * nw * (mw + 1) + 3) / 4) * 2;
+        mask = o;   o += ((sp * nw * sub * (mw + 1) + 3) / 4) * 2;
         total = o;
     }
 };
@@ -164,7 +164,8 @@ objective_uniform_kernel(ObjArgs a) {
     const int P = a.P, N = a.N, D = 4 + 3 * P, SP = a.sp;
     const int n_tiles = a.n_tiles, tile = blockIdx.y, NRP = n_tiles * NW;
     const int s0 = blockIdx.x * SP, nsp = min(SP, a.S - s0);
-    const UniSmem L(SP, P, THREADS, R, TB, NSUM);
+    const int SUB = a.sub;
+    const UniSmem L(SP, P, THREADS, R, TB, NSUM, SUB);
     double* tab = smem + L.tab;
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
     double* swt = smem + L.wt;
@@ -188,16 +189,17 @@ objective_uniform_kernel(ObjArgs a) {
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t b_coef = SP * P * 8 * 8, b_part = SP * kPartDoubles * 8, b_far = NW * kFarTerms * 8;
-        const uint32_t b_anchor = NW * 2 * 8, b_mask = NW * (MW + 1) * 4;
+        const uint32_t b_coef = SP * P * 8 * 8, b_part = SP * kPartDoubles * 8, b_far = NW * SUB * kFarTerms * 8;
+        const uint32_t b_anchor = NW * 2 * 8, b_mask = NW * SUB * (MW + 1) * 4;
         mbar_expect_tx(bar, b_coef + b_part + SP * (b_far + b_anchor + b_mask));
         bulk_g2s(smem + L.coef, a.prep_coef + q0 * P * 8, b_coef, bar);
         bulk_g2s(smem + L.part, a.prep_part + q0 * kPartDoubles, b_part, bar);
         for (int sp = 0; sp < SP; ++sp) {
             const size_t rs = (q0 + sp) * NRP + (size_t)tile * NW;
-            bulk_g2s(smem + L.far + sp * NW * kFarTerms, a.prep_far + rs * kFarTerms, b_far, bar);
+            bulk_g2s(smem + L.far + sp * NW * SUB * kFarTerms, a.prep_far + rs * SUB * kFarTerms, b_far, bar);
             bulk_g2s(smem + L.anchor + sp * NW * 2, a.prep_anchor + rs * 2, b_anchor, bar);
-            bulk_g2s(reinterpret_cast<unsigned*>(smem + L.mask) + sp * NW * (MW + 1), a.prep_mask + rs * (MW + 1), b_mask, bar);
+            bulk_g2s(reinterpret_cast<unsigned*>(smem + L.mask) + sp * NW * SUB * (MW + 1), a.prep_mask + rs * SUB * (MW + 1),
+                     b_mask, bar);
         }
     }
 
@@ -215,7 +217,8 @@ objective_uniform_kernel(ObjArgs a) {
         const double* src = ExpTabU<TB>::src();
         for (int i = tid; i < (1 << TB); i += THREADS) tab[i] = src[i];
     }
-    const double xi0 = ((double)(lane * R) - 0.5 * (32 * R - 1)) / H;      // first point's position inside its region
+    const double xi0 = cell_xi0<R>(lane, SUB);             // first point's position inside its far-field cell
+    const double inv_H = (double)SUB / H;
     __syncthreads();                                       // tile, table and the mbarrier initialisation are visible
     mbar_wait(bar, 0);                                     // the constants have landed
 
@@ -224,9 +227,9 @@ objective_uniform_kernel(ObjArgs a) {
     for (int sp = 0; sp < nsp; ++sp) {
         double ssi = 0.0;
         const double ss = eval_region<R, TB, KK>(
-            coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + warp) * (MW + 1),
-            farc + (size_t)(sp * NW + warp) * kFarTerms, anchor[sp * NW + warp], MW, P, lane, w_first, xi0, suv, swt, tid,
-            THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
+            coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + warp) * SUB * (MW + 1),
+            farc + (size_t)(sp * NW + warp) * SUB * kFarTerms, anchor[sp * NW + warp], MW, P, lane, SUB, w_first, xi0, inv_H,
+            suv, swt, tid, THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
         if (lane == 0) {
             wpart[(sp * NW + warp) * NSUM] = ss;
             if (KK) wpart[(sp * NW + warp) * NSUM + 1] = ssi;
@@ -246,7 +249,7 @@ objective_uniform_kernel(ObjArgs a) {
 template <int THREADS, int R, int TB, int KK>
 static cudaError_t launch_one(const ObjArgs& a, int B, cudaStream_t st) {
     static bool attr_set[NMRFIT_MAX_DEVICES] = {};
-    UniSmem L(a.sp, a.P, THREADS, R, TB, KK ? 2 : 1);
+    UniSmem L(a.sp, a.P, THREADS, R, TB, KK ? 2 : 1, a.sub);
     const size_t bytes = (size_t)L.total * sizeof(double);
     int dev = 0;
     cudaGetDevice(&dev);
@@ -272,19 +275,19 @@ static cudaError_t launch_tb(const ObjArgs& a, int tb, int B, cudaStream_t st) {
     }
 }
 
-void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, size_t* coef, size_t* part, size_t* far, size_t* anchor,
-                                  size_t* mask_words, int* pad_particles) {
+void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, int sub, size_t* coef, size_t* part, size_t* far,
+                                  size_t* anchor, size_t* mask_words, int* pad_particles) {
     const size_t nrp = (size_t)objective_tiles(N, t) * (t.threads / 32);
     *coef = (size_t)P * 8;                      // doubles per particle
     *part = kPartDoubles;
-    *far = nrp * kFarTerms;
+    *far = nrp * sub * kFarTerms;
     *anchor = nrp * 2;
-    *mask_words = nrp * ((P + 31) / 32 + 1);    // 32-bit words per particle
+    *mask_words = nrp * sub * ((P + 31) / 32 + 1);    // 32-bit words per particle
     *pad_particles = kPadParticles;
 }
 
-size_t objective_uniform_smem_bytes(int P, const ObjTune& t) {
-    return (size_t)UniSmem(t.sp, P, t.threads, t.r, t.tb).total * sizeof(double);
+size_t objective_uniform_smem_bytes(int P, const ObjTune& t, int sub) {
+    return (size_t)UniSmem(t.sp, P, t.threads, t.r, t.tb, 2, sub).total * sizeof(double);
 }
 
 // pass 1 (shared with the FP32 evaluation kernel); fills a.sp / a.n_tiles / a.nw

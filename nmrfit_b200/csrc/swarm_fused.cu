@@ -47,7 +47,7 @@ namespace {
 struct FusedSmem {
     int tab, uv, wt, cs, part, far, anchor, mask, wpart, state, red, misc, pairs, total;
     // NRP: region slots of the whole axis (tile sums of every region end up in every CTA); NRL: regions this CTA owns
-    __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP, int NRL, bool want_pairs) {
+    __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP, int NRL, bool want_pairs, int sub) {
         const int mw = (P + 31) / 32;
         const int De = (D + 1) & ~1;
         int o = 0;
@@ -56,16 +56,16 @@ struct FusedSmem {
         wt = o;     o += slots * threads * R;
         cs = o;     o += P * 8;
         part = o;   o += kPartDoubles;
-        far = o;    o += NRL * kFarTerms;
+        far = o;    o += NRL * sub * kFarTerms;              // per far-field cell (uniform_eval.cuh)
         anchor = o; o += NRL * 2;
-        mask = o;   o += ((NRL * (mw + 1) + 3) / 4) * 2;
+        mask = o;   o += ((NRL * sub * (mw + 1) + 3) / 4) * 2;
         wpart = o;  o += (NRP + 1) & ~1;
         state = o;  o += 9 * De;         // x, v, p, g, lb, ub, best_x, p_min, spare
         red = o;    o += 64;             // per-warp argmin values and indices
         misc = o;   o += 8;
-        // (region, peak) series scratch of the pair-parallel prepare, when one thread per pair (+ anchors) is available
-        pairs = want_pairs && NRL * P + NRL <= threads ? o : -1;
-        if (pairs >= 0) o += ((NRL * P * kPairDoubles + 1) & ~1);
+        // (cell, peak) series scratch of the pair-parallel prepare (one pair per thread, in rounds)
+        pairs = want_pairs ? o : -1;
+        if (pairs >= 0) o += ((NRL * sub * P * kPairDoubles + 1) & ~1);
         total = o;
     }
 };
@@ -118,7 +118,8 @@ swarm_fused_kernel(FusedArgs a) {
     const int st_lo = min(crank * per, n_super), st_hi = min(st_lo + per, n_super);
     const int r_lo = st_lo * NW, r_hi = min(st_hi * NW, NRP);
     const bool resident = a.slots >= per;
-    const FusedSmem L(P, D, THREADS, R, a.slots, NRP, per * NW, a.pairs != 0);
+    const int SUB = a.sub;
+    const FusedSmem L(P, D, THREADS, R, a.slots, NRP, per * NW, a.pairs != 0, SUB);
     double* tab = smem + L.tab;
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
     double* swt = smem + L.wt;
@@ -145,7 +146,8 @@ swarm_fused_kernel(FusedArgs a) {
     const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
     const size_t bs = (size_t)b * S + sl;
     constexpr double H = 16.0 * R;
-    const double xi0 = ((double)(lane * R) - 0.5 * (32 * R - 1)) / H;
+    const double xi0 = cell_xi0<R>(lane, SUB);
+    const double inv_H = (double)SUB / H;
 
     // ---- load the particle and the swarm's shared state
     for (int d = tid; d < D; d += THREADS) {
@@ -206,7 +208,7 @@ swarm_fused_kernel(FusedArgs a) {
 
         // ---- objective (equations.py:152-212) of the moved particle
         prepare_particle<R>(xs, sw, h, w_ulp, N, P, NR, NRP, tid, THREADS, cs, nullptr, part, farc, anchor, mask, pairs, r_lo,
-                            r_hi);
+                            r_hi, 1 << 30, 0, SUB);
         __syncthreads();
         FUSED_MARK(1);
         for (int st = st_lo; st < st_hi; ++st) {
@@ -222,10 +224,10 @@ swarm_fused_kernel(FusedArgs a) {
                 const int i_first = (st * THREADS + tid) * R;
                 const double w_first = i_first < N ? __ldg(sw + i_first) : fma((double)i_first, h, __ldg(sw));
                 const double2 ew = *reinterpret_cast<const double2*>(anchor + 2 * rl);
-                const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rl * (MW + 1), farc + (size_t)rl * kFarTerms,
-                                                     ew, MW, P, lane, w_first, xi0, suv + slot * THREADS * R,
-                                                     swt + slot * THREADS * R, tid, THREADS, tab, xs, sw + i_first,
-                                                     N - i_first, h, w_ulp);
+                const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rl * SUB * (MW + 1),
+                                                     farc + (size_t)rl * SUB * kFarTerms, ew, MW, P, lane, SUB, w_first, xi0,
+                                                     inv_H, suv + slot * THREADS * R, swt + slot * THREADS * R, tid, THREADS,
+                                                     tab, xs, sw + i_first, N - i_first, h, w_ulp);
                 if (!CL) {
                     if (lane == 0) wpart[rgn] = ss;
                 } else if (lane < G) {
@@ -422,7 +424,7 @@ static cudaError_t plan_one(const FusedArgs& a, int D, int particles, int thread
         const int slots = (attempt & 1) ? 1 : per;
         const bool pairs = attempt < 2;
         if ((attempt & 1) && per == 1) continue;
-        const size_t bytes = (size_t)FusedSmem(a.P, D, threads, r, slots, NRP, per * NW, pairs).total * sizeof(double);
+        const size_t bytes = (size_t)FusedSmem(a.P, D, threads, r, slots, NRP, per * NW, pairs, a.sub).total * sizeof(double);
         if (bytes > 200 * 1024) continue;
         long long capacity = 0;
         if (cluster > 1) {

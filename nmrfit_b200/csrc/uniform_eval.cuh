@@ -1,13 +1,22 @@
 // The two device routines of the uniform-axis objective, shared by the two-pass kernels
-// (objective_uniform.cu) and the fused swarm kernel (swarm_fused.cu) so that both evaluate a particle
-// with the SAME arithmetic in the SAME order - their objective values are bit-identical.
+// (objective_uniform.cu, objective_stream.cu) and the fused swarm kernel (swarm_fused.cu) so that all of them
+// evaluate a particle with the SAME arithmetic in the SAME order - their objective values are bit-identical.
 //
 //   prepare_particle  per-particle constants: span coefficients of its peaks, phase tables and, per
-//                     region of 32*R points, the near-peak mask, the far-field polynomial and the
-//                     phase anchor.  The destinations are plain pointers: global memory in the
+//                     far-field CELL, the near-peak mask and the far-field polynomial; per region of 32*R points
+//                     the phase anchor.  The destinations are plain pointers: global memory in the
 //                     two-pass path, shared memory in the fused kernel.
 //   eval_region       one warp's squared weighted residual over its region, from those constants
 //                     and the staged (u, v, weights) of the tile.
+//
+// Regions and cells.  A warp evaluates a REGION of 32*R consecutive points (a thread R of them).  The far-field
+// polynomial (nmrfit_math.cuh) lives on a CELL: the region itself, or one half / quarter of it (`sub` = 1, 2, 4 cells
+// per region, i.e. 32 / sub lanes each).  A peak is far from a cell when its centre is >= 8 cell lengths away (and
+// its Gaussian cannot reach the cell), so shorter cells leave fewer peaks to evaluate one by one: on a 4,096-point
+// axis with 6 peaks, 4.75 of them are near the average 256-point region but only 1.6 near the average 64-point cell.
+// The price is `sub` times the polynomials in the prepare pass, so long axes (where the Gaussian's reach, not the
+// series, decides what is near) keep sub = 1: far_cells_per_region() in nmrfit_internal.h, a function of the axis
+// length and R alone - never of how particles or spectra are sharded.
 #pragma once
 #include <cuda_runtime.h>
 #include "nmrfit_math.cuh"
@@ -16,12 +25,12 @@
 namespace nmrfit {
 
 // xs: the particle's D parameters; sw: its spectrum's w plane (N points); cs: shared [P][8] scratch that ends up
-// holding the span coefficients; coef_out: optional second copy of them; part [kPartDoubles]; far [NRP][kFarTerms];
-// anchor [NRP][2]; mask [NRP][MW+1].  NR regions cover the axis, NRP >= NR slots are filled (the rest neutral).
+// holding the span coefficients; coef_out: optional second copy of them; part [kPartDoubles]; far [cells][kFarTerms];
+// anchor [regions][2]; mask [cells][MW+1].  NR regions cover the axis, NRP >= NR slots are filled (the rest neutral).
 // Called by all `nthreads` (>= 128) threads of a CTA; contains __syncthreads().
-// `pairs` (optional shared scratch of NRP*P*kPairDoubles doubles, only when NRP*P + NRP <= nthreads): the
-// (region, peak) series are computed one pair per thread instead of one region per thread - same values, same order
-// of accumulation, but P times shorter on the critical path (the fused swarm kernel has one CTA per particle).
+// `pairs` (optional shared scratch of cells*P*kPairDoubles doubles): the (cell, peak) series are computed one pair per
+// thread instead of one cell per thread - same values, same order of accumulation, but P times shorter on the
+// critical path (the fused swarm kernel has one CTA per particle).
 constexpr int kPairDoubles = kFarTerms + 1;
 template <int R>
 __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, const double* __restrict__ sw, double h,
@@ -30,15 +39,17 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
                                                  double* __restrict__ part, double* __restrict__ far,
                                                  double* __restrict__ anchor, unsigned* __restrict__ mask,
                                                  double* __restrict__ pairs = nullptr, int r_lo = 0, int r_hi = -1,
-                                                 int slot_nw = 1 << 30, size_t slot_stride = 0) {
-    // regions [r_lo, r_hi) are filled, at index r - r_lo of far / anchor / mask (default: all NRP slots).
-    // Tile-major destinations (the streamed evaluation kernel reads one tile's regions of a whole particle group as
-    // one block): local region rl lands at slot (rl / slot_nw) * slot_stride + rl % slot_nw instead of rl.
+                                                 int slot_nw = 1 << 30, size_t slot_stride = 0, int sub = 1) {
+    // regions [r_lo, r_hi) are filled, at index r - r_lo of anchor and cell index (r - r_lo)*sub + c of far / mask
+    // (default: all NRP slots).  Tile-major destinations (the streamed evaluation kernel reads one tile's regions of a
+    // whole particle group as one block): local region rl lands at slot (rl / slot_nw) * slot_stride + rl % slot_nw.
     if (r_hi < 0) r_hi = NRP;
-    const int nr = r_hi - r_lo;
+    const int nr = r_hi - r_lo, nc = nr * sub;
     const int MW = (P + 31) / 32;
     const double p0 = xs[0], p1 = xs[1];
-    constexpr double H = 16.0 * R;
+    const int cell_pts = 32 * R / sub;
+    const double H = 0.5 * (double)cell_pts;                // half a cell, in points
+    (void)NR;
 
     for (int k = tid; k < P; k += nthreads) {
         SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
@@ -65,18 +76,28 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
         for (int k = 0; k < P; ++k) n += cs[k * 8 + 6] < 0.0;      // thr < 0 marks a nulled (exact-path) peak
         part[67] = (double)n;
     }
+    // region anchors, by the threads at the far end of the CTA
+    for (int ral = nthreads - 1 - tid; ral < nr; ral += nthreads) {
+        const int ra = r_lo + ral;
+        const size_t slot = (size_t)(ral / slot_nw) * slot_stride + (size_t)(ral % slot_nw);
+        double sn = 0.0, cn = 1.0;
+        if ((long long)ra * 32 * R < N) sincos(p0 + (p1 * (double)(ra * 32 * R)) / (double)N, &sn, &cn);
+        anchor[slot * 2] = cn;
+        anchor[slot * 2 + 1] = sn;
+    }
     if (pairs) {
-        // one (region, peak) pair per thread; the region anchors by the threads at the other end
-        if (tid < nr * P) {
-            const int rl = tid / P, k = tid - rl * P, r = r_lo + rl;
-            double* pr = pairs + (size_t)tid * kPairDoubles;
-            double kind = -1.0;                            // -1: padding region or exact-path peak (neither near nor far)
-            if (r < NR) {
+        // one (cell, peak) pair per thread, in rounds
+        for (int pi = tid; pi < nc * P; pi += nthreads) {
+            const int cl = pi / P, k = pi - cl * P;
+            const long long ic = ((long long)r_lo * sub + cl) * cell_pts;      // the cell's first point
+            double* pr = pairs + (size_t)pi * kPairDoubles;
+            double kind = -1.0;                            // -1: padding cell or exact-path peak (neither near nor far)
+            if (ic < N) {
                 const double* o = cs + k * 8;
                 SpanCoef c;
                 c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
                 if (!(c.thr < 0.0)) {
-                    const double w_c = fma(0.5 * (32 * R - 1), h, sw[r * 32 * R]);
+                    const double w_c = fma(0.5 * (double)(cell_pts - 1), h, sw[ic]);
                     double v[kFarTerms];
                     kind = (double)far_terms(w_c - c.loc, c, H, v);
 #pragma unroll
@@ -85,73 +106,46 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
             }
             pr[0] = kind;
         }
-        const int ral = nthreads - 1 - tid;
-        if (ral < nr) {
-            const int ra = r_lo + ral;
-            double sn = 0.0, cn = 1.0;
-            if (ra < NR) sincos(p0 + (p1 * (double)(ra * 32 * R)) / (double)N, &sn, &cn);
-            anchor[ral * 2] = cn;
-            anchor[ral * 2 + 1] = sn;
-        }
         __syncthreads();
-        if (tid < nr) {
-            const int r = tid;                             // local index
-            double C[kFarTerms];
-#pragma unroll
-            for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
-            unsigned any_far = 0;
-            unsigned* mk = mask + (size_t)r * (MW + 1);
-            for (int wd = 0; wd < MW; ++wd) {
-                unsigned m = 0;
-                const int kend = min(P, wd * 32 + 32);
-                for (int k = wd * 32; k < kend; ++k) {
-                    const double* pr = pairs + (size_t)(r * P + k) * kPairDoubles;
-                    const int kind = (int)pr[0];
-                    if (kind < 0) continue;
-                    if (kind == kFarNear) { m |= 1u << (k & 31); continue; }
-                    any_far = 1u;
-                    if (kind == kFarSeries) {
-                        double v[kFarTerms];
-#pragma unroll
-                        for (int n = 0; n < kFarTerms; ++n) v[n] = pr[1 + n];
-                        far_add(cs[k * 8 + 3], v, C);
-                    }
-                }
-                mk[wd] = m;
-            }
-            mk[MW] = any_far;
-            double* fc = far + (size_t)r * kFarTerms;
-#pragma unroll
-            for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
-        }
-        return;
     }
-    for (int rl = tid; rl < nr; rl += nthreads) {
-        const int r = r_lo + rl;
-        const size_t slot = (size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw);
+    for (int cl = tid; cl < nc; cl += nthreads) {
+        const int rl = cl / sub;
+        const size_t slot = ((size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw)) * sub + (size_t)(cl - rl * sub);
+        const long long ic = ((long long)r_lo * sub + cl) * cell_pts;
         double C[kFarTerms];
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
         unsigned any_far = 0;
         unsigned* mk = mask + slot * (MW + 1);
-        double sn = 0.0, cn = 1.0;
-        if (r < NR) {
-            const int ir = r * 32 * R;
-            const double w_c = fma(0.5 * (32 * R - 1), h, sw[ir]);
+        if (ic < N) {
+            const double w_c = pairs ? 0.0 : fma(0.5 * (double)(cell_pts - 1), h, sw[ic]);
             for (int wd = 0; wd < MW; ++wd) {
                 unsigned m = 0;
                 const int kend = min(P, wd * 32 + 32);
                 for (int k = wd * 32; k < kend; ++k) {
-                    const double* o = cs + k * 8;
-                    SpanCoef c;
-                    c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
-                    if (c.thr < 0.0) continue;             // exact-path peak: neither near nor far
-                    if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
-                    else m |= 1u << (k & 31);
+                    if (pairs) {
+                        const double* pr = pairs + (size_t)(cl * P + k) * kPairDoubles;
+                        const int kind = (int)pr[0];
+                        if (kind < 0) continue;
+                        if (kind == kFarNear) { m |= 1u << (k & 31); continue; }
+                        any_far = 1u;
+                        if (kind == kFarSeries) {
+                            double v[kFarTerms];
+#pragma unroll
+                            for (int n = 0; n < kFarTerms; ++n) v[n] = pr[1 + n];
+                            far_add(cs[k * 8 + 3], v, C);
+                        }
+                    } else {
+                        const double* o = cs + k * 8;
+                        SpanCoef c;
+                        c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
+                        if (c.thr < 0.0) continue;         // exact-path peak: neither near nor far
+                        if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
+                        else m |= 1u << (k & 31);
+                    }
                 }
                 mk[wd] = m;
             }
-            sincos(p0 + (p1 * (double)ir) / (double)N, &sn, &cn);
         } else {
             for (int wd = 0; wd < MW; ++wd) mk[wd] = 0u;
         }
@@ -159,58 +153,72 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
         double* fc = far + slot * kFarTerms;
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
-        anchor[slot * 2] = cn;
-        anchor[slot * 2 + 1] = sn;
     }
 }
 
 // Shared-memory placement of a tile's staged points.  Point e of the tile (thread t = e / R, j = e % R) lives in
-// row j at column t ^ j (double2 (u, v) array) resp. t ^ 2j (weights array): the evaluation reads row j with
-// consecutive t (a permutation inside each aligned group of 16 columns: conflict-free), and the staging loop,
-// whose consecutive lanes hold consecutive e - eight different rows of the same column - spreads over eight
-// different banks instead of colliding 8-way (ncu before: 18.3 M of 66.6 M shared wavefronts were such conflicts).
+// row j.  Swizzled (SWZ): at column t ^ j (double2 (u, v) array) resp. t ^ 2j (weights array) - the evaluation reads
+// row j with consecutive t (a permutation inside each aligned group of 16 columns: conflict-free), and the staging
+// loop, whose consecutive lanes hold consecutive e - eight different rows of the same column - spreads over eight
+// different banks instead of colliding 8-way.  Plain (!SWZ): at column t; the staging stores collide, which a kernel
+// that stages once per CTA and then evaluates hundreds of particles (objective_stream.cu) does not notice, and the
+// evaluation's addresses are one base plus compile-time offsets - no integer work per point.
 __device__ __forceinline__ int stage_slot_uv(int t, int j, int stride) { return j * stride + (t ^ j); }
 __device__ __forceinline__ int stage_slot_wt(int t, int j, int stride) { return j * stride + (t ^ (2 * j)); }
 
 // One warp, one particle, one region: sum over the warp's 32*R points of (weights * (V_data - V_fit))^2, identical
-// in every lane on return.  cf [P][8], pt [kPartDoubles], mk [MW+1], fc [kFarTerms] (16-byte aligned) and ew are the
-// particle's constants for this region; the R points of thread t of the tile sit at stage_slot_uv/wt(t, j, stride) of
-// suv / swt; w_first is the abscissa of its first point and xi0 that point's position inside the region.  The exact path
-// (peaks too narrow for the recurrences) reads the particle's parameters xs and the stored abscissae sw_first[0..n_valid).
+// in every lane on return.  cf [P][8], pt [kPartDoubles], mk [sub][MW+1], fc [sub][kFarTerms] (16-byte aligned) and ew
+// are the particle's constants for this region (`sub` far-field cells of 32/sub lanes each; xi0 is the lane's first
+// point's position inside ITS cell and inv_H the step of that coordinate per point); the R points of thread t of the
+// tile sit at stage_slot_uv/wt(t, j, stride) of suv / swt (SWZ) or at j*stride + t (!SWZ); w_first is the abscissa of its
+// first point.  The exact path (peaks too narrow for the recurrences) reads the particle's parameters xs and the stored
+// abscissae sw_first[0..n_valid).
 // KK = 1 (fit_im, reference semantics) also returns through *ss_im the same sum for the imaginary parts:
 // I_data = u sin(phi) + v cos(phi) against the last peak's Kramers-Kronig counterpart (closed form, nmrfit_math.cuh).
-template <int R, int TB, int KK = 0>
+template <int R, int TB, int KK = 0, bool SWZ = true>
 __device__ __forceinline__ double eval_region(const double* __restrict__ cf, const double* __restrict__ pt,
                                               const unsigned* __restrict__ mk, const double* __restrict__ fc,
-                                              const double2 ew, int MW, int P, int lane, double w_first, double xi0,
-                                              const double2* __restrict__ suv, const double* __restrict__ swt, int t,
-                                              int stride, const double* __restrict__ tab,
+                                              const double2 ew, int MW, int P, int lane, int sub, double w_first, double xi0,
+                                              double inv_H, const double2* __restrict__ suv, const double* __restrict__ swt,
+                                              int t, int stride, const double* __restrict__ tab,
                                               const double* __restrict__ xs, const double* __restrict__ sw_first,
                                               int n_valid, double h, double w_ulp, double* ss_im = nullptr) {
-    constexpr double H = 16.0 * R;                         // half a region, in points
+    const int cell = (lane * sub) >> 5;                    // this lane's cell inside the region
+    const unsigned* mkc = mk + cell * (MW + 1);
     double acc[R];
-#pragma unroll
-    for (int j = 0; j < R; ++j) acc[j] = 0.0;
-    for (int wd = 0; wd < MW; ++wd)
-    for (unsigned m = mk[wd]; m; m &= m - 1) {             // peaks near this warp's region
-        const int k = wd * 32 + __ffs(m) - 1;
-        const double2 c01 = *reinterpret_cast<const double2*>(cf + k * 8);
-        const double2 c23 = *reinterpret_cast<const double2*>(cf + k * 8 + 2);
-        const double2 c45 = *reinterpret_cast<const double2*>(cf + k * 8 + 4);
-        const double2 c67 = *reinterpret_cast<const double2*>(cf + k * 8 + 6);
-        SpanCoef c;
-        c.loc = c01.x; c.kL = c01.y; c.kG = c23.x; c.aL = c23.y;
-        c.aG = c45.x; c.dT = c45.y; c.thr = c67.x; c.c2 = c67.y;
-        peak_span<R, TB>(w_first - c.loc, c, tab, acc);
-    }
-    if (mk[MW]) {                                          // all far peaks at once
+    // all far peaks of this lane's cell at once; the accumulators start from it
+    unsigned any_far = mk[MW];
+    for (int c = 1; c < sub; ++c) any_far |= mk[c * (MW + 1) + MW];
+    if (any_far) {
+        const double* fcc = fc + cell * kFarTerms;
         double C[kFarTerms];
 #pragma unroll
         for (int n = 0; n < kFarTerms; n += 2) {
-            const double2 t = *reinterpret_cast<const double2*>(fc + n);
-            C[n] = t.x; C[n + 1] = t.y;
+            const double2 t2 = *reinterpret_cast<const double2*>(fcc + n);
+            C[n] = t2.x; C[n + 1] = t2.y;
         }
-        far_eval<R>(C, xi0, 1.0 / H, acc);
+        far_init<R>(C, xi0, inv_H, acc);
+    } else {
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[j] = 0.0;
+    }
+    for (int wd = 0; wd < MW; ++wd) {
+        unsigned m = mk[wd];                               // peaks near ANY cell of the region (uniform across the warp)
+        for (int c = 1; c < sub; ++c) m |= mk[c * (MW + 1) + wd];
+        const unsigned mine = mkc[wd];                     // ... and near this lane's cell
+        for (; m; m &= m - 1) {
+            const int kb = __ffs(m) - 1;
+            const int k = wd * 32 + kb;
+            const double2 c01 = *reinterpret_cast<const double2*>(cf + k * 8);
+            const double2 c23 = *reinterpret_cast<const double2*>(cf + k * 8 + 2);
+            const double2 c45 = *reinterpret_cast<const double2*>(cf + k * 8 + 4);
+            const double2 c67 = *reinterpret_cast<const double2*>(cf + k * 8 + 6);
+            SpanCoef c;
+            c.loc = c01.x; c.kL = c01.y; c.kG = c23.x; c.aL = c23.y;
+            c.aG = c45.x; c.dT = c45.y; c.thr = c67.x; c.c2 = c67.y;
+            // (in a cell for which the peak is far it is already inside that cell's polynomial)
+            if (sub == 1 || ((mine >> kb) & 1u)) peak_span<R, TB>(w_first - c.loc, c, tab, acc);
+        }
     }
     if (pt[67] != 0.0) {                                   // rare: peaks too narrow for the uniform-axis shortcuts
         for (int k = 0; k < P; ++k) {
@@ -241,10 +249,12 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
             kloc = cl[0]; kkL = cl[1]; kkG = cl[2]; kaL = cl[3]; kaG = cl[4] * kTwoOverSqrtPi;
         }
     }
+    const double2* puv = suv + t;                          // !SWZ: row j of this thread at a compile-time offset
+    const double* pwt = swt + t;
 #pragma unroll
     for (int j = 0; j < R; ++j) {
-        const double2 uv = suv[stage_slot_uv(t, j, stride)];
-        const double wt = swt[stage_slot_wt(t, j, stride)];
+        const double2 uv = SWZ ? suv[stage_slot_uv(t, j, stride)] : puv[j * stride];
+        const double wt = SWZ ? swt[stage_slot_wt(t, j, stride)] : pwt[j * stride];
         const double vd = fma(uv.x, cr, -fma(uv.y, ci, py));     // V_data - P*yoff
         const double res = wt * (vd - acc[j]);
         ss = fma(res, res, ss);
@@ -273,6 +283,14 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
     }
     if (KK) *ss_im = ssi;
     return ss;
+}
+
+// first point's position of a lane inside its far-field cell, in half-cells: xi in (-1, 1)
+template <int R>
+__device__ __forceinline__ double cell_xi0(int lane, int sub) {
+    const int lpc = 32 / sub;                              // lanes per cell
+    const double H = 0.5 * (double)(lpc * R);
+    return ((double)((lane % lpc) * R) - 0.5 * (double)(lpc * R - 1)) / H;
 }
 
 }  // namespace nmrfit

@@ -247,3 +247,27 @@ def test_streamed_and_one_group_kernels_agree_bit_for_bit(n_points, n_peaks, n_p
             ctx.set_tuning(0, 0, 0, sp)
             assert ctx.get_variant(n_particles)[0] == 1
             assert np.array_equal(ctx.objective_host(xs, fit_im), want), (stages, sp)
+
+
+@pytest.mark.parametrize('n_points,n_peaks', [(4096, 6), (1000, 6), (16384, 6), (3000, 36), (40, 6)])
+def test_far_field_cells_of_any_size_meet_the_contract(n_points, n_peaks):
+    """The far-field polynomial lives on cells of a region (uniform_eval.cuh): whole, halves or quarters.  Whatever the
+    split, either FP64 uniform-axis kernel stays within 1e-11 of the oracle, and the two kernels agree bit for bit."""
+    data, true = synth.multiplet(max(n_points, 600), n_peaks, seed=77 + n_points)
+    w, u, v = data.w[:n_points], data.u[:n_points], data.v[:n_points]
+    wts = utils.compute_weights(data.w, data.peaks)[:n_points]
+    lo, up = data.generate_solution_bounds()
+    xs = synth.particles(lo, up, 21, seed=4)
+    xs[0] = true
+    want = orc.objective_swarm(xs, w, u, v, wts)
+    with _cabi.Context(1, n_points, n_peaks) as ctx:
+        ctx.set_spectrum(0, w, u, v, wts)
+        for cells in (0, 1, 2, 4):
+            ctx.set_far_cells(cells)
+            for r in (4, 8, 16):
+                ctx.set_tuning(0, r, 0, 0)
+                ctx.set_variant(1)
+                got = ctx.objective_host(xs)
+                assert relerr(got, want) < TOL, (cells, r)
+                ctx.set_variant(0)
+                assert np.array_equal(ctx.objective_host(xs), got), (cells, r)

@@ -4,7 +4,7 @@
     python tools/kernel_probe.py [metric c2 c3 c4] [--tunes "0,0,0,0;256,8,6,8;..."] [--reps 10] [--out gpurun_out/probe.json]
 
 For each workload and each tuning (threads, points per thread, exp-table bits, particles per CTA; 0 = library default)
-(optionally followed by kernel variant and pipeline stages) it times the prepare pass and the evaluation kernel separately with CUDA events on the launching stream
+(optionally followed by kernel variant, pipeline stages and far-field cells per region) it times the prepare pass and the evaluation kernel separately with CUDA events on the launching stream
 (nmrfit_ctx_profile_read_split), checks the values against the first tuning's, and prints peak-points/s."""
 import argparse
 import json
@@ -49,6 +49,7 @@ def main():
             try:
                 ctx.set_tuning(*tune[:4])
                 ctx.set_variant(*(tune[4:6] if len(tune) > 4 else (-1, 0)))
+                ctx.set_far_cells(tune[6] if len(tune) > 6 else 0)
                 for _ in range(3):
                     ctx.objective_device(xs, S, f)
                 torch.cuda.synchronize()
@@ -66,7 +67,7 @@ def main():
                            peak_points_per_s=B * S * N * P / ((prep + ev) / n * 1e-3), evals_per_s=B * S / ((prep + ev) / n * 1e-3),
                            rel_dev_vs_first=dev)
                 rows.append(row)
-                print('%-7s tune=%-22s v=%s sp=%2d  prepare %8.4f ms  eval %8.4f ms  %.3e pp/s  %.3e evals/s  dev %.1e'
+                print('%-7s tune=%-25s v=%s sp=%2d  prepare %8.4f ms  eval %8.4f ms  %.3e pp/s  %.3e evals/s  dev %.1e'
                       % (name, tune, row['variant'], row['picked']['particles_per_cta'], row['prepare_ms'], row['eval_ms'],
                          row['peak_points_per_s'], row['evals_per_s'], dev), flush=True)
             except Exception as e:                          # a tuning the shape does not admit
