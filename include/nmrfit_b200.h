@@ -106,8 +106,9 @@ int nmrfit_ctx_get_tuning(nmrfit_ctx* ctx, int n_particles, int* threads, int* p
 /* Which FP64 uniform-axis evaluation kernel runs (development / A-B measurement knob; results are bit-identical):
  * variant -1 the library's choice (the streamed kernel), 0 one particle group per CTA (objective_uniform_kernel),
  * 1 streamed (objective_stream_kernel: a CTA keeps its point tile and walks many particle groups through a
- * `stages`-deep ring of TMA-filled shared-memory slots; stages 0 = auto, else 2..4). */
-int nmrfit_ctx_set_variant(nmrfit_ctx* ctx, int variant, int stages);
+ * `stages`-deep ring of TMA-filled shared-memory slots; stages 0 = auto, else 2..4; occupancy 0 = auto, else 2 or 3
+ * CTAs of 256 threads per SM - 2 trades resident warps for shared memory and registers). */
+int nmrfit_ctx_set_variant(nmrfit_ctx* ctx, int variant, int stages, int occupancy);
 int nmrfit_ctx_get_variant(nmrfit_ctx* ctx, int n_particles, int* variant, int* stages);
 /* Far-field cells per region of 32 * points_per_thread points (csrc/uniform_eval.cuh): 0 = the library's rule (a
  * function of the axis length only: 64-point cells below 8,192 points, 128-point cells below 32,768, else the whole

@@ -55,7 +55,7 @@ SIGNATURES = {
     'nmrfit_ctx_get_algorithm': (_i, [_vp, _i, c_int_p]),
     'nmrfit_ctx_set_tuning': (_i, [_vp, _i, _i, _i, _i]),
     'nmrfit_ctx_get_tuning': (_i, [_vp, _i, c_int_p, c_int_p, c_int_p, c_int_p, c_int_p]),
-    'nmrfit_ctx_set_variant': (_i, [_vp, _i, _i]),
+    'nmrfit_ctx_set_variant': (_i, [_vp, _i, _i, _i]),
     'nmrfit_ctx_get_variant': (_i, [_vp, _i, c_int_p, c_int_p]),
     'nmrfit_ctx_set_far_cells': (_i, [_vp, _i]),
     'nmrfit_ctx_set_fused': (_i, [_vp, _i]),
@@ -228,9 +228,10 @@ class Context:
         keys = ('threads', 'points_per_thread', 'exp_table_bits', 'particles_per_cta', 'n_point_tiles')
         return dict(zip(keys, (v.value for v in vals)))
 
-    def set_variant(self, variant=-1, stages=0):
-        """FP64 uniform-axis evaluation kernel: -1 library's choice, 0 one particle group per CTA, 1 streamed."""
-        check(lib().nmrfit_ctx_set_variant(self._h, int(variant), int(stages)))
+    def set_variant(self, variant=-1, stages=0, occupancy=0):
+        """FP64 uniform-axis evaluation kernel: -1 library's choice, 0 one particle group per CTA, 1 streamed
+        (``stages`` ring slots, ``occupancy`` 2 or 3 CTAs of 256 threads per SM; 0 = auto)."""
+        check(lib().nmrfit_ctx_set_variant(self._h, int(variant), int(stages), int(occupancy)))
 
     def set_far_cells(self, cells=0):
         """Far-field cells per region (0 = by axis length, or 1, 2, 4); applies to every FP64 uniform-axis kernel."""

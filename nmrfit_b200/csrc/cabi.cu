@@ -82,7 +82,7 @@ struct nmrfit_ctx {
     DevBuf<double> partials, x_stage, f_stage;
     DevBuf<double> prep_coef, prep_part, prep_far, prep_anchor;   // uniform-axis kernel, per-particle constants
     DevBuf<unsigned> prep_mask;
-    ObjTune user_tune{0, 0, 0, 0, -1, 0};   // variant -1: the library's choice
+    ObjTune user_tune{0, 0, 0, 0, -1, 0, 0};   // variant -1, occ 0: the library's choice
     // swarm
     bool swarm = false;
     SwarmState sw{};
@@ -186,9 +186,11 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
     // one-group-per-CTA kernel.  Its `sp` is the particles per pipeline stage: as many as leave three CTAs per SM.
     t.variant = 0;
     t.stages = 0;
+    t.occ = 3;
     if (uni && c->precision == NMRFIT_FP64 && c->user_tune.variant != 0) {
         t.variant = 1;
-        const size_t budget = 74 * 1024;
+        t.occ = c->user_tune.occ == 2 ? 2 : 3;
+        const size_t budget = (t.occ == 2 ? 112 : 74) * 1024;
         auto fit_sp = [&](int stg) {
             t.stages = stg;
             int spg = 0;
@@ -559,12 +561,14 @@ int nmrfit_ctx_set_tuning(nmrfit_ctx* c, int threads, int r, int tb, int sp) {
     return NMRFIT_OK;
 }
 
-int nmrfit_ctx_set_variant(nmrfit_ctx* c, int variant, int stages) {
+int nmrfit_ctx_set_variant(nmrfit_ctx* c, int variant, int stages, int occupancy) {
     if (int rc = check_ctx(c)) return rc;
     if (variant < -1 || variant > 1) return fail(NMRFIT_ERR_ARG, "variant must be -1 (auto), 0 (one group per CTA) or 1 (streamed)");
     if (stages != 0 && (stages < 2 || stages > 4)) return fail(NMRFIT_ERR_ARG, "stages must be 0 (auto) or 2..4");
+    if (occupancy != 0 && occupancy != 2 && occupancy != 3) return fail(NMRFIT_ERR_ARG, "occupancy must be 0 (auto), 2 or 3");
     c->user_tune.variant = variant;
     c->user_tune.stages = stages;
+    c->user_tune.occ = occupancy;
     return NMRFIT_OK;
 }
 

@@ -30,7 +30,7 @@ struct ObjArgs {
     // through a `stages`-deep pipeline of bulk copies; its prepare pass stores the per-region constants tile-major,
     // [B][n_tiles][S][nw][...], so that one tile's regions of a whole group are one contiguous block
     int tile_major;         // layout of prep_far / prep_anchor / prep_mask (0: [B][S][n_tiles*nw][...])
-    int stages, gpc;
+    int stages, gpc, occ;   // occ: CTAs of 256 threads per SM the streamed kernel is built for (2 or 3)
     int sub;                // far-field cells per region of 32*R points (1, 2 or 4; uniform_eval.cuh); far / mask hold
                             // `sub` entries per region
 };
@@ -51,6 +51,7 @@ struct ObjTune {
     int sp;                 // particles per CTA (streamed kernel: per pipeline stage)
     int variant;            // uniform-axis FP64 evaluation kernel: 0 one particle group per CTA, 1 streamed (objective_stream.cu)
     int stages;             // streamed kernel: pipeline depth
+    int occ;                // streamed kernel: CTAs of 256 threads per SM (2 or 3)
 };
 
 int objective_tiles(int N, const ObjTune& t);

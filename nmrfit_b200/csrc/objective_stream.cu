@@ -14,7 +14,7 @@
 //     tile-major, so a slot is five copies whatever the group size;
 //   * a slot is refilled by whichever warp releases it LAST (a ticket in shared memory), so nobody ever waits for a
 //     slot to drain: the only waits left are on data that is not there yet;
-//   * the CTA's warps take the tile's regions in rotation - particle n's region q is evaluated by warp (q - n) mod NW -
+//   * the CTA's warps take the tile's regions in rotation - group g's region q is evaluated by warp (q - g) mod NW -
 //     so every warp sees every region equally often and the regions' different costs (how many peaks are near) no
 //     longer make a CTA wait for its slowest warp;
 //   * a warp writes its region sums straight to global memory; there is no __syncthreads after the prologue.
@@ -60,7 +60,7 @@ struct StreamSmem {
         part = q;    q += spg * kPartDoubles;
         far = q;     q += spg * nw * sub * kFarTerms;       // per far-field cell (uniform_eval.cuh)
         anchor = q;  q += spg * nw * 2;
-        mask = q;    q += ((spg * nw * sub * (mw + 1) + 3) / 4) * 2;
+        mask = q;    q += ((spg * nw * mask_words_per_region(P, sub) + 3) / 4) * 2;
         slot = q;
         total = slot0 + stages * slot;
     }
@@ -68,8 +68,10 @@ struct StreamSmem {
 
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <int THREADS, int R, int TB, int KK>
-__global__ void __launch_bounds__(THREADS, (R <= 8 ? 768 : 512) / THREADS)
+// OCC: CTAs of 256 threads per SM the kernel is compiled for (3: 80 registers, 75 KB of shared memory each; 2: up to
+// 128 registers and 113 KB - room for deeper stages when the per-particle constants are large)
+template <int THREADS, int R, int TB, int KK, int OCC>
+__global__ void __launch_bounds__(THREADS, (R <= 8 ? OCC * 256 : 512) / THREADS)
 objective_stream_kernel(ObjArgs a) {
     constexpr int NSUM = KK ? 2 : 1;
     constexpr int NW = THREADS / 32;
@@ -103,7 +105,8 @@ objective_stream_kernel(ObjArgs a) {
     const size_t tb_ = ((size_t)b * n_tiles + tile) * a.S; // ... of this (spectrum, tile) in the tile-major arrays
 
     const uint32_t b_coef = SPG * P * 8 * 8, b_part = SPG * kPartDoubles * 8, b_far = SPG * NW * SUB * kFarTerms * 8;
-    const uint32_t b_anchor = SPG * NW * 2 * 8, b_mask = SPG * NW * SUB * (MW + 1) * 4;
+    const int MWR = mask_words_per_region(P, SUB);
+    const uint32_t b_anchor = SPG * NW * 2 * 8, b_mask = SPG * NW * MWR * 4;
     // one thread asks the TMA for group g (relative to g_lo) into slot g % ST.  Whole groups are copied (the
     // prepare buffers are padded); only the particles that exist are evaluated.
     auto fill = [&](int g) {
@@ -116,7 +119,7 @@ objective_stream_kernel(ObjArgs a) {
         bulk_g2s(dst + L.part, a.prep_part + (pb + q0) * kPartDoubles, b_part, bar);
         bulk_g2s(dst + L.far, a.prep_far + (tb_ + q0) * NW * SUB * kFarTerms, b_far, bar);
         bulk_g2s(dst + L.anchor, a.prep_anchor + (tb_ + q0) * NW * 2, b_anchor, bar);
-        bulk_g2s(dst + L.mask, a.prep_mask + (tb_ + q0) * NW * SUB * (MW + 1), b_mask, bar);
+        bulk_g2s(dst + L.mask, a.prep_mask + (tb_ + q0) * NW * MWR, b_mask, bar);
     };
 
     if (tid == 0) {
@@ -149,34 +152,39 @@ objective_stream_kernel(ObjArgs a) {
     const double inv_H = (double)SUB / H;
     __syncthreads();                                       // the only CTA-wide barrier: tile, table, mbarriers
 
-    int n = 0;                                             // particles this CTA has evaluated: drives the rotation
+    // strides between consecutive particles of a slot / of the output
+    const int s_coef = P * 8, s_far = NW * SUB * kFarTerms, s_mask = NW * MWR;
+    const size_t s_out = (size_t)n_tiles * NW * NSUM;
+    int sl = 0;
+    uint32_t phase = 0;
     for (int g = 0; g < my_groups; ++g) {
-        const int sl = g % ST;
         const double* slot = slots + (size_t)sl * L.slot;
         const size_t q0 = (size_t)(g_lo + g) * SPG;
         const int nsp = min(SPG, a.S - (int)q0);
-        mbar_wait(bars + sl, (uint32_t)((g / ST) & 1));    // this fill of the slot has landed
-        const double* coef = slot + L.coef;
-        const double* part = slot + L.part;
-        const double* farc = slot + L.far;
-        const double2* anchor = reinterpret_cast<const double2*>(slot + L.anchor);
-        const unsigned* mask = reinterpret_cast<const unsigned*>(slot + L.mask);
-        for (int sp = 0; sp < nsp; ++sp, ++n) {
-            const int rw = (warp + n) % NW;                // the region of the tile this warp takes for this particle
-            const int t = rw * 32 + lane;                  // ... and the thread span inside the tile this lane takes
-            const int i_first = tile0 + t * R;
+        // the region of the tile this warp takes for this group (rotation), and the thread span this lane takes
+        const int rw = (warp + g) & (NW - 1);
+        const int t = rw * 32 + lane;
+        const int i_first = tile0 + t * R;
+        const double w_first = swf[t];
+        const double* cf = slot + L.coef;
+        const double* pt = slot + L.part;
+        const double* fc = slot + L.far + rw * SUB * kFarTerms;
+        const double2* an = reinterpret_cast<const double2*>(slot + L.anchor) + rw;
+        const unsigned* mk = reinterpret_cast<const unsigned*>(slot + L.mask) + rw * MWR;
+        const double* xs = a.x + (pb + q0) * D;
+        double* out = a.partials + (((pb + q0) * n_tiles + tile) * NW + rw) * NSUM;
+        mbar_wait(bars + sl, phase);                       // this fill of the slot has landed
+        for (int sp = 0; sp < nsp; ++sp) {
             double ssi = 0.0;
-            const double ss = eval_region<R, TB, KK, false>(
-                coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + rw) * SUB * (MW + 1),
-                farc + (size_t)(sp * NW + rw) * SUB * kFarTerms, anchor[sp * NW + rw], MW, P, lane, SUB, swf[t], xi0, inv_H,
-                suv, swt, t, THREADS, tab, a.x + (pb + q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
+            const double ss = eval_region<R, TB, KK, false>(cf, pt, mk, fc, *an, MW, P, lane, SUB, w_first, xi0, inv_H, suv,
+                                                            swt, t, THREADS, tab, xs, sw + i_first, N - i_first, h, w_ulp,
+                                                            &ssi);
             if (lane == 0) {
-                double* out = a.partials + (((pb + q0 + sp) * n_tiles + tile) * NW + rw) * NSUM;
                 out[0] = ss;
                 if (KK) out[1] = ssi;
             }
+            cf += s_coef; pt += kPartDoubles; fc += s_far; an += NW; mk += s_mask; xs += D; out += s_out;
         }
-        n += SPG - nsp;                                    // (only in a spectrum's last group)
         // release the slot; the warp that releases it last refills it with the group ST further on
         __syncwarp();
         if (lane == 0) {
@@ -191,27 +199,33 @@ objective_stream_kernel(ObjArgs a) {
                 }
             }
         }
+        if (++sl == ST) { sl = 0; phase ^= 1u; }
     }
     (void)NRP;
 }
 
-template <int THREADS, int R, int TB, int KK>
-cudaError_t launch_one(const ObjArgs& a, int B, cudaStream_t st) {
+template <int THREADS, int R, int TB, int KK, int OCC>
+cudaError_t launch_occ(const ObjArgs& a, int B, cudaStream_t st) {
     static bool attr_set[NMRFIT_MAX_DEVICES] = {};
     StreamSmem L(a.sp, a.stages, a.P, THREADS, R, TB, a.sub);
     const size_t bytes = (size_t)L.total * sizeof(double);
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev % NMRFIT_MAX_DEVICES]) {
-        cudaError_t e = cudaFuncSetAttribute(objective_stream_kernel<THREADS, R, TB, KK>,
+        cudaError_t e = cudaFuncSetAttribute(objective_stream_kernel<THREADS, R, TB, KK, OCC>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev % NMRFIT_MAX_DEVICES] = true;
     }
     const int n_groups = (a.S + a.sp - 1) / a.sp;
     dim3 grid((n_groups + a.gpc - 1) / a.gpc, a.n_tiles, B);
-    objective_stream_kernel<THREADS, R, TB, KK><<<grid, THREADS, bytes, st>>>(a);
+    objective_stream_kernel<THREADS, R, TB, KK, OCC><<<grid, THREADS, bytes, st>>>(a);
     return cudaGetLastError();
+}
+
+template <int THREADS, int R, int TB, int KK>
+cudaError_t launch_one(const ObjArgs& a, int B, cudaStream_t st) {
+    return a.occ == 2 ? launch_occ<THREADS, R, TB, KK, 2>(a, B, st) : launch_occ<THREADS, R, TB, KK, 3>(a, B, st);
 }
 
 template <int THREADS, int R>

@@ -82,14 +82,14 @@ objective_prepare_kernel(ObjArgs a) {
     extern __shared__ __align__(16) double cs[];           // [P][8]
     const int b = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
     if (a.frozen && a.frozen[b]) return;
-    const int P = a.P, N = a.N, D = 4 + 3 * P, MW = (P + 31) / 32;
+    const int P = a.P, N = a.N, D = 4 + 3 * P;
     const int NR = (N + 32 * R - 1) / (32 * R), NRP = a.n_tiles * a.nw;
     const size_t ps = (size_t)b * a.S + s;
     const RegionDst rd(a, b, s, NRP);
     prepare_particle<R>(a.x + ps * D, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid,
                         128, cs, a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles,
                         a.prep_far + rd.base * a.sub * kFarTerms, a.prep_anchor + rd.base * 2,
-                        a.prep_mask + rd.base * a.sub * (MW + 1), nullptr, 0, -1, rd.slot_nw, rd.slot_stride, a.sub);
+                        a.prep_mask + rd.base * mask_words_per_region(P, a.sub), nullptr, 0, -1, rd.slot_nw, rd.slot_stride, a.sub);
 }
 
 // pass 1 with the swarm's move in front (pso.cu's swarm_move_kernel for this particle): one launch fewer
@@ -100,7 +100,7 @@ objective_move_prepare_kernel(ObjArgs a, MoveArgs mv) {
     const int b = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
     const SwarmState& s = mv.s;
     if (s.stop[b]) return;
-    const int P = a.P, N = a.N, D = 4 + 3 * P, MW = (P + 31) / 32;
+    const int P = a.P, N = a.N, D = 4 + 3 * P;
     const int NR = (N + 32 * R - 1) / (32 * R), NRP = a.n_tiles * a.nw;
     const size_t ps = (size_t)b * a.S + sl;
     double* xs = cs + P * 8;
@@ -126,7 +126,7 @@ objective_move_prepare_kernel(ObjArgs a, MoveArgs mv) {
     const RegionDst rd(a, b, sl, NRP);
     prepare_particle<R>(xs, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid, 128, cs,
                         a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles, a.prep_far + rd.base * a.sub * kFarTerms,
-                        a.prep_anchor + rd.base * 2, a.prep_mask + rd.base * a.sub * (MW + 1), nullptr, 0, -1, rd.slot_nw,
+                        a.prep_anchor + rd.base * 2, a.prep_mask + rd.base * mask_words_per_region(P, a.sub), nullptr, 0, -1, rd.slot_nw,
                         rd.slot_stride, a.sub);
 }
 
@@ -147,7 +147,7 @@ struct UniSmem {
         part = o;   o += sp * kPartDoubles;
         far = o;    o += sp * nw * sub * kFarTerms;       // far-field polynomial per (particle, cell of a warp region)
         anchor = o; o += sp * nw * 2;                     // phase at the first point of each warp region
-        mask = o;   o += ((sp * nw * sub * (mw + 1) + 3) / 4) * 2;
+        mask = o;   o += ((sp * nw * mask_words_per_region(P, sub) + 3) / 4) * 2;
         total = o;
     }
 };
@@ -190,7 +190,8 @@ objective_uniform_kernel(ObjArgs a) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         const uint32_t b_coef = SP * P * 8 * 8, b_part = SP * kPartDoubles * 8, b_far = NW * SUB * kFarTerms * 8;
-        const uint32_t b_anchor = NW * 2 * 8, b_mask = NW * SUB * (MW + 1) * 4;
+        const int MWR = mask_words_per_region(P, SUB);
+        const uint32_t b_anchor = NW * 2 * 8, b_mask = NW * MWR * 4;
         mbar_expect_tx(bar, b_coef + b_part + SP * (b_far + b_anchor + b_mask));
         bulk_g2s(smem + L.coef, a.prep_coef + q0 * P * 8, b_coef, bar);
         bulk_g2s(smem + L.part, a.prep_part + q0 * kPartDoubles, b_part, bar);
@@ -198,7 +199,7 @@ objective_uniform_kernel(ObjArgs a) {
             const size_t rs = (q0 + sp) * NRP + (size_t)tile * NW;
             bulk_g2s(smem + L.far + sp * NW * SUB * kFarTerms, a.prep_far + rs * SUB * kFarTerms, b_far, bar);
             bulk_g2s(smem + L.anchor + sp * NW * 2, a.prep_anchor + rs * 2, b_anchor, bar);
-            bulk_g2s(reinterpret_cast<unsigned*>(smem + L.mask) + sp * NW * SUB * (MW + 1), a.prep_mask + rs * SUB * (MW + 1),
+            bulk_g2s(reinterpret_cast<unsigned*>(smem + L.mask) + sp * NW * MWR, a.prep_mask + rs * MWR,
                      b_mask, bar);
         }
     }
@@ -227,7 +228,7 @@ objective_uniform_kernel(ObjArgs a) {
     for (int sp = 0; sp < nsp; ++sp) {
         double ssi = 0.0;
         const double ss = eval_region<R, TB, KK>(
-            coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + warp) * SUB * (MW + 1),
+            coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + warp) * mask_words_per_region(P, SUB),
             farc + (size_t)(sp * NW + warp) * SUB * kFarTerms, anchor[sp * NW + warp], MW, P, lane, SUB, w_first, xi0, inv_H,
             suv, swt, tid, THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
         if (lane == 0) {
@@ -282,7 +283,7 @@ void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, int sub, size_
     *part = kPartDoubles;
     *far = nrp * sub * kFarTerms;
     *anchor = nrp * 2;
-    *mask_words = nrp * sub * ((P + 31) / 32 + 1);    // 32-bit words per particle
+    *mask_words = nrp * mask_words_per_region(P, sub);    // 32-bit words per particle
     *pad_particles = kPadParticles;
 }
 
@@ -333,6 +334,7 @@ cudaError_t launch_objective_uniform(ObjArgs a, const ObjTune& t, int B, double*
     if (nw_out) *nw_out = 1;
     if (t.variant == 1) {
         a.stages = t.stages;
+        a.occ = t.occ;
         a.gpc = stream_groups_per_cta(a.S, a.sp, a.n_tiles, B);
         e = launch_objective_stream(a, t, B, st);
         if (ev1) cudaEventRecord(ev1, st);

@@ -48,7 +48,6 @@ struct FusedSmem {
     int tab, uv, wt, cs, part, far, anchor, mask, wpart, state, red, misc, pairs, total;
     // NRP: region slots of the whole axis (tile sums of every region end up in every CTA); NRL: regions this CTA owns
     __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP, int NRL, bool want_pairs, int sub) {
-        const int mw = (P + 31) / 32;
         const int De = (D + 1) & ~1;
         int o = 0;
         tab = o;    o += 64;
@@ -58,7 +57,7 @@ struct FusedSmem {
         part = o;   o += kPartDoubles;
         far = o;    o += NRL * sub * kFarTerms;              // per far-field cell (uniform_eval.cuh)
         anchor = o; o += NRL * 2;
-        mask = o;   o += ((NRL * sub * (mw + 1) + 3) / 4) * 2;
+        mask = o;   o += ((NRL * mask_words_per_region(P, sub) + 3) / 4) * 2;
         wpart = o;  o += (NRP + 1) & ~1;
         state = o;  o += 9 * De;         // x, v, p, g, lb, ub, best_x, p_min, spare
         red = o;    o += 64;             // per-warp argmin values and indices
@@ -224,7 +223,7 @@ swarm_fused_kernel(FusedArgs a) {
                 const int i_first = (st * THREADS + tid) * R;
                 const double w_first = i_first < N ? __ldg(sw + i_first) : fma((double)i_first, h, __ldg(sw));
                 const double2 ew = *reinterpret_cast<const double2*>(anchor + 2 * rl);
-                const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rl * SUB * (MW + 1),
+                const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rl * mask_words_per_region(P, SUB),
                                                      farc + (size_t)rl * SUB * kFarTerms, ew, MW, P, lane, SUB, w_first, xi0,
                                                      inv_H, suv + slot * THREADS * R, swt + slot * THREADS * R, tid, THREADS,
                                                      tab, xs, sw + i_first, N - i_first, h, w_ulp);

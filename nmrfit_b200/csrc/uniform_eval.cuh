@@ -108,15 +108,19 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
         }
         __syncthreads();
     }
+    // mask words of a region: one cell - [MW near words][has-far]; several - the same block for the UNION of its
+    // cells first (what the warp as a whole has to visit), then one block per cell
+    const int mblocks = sub == 1 ? 1 : sub + 1;
     for (int cl = tid; cl < nc; cl += nthreads) {
-        const int rl = cl / sub;
-        const size_t slot = ((size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw)) * sub + (size_t)(cl - rl * sub);
+        const int rl = cl / sub, ci = cl - rl * sub;
+        const size_t rslot = (size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw);
+        const size_t slot = rslot * sub + (size_t)ci;
         const long long ic = ((long long)r_lo * sub + cl) * cell_pts;
         double C[kFarTerms];
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
         unsigned any_far = 0;
-        unsigned* mk = mask + slot * (MW + 1);
+        unsigned* mk = mask + (rslot * mblocks + (size_t)(sub == 1 ? 0 : 1 + ci)) * (MW + 1);
         if (ic < N) {
             const double w_c = pairs ? 0.0 : fma(0.5 * (double)(cell_pts - 1), h, sw[ic]);
             for (int wd = 0; wd < MW; ++wd) {
@@ -154,7 +158,21 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
 #pragma unroll
         for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
     }
+    if (sub > 1) {
+        __syncthreads();                                   // the cells' words (global or shared) are visible to the CTA
+        for (int e = tid; e < nr * (MW + 1); e += nthreads) {
+            const int rl = e / (MW + 1), wd = e - rl * (MW + 1);
+            const size_t rslot = (size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw);
+            unsigned* mk = mask + rslot * mblocks * (MW + 1);
+            unsigned m = 0;
+            for (int ci = 0; ci < sub; ++ci) m |= mk[(1 + ci) * (MW + 1) + wd];
+            mk[wd] = m;
+        }
+    }
 }
+
+// 32-bit mask words per region (see prepare_particle)
+__host__ __device__ inline int mask_words_per_region(int P, int sub) { return (sub == 1 ? 1 : sub + 1) * ((P + 31) / 32 + 1); }
 
 // Shared-memory placement of a tile's staged points.  Point e of the tile (thread t = e / R, j = e % R) lives in
 // row j.  Swizzled (SWZ): at column t ^ j (double2 (u, v) array) resp. t ^ 2j (weights array) - the evaluation reads
@@ -167,7 +185,7 @@ __device__ __forceinline__ int stage_slot_uv(int t, int j, int stride) { return 
 __device__ __forceinline__ int stage_slot_wt(int t, int j, int stride) { return j * stride + (t ^ (2 * j)); }
 
 // One warp, one particle, one region: sum over the warp's 32*R points of (weights * (V_data - V_fit))^2, identical
-// in every lane on return.  cf [P][8], pt [kPartDoubles], mk [sub][MW+1], fc [sub][kFarTerms] (16-byte aligned) and ew
+// in every lane on return.  cf [P][8], pt [kPartDoubles], mk [mask_words_per_region], fc [sub][kFarTerms] (16-byte aligned) and ew
 // are the particle's constants for this region (`sub` far-field cells of 32/sub lanes each; xi0 is the lane's first
 // point's position inside ITS cell and inv_H the step of that coordinate per point); the R points of thread t of the
 // tile sit at stage_slot_uv/wt(t, j, stride) of suv / swt (SWZ) or at j*stride + t (!SWZ); w_first is the abscissa of its
@@ -184,12 +202,10 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
                                               const double* __restrict__ xs, const double* __restrict__ sw_first,
                                               int n_valid, double h, double w_ulp, double* ss_im = nullptr) {
     const int cell = (lane * sub) >> 5;                    // this lane's cell inside the region
-    const unsigned* mkc = mk + cell * (MW + 1);
+    const unsigned* mkc = mk + (sub == 1 ? 0 : 1 + cell) * (MW + 1);   // mk: the union's block (prepare_particle)
     double acc[R];
     // all far peaks of this lane's cell at once; the accumulators start from it
-    unsigned any_far = mk[MW];
-    for (int c = 1; c < sub; ++c) any_far |= mk[c * (MW + 1) + MW];
-    if (any_far) {
+    if (mk[MW]) {
         const double* fcc = fc + cell * kFarTerms;
         double C[kFarTerms];
 #pragma unroll
@@ -203,10 +219,8 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
         for (int j = 0; j < R; ++j) acc[j] = 0.0;
     }
     for (int wd = 0; wd < MW; ++wd) {
-        unsigned m = mk[wd];                               // peaks near ANY cell of the region (uniform across the warp)
-        for (int c = 1; c < sub; ++c) m |= mk[c * (MW + 1) + wd];
-        const unsigned mine = mkc[wd];                     // ... and near this lane's cell
-        for (; m; m &= m - 1) {
+        const unsigned mine = mkc[wd];                     // peaks near this lane's cell
+        for (unsigned m = mk[wd]; m; m &= m - 1) {         // peaks near ANY cell of the region (uniform across the warp)
             const int kb = __ffs(m) - 1;
             const int k = wd * 32 + kb;
             const double2 c01 = *reinterpret_cast<const double2*>(cf + k * 8);

@@ -243,7 +243,7 @@ def test_streamed_and_one_group_kernels_agree_bit_for_bit(n_points, n_peaks, n_p
         assert ctx.get_variant(n_particles)[0] == 0
         want = ctx.objective_host(xs, fit_im)
         for stages, sp in ((0, 0), (2, 1), (2, 3), (3, 4), (4, 2), (3, 7)):
-            ctx.set_variant(1, stages)
+            ctx.set_variant(1, stages, 2 if stages == 4 else 0)
             ctx.set_tuning(0, 0, 0, sp)
             assert ctx.get_variant(n_particles)[0] == 1
             assert np.array_equal(ctx.objective_host(xs, fit_im), want), (stages, sp)

@@ -48,7 +48,7 @@ def main():
         for tune in tunes:
             try:
                 ctx.set_tuning(*tune[:4])
-                ctx.set_variant(*(tune[4:6] if len(tune) > 4 else (-1, 0)))
+                ctx.set_variant(*(tune[4:6] if len(tune) > 4 else (-1, 0)), tune[7] if len(tune) > 7 else 0)
                 ctx.set_far_cells(tune[6] if len(tune) > 6 else 0)
                 for _ in range(3):
                     ctx.objective_device(xs, S, f)
