@@ -60,6 +60,7 @@ extern "C" {
 #define NMRFIT_STOP_MINFUNC 1
 #define NMRFIT_STOP_MINSTEP 2
 #define NMRFIT_STOP_MAXITER 3
+#define NMRFIT_STOP_PEER_LOST 4   /* particle sharding over peer memory: a peer's record never arrived (error state) */
 
 typedef struct nmrfit_ctx nmrfit_ctx;
 
@@ -178,8 +179,12 @@ int nmrfit_pso_step(nmrfit_ctx* ctx, const double* rp, const double* rg, void* s
  * Each rank's context owns a window of records and generation tokens; every rank maps every window (CUDA IPC between
  * processes, plain pointers between contexts of one process).  nmrfit_pso_commit_peers replaces "all-gather the records,
  * nmrfit_pso_commit": one kernel stores this rank's record into every peer's window, publishes the generation token,
- * waits (bounded) for all ranks' tokens and commits.  nmrfit_pso_step_peers = nmrfit_pso_advance + that: a generation
- * in four launches with no NCCL call.  Same results as the all-gather path, bit for bit.
+ * waits (bounded in wall time) for all ranks' tokens and commits.  nmrfit_pso_step_peers is a whole sharded generation
+ * with that exchange folded into the finish kernel's last CTA: the same THREE launches as an unsharded generation and no
+ * NCCL call; nmrfit_pso_run_peers runs a chunk of generations in one call (no per-generation host round trip) and
+ * synchronises.  Same results as the all-gather path, bit for bit.  On a timeout (nmrfit_pso_peer_timeout, default 20 s)
+ * the rank raises its error flag and marks the spectrum stopped with NMRFIT_STOP_PEER_LOST; the other ranks then time
+ * out one generation later.  The caller makes the failure collective (swarm.pso_sharded all-reduces the flag).
  *   export: allocate the window for n_ranks; ipc_handle_out (64 bytes, nullable) for other processes, base_out
  *           (nullable) for other contexts of this process.
  *   open:   ipc_handles [n_ranks][64] and/or local_bases [n_ranks] (entry `rank` is ignored).
@@ -188,6 +193,9 @@ int nmrfit_pso_peer_export(nmrfit_ctx* ctx, int n_ranks, int rank, void* ipc_han
 int nmrfit_pso_peer_open(nmrfit_ctx* ctx, const void* ipc_handles, void* const* local_bases);
 int nmrfit_pso_commit_peers(nmrfit_ctx* ctx, void* stream);
 int nmrfit_pso_step_peers(nmrfit_ctx* ctx, const double* rp, const double* rg, void* stream);
+int nmrfit_pso_run_peers(nmrfit_ctx* ctx, int n_generations, const double* rp_all, const double* rg_all, int* n_running,
+                         int* timed_out, void* stream);
+int nmrfit_pso_peer_timeout(nmrfit_ctx* ctx, double milliseconds);
 int nmrfit_pso_peer_error(nmrfit_ctx* ctx, int* timed_out);
 /* Device pointer and length (doubles) of the local best record, [n_spectra][D+2] = (f, global index, x[D]). */
 int nmrfit_pso_record(nmrfit_ctx* ctx, double** rec_dev, int* n_doubles);

@@ -17,7 +17,7 @@ FP64, FP32 = 0, 1
 REAL_ONLY, IM_REFERENCE, IM_SUM = 0, 1, 2
 ALGO_AUTO, ALGO_GENERAL, ALGO_UNIFORM = 0, 1, 2
 FUSED_AUTO, FUSED_OFF, FUSED_REQUIRE = 0, 1, 2
-RUNNING, STOP_MINFUNC, STOP_MINSTEP, STOP_MAXITER = 0, 1, 2, 3
+RUNNING, STOP_MINFUNC, STOP_MINSTEP, STOP_MAXITER, STOP_PEER_LOST = 0, 1, 2, 3, 4
 
 c_double_p = ctypes.POINTER(ctypes.c_double)
 c_int_p = ctypes.POINTER(ctypes.c_int)
@@ -74,6 +74,8 @@ SIGNATURES = {
     'nmrfit_pso_commit_peers': (_i, [_vp, _vp]),
     'nmrfit_pso_step_peers': (_i, [_vp, _vp, _vp, _vp]),
     'nmrfit_pso_peer_error': (_i, [_vp, c_int_p]),
+    'nmrfit_pso_run_peers': (_i, [_vp, _i, _vp, _vp, c_int_p, c_int_p, _vp]),
+    'nmrfit_pso_peer_timeout': (_i, [_vp, _d]),
     'nmrfit_pso_record': (_i, [_vp, ctypes.POINTER(_vp), c_int_p]),
     'nmrfit_pso_commit': (_i, [_vp, _vp, _i, _vp]),
     'nmrfit_pso_run': (_i, [_vp, _i, _vp, _vp, c_int_p, _vp]),
@@ -353,6 +355,19 @@ class Context:
     def pso_step_peers(self, rp=None, rg=None, stream=None):
         rp, rg = self._rand(rp, self._swarmsize), self._rand(rg, self._swarmsize)
         check(lib().nmrfit_pso_step_peers(self._h, ptr(rp), ptr(rg), ptr(stream)))
+
+    def pso_run_peers(self, n_generations, rp_all=None, rg_all=None, stream=None):
+        """A chunk of sharded generations in one call (records exchanged over peer memory inside the finish kernel);
+        synchronises.  Returns (spectra still running, 1 if a wait for a peer expired)."""
+        rp_all = self._rand(rp_all, self._swarmsize, n_generations)
+        rg_all = self._rand(rg_all, self._swarmsize, n_generations)
+        running, lost = ctypes.c_int(0), ctypes.c_int(0)
+        check(lib().nmrfit_pso_run_peers(self._h, int(n_generations), ptr(rp_all), ptr(rg_all), ctypes.byref(running),
+                                         ctypes.byref(lost), ptr(stream)))
+        return running.value, lost.value
+
+    def peer_timeout(self, milliseconds):
+        check(lib().nmrfit_pso_peer_timeout(self._h, float(milliseconds)))
 
     def peer_error(self):
         e = ctypes.c_int(0)

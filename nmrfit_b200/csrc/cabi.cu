@@ -103,6 +103,7 @@ struct nmrfit_ctx {
     DevBuf<long long*> peer_tok_dev;
     DevBuf<int> peer_err;
     long long epoch = 0;               // fits begun on this context: part of the exchange token
+    double peer_timeout_ms = 20000.0;  // wall-time bound of a wait for the peers' tokens
     DevBuf<double> wscratch, wbounds;  // batched weights: sweep scratch [B][N], windows + values
     int far_cells = 0;                 // far-field cells per region: 0 = far_cells_per_region(N, R), else 1 | 2 | 4
     int fused_mode = NMRFIT_FUSED_AUTO;
@@ -350,15 +351,31 @@ int fused_setup(nmrfit_ctx* c, int n_gen, const double* rp_d, const double* rg_d
 // One generation of the per-step path in three launches: [move + per-particle constants], [objective tiles],
 // [tile sums + personal bests + local best record (+ swarm-best commit)].  generation 0 (`move` false) evaluates
 // the freshly initialised swarm.
+PeerArgs make_peer_args(const nmrfit_ctx* c) {
+    PeerArgs pa{};
+    pa.recs = c->peer_recs_dev.ptr;
+    pa.tokens = c->peer_tok_dev.ptr;
+    pa.n_ranks = c->peer_ranks;
+    pa.rank = c->peer_rank;
+    pa.token = (c->epoch << 32) | (long long)c->generation;
+    pa.max_wait_ns = (long long)(c->peer_timeout_ms * 1e6);
+    pa.error = c->peer_err.ptr;
+    return pa;
+}
+
+// commit: 0 none (the caller exchanges the records itself), 1 this context's own record, 2 the ranks' records
+// exchanged over peer memory inside the finish kernel
 int swarm_generation(nmrfit_ctx* c, bool move, const double* rp_d, const double* rg_d, int commit, cudaStream_t st) {
     SwarmState& s = c->sw;
+    if (commit == 2 && !c->peers_ready) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_peer_open has not been called");
+    const PeerArgs pa = commit == 2 ? make_peer_args(c) : PeerArgs{};
     MoveArgs mv{s, rp_d, rg_d, c->generation};
     int n_tiles = 0, nsum = 1, nw = 1;
     if (int rc = run_objective(c, s.x, s.S, c->kk, nullptr, move ? s.stop : nullptr, st, move ? &mv : nullptr, &n_tiles, &nsum,
                                &nw))
         return rc;
     cudaError_t e = launch_swarm_finish(s, c->partials.ptr, n_tiles, nsum, c->N, s.rec, c->fin_scratch.ptr,
-                                        c->fin_tickets.ptr, commit, c->maxiter, st, nw);
+                                        c->fin_tickets.ptr, commit, c->maxiter, st, nw, commit == 2 ? &pa : nullptr);
     if (e != cudaSuccess) return fail_cuda(e, "swarm finish");
     return NMRFIT_OK;
 }
@@ -779,7 +796,10 @@ int nmrfit_pso_peer_export(nmrfit_ctx* c, int n_ranks, int rank, void* ipc_handl
     CK(cudaSetDevice(c->device));
     const size_t W = (size_t)c->D + 2;
     c->peer_rec_bytes = (2 * (size_t)n_ranks * c->B * W * sizeof(double) + 15) & ~(size_t)15;
-    const size_t bytes = c->peer_rec_bytes + (size_t)n_ranks * c->B * sizeof(long long);
+    // CUDA IPC exports the whole backing block of an allocation: the window gets blocks of its own (a multiple of the
+    // 2 MiB granule), so that a peer that opens the handle cannot reach any other allocation of this process
+    const size_t granule = (size_t)2 << 20;
+    const size_t bytes = ((c->peer_rec_bytes + (size_t)n_ranks * c->B * sizeof(long long) + granule - 1) / granule) * granule;
     CK(cudaMalloc(&c->peer_win, bytes));
     CK(cudaMemset(c->peer_win, 0, bytes));                 // tokens start at 0; the first real token is (1 << 32)
     CK(cudaDeviceSynchronize());
@@ -831,14 +851,7 @@ int nmrfit_pso_peer_open(nmrfit_ctx* c, const void* ipc_handles, void* const* lo
 namespace {
 int exchange_commit(nmrfit_ctx* c, cudaStream_t st) {
     if (!c->peers_ready) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_peer_open has not been called");
-    PeerArgs pa{};
-    pa.recs = c->peer_recs_dev.ptr;
-    pa.tokens = c->peer_tok_dev.ptr;
-    pa.n_ranks = c->peer_ranks;
-    pa.rank = c->peer_rank;
-    pa.token = (c->epoch << 32) | (long long)c->generation;
-    pa.max_spins = 1LL << 23;                              // a few seconds of polling, then the error flag
-    pa.error = c->peer_err.ptr;
+    const PeerArgs pa = make_peer_args(c);
     cudaError_t e = launch_swarm_exchange_commit(c->sw, pa, c->generation == 0, c->maxiter, st);
     if (e != cudaSuccess) return fail_cuda(e, "exchange + commit launch");
     return NMRFIT_OK;
@@ -853,8 +866,55 @@ int nmrfit_pso_commit_peers(nmrfit_ctx* c, void* stream) {
 }
 
 int nmrfit_pso_step_peers(nmrfit_ctx* c, const double* rp, const double* rg, void* stream) {
-    if (int rc = nmrfit_pso_advance(c, rp, rg, stream)) return rc;
-    return exchange_commit(c, (cudaStream_t)stream);
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    if ((rp == nullptr) != (rg == nullptr)) return fail(NMRFIT_ERR_ARG, "rp and rg must both be given or both be NULL");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SwarmState& s = c->sw;
+    size_t nsd = (size_t)s.B * s.S * s.D;
+    const double *rp_d = nullptr, *rg_d = nullptr;
+    if (int rc = stage(rp, nsd, c->rnd_a, st, &rp_d)) return rc;
+    if (int rc = stage(rg, nsd, c->rnd_b, st, &rg_d)) return rc;
+    c->generation += 1;
+    return swarm_generation(c, true, rp_d, rg_d, 2, st);
+}
+
+int nmrfit_pso_run_peers(nmrfit_ctx* c, int n_generations, const double* rp_all, const double* rg_all, int* n_running,
+                         int* timed_out, void* stream) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called");
+    if ((rp_all == nullptr) != (rg_all == nullptr)) return fail(NMRFIT_ERR_ARG, "rp_all and rg_all must both be given or both be NULL");
+    if (n_generations < 0) return fail(NMRFIT_ERR_ARG, "n_generations must be >= 0");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    SwarmState& s = c->sw;
+    size_t nsd = (size_t)s.B * s.S * s.D;
+    const double *rp_d = nullptr, *rg_d = nullptr;
+    if (n_generations > 0) {
+        if (int rc = stage(rp_all, nsd * n_generations, c->rnd_a, st, &rp_d)) return rc;
+        if (int rc = stage(rg_all, nsd * n_generations, c->rnd_b, st, &rg_d)) return rc;
+    }
+    for (int k = 0; k < n_generations; ++k) {
+        c->generation += 1;
+        if (int rc = swarm_generation(c, true, rp_d ? rp_d + nsd * k : nullptr, rg_d ? rg_d + nsd * k : nullptr, 2, st))
+            return rc;
+    }
+    CK(cudaMemcpyAsync(c->h_flags, s.stop, sizeof(int) * s.B, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(c->h_flags + s.B, c->peer_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    int running = 0;
+    for (int b = 0; b < s.B; ++b) running += c->h_flags[b] == 0;
+    if (n_running) *n_running = running;
+    if (timed_out) *timed_out = c->h_flags[s.B];
+    return NMRFIT_OK;
+}
+
+int nmrfit_pso_peer_timeout(nmrfit_ctx* c, double milliseconds) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!(milliseconds > 0.0)) return fail(NMRFIT_ERR_ARG, "the timeout must be positive");
+    c->peer_timeout_ms = milliseconds;
+    return NMRFIT_OK;
 }
 
 int nmrfit_pso_peer_error(nmrfit_ctx* c, int* timed_out) {

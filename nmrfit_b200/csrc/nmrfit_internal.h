@@ -112,21 +112,22 @@ struct MoveArgs {
     const double* rg;
     int generation;
 };
-// finalize + personal bests + local best record (+ swarm-best commit when `commit`) in one launch:
-// partials [B][S][n_tiles][nsum] -> fx, fp, p, rec; `scratch` holds [B][ceil(S/8)][2] doubles, `tickets` [B] zeroed once
-cudaError_t launch_swarm_finish(const SwarmState& s, const double* partials, int n_tiles, int nsum, int N, double* rec,
-                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st, int nw = 1);
-size_t swarm_finish_scratch_doubles(int B, int S);
-
 // record exchange over peer memory (pso.cu): device arrays of per-rank window pointers
 struct PeerArgs {
     double* const* recs;        // [n_ranks] -> that rank's record window [2][n_ranks][B][D+2]
     long long* const* tokens;   // [n_ranks] -> that rank's token array [n_ranks][B]
     int n_ranks, rank;
     long long token;            // (fit epoch << 32) | generation: monotonic over the life of the windows
-    long long max_spins;        // bound of the wait
+    long long max_wait_ns;      // bound of the wait, wall time (%globaltimer)
     int* error;                 // set to 1 when the wait expired
 };
+// finalize + personal bests + local best record (+ swarm-best commit when `commit`) in one launch:
+// partials [B][S][n_tiles][nsum] -> fx, fp, p, rec; `scratch` holds [B][ceil(S/8)][2] doubles, `tickets` [B] zeroed once
+cudaError_t launch_swarm_finish(const SwarmState& s, const double* partials, int n_tiles, int nsum, int N, double* rec,
+                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st, int nw = 1,
+                                const PeerArgs* pa = nullptr);   // commit 2 (with pa): exchange over peer memory, then commit
+size_t swarm_finish_scratch_doubles(int B, int S);
+
 cudaError_t launch_swarm_exchange_commit(const SwarmState& s, const PeerArgs& pa, int initial, int maxiter,
                                          cudaStream_t st);
 

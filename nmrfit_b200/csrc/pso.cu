@@ -144,6 +144,73 @@ __global__ void __launch_bounds__(128) swarm_commit_kernel(SwarmState s, const d
     commit_spectrum(s, recs, n_ranks, initial, maxiter, b, threadIdx.x, 128, (size_t)s.B * (s.D + 2), (size_t)b * (s.D + 2));
 }
 
+// ---- record exchange over peer memory (particle sharding without a collective call) -------------------------
+// Every rank's context owns a window [2 parities][n_ranks][B][D+2] of records plus [n_ranks][B] 64-bit tokens,
+// mapped into every peer (CUDA IPC between processes; plain pointers between contexts of one process).  One CTA per
+// spectrum stores this rank's local best record into slot `rank` of EVERY peer's window (NVLink stores), fences at
+// system scope, stores the generation token into every peer's token array, waits until the tokens of all ranks have
+// arrived in its own window, and applies the same commit as every other rank on the same n_ranks records - the
+// all-gather + commit of the NCCL path without a collective call.  It runs inside the finish kernel's last CTA of the
+// spectrum (a sharded generation is then the same three launches as an unsharded one) or, for generation 0, as a kernel
+// of its own.  Windows are double-buffered by generation parity: a rank cannot be two generations ahead, because its next
+// commit needs the slowest rank's next token.  The wait is bounded in WALL TIME (%globaltimer): on expiry the CTA
+// raises *error, marks the spectrum stopped (kStopPeerLost) so that this rank does not step it any further - every
+// other rank then runs into the same timeout one generation later - and returns without committing.
+__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
+    long long v;
+    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
+    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Called by all `nthreads` threads of one CTA for spectrum b; srec: shared [n_ranks][D+2].  Returns false on timeout.
+__device__ __forceinline__ bool exchange_records(const SwarmState& s, const PeerArgs& pa, int b, int tid, int nthreads,
+                                                 double* srec) {
+    const int W = s.D + 2, R = pa.n_ranks;
+    const int par = (int)(pa.token & 1);
+    const double* mine = s.rec + (size_t)b * W;
+    for (int q = 0; q < R; ++q) {
+        double* dst = pa.recs[q] + (((size_t)par * R + pa.rank) * s.B + b) * W;
+        for (int d = tid; d < W; d += nthreads) dst[d] = mine[d];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid < R) st_release_sys(pa.tokens[tid] + (size_t)pa.rank * s.B + b, pa.token);
+    __shared__ int s_timeout;
+    if (tid == 0) s_timeout = 0;
+    __syncthreads();
+    if (tid < R) {
+        const long long* mytok = pa.tokens[pa.rank] + (size_t)tid * s.B + b;
+        const unsigned long long t0 = global_timer_ns();
+        unsigned spins = 0;
+        while (ld_acquire_sys(mytok) < pa.token) {
+            if ((++spins & 255u) == 0 && global_timer_ns() - t0 > (unsigned long long)pa.max_wait_ns) { s_timeout = 1; break; }
+        }
+    }
+    __syncthreads();
+    if (s_timeout) {
+        if (tid == 0) {
+            atomicExch(pa.error, 1);
+            s.stop[b] = kStopPeerLost;
+        }
+        return false;
+    }
+    const double* win = pa.recs[pa.rank] + ((size_t)par * R * s.B + b) * W;
+    for (int i = tid; i < R * W; i += nthreads) {
+        const int q = i / W, d = i - q * W;
+        srec[i] = __ldcv(win + (size_t)q * s.B * W + d);   // written by peers: never from a stale L1 line
+    }
+    __syncthreads();
+    return true;
+}
+
 // ---- finish: everything after the objective's tile sums, in ONE launch --------------------------------------
 // Per particle (one warp each): fixed-order sum of its tile partials -> fx = sqrt(mean) (equations.py:202,
 // 205-209), personal-best update (value and position), and a candidate (fp, index) for the swarm's argmin.
@@ -155,7 +222,8 @@ constexpr int kFinWarps = 8;
 __global__ void __launch_bounds__(kFinWarps * 32)
 swarm_finish_kernel(SwarmState s, const double* __restrict__ partials, int n_tiles, int nsum, int N,
                     double* rec, double* __restrict__ scratch, unsigned* __restrict__ tickets, int commit,
-                    int maxiter, int nw) {
+                    int maxiter, int nw, PeerArgs pa) {
+    extern __shared__ __align__(16) double srec[];         // commit == 2: the ranks' records of this spectrum
     const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
     if (s.stop[b]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -252,25 +320,14 @@ swarm_finish_kernel(SwarmState s, const double* __restrict__ partials, int n_til
     for (int d = tid; d < s.D; d += kFinWarps * 32) r[2 + d] = __ldcg(src + ((size_t)b * s.S + best) * s.D + d);
     if (!commit) return;
     __syncthreads();                                       // the record is complete (same CTA wrote it)
+    if (commit == 2) {
+        // particle sharding: exchange the ranks' records over peer memory, then the same commit on all of them
+        __threadfence();
+        if (!exchange_records(s, pa, b, tid, kFinWarps * 32, srec)) return;
+        commit_spectrum(s, srec, pa.n_ranks, 0, maxiter, b, tid, kFinWarps * 32, (size_t)(s.D + 2), 0);
+        return;
+    }
     commit_spectrum(s, rec, 1, 0, maxiter, b, tid, kFinWarps * 32, (size_t)s.B * (s.D + 2), (size_t)b * (s.D + 2));
-}
-
-// ---- record exchange over peer memory (particle sharding without a collective call) -------------------------
-// Every rank's context owns a window [2 parities][n_ranks][B][D+2] of records plus [n_ranks][B] 64-bit tokens,
-// mapped into every peer (CUDA IPC between processes; plain pointers between contexts of one process).  One CTA per
-// spectrum stores this rank's local best record into slot `rank` of EVERY peer's window (NVLink stores), fences at
-// system scope, stores the generation token into every peer's token array, waits until the tokens of all ranks have
-// arrived in its own window, and applies the same commit as every other rank on the same n_ranks records - the
-// all-gather + commit of the NCCL path in one kernel.  Windows are double-buffered by generation parity: a rank cannot
-// be two generations ahead, because its next commit needs the slowest rank's next token.  The wait is bounded: on
-// expiry the kernel raises *error and returns without committing.
-__device__ __forceinline__ long long ld_acquire_sys(const long long* p) {
-    long long v;
-    asm volatile("ld.acquire.sys.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(long long* p, long long v) {
-    asm volatile("st.release.sys.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 __global__ void __launch_bounds__(128)
@@ -278,39 +335,10 @@ swarm_exchange_commit_kernel(SwarmState s, PeerArgs pa, int initial, int maxiter
     extern __shared__ __align__(16) double srec[];         // [n_ranks][D+2] of this spectrum
     const int b = blockIdx.x, tid = threadIdx.x;
     if (s.stop[b]) return;                                 // identical on every rank
-    const int W = s.D + 2, R = pa.n_ranks;
-    const int par = (int)(pa.token & 1);
-    const double* mine = s.rec + (size_t)b * W;
-    for (int q = 0; q < R; ++q) {
-        double* dst = pa.recs[q] + (((size_t)par * R + pa.rank) * s.B + b) * W;
-        for (int d = tid; d < W; d += 128) dst[d] = mine[d];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (tid < R) st_release_sys(pa.tokens[tid] + (size_t)pa.rank * s.B + b, pa.token);
-    __shared__ int s_timeout;
-    if (tid == 0) s_timeout = 0;
-    __syncthreads();
-    if (tid < R) {
-        const long long* mytok = pa.tokens[pa.rank] + (size_t)tid * s.B + b;
-        long long spins = 0;
-        while (ld_acquire_sys(mytok) < pa.token) {
-            if (++spins > pa.max_spins) { s_timeout = 1; break; }
-        }
-    }
-    __syncthreads();
-    if (s_timeout) {
-        if (tid == 0) atomicExch(pa.error, 1);
-        return;
-    }
-    const double* win = pa.recs[pa.rank] + ((size_t)par * R * s.B + b) * W;
-    for (int i = tid; i < R * W; i += 128) {
-        const int q = i / W, d = i - q * W;
-        srec[i] = __ldcv(win + (size_t)q * s.B * W + d);   // written by peers: never from a stale L1 line
-    }
-    __syncthreads();
-    commit_spectrum(s, srec, R, initial, maxiter, b, tid, 128, (size_t)W, 0);
+    if (!exchange_records(s, pa, b, tid, 128, srec)) return;
+    commit_spectrum(s, srec, pa.n_ranks, initial, maxiter, b, tid, 128, (size_t)(s.D + 2), 0);
 }
+
 
 cudaError_t launch_swarm_exchange_commit(const SwarmState& s, const PeerArgs& pa, int initial, int maxiter,
                                          cudaStream_t st) {
@@ -347,10 +375,12 @@ cudaError_t launch_swarm_move(const SwarmState& s, const double* rp, const doubl
 size_t swarm_finish_scratch_doubles(int B, int S) { return (size_t)B * ((S + kFinWarps - 1) / kFinWarps) * 2; }
 
 cudaError_t launch_swarm_finish(const SwarmState& s, const double* partials, int n_tiles, int nsum, int N, double* rec,
-                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st, int nw) {
+                                double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st, int nw,
+                                const PeerArgs* pa) {
     dim3 grid((s.S + kFinWarps - 1) / kFinWarps, s.B);
-    swarm_finish_kernel<<<grid, kFinWarps * 32, 0, st>>>(s, partials, n_tiles, nsum, N, rec, scratch, tickets, commit, maxiter,
-                                                         nw);
+    const size_t smem = commit == 2 ? (size_t)pa->n_ranks * (s.D + 2) * sizeof(double) : 0;
+    swarm_finish_kernel<<<grid, kFinWarps * 32, smem, st>>>(s, partials, n_tiles, nsum, N, rec, scratch, tickets, commit,
+                                                            maxiter, nw, pa ? *pa : PeerArgs{});
     count_launches(1);
     return cudaGetLastError();
 }

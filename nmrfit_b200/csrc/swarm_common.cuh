@@ -7,7 +7,7 @@
 
 namespace nmrfit {
 
-enum { kStopRunning = 0, kStopMinFunc = 1, kStopMinStep = 2, kStopMaxIter = 3 };
+enum { kStopRunning = 0, kStopMinFunc = 1, kStopMinStep = 2, kStopMaxIter = 3, kStopPeerLost = 4 };
 constexpr int kMaxParams = 4 + 3 * 256;                   // nmrfit_ctx_create admits up to 256 peaks
 
 __device__ __forceinline__ unsigned long long elem_counter(const SwarmState& s, int b, int sl, int d) {

@@ -24,6 +24,7 @@ STOP_TEXT = {
     _cabi.STOP_MINSTEP: 'Stopping search: Swarm best position change less than {minstep}',
     _cabi.STOP_MAXITER: 'Stopping search: maximum iterations reached --> {maxiter}',
     _cabi.RUNNING: 'Stopping search: maximum iterations reached --> {maxiter}',
+    _cabi.STOP_PEER_LOST: 'Stopping search: a peer rank never delivered its best record (exchange timed out)',
 }
 
 
@@ -311,20 +312,36 @@ def pso_sharded(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, max
             ctx.pso_commit(recs, world, stream=stream)
         gen = 0
         stop = np.zeros(1, dtype=np.int32)
+        lost = 0
         while gen < maxiter:
-            for _ in range(min(check_every, maxiter - gen)):
-                gen += 1
-                rp, rg = host_random['gen'](gen) if host_random else (None, None)
-                rp, rg = (rp[sl], rg[sl]) if host_random else (None, None)
-                if p2p:
-                    ctx.pso_step_peers(rp, rg, stream=stream)
-                else:
+            n = min(check_every, maxiter - gen)
+            if p2p:
+                # a chunk of generations in ONE library call: three launches per generation, the record exchange inside
+                # the finish kernel, no per-generation host work
+                rp = rg = None
+                if host_random:
+                    drawn = [host_random['gen'](gen + 1 + k) for k in range(n)]
+                    rp = np.ascontiguousarray(np.stack([d[0][sl] for d in drawn]))
+                    rg = np.ascontiguousarray(np.stack([d[1][sl] for d in drawn]))
+                _, lost = ctx.pso_run_peers(n, rp, rg, stream=stream)
+                gen += n
+            else:
+                for _ in range(n):
+                    gen += 1
+                    rp, rg = host_random['gen'](gen) if host_random else (None, None)
+                    rp, rg = (rp[sl], rg[sl]) if host_random else (None, None)
                     ctx.pso_advance(rp, rg, stream=stream)
                     recs = gather_records(rec, group)
                     ctx.pso_commit(recs, world, stream=stream)
             x, f, it, stop = ctx.pso_best()
-            if p2p and ctx.peer_error():
-                raise _cabi.NmrfitError(-3, 'record exchange over peer memory: a peer never arrived (wait expired)')
+            if p2p:
+                # a timeout on ANY rank is everybody's failure: agree on it before anyone raises or leaves
+                flag = torch.tensor([int(lost or ctx.peer_error() or stop[0] == _cabi.STOP_PEER_LOST)], device='cuda:%d' % dev)
+                dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+                if int(flag.item()):
+                    dist.barrier(group)                    # nobody unmaps a window a peer may still store into
+                    raise _cabi.NmrfitError(-3, 'record exchange over peer memory: a rank\'s wait for its peers expired '
+                                                '(the failure is reported on every rank)')
             if stop[0] != _cabi.RUNNING:
                 break
         x, f, it, stop = ctx.pso_best()
