@@ -188,9 +188,9 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
     t.variant = 0;
     t.stages = 0;
     t.occ = 3;
-    if (uni && c->precision == NMRFIT_FP64 && c->user_tune.variant != 0) {
+    if (uni && c->precision == NMRFIT_FP64 && c->user_tune.variant != 0 && t.tb == 6) {     // (built for the default table)
         t.variant = 1;
-        t.occ = c->user_tune.occ == 2 ? 2 : 3;
+        t.occ = c->user_tune.occ == 3 ? 3 : 2;
         const size_t budget = (t.occ == 2 ? 112 : 74) * 1024;
         auto fit_sp = [&](int stg) {
             t.stages = stg;

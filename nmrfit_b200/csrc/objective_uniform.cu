@@ -54,7 +54,7 @@ template <> struct ExpTabU<8> { static __device__ __forceinline__ const double* 
 template <> struct ExpTabU<10> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB10; } };
 
 
-// Where particle s of spectrum b keeps its per-region constants (in regions; times 12, 2 or MW+1 entries each):
+// Where particle s of spectrum b keeps its per-region constants (in regions; times sub*12, 2 or mask words each):
 // particle-major [B][S][n_tiles*nw] for objective_uniform_kernel, tile-major [B][n_tiles][S][nw] for the streamed
 // kernel, whose CTA reads one tile's regions of a whole particle group as ONE contiguous block.
 struct RegionDst {
@@ -71,63 +71,85 @@ struct RegionDst {
             slot_stride = 0;
         }
     }
+    __device__ size_t region(int rl) const { return base + (size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw); }
 };
 
 // ---- pass 1: per-particle constants, once per swarm generation ------------------------------------
-// Regions (32*R points each) are stored in axis order, padded to a whole number of tiles; the slots of
-// regions past the end of the axis are neutral.
-template <int R>
-__global__ void __launch_bounds__(128)
-objective_prepare_kernel(ObjArgs a) {
-    extern __shared__ __align__(16) double cs[];           // [P][8]
-    const int b = blockIdx.y, s = blockIdx.x, tid = threadIdx.x;
-    if (a.frozen && a.frozen[b]) return;
-    const int P = a.P, N = a.N, D = 4 + 3 * P;
-    const int NR = (N + 32 * R - 1) / (32 * R), NRP = a.n_tiles * a.nw;
-    const size_t ps = (size_t)b * a.S + s;
-    const RegionDst rd(a, b, s, NRP);
-    prepare_particle<R>(a.x + ps * D, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid,
-                        128, cs, a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles,
-                        a.prep_far + rd.base * a.sub * kFarTerms, a.prep_anchor + rd.base * 2,
-                        a.prep_mask + rd.base * mask_words_per_region(P, a.sub), nullptr, 0, -1, rd.slot_nw, rd.slot_stride, a.sub);
-}
-
-// pass 1 with the swarm's move in front (pso.cu's swarm_move_kernel for this particle): one launch fewer
-template <int R>
-__global__ void __launch_bounds__(128)
-objective_move_prepare_kernel(ObjArgs a, MoveArgs mv) {
-    extern __shared__ __align__(16) double cs[];           // [P][8] then the moved particle [D]
-    const int b = blockIdx.y, sl = blockIdx.x, tid = threadIdx.x;
-    const SwarmState& s = mv.s;
-    if (s.stop[b]) return;
-    const int P = a.P, N = a.N, D = 4 + 3 * P;
-    const int NR = (N + 32 * R - 1) / (32 * R), NRP = a.n_tiles * a.nw;
-    const size_t ps = (size_t)b * a.S + sl;
-    double* xs = cs + P * 8;
-    for (int d = tid; d < D; d += 128) {
-        const size_t idx = ps * D + d;
-        double rp, rg;
-        if (mv.rp) {
-            rp = mv.rp[idx];
-            rg = mv.rg[idx];
-        } else {
-            const Philox2 u = philox_uniform2(s.seed, elem_counter(s, b, sl, d), (unsigned long long)mv.generation);
-            rp = u.a;
-            rg = u.b;
+// A CTA of kPrepThreads threads takes G consecutive particles of one spectrum and spreads their work items
+// (uniform_eval.cuh: span coefficients, phase table, region anchors, then the far-field cells) over all its threads,
+// so that every warp is busy in either phase whatever the shape: with one particle per CTA, 6 peaks and 16 regions
+// left most lanes idle (r02a: 0.17 ms of a 1.3 ms generation at 6 peaks x 4,096 points x 65,536 particles).
+// MOVE: the swarm's move (pso.cu's swarm_move_kernel for these particles) in front: one launch fewer per generation.
+// Regions are stored in axis order, padded to a whole number of tiles; the slots of regions past the end of the axis
+// are neutral.
+constexpr int kPrepThreads = 256;
+template <int R, bool MOVE>
+__global__ void __launch_bounds__(kPrepThreads)
+objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
+    extern __shared__ __align__(16) double sm[];           // cs [G][P][8], then (MOVE) the moved particles [G][D]
+    const int b = blockIdx.y, s0 = blockIdx.x * G, tid = threadIdx.x;
+    if (MOVE ? mv.s.stop[b] != 0 : (a.frozen && a.frozen[b])) return;
+    const int P = a.P, N = a.N, D = 4 + 3 * P, sub = a.sub;
+    const int NRP = a.n_tiles * a.nw, nc = NRP * sub, cell_pts = 32 * R / sub;
+    const int MWR = mask_words_per_region(P, sub);
+    const int ng = min(G, a.S - s0);
+    double* cs = sm;
+    double* xsm = sm + (size_t)G * P * 8;
+    const double* sw = a.spec + (size_t)b * 4 * N;
+    const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
+    const size_t ps0 = (size_t)b * a.S + s0;
+    if (MOVE) {
+        const SwarmState& s = mv.s;
+        for (int e = tid; e < ng * D; e += kPrepThreads) {
+            const int g = e / D, d = e - g * D;
+            const size_t idx = (ps0 + g) * D + d;
+            double rp, rg;
+            if (mv.rp) {
+                rp = mv.rp[idx];
+                rg = mv.rg[idx];
+            } else {
+                const Philox2 u = philox_uniform2(s.seed, elem_counter(s, b, s0 + g, d), (unsigned long long)mv.generation);
+                rp = u.a;
+                rg = u.b;
+            }
+            double x = s.x[idx], v = s.v[idx];
+            move_element(s.omega, s.phip, s.phig, rp, rg, s.p[idx], s.g[(size_t)b * D + d], s.lb[(size_t)b * D + d],
+                         s.ub[(size_t)b * D + d], x, v);
+            s.v[idx] = v;
+            s.x[idx] = x;
+            xsm[e] = x;
         }
-        double x = s.x[idx], v = s.v[idx];
-        move_element(s.omega, s.phip, s.phig, rp, rg, s.p[idx], s.g[(size_t)b * D + d], s.lb[(size_t)b * D + d],
-                     s.ub[(size_t)b * D + d], x, v);
-        s.v[idx] = v;
-        s.x[idx] = x;
-        xs[d] = x;
+        __syncthreads();
+    }
+    // ---- phase 1: per particle P span coefficients + the phase table + NRP anchors
+    const int per = P + kTableItems + NRP;
+    for (int e = tid; e < ng * per; e += kPrepThreads) {
+        const int g = e / per, it = e - g * per;
+        const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
+        if (it < P) {
+            prep_item_coef<R>(xs, it, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8);
+        } else if (it < P + kTableItems) {
+            prep_item_table<R>(xs, it - P, N, P, a.prep_part + (ps0 + g) * kPartDoubles);
+        } else {
+            const int rl = it - P - kTableItems;
+            const RegionDst rd(a, b, s0 + g, NRP);
+            prep_item_anchor<R>(xs, rl, N, a.prep_anchor + rd.region(rl) * 2);
+        }
     }
     __syncthreads();
-    const RegionDst rd(a, b, sl, NRP);
-    prepare_particle<R>(xs, a.spec + (size_t)b * 4 * N, a.grid_h[2 * b], a.grid_h[2 * b + 1], N, P, NR, NRP, tid, 128, cs,
-                        a.prep_coef + ps * P * 8, a.prep_part + ps * kPartDoubles, a.prep_far + rd.base * a.sub * kFarTerms,
-                        a.prep_anchor + rd.base * 2, a.prep_mask + rd.base * mask_words_per_region(P, a.sub), nullptr, 0, -1, rd.slot_nw,
-                        rd.slot_stride, a.sub);
+    // ---- phase 2: the far-field cells of all ng particles, whole warps (prep_item_cell shuffles)
+    for (int e = tid; e < ng; e += kPrepThreads)
+        prep_item_exact_count(cs + (size_t)e * P * 8, P, a.prep_part + (ps0 + e) * kPartDoubles);
+    for (int base = tid & ~31; base < ng * nc; base += kPrepThreads) {
+        const int e = base + (tid & 31);
+        const bool ok = e < ng * nc;
+        const int g = ok ? e / nc : 0, cl = ok ? e - g * nc : 0;
+        const int rl = cl / sub, ci = cl - rl * sub;
+        const RegionDst rd(a, b, s0 + g, NRP);
+        const size_t rs = rd.region(rl);
+        prep_item_cell<R>(ok, cs + (size_t)g * P * 8, sw, h, N, P, sub, (long long)cl * cell_pts, ci, nullptr,
+                          a.prep_far + (rs * sub + ci) * kFarTerms, a.prep_mask + rs * MWR);
+    }
 }
 
 // ---- pass 2: evaluation ------------------------------------------------------------------------------
@@ -297,19 +319,23 @@ cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaSt
     a.sp = t.sp;
     a.n_tiles = objective_tiles(a.N, t);
     a.nw = t.threads / 32;
-    dim3 pgrid(a.S, B);
-    const size_t pbytes = (size_t)a.P * 8 * sizeof(double);
+    if (a.sub < 1) a.sub = 1;
+    // particles per CTA: about two rounds of far-field cells for its 256 threads
+    const int nc = a.n_tiles * a.nw * a.sub;
+    const int G = std::max(1, std::min(16, std::min(a.S, 2 * kPrepThreads / nc)));
+    dim3 pgrid((a.S + G - 1) / G, B);
+    const size_t bytes = (size_t)G * (a.P * 8 + (mv ? 4 + 3 * a.P : 0)) * sizeof(double);
+    const MoveArgs none{};
     if (mv) {
-        const size_t mbytes = pbytes + (size_t)(4 + 3 * a.P) * sizeof(double);
-        if (t.r == 4) objective_move_prepare_kernel<4><<<pgrid, 128, mbytes, st>>>(a, *mv);
-        else if (t.r == 8) objective_move_prepare_kernel<8><<<pgrid, 128, mbytes, st>>>(a, *mv);
-        else if (t.r == 16) objective_move_prepare_kernel<16><<<pgrid, 128, mbytes, st>>>(a, *mv);
+        if (t.r == 4) objective_prepare_kernel<4, true><<<pgrid, kPrepThreads, bytes, st>>>(a, *mv, G);
+        else if (t.r == 8) objective_prepare_kernel<8, true><<<pgrid, kPrepThreads, bytes, st>>>(a, *mv, G);
+        else if (t.r == 16) objective_prepare_kernel<16, true><<<pgrid, kPrepThreads, bytes, st>>>(a, *mv, G);
         else return cudaErrorInvalidValue;
         return cudaGetLastError();
     }
-    if (t.r == 4) objective_prepare_kernel<4><<<pgrid, 128, pbytes, st>>>(a);
-    else if (t.r == 8) objective_prepare_kernel<8><<<pgrid, 128, pbytes, st>>>(a);
-    else if (t.r == 16) objective_prepare_kernel<16><<<pgrid, 128, pbytes, st>>>(a);
+    if (t.r == 4) objective_prepare_kernel<4, false><<<pgrid, kPrepThreads, bytes, st>>>(a, none, G);
+    else if (t.r == 8) objective_prepare_kernel<8, false><<<pgrid, kPrepThreads, bytes, st>>>(a, none, G);
+    else if (t.r == 16) objective_prepare_kernel<16, false><<<pgrid, kPrepThreads, bytes, st>>>(a, none, G);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }

@@ -207,7 +207,7 @@ swarm_fused_kernel(FusedArgs a) {
 
         // ---- objective (equations.py:152-212) of the moved particle
         prepare_particle<R>(xs, sw, h, w_ulp, N, P, NR, NRP, tid, THREADS, cs, nullptr, part, farc, anchor, mask, pairs, r_lo,
-                            r_hi, 1 << 30, 0, SUB);
+                            r_hi, SUB);
         __syncthreads();
         FUSED_MARK(1);
         for (int st = st_lo; st < st_hi; ++st) {

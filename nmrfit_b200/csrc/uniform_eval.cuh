@@ -24,14 +24,158 @@
 
 namespace nmrfit {
 
-// xs: the particle's D parameters; sw: its spectrum's w plane (N points); cs: shared [P][8] scratch that ends up
-// holding the span coefficients; coef_out: optional second copy of them; part [kPartDoubles]; far [cells][kFarTerms];
-// anchor [regions][2]; mask [cells][MW+1].  NR regions cover the axis, NRP >= NR slots are filled (the rest neutral).
-// Called by all `nthreads` (>= 128) threads of a CTA; contains __syncthreads().
-// `pairs` (optional shared scratch of cells*P*kPairDoubles doubles): the (cell, peak) series are computed one pair per
-// thread instead of one cell per thread - same values, same order of accumulation, but P times shorter on the
-// critical path (the fused swarm kernel has one CTA per particle).
-constexpr int kPairDoubles = kFarTerms + 1;
+// 32-bit mask words per region: one cell - [MW near words][has-far]; several cells - the same block for the UNION of
+// the region's cells first (what the warp as a whole has to visit), then one block per cell.
+__host__ __device__ inline int mask_words_per_region(int P, int sub) { return (sub == 1 ? 1 : sub + 1) * ((P + 31) / 32 + 1); }
+
+// ---- the items of the prepare pass.  One particle's constants are a few dozen independent work items; the prepare
+// kernel (objective_uniform.cu) spreads the items of SEVERAL particles over the threads of a CTA so that no warp idles,
+// the fused swarm kernel (one CTA per particle) those of one.  Same item, same arithmetic, whoever executes it.
+constexpr int kPairDoubles = kFarTerms + 1;                // a (cell, peak) series: kind, then v[n]
+constexpr int kTableItems = 34;                            // phase table: 32 lane factors, the per-point step, P*yoff
+
+// span coefficients of peak k -> cs[k][8] (shared) and optionally a second copy
+template <int R>
+__device__ __forceinline__ void prep_item_coef(const double* __restrict__ xs, int k, double h, double w_ulp,
+                                               double* __restrict__ cs, double* __restrict__ coef_out) {
+    SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
+    if (c.exact) c = null_span_coef();                     // the span loop adds zero; the peak is handled after it
+    double* o = cs + k * 8;
+    o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.thr; o[7] = c.c2;
+    if (coef_out) {
+        double* g = coef_out + k * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) g[i] = o[i];
+    }
+}
+
+// phase table entry e: phi_i = p0 + (p1*i)/N with i = i_r + lane*R + j is anchor(i_r) * e^{i p1 (lane R)/N} *
+// (e^{i p1/N})^j; entries 0..31 are the lanes' factors, 32 the per-point step, 33 holds P*yoff
+template <int R>
+__device__ __forceinline__ void prep_item_table(const double* __restrict__ xs, int e, int N, int P, double* __restrict__ part) {
+    if (e == 33) {
+        part[66] = (double)P * xs[3];                      // yoff is added once per peak (equations.py:147,195)
+        return;
+    }
+    const double p1 = xs[1];
+    double sn, cn;
+    sincos(e < 32 ? (p1 * (double)(e * R)) / (double)N : p1 / (double)N, &sn, &cn);
+    part[2 * e] = cn;
+    part[2 * e + 1] = sn;
+}
+
+// phase at the first point of region ra -> dst[2]
+template <int R>
+__device__ __forceinline__ void prep_item_anchor(const double* __restrict__ xs, int ra, int N, double* __restrict__ dst) {
+    double sn = 0.0, cn = 1.0;
+    if ((long long)ra * 32 * R < N) sincos(xs[0] + (xs[1] * (double)(ra * 32 * R)) / (double)N, &sn, &cn);
+    dst[0] = cn;
+    dst[1] = sn;
+}
+
+// number of exact-path peaks (thr < 0 marks a nulled peak) -> part[67]; needs the particle's cs complete
+__device__ __forceinline__ void prep_item_exact_count(const double* __restrict__ cs, int P, double* __restrict__ part) {
+    int n = 0;
+    for (int k = 0; k < P; ++k) n += cs[k * 8 + 6] < 0.0;
+    part[67] = (double)n;
+}
+
+// the series of one (cell, peak) pair -> pr[kPairDoubles]; `ic` = the cell's first point; needs cs complete
+template <int R>
+__device__ __forceinline__ void prep_item_pair(const double* __restrict__ cs, const double* __restrict__ sw, double h, int N,
+                                               int sub, long long ic, int k, double* __restrict__ pr) {
+    const int cell_pts = 32 * R / sub;
+    const double H = 0.5 * (double)cell_pts;               // half a cell, in points
+    double kind = -1.0;                                    // -1: padding cell or exact-path peak (neither near nor far)
+    if (ic < N) {
+        const double* o = cs + k * 8;
+        SpanCoef c;
+        c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
+        if (!(c.thr < 0.0)) {
+            const double w_c = fma(0.5 * (double)(cell_pts - 1), h, sw[ic]);
+            double v[kFarTerms];
+            kind = (double)far_terms(w_c - c.loc, c, H, v);
+#pragma unroll
+            for (int n = 0; n < kFarTerms; ++n) pr[1 + n] = v[n];
+        }
+    }
+    pr[0] = kind;
+}
+
+// One far-field cell: classify every peak as near / far, sum the far ones' series into the cell's polynomial (peaks in
+// index order), write the polynomial and the cell's mask block.  `ic` = the cell's first point (cells past the end of
+// the axis are neutral); `pairs_row` (optional): the cell's (cell, peak) series precomputed by prep_item_pair.  Must be
+// called by ALL lanes of a warp (`ok` false for lanes without a cell): the union block of a region is combined from
+// its `sub` cells - consecutive lanes - by shuffles; mask_region points at the region's first block, ci = cell in region.
+template <int R>
+__device__ __forceinline__ void prep_item_cell(bool ok, const double* __restrict__ cs, const double* __restrict__ sw, double h,
+                                               int N, int P, int sub, long long ic, int ci,
+                                               const double* __restrict__ pairs_row, double* __restrict__ far_dst,
+                                               unsigned* __restrict__ mask_region) {
+    const int MW = (P + 31) / 32;
+    const int cell_pts = 32 * R / sub;
+    const double H = 0.5 * (double)cell_pts;
+    double C[kFarTerms];
+#pragma unroll
+    for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
+    unsigned any_far = 0;
+    unsigned* mk = mask_region + (sub == 1 ? 0 : 1 + ci) * (MW + 1);
+    const bool live = ok && ic < N;
+    const double w_c = (live && !pairs_row) ? fma(0.5 * (double)(cell_pts - 1), h, sw[ic]) : 0.0;
+    for (int wd = 0; wd < MW; ++wd) {
+        unsigned m = 0;
+        if (live) {
+            const int kend = min(P, wd * 32 + 32);
+            for (int k = wd * 32; k < kend; ++k) {
+                if (pairs_row) {
+                    const double* pr = pairs_row + (size_t)k * kPairDoubles;
+                    const int kind = (int)pr[0];
+                    if (kind < 0) continue;
+                    if (kind == kFarNear) { m |= 1u << (k & 31); continue; }
+                    any_far = 1u;
+                    if (kind == kFarSeries) {
+                        double v[kFarTerms];
+#pragma unroll
+                        for (int n = 0; n < kFarTerms; ++n) v[n] = pr[1 + n];
+                        far_add(cs[k * 8 + 3], v, C);
+                    }
+                } else {
+                    const double* o = cs + k * 8;
+                    SpanCoef c;
+                    c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
+                    if (c.thr < 0.0) continue;             // exact-path peak: neither near nor far
+                    if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
+                    else m |= 1u << (k & 31);
+                }
+            }
+        }
+        if (ok) mk[wd] = m;
+        if (sub > 1) {                                     // the region's union: its cells sit in `sub` consecutive lanes
+            unsigned mu = m;
+            for (int o = 1; o < sub; o <<= 1) mu |= __shfl_xor_sync(0xffffffffu, mu, o);
+            if (ok && ci == 0) mask_region[wd] = mu;
+        }
+    }
+    if (ok) mk[MW] = any_far;
+    if (sub > 1) {
+        unsigned fu = any_far;
+        for (int o = 1; o < sub; o <<= 1) fu |= __shfl_xor_sync(0xffffffffu, fu, o);
+        if (ok && ci == 0) mask_region[MW] = fu;
+    }
+    if (ok) {
+#pragma unroll
+        for (int n = 0; n < kFarTerms; ++n) far_dst[n] = C[n];
+    }
+}
+
+// All items of ONE particle by the `nthreads` (a multiple of 32) threads of a CTA - what the fused swarm kernel runs
+// per generation.  xs: the particle's D parameters; sw: its spectrum's w plane (N points); cs: shared [P][8] scratch
+// that ends up holding the span coefficients; coef_out: optional second copy of them; part [kPartDoubles];
+// far [cells][kFarTerms]; anchor [regions][2]; mask [regions][mask_words_per_region].  Regions [r_lo, r_hi) are filled,
+// at index r - r_lo (default: all NRP slots; the slots of regions past the end of the axis are neutral).  Contains
+// __syncthreads().  `pairs` (optional shared scratch of cells*P*kPairDoubles doubles): the (cell, peak) series are
+// computed one pair per thread instead of one cell per thread - same values, same order of accumulation, but P times
+// shorter on the critical path.
 template <int R>
 __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, const double* __restrict__ sw, double h,
                                                  double w_ulp, int N, int P, int NR, int NRP, int tid, int nthreads,
@@ -39,140 +183,36 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
                                                  double* __restrict__ part, double* __restrict__ far,
                                                  double* __restrict__ anchor, unsigned* __restrict__ mask,
                                                  double* __restrict__ pairs = nullptr, int r_lo = 0, int r_hi = -1,
-                                                 int slot_nw = 1 << 30, size_t slot_stride = 0, int sub = 1) {
-    // regions [r_lo, r_hi) are filled, at index r - r_lo of anchor and cell index (r - r_lo)*sub + c of far / mask
-    // (default: all NRP slots).  Tile-major destinations (the streamed evaluation kernel reads one tile's regions of a
-    // whole particle group as one block): local region rl lands at slot (rl / slot_nw) * slot_stride + rl % slot_nw.
+                                                 int sub = 1) {
     if (r_hi < 0) r_hi = NRP;
     const int nr = r_hi - r_lo, nc = nr * sub;
-    const int MW = (P + 31) / 32;
-    const double p0 = xs[0], p1 = xs[1];
     const int cell_pts = 32 * R / sub;
-    const double H = 0.5 * (double)cell_pts;                // half a cell, in points
+    const int MWR = mask_words_per_region(P, sub);
     (void)NR;
-
-    for (int k = tid; k < P; k += nthreads) {
-        SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
-        if (c.exact) c = null_span_coef();                 // the span loop adds zero; the peak is handled after it
-        double* o = cs + k * 8;
-        o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.thr; o[7] = c.c2;
-        if (coef_out) {
-            double* g = coef_out + k * 8;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) g[i] = o[i];
-        }
+    for (int k = tid; k < P; k += nthreads) prep_item_coef<R>(xs, k, h, w_ulp, cs, coef_out);
+    // the threads at the far end of the CTA do the phase tables and the anchors while the first do the peaks
+    for (int e = nthreads - 1 - tid; e < kTableItems + nr; e += nthreads) {
+        if (e < kTableItems) prep_item_table<R>(xs, e, N, P, part);
+        else prep_item_anchor<R>(xs, r_lo + e - kTableItems, N, anchor + 2 * (e - kTableItems));
     }
-    // phi_i = p0 + (p1*i)/N with i = i_r + lane*R + j:  anchor(i_r) * e^{i p1 (lane R)/N} * (e^{i p1/N})^j
-    for (int e = nthreads - 1 - tid; e < 33; e += nthreads) {   // the last warps do these while the first does the peaks
-        double sn, cn;
-        sincos(e < 32 ? (p1 * (double)(e * R)) / (double)N : p1 / (double)N, &sn, &cn);
-        part[2 * e] = cn;
-        part[2 * e + 1] = sn;
-    }
-    if (tid == 64) part[66] = (double)P * xs[3];           // yoff is added once per peak (equations.py:147,195)
     __syncthreads();
-    if (tid == 64) {
-        int n = 0;
-        for (int k = 0; k < P; ++k) n += cs[k * 8 + 6] < 0.0;      // thr < 0 marks a nulled (exact-path) peak
-        part[67] = (double)n;
-    }
-    // region anchors, by the threads at the far end of the CTA
-    for (int ral = nthreads - 1 - tid; ral < nr; ral += nthreads) {
-        const int ra = r_lo + ral;
-        const size_t slot = (size_t)(ral / slot_nw) * slot_stride + (size_t)(ral % slot_nw);
-        double sn = 0.0, cn = 1.0;
-        if ((long long)ra * 32 * R < N) sincos(p0 + (p1 * (double)(ra * 32 * R)) / (double)N, &sn, &cn);
-        anchor[slot * 2] = cn;
-        anchor[slot * 2 + 1] = sn;
-    }
+    if (tid == nthreads - 1) prep_item_exact_count(cs, P, part);
     if (pairs) {
-        // one (cell, peak) pair per thread, in rounds
-        for (int pi = tid; pi < nc * P; pi += nthreads) {
+        for (int pi = tid; pi < nc * P; pi += nthreads) {  // one (cell, peak) pair per thread, in rounds
             const int cl = pi / P, k = pi - cl * P;
-            const long long ic = ((long long)r_lo * sub + cl) * cell_pts;      // the cell's first point
-            double* pr = pairs + (size_t)pi * kPairDoubles;
-            double kind = -1.0;                            // -1: padding cell or exact-path peak (neither near nor far)
-            if (ic < N) {
-                const double* o = cs + k * 8;
-                SpanCoef c;
-                c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
-                if (!(c.thr < 0.0)) {
-                    const double w_c = fma(0.5 * (double)(cell_pts - 1), h, sw[ic]);
-                    double v[kFarTerms];
-                    kind = (double)far_terms(w_c - c.loc, c, H, v);
-#pragma unroll
-                    for (int n = 0; n < kFarTerms; ++n) pr[1 + n] = v[n];
-                }
-            }
-            pr[0] = kind;
+            prep_item_pair<R>(cs, sw, h, N, sub, ((long long)r_lo * sub + cl) * cell_pts, k, pairs + (size_t)pi * kPairDoubles);
         }
         __syncthreads();
     }
-    // mask words of a region: one cell - [MW near words][has-far]; several - the same block for the UNION of its
-    // cells first (what the warp as a whole has to visit), then one block per cell
-    const int mblocks = sub == 1 ? 1 : sub + 1;
-    for (int cl = tid; cl < nc; cl += nthreads) {
+    for (int base = tid & ~31; base < nc; base += nthreads) {      // whole warps: prep_item_cell shuffles
+        const int cl = base + (tid & 31);
+        const bool ok = cl < nc;
         const int rl = cl / sub, ci = cl - rl * sub;
-        const size_t rslot = (size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw);
-        const size_t slot = rslot * sub + (size_t)ci;
-        const long long ic = ((long long)r_lo * sub + cl) * cell_pts;
-        double C[kFarTerms];
-#pragma unroll
-        for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
-        unsigned any_far = 0;
-        unsigned* mk = mask + (rslot * mblocks + (size_t)(sub == 1 ? 0 : 1 + ci)) * (MW + 1);
-        if (ic < N) {
-            const double w_c = pairs ? 0.0 : fma(0.5 * (double)(cell_pts - 1), h, sw[ic]);
-            for (int wd = 0; wd < MW; ++wd) {
-                unsigned m = 0;
-                const int kend = min(P, wd * 32 + 32);
-                for (int k = wd * 32; k < kend; ++k) {
-                    if (pairs) {
-                        const double* pr = pairs + (size_t)(cl * P + k) * kPairDoubles;
-                        const int kind = (int)pr[0];
-                        if (kind < 0) continue;
-                        if (kind == kFarNear) { m |= 1u << (k & 31); continue; }
-                        any_far = 1u;
-                        if (kind == kFarSeries) {
-                            double v[kFarTerms];
-#pragma unroll
-                            for (int n = 0; n < kFarTerms; ++n) v[n] = pr[1 + n];
-                            far_add(cs[k * 8 + 3], v, C);
-                        }
-                    } else {
-                        const double* o = cs + k * 8;
-                        SpanCoef c;
-                        c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
-                        if (c.thr < 0.0) continue;         // exact-path peak: neither near nor far
-                        if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
-                        else m |= 1u << (k & 31);
-                    }
-                }
-                mk[wd] = m;
-            }
-        } else {
-            for (int wd = 0; wd < MW; ++wd) mk[wd] = 0u;
-        }
-        mk[MW] = any_far;
-        double* fc = far + slot * kFarTerms;
-#pragma unroll
-        for (int n = 0; n < kFarTerms; ++n) fc[n] = C[n];
-    }
-    if (sub > 1) {
-        __syncthreads();                                   // the cells' words (global or shared) are visible to the CTA
-        for (int e = tid; e < nr * (MW + 1); e += nthreads) {
-            const int rl = e / (MW + 1), wd = e - rl * (MW + 1);
-            const size_t rslot = (size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw);
-            unsigned* mk = mask + rslot * mblocks * (MW + 1);
-            unsigned m = 0;
-            for (int ci = 0; ci < sub; ++ci) m |= mk[(1 + ci) * (MW + 1) + wd];
-            mk[wd] = m;
-        }
+        prep_item_cell<R>(ok, cs, sw, h, N, P, sub, ((long long)r_lo * sub + cl) * cell_pts, ci,
+                          pairs ? pairs + (size_t)cl * P * kPairDoubles : nullptr, far + (size_t)cl * kFarTerms,
+                          mask + (size_t)rl * MWR);
     }
 }
-
-// 32-bit mask words per region (see prepare_particle)
-__host__ __device__ inline int mask_words_per_region(int P, int sub) { return (sub == 1 ? 1 : sub + 1) * ((P + 31) / 32 + 1); }
 
 // Shared-memory placement of a tile's staged points.  Point e of the tile (thread t = e / R, j = e % R) lives in
 // row j.  Swizzled (SWZ): at column t ^ j (double2 (u, v) array) resp. t ^ 2j (weights array) - the evaluation reads
