@@ -82,10 +82,11 @@ struct RegionDst {
 // MOVE: the swarm's move (pso.cu's swarm_move_kernel for these particles) in front: one launch fewer per generation.
 // Regions are stored in axis order, padded to a whole number of tiles; the slots of regions past the end of the axis
 // are neutral.
-constexpr int kPrepThreads = 256;
+constexpr int kPrepThreads = 256;                          // at most; 128 when a particle alone fills the CTA
 template <int R, bool MOVE>
 __global__ void __launch_bounds__(kPrepThreads)
 objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
+    const int nthreads = blockDim.x;
     extern __shared__ __align__(16) double sm[];           // cs [G][P][8], then (MOVE) the moved particles [G][D]
     const int b = blockIdx.y, s0 = blockIdx.x * G, tid = threadIdx.x;
     if (MOVE ? mv.s.stop[b] != 0 : (a.frozen && a.frozen[b])) return;
@@ -100,7 +101,7 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     const size_t ps0 = (size_t)b * a.S + s0;
     if (MOVE) {
         const SwarmState& s = mv.s;
-        for (int e = tid; e < ng * D; e += kPrepThreads) {
+        for (int e = tid; e < ng * D; e += nthreads) {
             const int g = e / D, d = e - g * D;
             const size_t idx = (ps0 + g) * D + d;
             double rp, rg;
@@ -123,7 +124,7 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     }
     // ---- phase 1: per particle P span coefficients + the phase table + NRP anchors
     const int per = P + kTableItems + NRP;
-    for (int e = tid; e < ng * per; e += kPrepThreads) {
+    for (int e = tid; e < ng * per; e += nthreads) {
         const int g = e / per, it = e - g * per;
         const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
         if (it < P) {
@@ -138,9 +139,9 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     }
     __syncthreads();
     // ---- phase 2: the far-field cells of all ng particles, whole warps (prep_item_cell shuffles)
-    for (int e = tid; e < ng; e += kPrepThreads)
+    for (int e = tid; e < ng; e += nthreads)
         prep_item_exact_count(cs + (size_t)e * P * 8, P, a.prep_part + (ps0 + e) * kPartDoubles);
-    for (int base = tid & ~31; base < ng * nc; base += kPrepThreads) {
+    for (int base = tid & ~31; base < ng * nc; base += nthreads) {
         const int e = base + (tid & 31);
         const bool ok = e < ng * nc;
         const int g = ok ? e / nc : 0, cl = ok ? e - g * nc : 0;
@@ -322,20 +323,25 @@ cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaSt
     if (a.sub < 1) a.sub = 1;
     // particles per CTA: about two rounds of far-field cells for its 256 threads
     const int nc = a.n_tiles * a.nw * a.sub;
-    const int G = std::max(1, std::min(16, std::min(a.S, 2 * kPrepThreads / nc)));
+    const size_t per_particle = (size_t)(a.P * 8 + (mv ? 4 + 3 * a.P : 0)) * sizeof(double);
+    int G = std::max(1, std::min(16, std::min(a.S, 2 * kPrepThreads / nc)));
+    while (G > 1 && G * per_particle > 40 * 1024) --G;     // stay inside the default dynamic shared-memory limit
+    // a particle with >= 128 cells fills a CTA of 128 threads on its own (and many small CTAs schedule better)
+    const int pthreads = nc >= 128 ? 128 : kPrepThreads;
+    if (nc >= 128) G = 1;
     dim3 pgrid((a.S + G - 1) / G, B);
-    const size_t bytes = (size_t)G * (a.P * 8 + (mv ? 4 + 3 * a.P : 0)) * sizeof(double);
+    const size_t bytes = G * per_particle;
     const MoveArgs none{};
     if (mv) {
-        if (t.r == 4) objective_prepare_kernel<4, true><<<pgrid, kPrepThreads, bytes, st>>>(a, *mv, G);
-        else if (t.r == 8) objective_prepare_kernel<8, true><<<pgrid, kPrepThreads, bytes, st>>>(a, *mv, G);
-        else if (t.r == 16) objective_prepare_kernel<16, true><<<pgrid, kPrepThreads, bytes, st>>>(a, *mv, G);
+        if (t.r == 4) objective_prepare_kernel<4, true><<<pgrid, pthreads, bytes, st>>>(a, *mv, G);
+        else if (t.r == 8) objective_prepare_kernel<8, true><<<pgrid, pthreads, bytes, st>>>(a, *mv, G);
+        else if (t.r == 16) objective_prepare_kernel<16, true><<<pgrid, pthreads, bytes, st>>>(a, *mv, G);
         else return cudaErrorInvalidValue;
         return cudaGetLastError();
     }
-    if (t.r == 4) objective_prepare_kernel<4, false><<<pgrid, kPrepThreads, bytes, st>>>(a, none, G);
-    else if (t.r == 8) objective_prepare_kernel<8, false><<<pgrid, kPrepThreads, bytes, st>>>(a, none, G);
-    else if (t.r == 16) objective_prepare_kernel<16, false><<<pgrid, kPrepThreads, bytes, st>>>(a, none, G);
+    if (t.r == 4) objective_prepare_kernel<4, false><<<pgrid, pthreads, bytes, st>>>(a, none, G);
+    else if (t.r == 8) objective_prepare_kernel<8, false><<<pgrid, pthreads, bytes, st>>>(a, none, G);
+    else if (t.r == 16) objective_prepare_kernel<16, false><<<pgrid, pthreads, bytes, st>>>(a, none, G);
     else return cudaErrorInvalidValue;
     return cudaGetLastError();
 }
