@@ -44,25 +44,61 @@ __device__ __forceinline__ double block_max(double x, double* sm) {
     return t;
 }
 
-// np.mean of n <= 128 doubles as numpy computes it: pairwise summation's base case - eight running sums over
-// blocks of eight, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail - divided by n.
+// np.sum of n <= 128 doubles at(off), at(off + 1), ... as numpy computes it: pairwise summation's base case - eight
+// running sums over blocks of eight, combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the tail.
 template <typename F>
-__device__ __forceinline__ double numpy_mean_small(F at, int n) {
+__device__ __forceinline__ double numpy_sum_block(F at, int off, int n) {
     double s;
     if (n < 8) {
         s = 0.0;
-        for (int i = 0; i < n; ++i) s = __dadd_rn(s, at(i));
+        for (int i = 0; i < n; ++i) s = __dadd_rn(s, at(off + i));
     } else {
         double r[8];
-        for (int k = 0; k < 8; ++k) r[k] = at(k);
+        for (int k = 0; k < 8; ++k) r[k] = at(off + k);
         int i = 8;
         for (; i < n - (n % 8); i += 8)
-            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], at(i + k));
+            for (int k = 0; k < 8; ++k) r[k] = __dadd_rn(r[k], at(off + i + k));
         s = __dadd_rn(__dadd_rn(__dadd_rn(r[0], r[1]), __dadd_rn(r[2], r[3])),
                       __dadd_rn(__dadd_rn(r[4], r[5]), __dadd_rn(r[6], r[7])));
-        for (; i < n; ++i) s = __dadd_rn(s, at(i));
+        for (; i < n; ++i) s = __dadd_rn(s, at(off + i));
     }
-    return s / (double)n;
+    return s;
+}
+
+// np.mean of ANY number of doubles as numpy computes it (V[:n].mean() of containers.py:103-104 with n = N/5000, i.e.
+// n > 128 from 645,000 points on): above 128 elements pairwise summation splits at n/2 rounded down to a multiple of
+// eight and adds the halves' sums; the recursion is unrolled on a small explicit stack (depth <= log2(n/128) + 1).
+template <typename F>
+__device__ __forceinline__ double numpy_mean(F at, int n) {
+    if (n <= 128) return numpy_sum_block(at, 0, n) / (double)n;
+    int off[32], len[32], state[32];
+    double left[32];
+    int sp = 0;
+    off[0] = 0; len[0] = n; state[0] = 0; left[0] = 0.0;
+    double ret = 0.0;
+    while (sp >= 0) {
+        if (len[sp] <= 128) {
+            ret = numpy_sum_block(at, off[sp], len[sp]);
+            --sp;
+            continue;
+        }
+        int n2 = len[sp] / 2;
+        n2 -= n2 % 8;
+        if (state[sp] == 0) {                              // descend into the left half
+            state[sp] = 1;
+            off[sp + 1] = off[sp]; len[sp + 1] = n2; state[sp + 1] = 0;
+            ++sp;
+        } else if (state[sp] == 1) {                       // left half done: keep it, descend into the right half
+            left[sp] = ret;
+            state[sp] = 2;
+            off[sp + 1] = off[sp] + n2; len[sp + 1] = len[sp] - n2; state[sp + 1] = 0;
+            ++sp;
+        } else {                                           // both done
+            ret = __dadd_rn(left[sp], ret);
+            --sp;
+        }
+    }
+    return ret / (double)n;
 }
 
 // brute scan: err[b][k], ok[b][k] for candidate p0_k (p1 = 0)
@@ -87,7 +123,7 @@ phase_brute_kernel(const double* __restrict__ u, const double* __restrict__ v, i
         const int n = max(1, N / 5000);
         auto head = [&](int i) { return __dsub_rn(__dmul_rn(ub[i], cs), __dmul_rn(vb[i], sn)); };
         auto tail = [&](int i) { const int j = N - n + i; return __dsub_rn(__dmul_rn(ub[j], cs), __dmul_rn(vb[j], sn)); };
-        const double d = __dsub_rn(numpy_mean_small(head, min(n, 128)), numpy_mean_small(tail, min(n, 128)));
+        const double d = __dsub_rn(numpy_mean(head, n), numpy_mean(tail, n));
         err[(size_t)b * K + k] = sqrt(__dmul_rn(d, d));
         ok[(size_t)b * K + k] = hi > fabs(lo);
     }

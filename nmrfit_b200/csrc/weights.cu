@@ -51,10 +51,10 @@ weights_kernel(double* __restrict__ spec, double* __restrict__ scratch, const do
     }
     for (int k = tid; k < n_windows; k += kWThreads) sval[k] = values[(size_t)b * n_windows + k];
     __syncthreads();
-    if (tid < n_windows) {                                 // utils.py:208-211: order the pair
-        const int a = win[2 * tid], c = win[2 * tid + 1];
-        win[2 * tid] = min(a, c);
-        win[2 * tid + 1] = max(a, c);
+    for (int k = tid; k < n_windows; k += kWThreads) {     // utils.py:208-211: order the pair
+        const int a = win[2 * k], c = win[2 * k + 1];
+        win[2 * k] = min(a, c);
+        win[2 * k + 1] = max(a, c);
     }
     __syncthreads();
 
@@ -88,6 +88,16 @@ weights_kernel(double* __restrict__ spec, double* __restrict__ scratch, const do
 cudaError_t launch_weights(double* spec, double* scratch, const double* bounds_dev, const double* values_dev, int B,
                            int N, int n_windows, int sweeps, double omega, cudaStream_t st) {
     const size_t smem = sizeof(int) * 2 * ((n_windows + 1) & ~1) + sizeof(double) * n_windows;
+    if (smem > 48 * 1024) {                                // up to 4,096 windows (64 KB): beyond the default limit
+        static bool attr_set[NMRFIT_MAX_DEVICES] = {};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (!attr_set[dev % NMRFIT_MAX_DEVICES]) {
+            cudaError_t e = cudaFuncSetAttribute(weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+            if (e != cudaSuccess) return e;
+            attr_set[dev % NMRFIT_MAX_DEVICES] = true;
+        }
+    }
     // numpy evaluates (1. - omega) * x[1:-1] + omega * 0.5 * (x[2:] + x[:-2]) with the scalars folded first
     weights_kernel<<<B, kWThreads, smem, st>>>(spec, scratch, bounds_dev, values_dev, N, n_windows, sweeps, 1.0 - omega,
                                                omega * 0.5);

@@ -20,7 +20,15 @@ from . import swarm as _swarm
 
 
 def _is_nmrfit_objective(func):
-    return getattr(func, '__name__', '') == 'objective' and str(getattr(func, '__module__', '')).endswith('equations')
+    """True only for the reference package's own ``nmrfit.equations.objective`` (or this package's mirror of it): the
+    function object must be the ``objective`` attribute of an imported module named exactly ``nmrfit.equations`` /
+    ``nmrfit_b200.equations`` - a look-alike from any other ``*.equations`` module is not silently replaced."""
+    import sys
+    mod_name = getattr(func, '__module__', None)
+    if mod_name not in ('nmrfit.equations', 'nmrfit_b200.equations') or getattr(func, '__qualname__', '') != 'objective':
+        return False
+    mod = sys.modules.get(mod_name)
+    return mod is not None and getattr(mod, 'objective', None) is func
 
 
 def pso(func, lb, ub, ieqcons=[], f_ieqcons=None, args=(), kwargs={}, swarmsize=100, omega=0.5, phip=0.5, phig=0.5,

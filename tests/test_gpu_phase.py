@@ -50,6 +50,22 @@ def test_brute_phase_batch_and_ragged_sizes():
         orc.brute_phase(data.u, data.v, step=np.pi / 90)[0]
 
 
+def test_brute_phase_long_axis_means_over_more_than_128_points():
+    """N >= 645,000: the baseline means V[:n].mean(), V[-n:].mean() (containers.py:103-104, n = N // 5000) cover more
+    than 128 points, where numpy's pairwise summation starts to split recursively - the device follows it, so the
+    per-candidate errors are the oracle's to the last bit and the pick is the same."""
+    N = 1_300_000                                          # n = 260: two levels of the recursion
+    rng = np.random.default_rng(3)
+    data, _ = synth.multiplet(4096, 6, seed=5)
+    u = np.interp(np.linspace(0, 1, N), np.linspace(0, 1, 4096), data.u) + rng.normal(0, 1e-3, N)
+    v = np.interp(np.linspace(0, 1, N), np.linspace(0, 1, 4096), data.v) + rng.normal(0, 1e-3, N)
+    cands, err, ok = orc.brute_phase_errors(u, v, step=np.pi / 30)
+    with _cabi.PhaseScorer(u, v) as sc:
+        best, berr, gerr, gok = sc.brute(cands, details=True)
+    assert np.array_equal(gok[0], ok) and np.array_equal(gerr[0], err)
+    assert best[0] == orc.brute_phase(u, v, step=np.pi / 30)[0]
+
+
 @pytest.mark.parametrize('tag', CASES)
 def test_acme_score_matches_reference(tag):
     g = load_golden('phase')

@@ -127,6 +127,15 @@ def test_pyswarm_compat_refuses_what_it_cannot_accelerate():
         pyswarm_compat.pso(lambda x: float(np.sum(x ** 2)), [0, 0], [1, 1])
     from nmrfit_b200 import equations
     assert pyswarm_compat._is_nmrfit_objective(equations.objective)
+    # a look-alike - same name, a module that merely ends in "equations" - is not silently replaced by the nmrfit objective
+    import types
+    fake = types.ModuleType('other.equations')
+    exec('def objective(x, *a):\n    return 0.0', fake.__dict__)
+    fake.objective.__module__ = 'other.equations'
+    assert not pyswarm_compat._is_nmrfit_objective(fake.objective)
+    impostor = types.FunctionType(fake.objective.__code__, {}, 'objective')
+    impostor.__module__ = 'nmrfit_b200.equations'        # claims the module, but is not the module's attribute
+    assert not pyswarm_compat._is_nmrfit_objective(impostor)
     with pytest.raises(NotImplementedError, match='constraints'):
         pyswarm_compat.pso(equations.objective, [0] * 7, [1] * 7, ieqcons=[lambda x: 1.0], args=(None,) * 5)
     with pytest.raises(ValueError, match='args'):
