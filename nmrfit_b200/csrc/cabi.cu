@@ -91,6 +91,7 @@ struct nmrfit_ctx {
     DevBuf<int> sstop, sit;
     DevBuf<double> frec_f, frec_x;     // fused swarm kernel: published records
     DevBuf<unsigned> fbarrier;
+    DevBuf<int> ferror;                // fused swarm kernel: barrier-timeout flag
     DevBuf<double> fin_scratch;        // finish kernel: per-CTA candidates
     DevBuf<unsigned> fin_tickets;
     // record exchange over peer memory (particle sharding without a collective call)
@@ -341,6 +342,12 @@ int fused_setup(nmrfit_ctx* c, int n_gen, const double* rp_d, const double* rg_d
     CK(c->frec_f.reserve(2 * (size_t)s.B * s.S));
     CK(c->frec_x.reserve(2 * (size_t)s.B * s.S * s.D));
     CK(c->fbarrier.reserve(s.B));
+    if (!c->ferror.ptr) {
+        CK(c->ferror.reserve(1));
+        CK(cudaMemset(c->ferror.ptr, 0, sizeof(int)));
+    }
+    a->error = c->ferror.ptr;
+    a->max_wait_ns = 10LL * 1000 * 1000 * 1000;            // 10 s; the legitimate wait is microseconds
     a->rec_f = c->frec_f.ptr;
     a->rec_x = c->frec_x.ptr;
     a->barrier = c->fbarrier.ptr;
@@ -436,6 +443,7 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->frec_f.release();
     c->frec_x.release();
     c->fbarrier.release();
+    c->ferror.release();
     c->ftiming.release();
     for (void* p : c->peer_opened) cudaIpcCloseMemHandle(p);
     if (c->peer_win) cudaFree(c->peer_win);
@@ -981,7 +989,12 @@ int nmrfit_pso_run(nmrfit_ctx* c, int n_generations, const double* rp_all, const
             return rc;
     }
     CK(cudaMemcpyAsync(c->h_flags, s.stop, sizeof(int) * s.B, cudaMemcpyDeviceToHost, st));
+    c->h_flags[s.B] = 0;
+    if (c->ferror.ptr) CK(cudaMemcpyAsync(c->h_flags + s.B, c->ferror.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
+    if (c->h_flags[s.B])
+        return fail(NMRFIT_ERR_STATE, "fused swarm kernel: the barrier among the CTAs of a spectrum timed out (a CTA died); "
+                                      "the swarm state is undefined");
     int running = 0;
     for (int b = 0; b < s.B; ++b) running += c->h_flags[b] == 0;
     if (n_running) *n_running = running;

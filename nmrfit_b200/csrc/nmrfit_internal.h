@@ -157,6 +157,8 @@ struct FusedArgs {
     int cluster;            // CTAs (one thread-block cluster) per particle (filled by the launcher)
     int pairs;              // pair-parallel constants pass (needs its scratch in shared memory; filled by the launcher)
     long long* timing;      // optional [8] per-phase cycle counters (null: off)
+    int* error;             // raised when the inter-CTA barrier wait expired (a CTA of the spectrum died)
+    long long max_wait_ns;  // bound of that wait, wall time
 };
 struct FusedPlan {
     bool ok, dense, pairs;

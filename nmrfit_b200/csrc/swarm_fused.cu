@@ -271,9 +271,26 @@ swarm_fused_kernel(FusedArgs a) {
             // release: this CTA's record (ordered before by the bar.sync above) is visible to whoever acquires the count
             red_release_add(a.barrier + b, 1u);
             const unsigned target = (unsigned)(S * G) * (unsigned)(k + 1);
-            while (ld_acquire(a.barrier + b) < target) { }
+            // The cooperative launch guarantees that every CTA is resident, so this wait ends within microseconds -
+            // unless a CTA of the spectrum died.  Bounded in wall time: on expiry raise the context's error flag and
+            // leave (exited threads count as arrived at every later barrier, so nobody is left hanging).
+            unsigned spins = 0;
+            unsigned long long t0 = 0;
+            misc[7] = 0.0;
+            while (ld_acquire(a.barrier + b) < target) {
+                if ((++spins & 1023u) == 0) {
+                    unsigned long long now;
+                    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(now));
+                    if (t0 == 0) t0 = now;
+                    else if (now - t0 > (unsigned long long)a.max_wait_ns) { misc[7] = 1.0; break; }
+                }
+            }
         }
         __syncthreads();
+        if (misc[7] != 0.0) {
+            if (tid == 0) atomicExch(a.error, 1);
+            return;
+        }
         FUSED_MARK(5);
 
         // ---- swarm best: argmin over the personal bests, first index wins (np.argmin)

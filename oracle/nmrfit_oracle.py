@@ -295,3 +295,73 @@ def solution_bounds(peaks, p0=None, p1=None):
         lower.extend([pk.width * 0.5, pk.loc - 0.1 * (pk.loc - pk.bounds[0]), pk.area * 0.5])
         upper.extend([pk.width * 1.5, pk.loc - 0.1 * (pk.loc - pk.bounds[1]), pk.area * 1.5])
     return lower, upper
+
+
+# ---- auto peak selection (utils.py:670-783) ------------------------------------------------------------------
+class PeakRecord:
+    """The attributes AutoPeakSelector gives a ``Peak`` (utils.py:58-93, filled at :735-770)."""
+
+
+def argrelmax_clip(x, order):
+    """``scipy.signal.argrelmax(x, order=order)[0]`` (utils.py:733): indices whose value is STRICTLY greater than
+    every neighbour within ``order`` samples on either side, neighbours beyond the ends clipped to the end samples
+    (mode='clip').  scipy's own loop costs O(len(x) * order) - minutes for the 88,554-sample window of a 16,384-point
+    spectrum upsampled 100x - so candidates come from a running maximum and only those are checked exhaustively."""
+    import scipy.ndimage
+    n = x.size
+    order = max(int(order), 1)
+    run = scipy.ndimage.maximum_filter1d(x, size=2 * min(order, n) + 1, mode='nearest')
+    out = []
+    for i in np.nonzero(x == run)[0]:
+        lo, hi = max(0, i - order), min(n - 1, i + order)
+        if i == 0 or i == n - 1:                           # the clipped neighbour is the sample itself
+            continue
+        if np.all(x[lo:i] < x[i]) and np.all(x[i + 1:hi + 1] < x[i]):
+            out.append(i)
+    return np.array(out, dtype=np.int64)
+
+
+def auto_peaks(w, u, thresh, window, baseline_fn=None):
+    """AutoPeakSelector(w, u, thresh, window).find_peaks() restated step by step (utils.py:709-772).  Returns
+    (peaks, aux): ``peaks`` a list of PeakRecord (loc, i, height, width, bounds, baseline, area, idx_lo, idx_hi), ``aux``
+    the upsampled axis / signal / smoothed signal / global baseline / maxima before the width screen."""
+    import scipy.interpolate
+    import scipy.signal
+    if baseline_fn is None:
+        from . import peakutils_oracle
+        baseline_fn = peakutils_oracle.baseline
+    w, u = np.asarray(w, dtype=float), np.asarray(u, dtype=float)
+    f = scipy.interpolate.interp1d(w, u)                                      # utils.py:711
+    wu = np.linspace(w.min(), w.max(), int(len(w) * 100))                    # :713
+    uu = f(wu)                                                                # :714
+    us = scipy.signal.savgol_filter(uu, 11, 4)                                # :716
+    base = baseline_fn(us, 0)[0]                                              # :718
+    order = int(window / (wu[1] - wu[0]))                                     # :728-729
+    pre = []
+    for i in argrelmax_clip(us, order):                                       # :731
+        p = PeakRecord()
+        p.loc, p.i, p.height = wu[i], int(i), uu[i] - base                    # :735-737
+        if p.height > thresh:                                                 # :738
+            pre.append(p)
+    peaks = []
+    y = uu - base
+    for p in pre:                                                             # :747
+        half = p.height / 2.
+        d = np.sign(half - y[0:-1]) - np.sign(half - y[1:])                   # :748
+        right = np.where(d < 0)[0]
+        left = np.where(d > 0)[0]
+        if right.size == 0 or left.size == 0:
+            raise ValueError('attempt to get argmin of an empty sequence')   # what the reference raises here
+        x_right = wu[right[np.argmin(np.abs(wu[right] - p.loc))]]             # :752
+        x_left = wu[left[np.argmin(np.abs(wu[left] - p.loc))]]                # :753
+        if x_left < x_right:                                                  # :755
+            p.width = x_right - x_left
+            p.bounds = [p.loc - 2 * p.width, p.loc + 2 * p.width]             # :760
+            idx = np.where((wu >= p.bounds[0]) & (wu <= p.bounds[1]))[0]      # :763
+            p.idx_lo, p.idx_hi = int(idx[0]), int(idx[-1])
+            p.baseline = baseline_fn(uu[idx], 0)[0]                           # :766
+            p.pre_height = p.height
+            p.height = uu[p.i] - p.baseline                                   # :767
+            p.area = scipy.integrate.simpson(uu[idx] - p.baseline, x=wu[idx])  # :770 (simps renamed in scipy 1.14)
+            peaks.append(p)
+    return peaks, dict(wu=wu, uu=uu, us=us, baseline=base, pre=pre)

@@ -218,6 +218,41 @@ def main():
                          area_fraction=fobj.calculate_area_fraction())
         print(name, 'generations', info['it'], 'stop', info['stop'], 'error', fobj.error)
 
+    # ---- auto peak selection (utils.py:670-783) through the reference's own AutoPeakSelector ---------------------
+    # scipy.integrate.simps no longer exists (-> scipy.integrate.simpson, keyword x) and peakutils is absent
+    # (-> oracle/peakutils_oracle.py, PARITY UNPINNED for that piece); the class itself is the reference's.
+    if not ONLY or ONLY.startswith('peaks'):
+        import scipy.integrate
+        from oracle import peakutils_oracle
+        scipy.integrate.simps = lambda y, x: scipy.integrate.simpson(y, x=x)
+        sys.modules['peakutils'].baseline = peakutils_oracle.baseline
+        sp_cases = [('peaks_1024x6', 1024, 6, 3, 0.0, 0.02, False), ('peaks_2500x12', 2500, 12, 5, 0.004, 0.01, False),
+                    ('peaks_4096x6', 4096, 6, 1000, 0.002, 0.02, False), ('peaks_desc_1500x6', 1500, 6, 8, 0.0, 0.02, True)]
+        if 'peaks_c3' in ONLY:                             # ~6 minutes: argrelmax with an 88,554-point window
+            sp_cases = [('peaks_c3_16384x6', 16384, 6, 3000, 0.002, 0.02, False)]
+        for name, N, P, seed, thresh, window, descending in sp_cases:
+            if ONLY and not name.startswith(ONLY):
+                continue
+            data, true = synth.multiplet(N, P, seed=seed)
+            V, I = pa.ps2(data.u, data.v, true[0], true[1])
+            w = data.w[::-1].copy() if descending else data.w
+            Vin = V[::-1].copy() if descending else V
+            sel = ref.utils.AutoPeakSelector(w, Vin, thresh, window)
+            sel.find_maxima()
+            pre = [(p.i, p.loc, p.height) for p in sel.peaks]
+            sel.find_width()
+            M = sel.w.size
+            probe = np.unique(np.r_[np.arange(0, 12), np.arange(M - 12, M), np.arange(0, M, 997), [p.i for p in sel.peaks]])
+            out[name] = dict(w=w, V=Vin, thresh=thresh, window=window, baseline=sel.baseline, probe=probe,
+                             wu_probe=sel.w[probe], uu_probe=sel.u[probe], us_probe=sel.u_smoothed[probe],
+                             pre_i=[q[0] for q in pre], pre_loc=[q[1] for q in pre], pre_height=[q[2] for q in pre],
+                             i=[p.i for p in sel.peaks], loc=[p.loc for p in sel.peaks], height=[p.height for p in sel.peaks],
+                             width=[p.width for p in sel.peaks], area=[p.area for p in sel.peaks],
+                             local_baseline=[p.baseline for p in sel.peaks],
+                             bounds=[list(map(float, p.bounds)) for p in sel.peaks],
+                             idx_lo=[int(p.idx[0][0]) for p in sel.peaks], idx_hi=[int(p.idx[0][-1]) for p in sel.peaks])
+            print(name, 'maxima', len(pre), 'peaks', len(sel.peaks), 'baseline', sel.baseline)
+
     for name, d in out.items():
         if ONLY and not name.startswith(ONLY):
             continue
