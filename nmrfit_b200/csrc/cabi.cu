@@ -210,10 +210,19 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
         }
         t.stages = stg;
         t.sp = std::max(1, spg);
-        if (c->user_tune.sp > 0) t.sp = c->user_tune.sp;
-        t.sp = std::min(t.sp, std::max(1, S));
-        while (t.sp > 1 && objective_stream_smem_bytes(c->P, t, ctx_cells(c, t.r)) > 200 * 1024) t.sp -= 1;
-        return t;
+        bool fits = true;
+        if (c->user_tune.sp > 0) {                         // an explicit group size: fewer stages if need be, else the
+            t.sp = c->user_tune.sp;                        // one-group-per-CTA kernel below (which takes any size)
+            if (objective_stream_smem_bytes(c->P, t, ctx_cells(c, t.r)) > 200 * 1024 && c->user_tune.stages == 0) t.stages = 2;
+            fits = objective_stream_smem_bytes(c->P, t, ctx_cells(c, t.r)) <= 200 * 1024;
+        }
+        if (fits) {
+            t.sp = std::min(t.sp, std::max(1, S));
+            return t;
+        }
+        t.variant = 0;
+        t.stages = 0;
+        t.occ = 3;
     }
     // per-particle coefficients live in shared memory: keep the CTA under the 200 KB opt-in limit
     const bool f32 = c->precision == NMRFIT_FP32;

@@ -58,20 +58,20 @@ template <> struct ExpTabU<10> { static __device__ __forceinline__ const double*
 // particle-major [B][S][n_tiles*nw] for objective_uniform_kernel, tile-major [B][n_tiles][S][nw] for the streamed
 // kernel, whose CTA reads one tile's regions of a whole particle group as ONE contiguous block.
 struct RegionDst {
-    size_t base, slot_stride;
-    int slot_nw;
+    size_t base, tile_stride;
+    int shift, mask;                                       // nw = 4 or 8 regions per tile: region rl = (tile, rl & mask)
     __device__ RegionDst(const ObjArgs& a, int b, int s, int NRP) {
+        shift = a.nw == 8 ? 3 : 2;
+        mask = a.nw - 1;
         if (a.tile_major) {
             base = ((size_t)b * a.n_tiles * a.S + s) * a.nw;
-            slot_nw = a.nw;
-            slot_stride = (size_t)a.S * a.nw;
+            tile_stride = (size_t)a.S * a.nw;
         } else {
             base = ((size_t)b * a.S + s) * NRP;
-            slot_nw = 1 << 30;
-            slot_stride = 0;
+            tile_stride = (size_t)a.nw;
         }
     }
-    __device__ size_t region(int rl) const { return base + (size_t)(rl / slot_nw) * slot_stride + (size_t)(rl % slot_nw); }
+    __device__ size_t region(int rl) const { return base + (size_t)(rl >> shift) * tile_stride + (size_t)(rl & mask); }
 };
 
 // ---- pass 1: per-particle constants, once per swarm generation ------------------------------------
@@ -122,20 +122,14 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
         }
         __syncthreads();
     }
-    // ---- phase 1: per particle P span coefficients + the phase table + NRP anchors
-    const int per = P + kTableItems + NRP;
+    // ---- phase 1: per particle the phase table (from the far end of the CTA) and P span coefficients
+    const int per = P + kTableItems;
     for (int e = tid; e < ng * per; e += nthreads) {
-        const int g = e / per, it = e - g * per;
+        const int q = ng * per - 1 - e;                    // the heavy items (sincos) first
+        const int g = q / per, it = q - g * per;
         const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
-        if (it < P) {
-            prep_item_coef<R>(xs, it, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8);
-        } else if (it < P + kTableItems) {
-            prep_item_table<R>(xs, it - P, N, P, a.prep_part + (ps0 + g) * kPartDoubles);
-        } else {
-            const int rl = it - P - kTableItems;
-            const RegionDst rd(a, b, s0 + g, NRP);
-            prep_item_anchor<R>(xs, rl, N, a.prep_anchor + rd.region(rl) * 2);
-        }
+        if (it < P) prep_item_coef<R>(xs, it, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8);
+        else prep_item_table<R>(xs, it - P, N, P, a.prep_part + (ps0 + g) * kPartDoubles);
     }
     __syncthreads();
     // ---- phase 2: the far-field cells of all ng particles, whole warps (prep_item_cell shuffles)
@@ -150,6 +144,8 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
         const size_t rs = rd.region(rl);
         prep_item_cell<R>(ok, cs + (size_t)g * P * 8, sw, h, N, P, sub, (long long)cl * cell_pts, ci, nullptr,
                           a.prep_far + (rs * sub + ci) * kFarTerms, a.prep_mask + rs * MWR);
+        if (ok && ci == 0)                                 // ... and the region's phase anchor
+            prep_item_anchor<R>(MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D, rl, N, a.prep_anchor + rs * 2);
     }
 }
 

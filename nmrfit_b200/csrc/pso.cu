@@ -237,29 +237,21 @@ swarm_finish_kernel(SwarmState s, const double* __restrict__ partials, int n_til
         const size_t bs = (size_t)b * s.S + i;
         // partial sums per tile (nw == 1) or per region, [n_tiles][nw] (the streamed kernel; nw = 4 or 8 divides 32):
         // the regions of a tile are added first, then the tiles
-        const int n_units = n_tiles * nw;
-        const double* p = partials + bs * n_units * nsum;
+        const double* p = partials + bs * n_tiles * nw * nsum;
         double sv = 0.0, sim = 0.0;
-        for (int t0 = 0; t0 < n_units; t0 += 32) {         // coalesced load, then the same sequential order as
-            const int t = t0 + lane;                       // objective_finalize_kernel (every lane sums all of them)
-            const double a0 = t < n_units ? p[t * nsum] : 0.0;
-            const double a1 = (nsum == 2 && t < n_units) ? p[t * nsum + 1] : 0.0;
-            const int cnt = min(32, n_units - t0);
-            if (nw == 1) {
-                for (int k = 0; k < cnt; ++k) {
-                    sv += __shfl_sync(0xffffffffu, a0, k);
-                    if (nsum == 2) sim += __shfl_sync(0xffffffffu, a1, k);
+        for (int t0 = 0; t0 < n_tiles; t0 += 32) {         // a lane per tile: its regions in order (in parallel over the
+            const int t = t0 + lane;                       // lanes), then the tiles in order - every lane sums all of
+            double a0 = 0.0, a1 = 0.0;                     // them, the same sequential order as objective_finalize_kernel
+            if (t < n_tiles) {
+                for (int w = 0; w < nw; ++w) {
+                    a0 += p[(t * nw + w) * nsum];
+                    if (nsum == 2) a1 += p[(t * nw + w) * nsum + 1];
                 }
-            } else {
-                for (int k = 0; k < cnt; k += nw) {
-                    double tv = 0.0, ti = 0.0;
-                    for (int w = 0; w < nw; ++w) {
-                        tv += __shfl_sync(0xffffffffu, a0, k + w);
-                        if (nsum == 2) ti += __shfl_sync(0xffffffffu, a1, k + w);
-                    }
-                    sv += tv;
-                    sim += ti;
-                }
+            }
+            const int cnt = min(32, n_tiles - t0);
+            for (int k = 0; k < cnt; ++k) {
+                sv += __shfl_sync(0xffffffffu, a0, k);
+                if (nsum == 2) sim += __shfl_sync(0xffffffffu, a1, k);
             }
         }
         double fx = sqrt(sv / (double)N);
