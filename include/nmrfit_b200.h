@@ -252,6 +252,31 @@ int nmrfit_phase_brute(nmrfit_phase* h, const double* p0_candidates, int K, doub
  * converts its degree arguments first, proc_autophase.py:60-62) -> score [n_spectra][K].  Host pointers. */
 int nmrfit_phase_acme(nmrfit_phase* h, const double* ph, int K, double* score);
 
+/* ---- automatic peak selection for a batch of spectra (csrc/peaks.cu) ------------------------------------------
+ * Replaces utils.AutoPeakSelector (utils.py:670-783; reached through Data.select_peaks('auto'), containers.py:159-161):
+ * linear upsampling onto np.linspace(w.min(), w.max(), upsample * n_points) (utils.py:711-714), Savitzky-Golay(11, 4)
+ * smoothing (:716), peakutils.baseline(., 0) (:718), scipy.signal.argrelmax with a window of `window` axis units (:728-733)
+ * and, per maximum, half-height crossings, +-2-width bounds, local baseline, height and Simpson area (:747-770).
+ *   maxima:  w, u [n_spectra][n_points] (host or device), w ASCENDING (interp1d sorts its input; the caller mirrors that).
+ *            sg_coeffs (nullable): 11 smoothing coefficients + the two [5][11] edge maps (tools/gen_sg.py).
+ *            Out: n_maxima [n_spectra]; maxima [n_spectra][max_peaks] upsampled indices in NO particular order; the
+ *            upsampled signal there; the global baseline [n_spectra].  NMRFIT_ERR_STATE if a spectrum has more.
+ *   measure: the caller sorts the maxima, forms height = uu - baseline, applies the threshold (utils.py:735-738) and hands
+ *            the survivors back: n_peaks [n_spectra], peak_i / peak_height [n_spectra][max_peaks].  Out, same shape:
+ *            ok (1 kept, 0 dropped by x_left < x_right at utils.py:755, -1 no crossing found: the reference raises),
+ *            loc, width, bounds [..][2], local_baseline, height, area, idx_range [..][2] (first / last sample in bounds).
+ *   probe:   upsampled axis, signal and smoothed signal of spectrum b at n indices (for tests). */
+typedef struct nmrfit_peaks nmrfit_peaks;
+int nmrfit_peaks_create(nmrfit_peaks** out, int device, int n_spectra, int n_points, int upsample, int max_peaks);
+void nmrfit_peaks_destroy(nmrfit_peaks* h);
+int nmrfit_peaks_maxima(nmrfit_peaks* h, const double* w, const double* u, double window, const double* sg_coeffs,
+                        int baseline_max_it, double baseline_tol, int* n_maxima, long long* maxima, double* uu_at_maxima,
+                        double* baseline);
+int nmrfit_peaks_measure(nmrfit_peaks* h, const int* n_peaks, const long long* peak_i, const double* peak_height,
+                         int baseline_max_it, double baseline_tol, int* ok, double* loc, double* width, double* bounds,
+                         double* local_baseline, double* height, double* area, long long* idx_range);
+int nmrfit_peaks_probe(nmrfit_peaks* h, int b, const long long* idx, int n, double* wu, double* uu, double* us);
+
 /* Page-locked host memory for result buffers: device-to-host copies into it run at PCIe speed and skip the page
  * faults of freshly allocated pageable memory (generate_result at scale 16 writes 109 MB).  The Python layer pools these. */
 int nmrfit_host_alloc(size_t bytes, void** out);

@@ -93,6 +93,11 @@ SIGNATURES = {
     'nmrfit_phase_destroy': (None, [_vp]),
     'nmrfit_phase_brute': (_i, [_vp, _vp, _i, _vp, _vp, _vp, _vp]),
     'nmrfit_phase_acme': (_i, [_vp, _vp, _i, _vp]),
+    'nmrfit_peaks_create': (_i, [ctypes.POINTER(_vp), _i, _i, _i, _i, _i]),
+    'nmrfit_peaks_destroy': (None, [_vp]),
+    'nmrfit_peaks_maxima': (_i, [_vp, _vp, _vp, _d, _vp, _i, _d, _vp, _vp, _vp, _vp]),
+    'nmrfit_peaks_measure': (_i, [_vp, _vp, _vp, _vp, _i, _d, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    'nmrfit_peaks_probe': (_i, [_vp, _i, _vp, _i, _vp, _vp, _vp]),
     'nmrfit_host_alloc': (_i, [ctypes.c_size_t, ctypes.POINTER(_vp)]),
     'nmrfit_host_free': (_i, [_vp]),
     'nmrfit_fp64_peak': (_i, [_i, _i, _i, c_double_p, c_double_p]),
@@ -448,6 +453,67 @@ class PhaseScorer:
         score = np.empty((self.B, ph.shape[0]))
         check(lib().nmrfit_phase_acme(self._h, ptr(ph), ph.shape[0], ptr(score)))
         return score
+
+
+class PeakPicker:
+    """Device side of the automatic peak selection for a batch of spectra (csrc/peaks.cu): ``maxima`` then ``measure``."""
+
+    def __init__(self, n_spectra, n_points, upsample=100, max_peaks=64, device=None):
+        self._h = ctypes.c_void_p()
+        self.B, self.N, self.upsample, self.max_peaks = int(n_spectra), int(n_points), int(upsample), int(max_peaks)
+        self.M = self.N * self.upsample
+        dev = default_device() if device is None else int(device)
+        check(lib().nmrfit_peaks_create(ctypes.byref(self._h), dev, self.B, self.N, self.upsample, self.max_peaks))
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            lib().nmrfit_peaks_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def maxima(self, w, u, window, sg_coeffs=None, max_it=100, tol=1e-3):
+        """-> (n_maxima [B], maxima [B, max_peaks] (unsorted upsampled indices), signal there, global baseline [B])"""
+        w, u = as_f64(np.atleast_2d(w)), as_f64(np.atleast_2d(u))
+        if w.shape != (self.B, self.N) or u.shape != (self.B, self.N):
+            raise ValueError('w and u must have shape (%d, %d)' % (self.B, self.N))
+        sg = None if sg_coeffs is None else as_f64(sg_coeffs)
+        if sg is not None and sg.size != 121:
+            raise ValueError('sg_coeffs must hold 11 + 2*5*11 values')
+        n = np.zeros(self.B, dtype=np.int32)
+        idx = np.zeros((self.B, self.max_peaks), dtype=np.int64)
+        val = np.zeros((self.B, self.max_peaks))
+        base = np.zeros(self.B)
+        check(lib().nmrfit_peaks_maxima(self._h, ptr(w), ptr(u), float(window), ptr(sg), int(max_it), float(tol), ptr(n),
+                                        ptr(idx), ptr(val), ptr(base)))
+        return n, idx, val, base
+
+    def measure(self, n_peaks, peak_i, peak_height, max_it=100, tol=1e-3):
+        n_peaks = np.ascontiguousarray(n_peaks, dtype=np.int32)
+        peak_i = np.ascontiguousarray(peak_i, dtype=np.int64)
+        peak_height = as_f64(peak_height)
+        shape = (self.B, self.max_peaks)
+        if peak_i.shape != shape or peak_height.shape != shape or n_peaks.shape != (self.B,):
+            raise ValueError('peak arrays must have shape %s' % (shape,))
+        out = dict(ok=np.zeros(shape, dtype=np.int32), loc=np.zeros(shape), width=np.zeros(shape), bounds=np.zeros(shape + (2,)),
+                   baseline=np.zeros(shape), height=np.zeros(shape), area=np.zeros(shape),
+                   idx_range=np.zeros(shape + (2,), dtype=np.int64))
+        check(lib().nmrfit_peaks_measure(self._h, ptr(n_peaks), ptr(peak_i), ptr(peak_height), int(max_it), float(tol),
+                                         *[ptr(out[k]) for k in ('ok', 'loc', 'width', 'bounds', 'baseline', 'height', 'area',
+                                                                 'idx_range')]))
+        return out
+
+    def probe(self, b, idx):
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        wu, uu, us = np.zeros(idx.size), np.zeros(idx.size), np.zeros(idx.size)
+        check(lib().nmrfit_peaks_probe(self._h, int(b), ptr(idx), idx.size, ptr(wu), ptr(uu), ptr(us)))
+        return wu, uu, us
 
 
 # ---- pinned result buffers --------------------------------------------------------------------------

@@ -4,9 +4,9 @@ roibounds``; ``shift_phase(method='manual', p0=, p1=)``; ``select_bounds(low, hi
 ``generate_solution_bounds``; ``approximate_areas``; ``approximate_area_fraction``.
 
 Phase estimation (``shift_phase(method='auto'|'brute')``, containers.py:71-74, 98-110) runs on
-the GPU (csrc/phase.cu).  Interactive or automatic peak picking (containers.py:132-173) is
-outside the accelerated path: it raises NotImplementedError
-here and peaks are attached with ``set_peaks``.
+the GPU (csrc/phase.cu), and so does automatic peak picking (``select_peaks('auto')``,
+containers.py:159-161 -> csrc/peaks.cu).  The interactive matplotlib selectors (containers.py:112-158)
+are outside the accelerated path: they raise NotImplementedError and peaks can be attached with ``set_peaks``.
 """
 import numpy as np
 
@@ -48,9 +48,17 @@ class Data:
         self.w, self.u, self.v = self.w[idx], self.u[idx], self.v[idx]
 
     def select_peaks(self, method='auto', n=None, one_click=False, thresh=0.0, window=0.02, plot=False):
-        raise NotImplementedError(
-            'peak picking is preprocessing outside the accelerated path; build Peak records '
-            '(loc, width, area, height, bounds) and attach them with Data.set_peaks')
+        """Automatic peak selection on the GPU (containers.py:159-161 -> utils.AutoPeakSelector on ``self.V``); the
+        interactive ``method='manual'`` selector of the reference is not provided."""
+        if method.lower() == 'manual':
+            raise NotImplementedError('interactive peak picking is not provided; attach Peak records with Data.set_peaks')
+        if method.lower() != 'auto':
+            raise ValueError("Method must be 'auto' or 'manual'.")
+        from . import utils
+        ps = utils.AutoPeakSelector(self.w, self.V, thresh=thresh, window=window)
+        ps.find_peaks()
+        self.peaks = ps.peaks
+        self.roibounds = [p.bounds for p in self.peaks]
 
     def set_peaks(self, peaks):
         from .utils import Peaks

@@ -124,6 +124,18 @@ struct nmrfit_phase {
     DevBuf<int> ok;
 };
 
+struct nmrfit_peaks {
+    int device = 0, B = 0, N = 0, upsample = 100, max_peaks = 0;
+    long long M = 0;
+    int nblk = 0;
+    DevBuf<double> w, u, uu, us, bmax, base, uu_at, pk_h, sg;
+    DevBuf<long long> maxima, pk_i, cross, probe_idx;
+    DevBuf<int> n_maxima, n_pk;
+    DevBuf<char> out;
+    DevBuf<double> probe_out;
+    bool ran = false;
+};
+
 namespace {
 
 // Is the axis uniform?  h = (w_last - w_0)/(N-1); every stored w_i within 4 ulp of w_0 + i*h.
@@ -1247,6 +1259,159 @@ int nmrfit_phase_acme(nmrfit_phase* h, const double* ph, int K, double* score) {
     cudaError_t e = launch_phase_acme(h->u.ptr, h->v.ptr, h->B, h->N, h->cands.ptr, K, h->out.ptr, nullptr);
     if (e != cudaSuccess) return fail_cuda(e, "ACME launch");
     CK(cudaMemcpy(score, h->out.ptr, sizeof(double) * BK, cudaMemcpyDeviceToHost));
+    return NMRFIT_OK;
+}
+
+// ---- auto peak selection --------------------------------------------------------------------------
+
+namespace {
+// scipy.signal.savgol_coeffs(11, 4) and the degree-4 edge fits of scipy's mode='interp' (first / last 11 samples ->
+// samples 0..4 / 6..10), as numpy computes them (tools/gen_sg.py); callers may pass their own
+const double kSgDefault[11 + 110] = {
+#include "sg_coeffs.inc"
+};
+}  // namespace
+
+int nmrfit_peaks_create(nmrfit_peaks** out, int device, int n_spectra, int n_points, int upsample, int max_peaks) {
+    if (!out) return fail(NMRFIT_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (n_spectra < 1 || n_points < 2 || upsample < 1 || max_peaks < 1) return fail(NMRFIT_ERR_ARG, "bad peak-selector arguments");
+    if ((long long)n_points * upsample < 11) return fail(NMRFIT_ERR_ARG, "the upsampled axis needs at least 11 samples (Savitzky-Golay window)");
+    int ndev = 0;
+    CK(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) return fail(NMRFIT_ERR_ARG, "no such CUDA device");
+    CK(cudaSetDevice(device));
+    nmrfit_peaks* h = new (std::nothrow) nmrfit_peaks();
+    if (!h) return fail(NMRFIT_ERR_NOMEM, "out of host memory");
+    h->device = device; h->B = n_spectra; h->N = n_points; h->upsample = upsample; h->max_peaks = max_peaks;
+    h->M = (long long)n_points * upsample;
+    h->nblk = (int)((h->M + 1023) / 1024);
+    const size_t BN = (size_t)n_spectra * n_points, BM = (size_t)n_spectra * h->M, BK = (size_t)n_spectra * max_peaks;
+    cudaError_t e = h->w.reserve(BN);
+    if (e == cudaSuccess) e = h->u.reserve(BN);
+    if (e == cudaSuccess) e = h->uu.reserve(BM);
+    if (e == cudaSuccess) e = h->us.reserve(BM);
+    if (e == cudaSuccess) e = h->bmax.reserve((size_t)n_spectra * h->nblk);
+    if (e == cudaSuccess) e = h->base.reserve(n_spectra);
+    if (e == cudaSuccess) e = h->uu_at.reserve(BK);
+    if (e == cudaSuccess) e = h->pk_h.reserve(BK);
+    if (e == cudaSuccess) e = h->sg.reserve(121);
+    if (e == cudaSuccess) e = h->maxima.reserve(BK);
+    if (e == cudaSuccess) e = h->pk_i.reserve(BK);
+    if (e == cudaSuccess) e = h->cross.reserve(2 * BK);
+    if (e == cudaSuccess) e = h->n_maxima.reserve(n_spectra);
+    if (e == cudaSuccess) e = h->n_pk.reserve(n_spectra);
+    if (e == cudaSuccess) e = h->out.reserve(BK * peaks_out_bytes());
+    if (e != cudaSuccess) {
+        nmrfit_peaks_destroy(h);
+        return fail_cuda(e, "peak-selector allocation");
+    }
+    *out = h;
+    return NMRFIT_OK;
+}
+
+void nmrfit_peaks_destroy(nmrfit_peaks* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (DevBuf<double>* b : {&h->w, &h->u, &h->uu, &h->us, &h->bmax, &h->base, &h->uu_at, &h->pk_h, &h->sg, &h->probe_out})
+        b->release();
+    for (DevBuf<long long>* b : {&h->maxima, &h->pk_i, &h->cross, &h->probe_idx}) b->release();
+    h->n_maxima.release(); h->n_pk.release(); h->out.release();
+    delete h;
+}
+
+int nmrfit_peaks_maxima(nmrfit_peaks* h, const double* w, const double* u, double window, const double* sg_coeffs,
+                        int baseline_max_it, double baseline_tol, int* n_maxima, long long* maxima, double* uu_at_maxima,
+                        double* baseline) {
+    if (!h) return fail(NMRFIT_ERR_ARG, "handle is NULL");
+    if (!w || !u || !n_maxima || !maxima || !uu_at_maxima || !baseline) return fail(NMRFIT_ERR_ARG, "NULL argument");
+    if (baseline_max_it < 1 || !(baseline_tol > 0.0)) return fail(NMRFIT_ERR_ARG, "bad baseline iteration arguments");
+    CK(cudaSetDevice(h->device));
+    const size_t BN = (size_t)h->B * h->N, BK = (size_t)h->B * h->max_peaks;
+    CK(cudaMemcpy(h->w.ptr, w, sizeof(double) * BN, cudaMemcpyDefault));
+    CK(cudaMemcpy(h->u.ptr, u, sizeof(double) * BN, cudaMemcpyDefault));
+    // the axis must ascend (interp1d sorts; the caller mirrors that) and the window is in its units
+    std::vector<double> ends(2 * (size_t)h->B);
+    CK(cudaMemcpy2D(ends.data(), 2 * sizeof(double), h->w.ptr, sizeof(double) * h->N, sizeof(double), h->B, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy2D(ends.data() + 1, 2 * sizeof(double), h->w.ptr + (h->N - 1), sizeof(double) * h->N, sizeof(double), h->B,
+                    cudaMemcpyDeviceToHost));
+    long long order = -1;
+    for (int b = 0; b < h->B; ++b) {
+        const double start = ends[2 * b], stop = ends[2 * b + 1];
+        if (!(stop > start)) return fail(NMRFIT_ERR_ARG, "w must be ascending (sort it as scipy's interp1d would)");
+        // utils.py:728-729: x_spacing = w[1] - w[0] of the upsampled axis; window = int(window / x_spacing)
+        const double step = (stop - start) / (double)(h->M - 1);
+        const double w1 = h->M == 2 ? stop : 1.0 * step + start;
+        const long long ob = (long long)(window / (w1 - start));
+        if (order < 0) order = ob;
+        else if (ob != order) return fail(NMRFIT_ERR_ARG, "every spectrum of a batch must give the same window in samples");
+    }
+    if (order < 1) return fail(NMRFIT_ERR_ARG, "window is shorter than one upsampled sample");      // scipy: order >= 1
+    CK(cudaMemcpy(h->sg.ptr, sg_coeffs ? sg_coeffs : kSgDefault, sizeof(double) * 121, cudaMemcpyHostToDevice));
+    std::vector<double> sg(121);
+    std::memcpy(sg.data(), sg_coeffs ? sg_coeffs : kSgDefault, sizeof(double) * 121);
+    cudaError_t e = launch_peaks_front(h->w.ptr, h->u.ptr, h->B, h->N, h->M, sg.data(), h->uu.ptr, h->us.ptr, h->bmax.ptr,
+                                       h->nblk, h->base.ptr, baseline_max_it, baseline_tol, order, h->max_peaks,
+                                       h->maxima.ptr, h->n_maxima.ptr, h->uu_at.ptr, nullptr);
+    if (e != cudaSuccess) return fail_cuda(e, "peak-selector front launch");
+    CK(cudaMemcpy(n_maxima, h->n_maxima.ptr, sizeof(int) * h->B, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(maxima, h->maxima.ptr, sizeof(long long) * BK, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(uu_at_maxima, h->uu_at.ptr, sizeof(double) * BK, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(baseline, h->base.ptr, sizeof(double) * h->B, cudaMemcpyDeviceToHost));
+    for (int b = 0; b < h->B; ++b)
+        if (n_maxima[b] > h->max_peaks)
+            return fail(NMRFIT_ERR_STATE, "more maxima than max_peaks in spectrum " + std::to_string(b) + " (" +
+                                          std::to_string(n_maxima[b]) + "): raise max_peaks or the window");
+    h->ran = true;
+    return NMRFIT_OK;
+}
+
+int nmrfit_peaks_measure(nmrfit_peaks* h, const int* n_peaks, const long long* peak_i, const double* peak_height,
+                         int baseline_max_it, double baseline_tol, int* ok, double* loc, double* width, double* bounds,
+                         double* local_baseline, double* height, double* area, long long* idx_range) {
+    if (!h) return fail(NMRFIT_ERR_ARG, "handle is NULL");
+    if (!h->ran) return fail(NMRFIT_ERR_STATE, "nmrfit_peaks_maxima has not been called");
+    if (!n_peaks || !peak_i || !peak_height || !ok || !loc || !width || !bounds || !local_baseline || !height || !area || !idx_range)
+        return fail(NMRFIT_ERR_ARG, "NULL argument");
+    CK(cudaSetDevice(h->device));
+    const size_t BK = (size_t)h->B * h->max_peaks;
+    for (int b = 0; b < h->B; ++b)
+        if (n_peaks[b] < 0 || n_peaks[b] > h->max_peaks) return fail(NMRFIT_ERR_ARG, "n_peaks out of range");
+    CK(cudaMemcpy(h->n_pk.ptr, n_peaks, sizeof(int) * h->B, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->pk_i.ptr, peak_i, sizeof(long long) * BK, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->pk_h.ptr, peak_height, sizeof(double) * BK, cudaMemcpyHostToDevice));
+    CK(cudaMemset(h->out.ptr, 0, BK * peaks_out_bytes()));
+    cudaError_t e = launch_peaks_back(h->w.ptr, h->uu.ptr, h->B, h->N, h->M, h->base.ptr, h->pk_i.ptr, h->pk_h.ptr, h->n_pk.ptr,
+                                      h->max_peaks, h->cross.ptr, baseline_max_it, baseline_tol, h->out.ptr, nullptr);
+    if (e != cudaSuccess) return fail_cuda(e, "peak-selector back launch");
+    struct PeakOutHost { double loc, width, b0, b1, baseline, height, area; long long lo, hi; int ok; int pad; };
+    static_assert(sizeof(PeakOutHost) == 80, "PeakOut layout");
+    if (peaks_out_bytes() != sizeof(PeakOutHost)) return fail(NMRFIT_ERR_STATE, "PeakOut layout mismatch");
+    std::vector<PeakOutHost> res(BK);
+    CK(cudaMemcpy(res.data(), h->out.ptr, BK * sizeof(PeakOutHost), cudaMemcpyDeviceToHost));
+    for (size_t q = 0; q < BK; ++q) {
+        ok[q] = res[q].ok; loc[q] = res[q].loc; width[q] = res[q].width; bounds[2 * q] = res[q].b0; bounds[2 * q + 1] = res[q].b1;
+        local_baseline[q] = res[q].baseline; height[q] = res[q].height; area[q] = res[q].area;
+        idx_range[2 * q] = res[q].lo; idx_range[2 * q + 1] = res[q].hi;
+    }
+    return NMRFIT_OK;
+}
+
+int nmrfit_peaks_probe(nmrfit_peaks* h, int b, const long long* idx, int n, double* wu, double* uu, double* us) {
+    if (!h) return fail(NMRFIT_ERR_ARG, "handle is NULL");
+    if (!h->ran) return fail(NMRFIT_ERR_STATE, "nmrfit_peaks_maxima has not been called");
+    if (b < 0 || b >= h->B || n < 1 || !idx || !wu || !uu || !us) return fail(NMRFIT_ERR_ARG, "bad probe arguments");
+    for (int k = 0; k < n; ++k)
+        if (idx[k] < 0 || idx[k] >= h->M) return fail(NMRFIT_ERR_ARG, "probe index out of range");
+    CK(cudaSetDevice(h->device));
+    CK(h->probe_idx.reserve(n));
+    CK(h->probe_out.reserve(3 * (size_t)n));
+    CK(cudaMemcpy(h->probe_idx.ptr, idx, sizeof(long long) * n, cudaMemcpyHostToDevice));
+    cudaError_t e = launch_peaks_probe(h->w.ptr, h->N, h->M, h->uu.ptr, h->us.ptr, b, h->probe_idx.ptr, n, h->probe_out.ptr, nullptr);
+    if (e != cudaSuccess) return fail_cuda(e, "peak-selector probe launch");
+    CK(cudaMemcpy(wu, h->probe_out.ptr, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(uu, h->probe_out.ptr + n, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(us, h->probe_out.ptr + 2 * (size_t)n, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return NMRFIT_OK;
 }
 

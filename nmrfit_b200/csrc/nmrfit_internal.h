@@ -181,6 +181,20 @@ cudaError_t launch_phase_brute(const double* u, const double* v, int B, int N, c
 cudaError_t launch_phase_acme(const double* u, const double* v, int B, int N, const double* ph_dev, int K, double* score,
                               cudaStream_t st);
 
+// ---- K10 auto peak selection (peaks.cu) ----------------------------------------------
+// front: upsample, smooth, global baseline, maxima (unsorted indices + the upsampled signal there);
+// back: per accepted maximum the half-height crossings, local baseline, height, Simpson area
+cudaError_t launch_peaks_front(const double* w, const double* u, int B, int N, long long M, const double* sg,
+                               double* uu, double* us, double* bmax, int nblk, double* base, int max_it, double tol,
+                               long long order, int max_out, long long* maxima, int* n_maxima, double* uu_at_maxima,
+                               cudaStream_t st);
+cudaError_t launch_peaks_back(const double* w, const double* uu, int B, int N, long long M, const double* base,
+                              const long long* pk_i, const double* pk_h, const int* n_pk, int max_peaks, long long* cross,
+                              int max_it, double tol, void* out, cudaStream_t st);
+cudaError_t launch_peaks_probe(const double* w, int N, long long M, const double* uu, const double* us, int b,
+                               const long long* idx, int n, double* out, cudaStream_t st);
+size_t peaks_out_bytes();
+
 // ---- K4/K5 curves -------------------------------------------------------------
 cudaError_t launch_ps2(const double* u, const double* v, int n, double p0, double p1, int inv, double* re, double* im,
                        cudaStream_t st);

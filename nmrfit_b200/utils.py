@@ -4,10 +4,10 @@
 (utils.py:96-339); what changes is underneath: the swarm lives on the GPU and a
 generation is one batched launch instead of ``swarmsize`` Python callbacks.
 
-``Peak`` / ``Peaks`` are the plain records the driver reads (utils.py:14-93).  The
-interactive selectors of the reference (BoundsSelector, PeakSelector,
-AutoPeakSelector: utils.py:342-816) are outside the accelerated path and are not
-provided.
+``Peak`` / ``Peaks`` are the plain records the driver reads (utils.py:14-93).
+``AutoPeakSelector`` (utils.py:670-783) and its batched form ``select_peaks_batch`` run on the GPU
+(csrc/peaks.cu).  The interactive, matplotlib-driven selectors of the reference (BoundsSelector,
+PeakSelector: utils.py:342-667) are outside the accelerated path and are not provided.
 """
 import numpy as np
 
@@ -195,3 +195,125 @@ class FitUtility:
         print('\nPeak parameters')
         print(res_peaks.to_string(index=False))
         print("Error:\t", self.error)
+
+
+# ---- automatic peak selection (utils.py:670-783) on the GPU ----------------------------------------------------
+_SG_TABLES = None
+
+
+def _sg_tables():
+    """Savitzky-Golay(11, 4) coefficients and edge maps handed to the device: scipy's own when scipy is importable
+    (what the reference would compute: utils.py:716), else the library's built-in copy (None)."""
+    global _SG_TABLES
+    if _SG_TABLES is None:
+        try:
+            import scipy.signal
+            c = scipy.signal.savgol_coeffs(11, 4)
+            pinv = np.linalg.pinv(np.vander(np.arange(11.0), 5))
+            left = np.vander(np.arange(0, 5.0), 5) @ pinv
+            right = np.vander(np.arange(6, 11.0), 5) @ pinv
+            _SG_TABLES = (np.concatenate([c, left.ravel(), right.ravel()]),)
+        except ImportError:
+            _SG_TABLES = (None,)
+    return _SG_TABLES[0]
+
+
+def _ascending(w, u):
+    """interp1d sorts its abscissae (stable argsort) before interpolating (utils.py:711): mirror it on the host."""
+    w, u = _cabi.as_f64(w), _cabi.as_f64(u)
+    if w.size > 1 and np.all(w[1:] > w[:-1]):
+        return w, u
+    ind = np.argsort(w, kind='mergesort')
+    return np.ascontiguousarray(w[ind]), np.ascontiguousarray(u[ind])
+
+
+def select_peaks_batch(ws, us, thresh=0.0, window=0.02, upsample=100, max_peaks=64, device=None, details=False):
+    """``AutoPeakSelector(w, u, thresh, window).find_peaks()`` for every spectrum of a batch in one pass on the GPU.
+
+    ``ws``, ``us``: [B, N] (or [N]) axis and phased real part of each spectrum.  Returns a list of ``Peaks`` (one per
+    spectrum; ``Peak`` records with ``loc, i, height, width, bounds, baseline, area, idx``), or with ``details`` also the
+    global baselines and the maxima before the width screen.  Raises ValueError where the reference does (a maximum
+    without a half-height crossing of either kind: utils.py:752-753 take the argmin of an empty sequence)."""
+    ws, us = np.atleast_2d(np.asarray(ws, dtype=np.float64)), np.atleast_2d(np.asarray(us, dtype=np.float64))
+    if ws.shape != us.shape:
+        raise ValueError('ws and us must have the same shape')
+    B, N = ws.shape
+    rows = [_ascending(ws[b], us[b]) for b in range(B)]
+    W = np.ascontiguousarray(np.stack([r[0] for r in rows]))
+    U = np.ascontiguousarray(np.stack([r[1] for r in rows]))
+    with _cabi.PeakPicker(B, N, upsample=upsample, max_peaks=max_peaks, device=device) as pk:
+        n_max, idx, val, base = pk.maxima(W, U, window, sg_coeffs=_sg_tables())
+        n_keep = np.zeros(B, dtype=np.int32)
+        keep_i = np.zeros((B, max_peaks), dtype=np.int64)
+        keep_h = np.zeros((B, max_peaks))
+        pre = []
+        for b in range(B):
+            order = np.argsort(idx[b, :n_max[b]])            # argrelmax returns ascending indices (utils.py:731)
+            i_b, h_b = idx[b, :n_max[b]][order], val[b, :n_max[b]][order] - base[b]      # :737
+            sel = h_b > thresh                              # :738
+            n_keep[b] = int(sel.sum())
+            keep_i[b, :n_keep[b]], keep_h[b, :n_keep[b]] = i_b[sel], h_b[sel]
+            pre.append((i_b[sel], h_b[sel]))
+        out = pk.measure(n_keep, keep_i, keep_h)
+    result = []
+    for b in range(B):
+        peaks = Peaks()
+        for k in range(n_keep[b]):
+            if out['ok'][b, k] < 0:
+                raise ValueError('attempt to get argmin of an empty sequence')       # as the reference does here
+            if out['ok'][b, k] == 0:
+                continue                                    # utils.py:755: x_left >= x_right, the peak is dropped
+            p = Peak()
+            p.loc, p.i = float(out['loc'][b, k]), int(keep_i[b, k])
+            p.width = float(out['width'][b, k])
+            p.bounds = [float(out['bounds'][b, k, 0]), float(out['bounds'][b, k, 1])]
+            lo, hi = (int(t) for t in out['idx_range'][b, k])
+            p.idx = (np.arange(lo, hi + 1),)                # what np.where returns (utils.py:763)
+            p.baseline = float(out['baseline'][b, k])
+            p.height = float(out['height'][b, k])
+            p.area = float(out['area'][b, k])
+            peaks.append(p)
+        result.append(peaks)
+    if details:
+        return result, dict(baseline=base, pre=pre)
+    return result
+
+
+class AutoPeakSelector:
+    """Drop-in for the reference's AutoPeakSelector (utils.py:670-783) with the arithmetic on the GPU: same constructor,
+    ``find_maxima`` / ``find_width`` / ``find_peaks``, ``peaks`` and ``baseline`` attributes.  The upsampled arrays
+    (``w``, ``u``, ``u_smoothed``: 100x the input, utils.py:713-716) stay on the device; ``plot`` is not provided."""
+
+    def __init__(self, w, u, thresh, window):
+        self.thresh = thresh
+        self.window = window
+        self._w, self._u = np.asarray(w, dtype=np.float64), np.asarray(u, dtype=np.float64)
+        self.peaks = Peaks()
+        self.baseline = None
+        self._found = None
+
+    def _run(self):
+        if self._found is None:
+            peaks, aux = select_peaks_batch(self._w[None], self._u[None], self.thresh, self.window, details=True)
+            self._found = peaks[0]
+            self.baseline = float(aux['baseline'][0])
+            self._pre = aux['pre'][0]
+
+    def find_maxima(self):
+        self._run()
+        w_lo, w_hi, M = self._w.min(), self._w.max(), self._w.size * 100
+        step = (w_hi - w_lo) / (M - 1)
+        self.peaks = Peaks()
+        for i, h in zip(*self._pre):
+            p = Peak()
+            p.i, p.height = int(i), float(h)
+            p.loc = float(w_hi if i == M - 1 else i * step + w_lo)     # np.linspace's own expression (utils.py:713)
+            self.peaks.append(p)
+
+    def find_width(self):
+        self._run()
+        self.peaks = self._found
+
+    def find_peaks(self):
+        self.find_maxima()
+        self.find_width()

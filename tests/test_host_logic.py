@@ -74,7 +74,9 @@ def test_data_contract():
     with pytest.raises(ValueError):
         d.shift_phase('nonsense')
     with pytest.raises(NotImplementedError):
-        d.select_peaks()
+        d.select_peaks(method='manual', n=6)                 # the interactive selector is not provided
+    with pytest.raises(ValueError):
+        d.select_peaks(method='nonsense')
 
 
 def test_fit_im_identity_semantics():
