@@ -122,14 +122,20 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
         }
         __syncthreads();
     }
-    // ---- phase 1: per particle the phase table (from the far end of the CTA) and P span coefficients
-    const int per = P + kTableItems;
+    // ---- phase 1: per particle P span coefficients + the phase table + NRP anchors
+    const int per = P + kTableItems + NRP;
     for (int e = tid; e < ng * per; e += nthreads) {
-        const int q = ng * per - 1 - e;                    // the heavy items (sincos) first
-        const int g = q / per, it = q - g * per;
+        const int g = e / per, it = e - g * per;
         const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
-        if (it < P) prep_item_coef<R>(xs, it, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8);
-        else prep_item_table<R>(xs, it - P, N, P, a.prep_part + (ps0 + g) * kPartDoubles);
+        if (it < P) {
+            prep_item_coef<R>(xs, it, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8);
+        } else if (it < P + kTableItems) {
+            prep_item_table<R>(xs, it - P, N, P, a.prep_part + (ps0 + g) * kPartDoubles);
+        } else {
+            const int rl = it - P - kTableItems;
+            const RegionDst rd(a, b, s0 + g, NRP);
+            prep_item_anchor<R>(xs, rl, N, a.prep_anchor + rd.region(rl) * 2);
+        }
     }
     __syncthreads();
     // ---- phase 2: the far-field cells of all ng particles, whole warps (prep_item_cell shuffles)
@@ -144,8 +150,6 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
         const size_t rs = rd.region(rl);
         prep_item_cell<R>(ok, cs + (size_t)g * P * 8, sw, h, N, P, sub, (long long)cl * cell_pts, ci, nullptr,
                           a.prep_far + (rs * sub + ci) * kFarTerms, a.prep_mask + rs * MWR);
-        if (ok && ci == 0)                                 // ... and the region's phase anchor
-            prep_item_anchor<R>(MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D, rl, N, a.prep_anchor + rs * 2);
     }
 }
 
