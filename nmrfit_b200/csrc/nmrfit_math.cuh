@@ -159,7 +159,7 @@ NMRFIT_HD double dawson(double s, const double* __restrict__ core, const double*
         for (int i = NMRFIT_DAW_DEG - 1; i >= 0; --i) p = NMRFIT_FMA(p, t, c[i]);
         res = p;
     } else {
-        double inv = 1.0 / as;
+        double inv = rcp_pos(as);                          // as >= 8: MUFU seed + cubic correction, no IEEE division
         double y = inv * inv - NMRFIT_DAW_TAIL_MID;
         double p = tail[NMRFIT_DAW_TAIL_DEG];
 #pragma unroll
