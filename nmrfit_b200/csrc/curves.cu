@@ -11,6 +11,8 @@
 // generate_result is bound by HBM writes: (2P + 4) doubles out and 1 double in per
 // grid point ((2*24+5)*8 B * 262,144 = 111 MB at BASELINE config 5).
 #include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdlib>
 #include "nmrfit_internal.h"
 #include "nmrfit_math.cuh"
 
@@ -67,7 +69,9 @@ constexpr int kGenMaxPeaks = 256;
 constexpr int kGenInlinePeaks = 64;
 struct GenParams { double v[4 + 3 * kGenInlinePeaks]; };
 
-template <bool INLINE>
+// PPT = 2: a thread owns two neighbouring points and stores them as one 16-byte word per plane (the planes are
+// 16-byte aligned for even n: checked by the launcher) - half the store instructions for the same bytes.
+template <bool INLINE, int PPT>
 __global__ void __launch_bounds__(kGenThreads)
 generate_result_kernel(const GenParams gp, const double* __restrict__ params_dev, int P, const double* __restrict__ w,
                        int n, double* __restrict__ real, double* __restrict__ imag, double* __restrict__ V,
@@ -83,37 +87,57 @@ generate_result_kernel(const GenParams gp, const double* __restrict__ params_dev
         o[0] = c.loc; o[1] = c.aL; o[2] = c.aG; o[3] = c.aG * kTwoOverSqrtPi; o[4] = iw; o[5] = iw * kSqrtLn2; o[6] = 0; o[7] = 0;
     }
     __syncthreads();
-    int i = blockIdx.x * kGenThreads + threadIdx.x;
-    if (i >= n) return;
-    const double wi = w[i];
-    double vs = 0.0, is = 0.0;
+    const int i0 = (blockIdx.x * kGenThreads + threadIdx.x) * PPT;
+    if (i0 >= n) return;
+    double wi[PPT], vs[PPT], is[PPT];
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        wi[q] = i0 + q < n ? w[i0 + q] : w[n - 1];
+        vs[q] = 0.0;
+        is[q] = 0.0;
+    }
+    const bool pair = PPT == 2 && i0 + 1 < n;
     for (int k = 0; k < P; ++k) {
         // one reciprocal serves the Lorentzian and its dispersion counterpart; the Gaussian is evaluated only within
         // 6.5 units of s of the centre (beyond: < 4.5e-19 of its height, below half an ulp of anything it is added
-        // to) - a warp's 32 neighbouring points are on the same side of that cut almost everywhere, so the branch is
+        // to) - a warp's neighbouring points are on the same side of that cut almost everywhere, so the branch is
         // uniform; Dawson's integral keeps its full range (its tail decays only as 1/s)
         const double2 c01 = *reinterpret_cast<const double2*>(sm + k * 8);        // loc, aL
         const double2 c23 = *reinterpret_cast<const double2*>(sm + k * 8 + 2);    // aG, aG * 2/sqrt(pi)
         const double2 c45 = *reinterpret_cast<const double2*>(sm + k * 8 + 4);    // kL, kG
-        const double d = wi - c01.x;
-        const double t = d * c45.x, s = d * c45.y;
-        const double rq = rcp_pos(fma(t, t, 1.0));
-        const double lor = c01.y * rq;
-        double body = lor;
-        if (fabs(s) <= kGaussCut) body = fma(c23.x, exp_neg<0>(-(s * s), nullptr), lor);
-        const double re = yoff + body;               // utils.py:267: every contribution carries yoff
-        const double im = fma(lor, t, c23.y * dawson(s, NMRFIT_DAW_TAB, NMRFIT_DAW_TAIL));
-        real[(size_t)k * n + i] = re;
-        imag[(size_t)k * n + i] = im;
-        vs += re;                                    // utils.py:276-277: both sums accumulate
-        is += im;
+        double re[PPT], im[PPT];
+#pragma unroll
+        for (int q = 0; q < PPT; ++q) {
+            const double d = wi[q] - c01.x;
+            const double t = d * c45.x, s = d * c45.y;
+            const double rq = rcp_pos(fma(t, t, 1.0));
+            const double lor = c01.y * rq;
+            double body = lor;
+            if (fabs(s) <= kGaussCut) body = fma(c23.x, exp_neg<0>(-(s * s), nullptr), lor);
+            re[q] = yoff + body;                     // utils.py:267: every contribution carries yoff
+            im[q] = fma(lor, t, c23.y * dawson(s, NMRFIT_DAW_TAB, NMRFIT_DAW_TAIL));
+            vs[q] += re[q];                          // utils.py:276-277: both sums accumulate
+            is[q] += im[q];
+        }
+        if (PPT == 2 && pair) {
+            *reinterpret_cast<double2*>(real + (size_t)k * n + i0) = make_double2(re[0], re[PPT - 1]);
+            *reinterpret_cast<double2*>(imag + (size_t)k * n + i0) = make_double2(im[0], im[PPT - 1]);
+        } else {
+            real[(size_t)k * n + i0] = re[0];
+            imag[(size_t)k * n + i0] = im[0];
+        }
     }
-    V[i] = vs;
-    I[i] = is;
-    double sn, cs;
-    sincos(p0 + (p1 * (double)i) / (double)n, &sn, &cs);   // utils.py:284: ramp over the UPSAMPLED length
-    u[i] = vs * cs + is * sn;
-    v[i] = is * cs - vs * sn;
+#pragma unroll
+    for (int q = 0; q < PPT; ++q) {
+        const int i = i0 + q;
+        if (i >= n) break;
+        V[i] = vs[q];
+        I[i] = is[q];
+        double sn, cs;
+        sincos(p0 + (p1 * (double)i) / (double)n, &sn, &cs);   // utils.py:284: ramp over the UPSAMPLED length
+        u[i] = vs[q] * cs + is[q] * sn;
+        v[i] = is[q] * cs - vs[q] * sn;
+    }
 }
 
 cudaError_t launch_ps2(const double* u, const double* v, int n, double p0, double p1, int inv, double* re, double* im,
@@ -147,12 +171,17 @@ cudaError_t launch_generate_result(const double* params_host, int P, const doubl
     if (P > kGenMaxPeaks) return cudaErrorInvalidValue;
     count_launches(1);
     const int D = 4 + 3 * P;
-    const unsigned grid = (n + kGenThreads - 1) / kGenThreads;
+    // two points per thread when every plane keeps its 16-byte alignment (even n, aligned bases)
+    static const int ppt_env = [] { const char* e = getenv("NMRFIT_GEN_PPT"); return e ? atoi(e) : 0; }();
+    const bool aligned = n % 2 == 0 && ((uintptr_t)real % 16 == 0) && ((uintptr_t)imag % 16 == 0);
+    const int ppt = (ppt_env == 1 || !aligned) ? 1 : 2;
+    const unsigned grid = (n + kGenThreads * ppt - 1) / (kGenThreads * ppt);
     const size_t smem = (size_t)P * 8 * sizeof(double);
     if (P <= kGenInlinePeaks) {
         GenParams gp;
         for (int d = 0; d < D; ++d) gp.v[d] = params_host[d];
-        generate_result_kernel<true><<<grid, kGenThreads, smem, st>>>(gp, nullptr, P, w, n, real, imag, V, I, u, v);
+        if (ppt == 2) generate_result_kernel<true, 2><<<grid, kGenThreads, smem, st>>>(gp, nullptr, P, w, n, real, imag, V, I, u, v);
+        else generate_result_kernel<true, 1><<<grid, kGenThreads, smem, st>>>(gp, nullptr, P, w, n, real, imag, V, I, u, v);
         return cudaGetLastError();
     }
     double* pd = nullptr;
@@ -161,7 +190,8 @@ cudaError_t launch_generate_result(const double* params_host, int P, const doubl
     e = cudaMemcpyAsync(pd, params_host, sizeof(double) * D, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         GenParams gp{};
-        generate_result_kernel<false><<<grid, kGenThreads, smem, st>>>(gp, pd, P, w, n, real, imag, V, I, u, v);
+        if (ppt == 2) generate_result_kernel<false, 2><<<grid, kGenThreads, smem, st>>>(gp, pd, P, w, n, real, imag, V, I, u, v);
+        else generate_result_kernel<false, 1><<<grid, kGenThreads, smem, st>>>(gp, pd, P, w, n, real, imag, V, I, u, v);
         e = cudaGetLastError();
     }
     cudaFreeAsync(pd, st);
