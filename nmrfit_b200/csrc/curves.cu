@@ -61,25 +61,30 @@ __global__ void kk_kernel(const double* __restrict__ w, int n, double r, double 
     out[i] = body_imag(c, iw, iw * kSqrtLn2, w[i]);
 }
 
-// one thread per grid point, all peaks; every store is coalesced along the grid.  The D parameters travel as
-// a kernel argument when they fit (up to kGenInlinePeaks peaks: no allocation, no copy, nothing to wait for
-// on the host); larger fits read them from `params_dev`.
-constexpr int kGenThreads = 256;
+// A CTA of 256 threads covers kGenPoints consecutive grid points x kGenGroups groups of peaks: thread (x, y) evaluates
+// the peaks k = y, y + kGenGroups, ... at point x.  Splitting the peaks over threads quarters every thread's serial
+// chain and quadruples the warps in flight (262,144 points x 24 peaks is only one wave of one-thread-per-point CTAs:
+// the first version spent its 34 us on latency, not on its 111 MB of stores).  The groups' partial sums of V and I
+// meet in shared memory and are added in group order.  Every store is coalesced along the grid.  The D parameters
+// travel as a kernel argument when they fit (up to kGenInlinePeaks peaks: no allocation, no copy, nothing to wait
+// for on the host); larger fits read them from `params_dev`.
+constexpr int kGenPoints = 64;
+constexpr int kGenGroups = 4;
+constexpr int kGenThreads = kGenPoints * kGenGroups;
 constexpr int kGenMaxPeaks = 256;
 constexpr int kGenInlinePeaks = 64;
 struct GenParams { double v[4 + 3 * kGenInlinePeaks]; };
 
-// PPT = 2: a thread owns two neighbouring points and stores them as one 16-byte word per plane (the planes are
-// 16-byte aligned for even n: checked by the launcher) - half the store instructions for the same bytes.
-template <bool INLINE, int PPT>
+template <bool INLINE>
 __global__ void __launch_bounds__(kGenThreads)
 generate_result_kernel(const GenParams gp, const double* __restrict__ params_dev, int P, const double* __restrict__ w,
                        int n, double* __restrict__ real, double* __restrict__ imag, double* __restrict__ V,
                        double* __restrict__ I, double* __restrict__ u, double* __restrict__ v) {
-    extern __shared__ __align__(16) double sm[];   // [P][8]
+    extern __shared__ __align__(16) double sm[];   // [P][8], then the groups' partial sums [2][kGenGroups][kGenPoints]
     const double* params = INLINE ? gp.v : params_dev;
     const double p0 = params[0], p1 = params[1], r = params[2], yoff = params[3];
-    for (int k = threadIdx.x; k < P; k += kGenThreads) {
+    const int tid = threadIdx.x, x = tid % kGenPoints, y = tid / kGenPoints;
+    for (int k = tid; k < P; k += kGenThreads) {
         double width = params[4 + 3 * k], loc = params[5 + 3 * k], a = params[6 + 3 * k];
         PeakCoef c = make_coef(r, width, loc, a);
         double iw = 2.0 / width;
@@ -87,57 +92,51 @@ generate_result_kernel(const GenParams gp, const double* __restrict__ params_dev
         o[0] = c.loc; o[1] = c.aL; o[2] = c.aG; o[3] = c.aG * kTwoOverSqrtPi; o[4] = iw; o[5] = iw * kSqrtLn2; o[6] = 0; o[7] = 0;
     }
     __syncthreads();
-    const int i0 = (blockIdx.x * kGenThreads + threadIdx.x) * PPT;
-    if (i0 >= n) return;
-    double wi[PPT], vs[PPT], is[PPT];
-#pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-        wi[q] = i0 + q < n ? w[i0 + q] : w[n - 1];
-        vs[q] = 0.0;
-        is[q] = 0.0;
-    }
-    const bool pair = PPT == 2 && i0 + 1 < n;
-    for (int k = 0; k < P; ++k) {
-        // one reciprocal serves the Lorentzian and its dispersion counterpart; the Gaussian is evaluated only within
-        // 6.5 units of s of the centre (beyond: < 4.5e-19 of its height, below half an ulp of anything it is added
-        // to) - a warp's neighbouring points are on the same side of that cut almost everywhere, so the branch is
-        // uniform; Dawson's integral keeps its full range (its tail decays only as 1/s)
-        const double2 c01 = *reinterpret_cast<const double2*>(sm + k * 8);        // loc, aL
-        const double2 c23 = *reinterpret_cast<const double2*>(sm + k * 8 + 2);    // aG, aG * 2/sqrt(pi)
-        const double2 c45 = *reinterpret_cast<const double2*>(sm + k * 8 + 4);    // kL, kG
-        double re[PPT], im[PPT];
-#pragma unroll
-        for (int q = 0; q < PPT; ++q) {
-            const double d = wi[q] - c01.x;
+    double* part = sm + (size_t)P * 8;
+    const int i = blockIdx.x * kGenPoints + x;
+    const bool ok = i < n;
+    const double wi = ok ? w[i] : 0.0;
+    double vs = 0.0, is = 0.0;
+    if (ok) {
+        for (int k = y; k < P; k += kGenGroups) {
+            // one reciprocal serves the Lorentzian and its dispersion counterpart; the Gaussian is evaluated only within
+            // 6.5 units of s of the centre (beyond: < 4.5e-19 of its height, below half an ulp of anything it is added
+            // to) - a warp's neighbouring points are on the same side of that cut almost everywhere, so the branch is
+            // uniform; Dawson's integral keeps its full range (its tail decays only as 1/s)
+            const double2 c01 = *reinterpret_cast<const double2*>(sm + k * 8);        // loc, aL
+            const double2 c23 = *reinterpret_cast<const double2*>(sm + k * 8 + 2);    // aG, aG * 2/sqrt(pi)
+            const double2 c45 = *reinterpret_cast<const double2*>(sm + k * 8 + 4);    // kL, kG
+            const double d = wi - c01.x;
             const double t = d * c45.x, s = d * c45.y;
             const double rq = rcp_pos(fma(t, t, 1.0));
             const double lor = c01.y * rq;
             double body = lor;
             if (fabs(s) <= kGaussCut) body = fma(c23.x, exp_neg<0>(-(s * s), nullptr), lor);
-            re[q] = yoff + body;                     // utils.py:267: every contribution carries yoff
-            im[q] = fma(lor, t, c23.y * dawson(s, NMRFIT_DAW_TAB, NMRFIT_DAW_TAIL));
-            vs[q] += re[q];                          // utils.py:276-277: both sums accumulate
-            is[q] += im[q];
-        }
-        if (PPT == 2 && pair) {
-            *reinterpret_cast<double2*>(real + (size_t)k * n + i0) = make_double2(re[0], re[PPT - 1]);
-            *reinterpret_cast<double2*>(imag + (size_t)k * n + i0) = make_double2(im[0], im[PPT - 1]);
-        } else {
-            real[(size_t)k * n + i0] = re[0];
-            imag[(size_t)k * n + i0] = im[0];
+            const double re = yoff + body;           // utils.py:267: every contribution carries yoff
+            const double im = fma(lor, t, c23.y * dawson(s, NMRFIT_DAW_TAB, NMRFIT_DAW_TAIL));
+            real[(size_t)k * n + i] = re;
+            imag[(size_t)k * n + i] = im;
+            vs += re;                                // utils.py:276-277: both sums accumulate
+            is += im;
         }
     }
+    part[y * kGenPoints + x] = vs;
+    part[(kGenGroups + y) * kGenPoints + x] = is;
+    __syncthreads();
+    if (y != 0 || !ok) return;
+    vs = 0.0;
+    is = 0.0;
 #pragma unroll
-    for (int q = 0; q < PPT; ++q) {
-        const int i = i0 + q;
-        if (i >= n) break;
-        V[i] = vs[q];
-        I[i] = is[q];
-        double sn, cs;
-        sincos(p0 + (p1 * (double)i) / (double)n, &sn, &cs);   // utils.py:284: ramp over the UPSAMPLED length
-        u[i] = vs[q] * cs + is[q] * sn;
-        v[i] = is[q] * cs - vs[q] * sn;
+    for (int g = 0; g < kGenGroups; ++g) {
+        vs += part[g * kGenPoints + x];
+        is += part[(kGenGroups + g) * kGenPoints + x];
     }
+    V[i] = vs;
+    I[i] = is;
+    double sn, cs;
+    sincos(p0 + (p1 * (double)i) / (double)n, &sn, &cs);   // utils.py:284: ramp over the UPSAMPLED length
+    u[i] = vs * cs + is * sn;
+    v[i] = is * cs - vs * sn;
 }
 
 cudaError_t launch_ps2(const double* u, const double* v, int n, double p0, double p1, int inv, double* re, double* im,
@@ -171,17 +170,12 @@ cudaError_t launch_generate_result(const double* params_host, int P, const doubl
     if (P > kGenMaxPeaks) return cudaErrorInvalidValue;
     count_launches(1);
     const int D = 4 + 3 * P;
-    // two points per thread when every plane keeps its 16-byte alignment (even n, aligned bases)
-    static const int ppt_env = [] { const char* e = getenv("NMRFIT_GEN_PPT"); return e ? atoi(e) : 0; }();
-    const bool aligned = n % 2 == 0 && ((uintptr_t)real % 16 == 0) && ((uintptr_t)imag % 16 == 0);
-    const int ppt = (ppt_env == 1 || !aligned) ? 1 : 2;
-    const unsigned grid = (n + kGenThreads * ppt - 1) / (kGenThreads * ppt);
-    const size_t smem = (size_t)P * 8 * sizeof(double);
+    const unsigned grid = (n + kGenPoints - 1) / kGenPoints;
+    const size_t smem = ((size_t)P * 8 + 2 * kGenGroups * kGenPoints) * sizeof(double);
     if (P <= kGenInlinePeaks) {
         GenParams gp;
         for (int d = 0; d < D; ++d) gp.v[d] = params_host[d];
-        if (ppt == 2) generate_result_kernel<true, 2><<<grid, kGenThreads, smem, st>>>(gp, nullptr, P, w, n, real, imag, V, I, u, v);
-        else generate_result_kernel<true, 1><<<grid, kGenThreads, smem, st>>>(gp, nullptr, P, w, n, real, imag, V, I, u, v);
+        generate_result_kernel<true><<<grid, kGenThreads, smem, st>>>(gp, nullptr, P, w, n, real, imag, V, I, u, v);
         return cudaGetLastError();
     }
     double* pd = nullptr;
@@ -190,8 +184,7 @@ cudaError_t launch_generate_result(const double* params_host, int P, const doubl
     e = cudaMemcpyAsync(pd, params_host, sizeof(double) * D, cudaMemcpyHostToDevice, st);
     if (e == cudaSuccess) {
         GenParams gp{};
-        if (ppt == 2) generate_result_kernel<false, 2><<<grid, kGenThreads, smem, st>>>(gp, pd, P, w, n, real, imag, V, I, u, v);
-        else generate_result_kernel<false, 1><<<grid, kGenThreads, smem, st>>>(gp, pd, P, w, n, real, imag, V, I, u, v);
+        generate_result_kernel<false><<<grid, kGenThreads, smem, st>>>(gp, pd, P, w, n, real, imag, V, I, u, v);
         e = cudaGetLastError();
     }
     cudaFreeAsync(pd, st);

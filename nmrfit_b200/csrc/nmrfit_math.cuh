@@ -66,12 +66,6 @@ NMRFIT_HD double rcp_pos(double q) {
     return NMRFIT_FMA(g, y0, y0);
 }
 
-// Constants of exp_neg<6> (the table the evaluation kernels use) in constant memory: an FMA takes a constant-bank
-// operand directly, whereas a 64-bit literal costs two moves every time register pressure evicts it.
-static __constant__ double NMRFIT_EXP6_K[8] = {
-    NMRFIT_EXP_T6_C4, NMRFIT_EXP_T6_C3, NMRFIT_EXP_T6_C2, NMRFIT_EXP_T6_C1, NMRFIT_EXP_T6_C0,
-    64.0 / 0.69314718055994530942, 0.69314718055994530942 / 64.0, 6755399441055744.0};
-
 template <int TB> struct ExpPoly;
 template <> struct ExpPoly<0> {
     static NMRFIT_HD double eval(double r) {   // (e^r - 1)/r, degree 10
@@ -91,11 +85,11 @@ template <> struct ExpPoly<0> {
 };
 template <> struct ExpPoly<6> {
     static NMRFIT_HD double eval(double r) {
-        double p = NMRFIT_EXP6_K[0];
-        p = NMRFIT_FMA(p, r, NMRFIT_EXP6_K[1]);
-        p = NMRFIT_FMA(p, r, NMRFIT_EXP6_K[2]);
-        p = NMRFIT_FMA(p, r, NMRFIT_EXP6_K[3]);
-        p = NMRFIT_FMA(p, r, NMRFIT_EXP6_K[4]);
+        double p = NMRFIT_EXP_T6_C4;
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C3);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C2);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C1);
+        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C0);
         return p;
     }
 };
@@ -131,14 +125,11 @@ NMRFIT_HD double exp_neg(double x, const double* __restrict__ tab) {
     unsigned hi = (unsigned)nmrfit_hi(x);
     hi = hi < (unsigned)kExpClampHi ? hi : (unsigned)kExpClampHi;
     x = nmrfit_mk((int)hi, nmrfit_lo(x));
-    constexpr double scale_c = (double)(1 << TB) / kLn2;
-    constexpr double step_c = kLn2 / (double)(1 << TB);
-    const double scale = TB == 6 ? NMRFIT_EXP6_K[5] : scale_c;       // (identical values; TB = 6 from constant memory)
-    const double step = TB == 6 ? NMRFIT_EXP6_K[6] : step_c;
-    const double magic = TB == 6 ? NMRFIT_EXP6_K[7] : kMagic;
-    double t = NMRFIT_FMA(x, scale, magic);
+    constexpr double scale = (double)(1 << TB) / kLn2;
+    constexpr double step = kLn2 / (double)(1 << TB);
+    double t = NMRFIT_FMA(x, scale, kMagic);
     int n = nmrfit_lo(t);
-    double nd = t - magic;
+    double nd = t - kMagic;
     double r = NMRFIT_FMA(nd, -step, x);
     double p = ExpPoly<TB>::eval(r);
     double res;
