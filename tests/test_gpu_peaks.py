@@ -11,7 +11,8 @@ from nmrfit_b200 import _cabi, synth, utils
 from oracle import nmrfit_oracle as orc
 
 pytestmark = pytest.mark.gpu
-CASES = ['peaks_1024x6', 'peaks_2500x12', 'peaks_4096x6', 'peaks_desc_1500x6']
+CASES = ['peaks_1024x6', 'peaks_2500x12', 'peaks_4096x6', 'peaks_desc_1500x6',
+         'peaks_c3_16384x6']      # the last: a BASELINE configs[2] spectrum (1,638,400 upsampled samples, window 88,554)
 TOL = 1e-12
 
 

@@ -8,7 +8,8 @@ import pytest
 from conftest import load_golden, relerr
 from oracle import nmrfit_oracle as orc, peakutils_oracle
 
-CASES = ['peaks_1024x6', 'peaks_2500x12', 'peaks_4096x6', 'peaks_desc_1500x6']
+CASES = ['peaks_1024x6', 'peaks_2500x12', 'peaks_4096x6', 'peaks_desc_1500x6',
+         'peaks_c3_16384x6']      # the last: a BASELINE configs[2] spectrum (1,638,400 upsampled samples, window 88,554)
 
 
 @pytest.mark.parametrize('case', CASES)
