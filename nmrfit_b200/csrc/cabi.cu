@@ -106,6 +106,7 @@ struct nmrfit_ctx {
     long long epoch = 0;               // fits begun on this context: part of the exchange token
     double peer_timeout_ms = 20000.0;  // wall-time bound of a wait for the peers' tokens
     DevBuf<double> wscratch, wbounds;  // batched weights: sweep scratch [B][N], windows + values
+    cudaStream_t pipe[2] = {nullptr, nullptr};   // nmrfit_objective_batch_host: slices of a large particle set
     int far_cells = 0;                 // far-field cells per region: 0 = far_cells_per_region(N, R), else 1 | 2 | 4
     int fused_mode = NMRFIT_FUSED_AUTO;
     DevBuf<long long> ftiming;         // optional per-phase cycle counters of the fused kernel
@@ -254,7 +255,9 @@ int check_ctx(const nmrfit_ctx* c) {
 
 int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double* f_dev, const int* frozen,
                   cudaStream_t st, const MoveArgs* mv = nullptr, int* tiles_out = nullptr, int* nsum_out = nullptr,
-                  int* nw_out = nullptr) {
+                  int* nw_out = nullptr, size_t slot0 = 0, size_t slots_total = 0) {
+    // slot0 / slots_total (one spectrum only): this launch is one slice of a larger particle set evaluated in pieces on
+    // several streams (nmrfit_objective_batch_host); it owns the scratch of particle slots [slot0, slot0 + S + pad)
     for (int b = 0; b < c->B; ++b)
         if (!c->spec_set[b]) return fail(NMRFIT_ERR_STATE, "spectrum " + std::to_string(b) + " was never set");
     if (fit_im < 0 || fit_im > 2) return fail(NMRFIT_ERR_ARG, "fit_im must be 0, 1 or 2");
@@ -269,25 +272,27 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
         return fail(NMRFIT_ERR_ARG, uni ? "points_per_thread must be 4, 8 or 16 for the uniform-axis kernel"
                                         : "points_per_thread must be 2, 4 or 8 for the general kernel");
     int n_tiles = objective_tiles(c->N, t);
-    CK(c->partials.reserve((size_t)c->B * S * n_tiles * 2 * (t.variant == 1 ? t.threads / 32 : 1)));
+    const size_t part_per = (size_t)n_tiles * 2 * (t.variant == 1 ? t.threads / 32 : 1);
+    CK(c->partials.reserve(std::max((size_t)c->B * S, slots_total) * part_per));
     ObjArgs a{};
     const int sub = (uni && c->precision == NMRFIT_FP64) ? ctx_cells(c, t.r) : 1;
     if (uni) {
         size_t nc, np, nf, na, nm;
         int pad = 0;
         objective_uniform_prep_sizes(c->N, c->P, t, sub, &nc, &np, &nf, &na, &nm, &pad);
-        const size_t slots = (size_t)c->B * S + pad;
+        const size_t slots = std::max((size_t)c->B * S, slots_total) + pad;
         CK(c->prep_coef.reserve(slots * nc));
         CK(c->prep_part.reserve(slots * np));
         CK(c->prep_far.reserve(slots * nf));
         CK(c->prep_anchor.reserve(slots * na));
         CK(c->prep_mask.reserve(slots * nm));
-        a.prep_coef = c->prep_coef.ptr; a.prep_part = c->prep_part.ptr; a.prep_far = c->prep_far.ptr;
-        a.prep_anchor = c->prep_anchor.ptr; a.prep_mask = c->prep_mask.ptr;
+        a.prep_coef = c->prep_coef.ptr + slot0 * nc; a.prep_part = c->prep_part.ptr + slot0 * np;
+        a.prep_far = c->prep_far.ptr + slot0 * nf; a.prep_anchor = c->prep_anchor.ptr + slot0 * na;
+        a.prep_mask = c->prep_mask.ptr + slot0 * nm;
     }
     a.spec = c->spec.ptr;
     a.x = x_dev;
-    a.partials = c->partials.ptr;
+    a.partials = c->partials.ptr + slot0 * part_per;
     a.frozen = frozen;
     a.grid_h = c->grid_h.ptr;
     a.N = c->N; a.P = c->P; a.S = S; a.kk = fit_im; a.sp = t.sp; a.sub = sub;
@@ -475,6 +480,8 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->fin_scratch.release();
     c->fin_tickets.release();
     c->wbounds.release();
+    for (int k = 0; k < 2; ++k)
+        if (c->pipe[k]) cudaStreamDestroy(c->pipe[k]);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     for (cudaEvent_t ev : c->prof_events) cudaEventDestroy(ev);
     delete c;
@@ -724,6 +731,28 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
     size_t nx = (size_t)c->B * S * c->D, nf = (size_t)c->B * S;
     CK(c->x_stage.reserve(nx));
     CK(c->f_stage.reserve(nf));
+    // A large particle set of one spectrum goes through in slices on two streams: while slice k is evaluated, slice
+    // k + 1's positions are on their way in and slice k - 1's values on their way out (each slice has its own scratch).
+    constexpr int kSlices = 4, kPad = 64;
+    if (c->B == 1 && S >= 4 * 4096 && !c->profiling) {
+        for (int k = 0; k < 2; ++k)
+            if (!c->pipe[k]) CK(cudaStreamCreateWithFlags(&c->pipe[k], cudaStreamNonBlocking));
+        const int chunk = ((S + kSlices - 1) / kSlices + 63) & ~63;
+        const size_t total = (size_t)kSlices * (chunk + kPad);
+        for (int k = 0, s0 = 0; s0 < S; ++k, s0 += chunk) {
+            const int ns = std::min(chunk, S - s0);
+            cudaStream_t ps = c->pipe[k & 1];
+            CK(cudaMemcpyAsync(c->x_stage.ptr + (size_t)s0 * c->D, x_host + (size_t)s0 * c->D, sizeof(double) * ns * c->D,
+                               cudaMemcpyHostToDevice, ps));
+            if (int rc = run_objective(c, c->x_stage.ptr + (size_t)s0 * c->D, ns, fit_im, c->f_stage.ptr + s0, nullptr, ps,
+                                       nullptr, nullptr, nullptr, nullptr, (size_t)k * (chunk + kPad), total))
+                return rc;
+            CK(cudaMemcpyAsync(f_host + s0, c->f_stage.ptr + s0, sizeof(double) * ns, cudaMemcpyDeviceToHost, ps));
+        }
+        CK(cudaStreamSynchronize(c->pipe[0]));
+        CK(cudaStreamSynchronize(c->pipe[1]));
+        return NMRFIT_OK;
+    }
     cudaStream_t st = 0;
     CK(cudaMemcpyAsync(c->x_stage.ptr, x_host, nx * sizeof(double), cudaMemcpyHostToDevice, st));
     if (int rc = run_objective(c, c->x_stage.ptr, S, fit_im, c->f_stage.ptr, nullptr, st)) return rc;
