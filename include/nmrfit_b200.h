@@ -175,6 +175,18 @@ int nmrfit_pso_advance(nmrfit_ctx* ctx, const double* rp, const double* rg, void
 /* One whole generation of a swarm held by ONE context (no rank exchange): advance + commit, asynchronous on `stream` -
  * what nmrfit_pso_run does per generation, without its final synchronisation.  Three launches. */
 int nmrfit_pso_step(nmrfit_ctx* ctx, const double* rp, const double* rg, void* stream);
+/* ---- numpy's legacy random stream, continued on the device (csrc/mt19937.cu) -----------------------------------
+ * pyswarm draws from numpy's global MT19937 (rand(S, D) twice, then uniform(size=(S, D)) twice per generation; call site
+ * utils.py:176-182).  Instead of drawing those arrays on the host and copying them, hand over the generator's state
+ * (np.random.get_state(): key [624], pos): the device produces the next n_arrays arrays of `elements_per_array`
+ * doubles exactly as RandomState.random_sample does, de-interleaved into two device buffers owned by the context
+ * (arrays 0, 2, 4, ... -> *a_dev, arrays 1, 3, 5, ... -> *b_dev: positions / velocities, or rp / rg per generation),
+ * and returns the advanced state (np.random.set_state) - bit-identical numbers, the stream left where pyswarm would
+ * have left it.  The pointers are valid until the next call and may be passed to nmrfit_pso_begin / nmrfit_pso_run. */
+int nmrfit_ctx_mt19937_shape(nmrfit_ctx* ctx, long long elements_per_array);
+int nmrfit_ctx_mt19937(nmrfit_ctx* ctx, unsigned* key, int* pos, long long n_arrays, double** a_dev, double** b_dev,
+                       void* stream);
+
 /* ---- particle sharding without a collective call: the record exchange over peer memory (NVLink stores) -----------
  * Each rank's context owns a window of records and generation tokens; every rank maps every window (CUDA IPC between
  * processes, plain pointers between contexts of one process).  nmrfit_pso_commit_peers replaces "all-gather the records,

@@ -66,6 +66,8 @@ SIGNATURES = {
     'nmrfit_ctx_profile_read_split': (_i, [_vp, c_double_p, c_double_p, ctypes.POINTER(ctypes.c_longlong)]),
     'nmrfit_objective_batch': (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     'nmrfit_objective_batch_host': (_i, [_vp, _vp, _i, _i, _vp]),
+    'nmrfit_ctx_mt19937_shape': (_i, [_vp, ctypes.c_longlong]),
+    'nmrfit_ctx_mt19937': (_i, [_vp, _vp, c_int_p, ctypes.c_longlong, ctypes.POINTER(_vp), ctypes.POINTER(_vp), _vp]),
     'nmrfit_pso_begin': (_i, [_vp, _vp, _vp, ctypes.POINTER(PsoOpts), _vp, _vp, _vp]),
     'nmrfit_pso_advance': (_i, [_vp, _vp, _vp, _vp]),
     'nmrfit_pso_step': (_i, [_vp, _vp, _vp, _vp]),
@@ -332,6 +334,22 @@ class Context:
         """One whole single-context generation (advance + commit), asynchronous."""
         rp, rg = self._rand(rp, self._swarmsize), self._rand(rg, self._swarmsize)
         check(lib().nmrfit_pso_step(self._h, ptr(rp), ptr(rg), ptr(stream)))
+
+    def legacy_uniform_pairs(self, n_pairs, elements, stream=None):
+        """The next ``2 * n_pairs`` arrays of ``elements`` doubles of numpy's GLOBAL legacy stream (np.random.rand /
+        np.random.uniform), generated on the device: returns two device addresses - arrays 0, 2, 4, ... and arrays
+        1, 3, 5, ... back to back - and advances ``np.random``'s state exactly as drawing them on the host would."""
+        kind, key, pos, has_gauss, cached = np.random.get_state()
+        if kind != 'MT19937':
+            raise RuntimeError('numpy legacy generator is not MT19937')
+        key = np.ascontiguousarray(key, dtype=np.uint32).copy()
+        p = ctypes.c_int(int(pos))
+        a, b = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().nmrfit_ctx_mt19937_shape(self._h, int(elements)))
+        check(lib().nmrfit_ctx_mt19937(self._h, ptr(key), ctypes.byref(p), 2 * int(n_pairs), ctypes.byref(a),
+                                       ctypes.byref(b), ptr(stream)))
+        np.random.set_state((kind, key, p.value, has_gauss, cached))
+        return a.value, b.value
 
     # -- record exchange over peer memory
     def peer_export(self, n_ranks, rank):

@@ -92,6 +92,8 @@ struct nmrfit_ctx {
     DevBuf<double> frec_f, frec_x;     // fused swarm kernel: published records
     DevBuf<unsigned> fbarrier;
     DevBuf<int> ferror;                // fused swarm kernel: barrier-timeout flag
+    DevBuf<unsigned> mt_state;         // MT19937 key [624] + position, for nmrfit_ctx_mt19937
+    long long mt_elems = 0;            // elements of one random array (n_spectra * swarmsize * D)
     DevBuf<double> fin_scratch;        // finish kernel: per-CTA candidates
     DevBuf<unsigned> fin_tickets;
     // record exchange over peer memory (particle sharding without a collective call)
@@ -470,6 +472,7 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->frec_x.release();
     c->fbarrier.release();
     c->ferror.release();
+    c->mt_state.release();
     c->ftiming.release();
     for (void* p : c->peer_opened) cudaIpcCloseMemHandle(p);
     if (c->peer_win) cudaFree(c->peer_win);
@@ -843,6 +846,42 @@ int nmrfit_pso_step(nmrfit_ctx* c, const double* rp, const double* rg, void* str
     if (int rc = stage(rg, nsd, c->rnd_b, st, &rg_d)) return rc;
     c->generation += 1;
     return swarm_generation(c, true, rp_d, rg_d, 1, st);
+}
+
+int nmrfit_ctx_mt19937(nmrfit_ctx* c, unsigned* key, int* pos, long long n_arrays, double** a_dev, double** b_dev,
+                       void* stream) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!key || !pos || !a_dev || !b_dev) return fail(NMRFIT_ERR_ARG, "NULL argument");
+    if (*pos < 0 || *pos > 624) return fail(NMRFIT_ERR_ARG, "MT19937 position must be 0..624");
+    if (n_arrays < 2 || (n_arrays & 1)) return fail(NMRFIT_ERR_ARG, "n_arrays must be even: arrays come in (first, second) pairs");
+    if (c->mt_elems == 0) return fail(NMRFIT_ERR_STATE, "call nmrfit_ctx_mt19937_shape first");
+    CK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long nsd = c->mt_elems, pairs = n_arrays / 2;
+    CK(c->rnd_a.reserve((size_t)(pairs * nsd)));
+    CK(c->rnd_b.reserve((size_t)(pairs * nsd)));
+    CK(c->mt_state.reserve(625));
+    unsigned host[625];
+    std::memcpy(host, key, sizeof(unsigned) * 624);
+    host[624] = (unsigned)*pos;
+    CK(cudaMemcpyAsync(c->mt_state.ptr, host, sizeof(host), cudaMemcpyHostToDevice, st));
+    cudaError_t e = launch_mt19937(c->mt_state.ptr, reinterpret_cast<int*>(c->mt_state.ptr + 624), n_arrays * nsd,
+                                   c->rnd_a.ptr, c->rnd_b.ptr, nsd, st);
+    if (e != cudaSuccess) return fail_cuda(e, "MT19937 launch");
+    CK(cudaMemcpyAsync(host, c->mt_state.ptr, sizeof(host), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    std::memcpy(key, host, sizeof(unsigned) * 624);
+    *pos = (int)host[624];
+    *a_dev = c->rnd_a.ptr;
+    *b_dev = c->rnd_b.ptr;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_mt19937_shape(nmrfit_ctx* c, long long elements_per_array) {
+    if (int rc = check_ctx(c)) return rc;
+    if (elements_per_array < 1) return fail(NMRFIT_ERR_ARG, "elements_per_array must be >= 1");
+    c->mt_elems = elements_per_array;
+    return NMRFIT_OK;
 }
 
 // ---- record exchange over peer memory -------------------------------------------------------------

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstddef>
+#include <cstdint>
 
 #define NMRFIT_MAX_DEVICES 16
 
@@ -180,6 +181,10 @@ cudaError_t launch_phase_brute(const double* u, const double* v, int B, int N, c
                                double* err, int* ok, double* best_p0, double* best_err, cudaStream_t st);
 cudaError_t launch_phase_acme(const double* u, const double* v, int B, int N, const double* ph_dev, int K, double* score,
                               cudaStream_t st);
+
+// ---- numpy's legacy MT19937 stream continued on the device (mt19937.cu) --------------------
+cudaError_t launch_mt19937(unsigned* key_dev, int* pos_dev, long long n, double* out_a, double* out_b, long long nsd,
+                           cudaStream_t st);
 
 // ---- K10 auto peak selection (peaks.cu) ----------------------------------------------
 // front: upsample, smooth, global baseline, maxima (unsorted indices + the upsampled signal there);

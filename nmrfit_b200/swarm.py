@@ -95,17 +95,23 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
         raise ValueError('bounds must have 4 + 3*n_peaks entries')
     w = _cabi.as_f64(w)
     S = int(swarmsize)
-    host = rng == 'host'
-    if rng not in ('host', 'device'):
-        raise ValueError("rng must be 'host' or 'device'")
+    # 'host': numpy's global legacy stream, CONTINUED ON THE DEVICE from np.random's own state (csrc/mt19937.cu) - the
+    # same numbers pyswarm would draw, without drawing and shipping them; 'host_arrays': drawn on the host and copied
+    host = rng in ('host', 'host_arrays')
+    on_device = rng == 'host'
+    if rng not in ('host', 'host_arrays', 'device'):
+        raise ValueError("rng must be 'host', 'host_arrays' or 'device'")
     with _cabi.pooled_context(1, w.size, (D - 4) // 3, device=device, precision=_precision(precision)) as ctx:
         if tuning:
             ctx.set_tuning(**tuning)
         ctx.set_fused(_fused_mode(fused))
         ctx.set_spectrum(0, w, u, v, weights)
         opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed)
-        r_pos = np.random.rand(S, D) if host else None
-        r_vel = np.random.rand(S, D) if host else None
+        if on_device:
+            r_pos, r_vel = ctx.legacy_uniform_pairs(1, S * D)
+        else:
+            r_pos = np.random.rand(S, D) if host else None
+            r_vel = np.random.rand(S, D) if host else None
         ctx.pso_begin(lb, ub, opts, r_pos, r_vel)
         ctx.pso_commit()
         if trace is not None:
@@ -121,7 +127,7 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
                 chunk = min(2 * chunk, 256 if not host else 64)
             if host:
                 state = np.random.get_state()
-                rp, rg = _draw_generations(np.random, n, S, D)
+                rp, rg = ctx.legacy_uniform_pairs(n, S * D) if on_device else _draw_generations(np.random, n, S, D)
             else:
                 rp = rg = None
             running = ctx.pso_run(n, rp, rg)
@@ -136,7 +142,11 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
                     used = int(it[0]) - done
                     if used < n:
                         np.random.set_state(state)
-                        _draw_generations(np.random, used, S, D)
+                        if used > 0:
+                            if on_device:
+                                ctx.legacy_uniform_pairs(used, S * D)
+                            else:
+                                _draw_generations(np.random, used, S, D)
                 break
             done += n
         x, f, it, stop = ctx.pso_best()

@@ -87,9 +87,10 @@ class FitUtility:
     ``options`` understands the reference's keys (``swarmsize`` 204, ``maxiter``
     2000, ``omega`` -0.2134, ``phip`` -0.3344, ``phig`` 2.3259; utils.py:177-181)
     plus optional extras that do not exist upstream:
-      ``rng``       'host' (default): random numbers are drawn from numpy's legacy
-                    global stream in pyswarm's order, so ``np.random.seed(k)`` gives
-                    the reference's trajectory; 'device': Philox on the GPU.
+      ``rng``       'host' (default): numpy's legacy global stream in pyswarm's order, so
+                    ``np.random.seed(k)`` gives the reference's trajectory - the stream is continued ON THE
+                    DEVICE from np.random's own state (bit-identical numbers, state handed back);
+                    'host_arrays': the same numbers drawn on the host and copied; 'device': Philox on the GPU.
       ``seed``      Philox seed for rng='device'.
       ``minstep``, ``minfunc``   pyswarm's stop tolerances (1e-8).
       ``precision`` 'fp64' (default) or 'fp32'.

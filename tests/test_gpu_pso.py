@@ -324,3 +324,47 @@ def test_record_exchange_over_peer_memory_equals_unsharded(ranks):
     finally:
         for c in ctxs:
             c.close()
+
+
+@pytest.mark.parametrize('pos0', [624, 0, 1, 7, 311, 622, 623])
+def test_legacy_stream_continued_on_the_device_is_numpys(pos0):
+    """csrc/mt19937.cu: given np.random's state the device produces the numbers np.random.rand would, for every
+    position inside a 624-word block (a double's two words may straddle blocks), and hands back the advanced state."""
+    import torch
+    np.random.seed(12345)
+    if pos0 != 624:
+        np.random.random_sample(3 * 312)                    # land on a block boundary (three whole blocks) ...
+        kind, key, pos, hg, cg = np.random.get_state()
+        np.random.set_state((kind, key, pos0, hg, cg))     # ... then anywhere inside the block
+    state = np.random.get_state()
+    S, D, pairs = 37, 22, 5
+    want = np.random.random_sample((2 * pairs, S * D))
+    after_host = np.random.get_state()
+    np.random.set_state(state)
+    with _cabi.Context(1, 64, 6) as ctx:
+        a, b = ctx.legacy_uniform_pairs(pairs, S * D)
+        got_a = torch.as_tensor(swarm._DeviceArray(a, pairs * S * D), device='cuda').cpu().numpy().reshape(pairs, S * D)
+        got_b = torch.as_tensor(swarm._DeviceArray(b, pairs * S * D), device='cuda').cpu().numpy().reshape(pairs, S * D)
+    assert np.array_equal(got_a, want[0::2]) and np.array_equal(got_b, want[1::2])
+    after_dev = np.random.get_state()
+    assert after_dev[2] == after_host[2] and np.array_equal(after_dev[1], after_host[1])
+    assert np.random.rand() == (np.random.set_state(after_host) or np.random.rand())
+
+
+def test_fit_with_device_continued_stream_equals_host_drawn_arrays():
+    """The default parity mode (rng='host': legacy stream continued on the device) and rng='host_arrays' (drawn on the
+    host, copied) are the same fit - parameters, error, generations, and where np.random is left - including an early
+    stop in the middle of a chunk."""
+    import contextlib
+    import io
+    import nmrfit_b200
+    data, true = synth.multiplet(2048, 6, seed=2)
+    lo, up = data.generate_solution_bounds()
+    out = []
+    for rng in ('host', 'host_arrays'):
+        np.random.seed(4)
+        with contextlib.redirect_stdout(io.StringIO()):
+            fit = nmrfit_b200.fit(data, lo, up, summary=False, options={'rng': rng})      # defaults: stops on minfunc
+        out.append((fit.params.copy(), fit.error, fit.fit_info['generations'], fit.fit_info['stop'], np.random.rand()))
+    assert np.array_equal(out[0][0], out[1][0]) and out[0][1:] == out[1][1:]
+    assert out[0][3] in (_cabi.STOP_MINFUNC, _cabi.STOP_MINSTEP) and 0 < out[0][2] < 2000

@@ -14,6 +14,6 @@ timeout 300 python bench.py --steps 20 --warmup 3 --quick > gpurun_out/${TAG}_be
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 20 --warmup 3 --quick > gpurun_out/${TAG}_ncu_launches.log 2>&1
 for WL in metric c2 c3 c4; do
   timeout 300 python bench.py --steps 8 --warmup 3 --quick --workload $WL > gpurun_out/${TAG}_bench_short_$WL.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:objective_uniform_kernel -s 5 -c 1 -o gpurun_out/${TAG}_prof_$WL python bench.py --steps 8 --warmup 3 --quick --workload $WL > gpurun_out/${TAG}_ncu_full_$WL.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:objective_stream_kernel -s 5 -c 1 -o gpurun_out/${TAG}_prof_$WL python bench.py --steps 8 --warmup 3 --quick --workload $WL > gpurun_out/${TAG}_ncu_full_$WL.log 2>&1
 done
 ls -la gpurun_out/${TAG}_*
