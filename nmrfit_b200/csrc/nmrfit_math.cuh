@@ -334,6 +334,38 @@ constexpr double kFarRhoInv2 = 256.0;
 // region's point count.  Returns kFarNear (evaluate it with peak_span), kFarSeries (v[n] = Im[u^(n+1)]/A filled:
 // the peak adds (-1)^n aL v[n] to the region's coefficient n) or kFarNothing (infinitely far: adds nothing).
 enum { kFarNear = 0, kFarSeries = 1, kFarNothing = 2 };
+// The part of the classification that depends on the peak and the cell LENGTH only (not on where the cell is):
+// computed once per peak by the prepare pass (same expressions, same bits as far_terms evaluates on the fly).
+struct FarPeak { double A, A2, A2x, reach; };                 // H dT, A^2, 256 A^2, 6.5 + H |hG|
+NMRFIT_HD FarPeak make_far_peak(const SpanCoef& c, double H) {
+    FarPeak f;
+    f.A = H * c.dT;
+    f.A2 = f.A * f.A;
+    f.A2x = kFarRhoInv2 * f.A2;
+    f.reach = NMRFIT_FMA(H * kSqrtLn2, NMRFIT_ABS(c.dT), kGaussCut);
+    return f;
+}
+NMRFIT_HD int far_terms_pre(double Dc, double kL, double kG, const FarPeak& f, double (&v)[kFarTerms]) {
+    const double A = f.A;
+    const double tc = Dc * kL;
+    const double qc = NMRFIT_FMA(tc, tc, 1.0);
+    const double sc = Dc * kG;
+    if (NMRFIT_ABS(sc) <= f.reach) return kFarNear;           // the Gaussian reaches the region
+    if (!(f.A2x <= qc)) return kFarNear;                      // too close for the series (or NaN)
+    if (!(qc <= 1e300)) return kFarNothing;                   // infinitely far: contributes nothing
+    const double iq = rcp_pos(qc);
+    const double two_p = 2.0 * (A * tc) * iq;                 // 2 Re(u)
+    const double rho2 = f.A2 * iq;                            // |u|^2
+    double vm = 0.0, vc = iq;
+#pragma unroll
+    for (int n = 0; n < kFarTerms; ++n) {
+        v[n] = vc;
+        const double vn = NMRFIT_FMA(two_p, vc, -(rho2 * vm));
+        vm = vc;
+        vc = vn;
+    }
+    return kFarSeries;
+}
 NMRFIT_HD int far_terms(double Dc, const SpanCoef& c, double H, double (&v)[kFarTerms]) {
     const double A = H * c.dT;
     const double tc = Dc * c.kL;

@@ -87,7 +87,7 @@ template <int R, bool MOVE>
 __global__ void __launch_bounds__(kPrepThreads)
 objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     const int nthreads = blockDim.x;
-    extern __shared__ __align__(16) double sm[];           // cs [G][P][8], then (MOVE) the moved particles [G][D]
+    extern __shared__ __align__(16) double sm[];           // cs [G][P][8], farpk [G][P][4], then (MOVE) the moved particles [G][D]
     const int b = blockIdx.y, s0 = blockIdx.x * G, tid = threadIdx.x;
     if (MOVE ? mv.s.stop[b] != 0 : (a.frozen && a.frozen[b])) return;
     const int P = a.P, N = a.N, D = 4 + 3 * P, sub = a.sub;
@@ -95,7 +95,8 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     const int MWR = mask_words_per_region(P, sub);
     const int ng = min(G, a.S - s0);
     double* cs = sm;
-    double* xsm = sm + (size_t)G * P * 8;
+    double* farpk = sm + (size_t)G * P * 8;
+    double* xsm = farpk + (size_t)G * P * 4;
     const double* sw = a.spec + (size_t)b * 4 * N;
     const double h = a.grid_h[2 * b], w_ulp = a.grid_h[2 * b + 1];
     const size_t ps0 = (size_t)b * a.S + s0;
@@ -128,7 +129,8 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
         const int g = e / per, it = e - g * per;
         const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
         if (it < P) {
-            prep_item_coef<R>(xs, it, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8);
+            prep_item_coef<R>(xs, it, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8,
+                              farpk + (size_t)g * P * 4, sub);
         } else if (it < P + kTableItems) {
             prep_item_table<R>(xs, it - P, N, P, a.prep_part + (ps0 + g) * kPartDoubles);
         } else {
@@ -148,7 +150,7 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
         const int rl = cl / sub, ci = cl - rl * sub;
         const RegionDst rd(a, b, s0 + g, NRP);
         const size_t rs = rd.region(rl);
-        prep_item_cell<R>(ok, cs + (size_t)g * P * 8, sw, h, N, P, sub, (long long)cl * cell_pts, ci, nullptr,
+        prep_item_cell<R>(ok, cs + (size_t)g * P * 8, farpk + (size_t)g * P * 4, sw, h, N, P, sub, (long long)cl * cell_pts, ci, nullptr,
                           a.prep_far + (rs * sub + ci) * kFarTerms, a.prep_mask + rs * MWR);
     }
 }
@@ -323,7 +325,7 @@ cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaSt
     if (a.sub < 1) a.sub = 1;
     // particles per CTA: about two rounds of far-field cells for its 256 threads
     const int nc = a.n_tiles * a.nw * a.sub;
-    const size_t per_particle = (size_t)(a.P * 8 + (mv ? 4 + 3 * a.P : 0)) * sizeof(double);
+    const size_t per_particle = (size_t)(a.P * 12 + (mv ? 4 + 3 * a.P : 0)) * sizeof(double);
     int G = std::max(1, std::min(16, std::min(a.S, 2 * kPrepThreads / nc)));
     while (G > 1 && G * per_particle > 40 * 1024) --G;     // stay inside the default dynamic shared-memory limit
     // a particle with >= 128 cells fills a CTA of 128 threads on its own (and many small CTAs schedule better)

@@ -45,7 +45,7 @@ namespace {
 
 // shared-memory carve-up in doubles; every offset is even (16-byte alignment)
 struct FusedSmem {
-    int tab, uv, wt, cs, part, far, anchor, mask, wpart, state, red, misc, pairs, total;
+    int tab, uv, wt, cs, farpk, part, far, anchor, mask, wpart, state, red, misc, pairs, total;
     // NRP: region slots of the whole axis (tile sums of every region end up in every CTA); NRL: regions this CTA owns
     __host__ __device__ FusedSmem(int P, int D, int threads, int R, int slots, int NRP, int NRL, bool want_pairs, int sub) {
         const int De = (D + 1) & ~1;
@@ -54,6 +54,7 @@ struct FusedSmem {
         uv = o;     o += slots * threads * R * 2;
         wt = o;     o += slots * threads * R;
         cs = o;     o += P * 8;
+        farpk = o;  o += P * 4;
         part = o;   o += kPartDoubles;
         far = o;    o += NRL * sub * kFarTerms;              // per far-field cell (uniform_eval.cuh)
         anchor = o; o += NRL * 2;
@@ -123,6 +124,7 @@ swarm_fused_kernel(FusedArgs a) {
     double2* suv = reinterpret_cast<double2*>(smem + L.uv);
     double* swt = smem + L.wt;
     double* cs = smem + L.cs;
+    double* farpk = smem + L.farpk;
     double* part = smem + L.part;
     double* farc = smem + L.far;
     double* anchor = smem + L.anchor;
@@ -206,8 +208,8 @@ swarm_fused_kernel(FusedArgs a) {
         FUSED_MARK(0);
 
         // ---- objective (equations.py:152-212) of the moved particle
-        prepare_particle<R>(xs, sw, h, w_ulp, N, P, NR, NRP, tid, THREADS, cs, nullptr, part, farc, anchor, mask, pairs, r_lo,
-                            r_hi, SUB);
+        prepare_particle<R>(xs, sw, h, w_ulp, N, P, NR, NRP, tid, THREADS, cs, nullptr, part, farc, anchor, mask, farpk, pairs,
+                            r_lo, r_hi, SUB);
         __syncthreads();
         FUSED_MARK(1);
         for (int st = st_lo; st < st_hi; ++st) {

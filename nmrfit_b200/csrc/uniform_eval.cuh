@@ -35,13 +35,19 @@ constexpr int kPairDoubles = kFarTerms + 1;                // a (cell, peak) ser
 constexpr int kTableItems = 34;                            // phase table: 32 lane factors, the per-point step, P*yoff
 
 // span coefficients of peak k -> cs[k][8] (shared) and optionally a second copy
+// (farpk [P][4], shared: what the far-field classification of this peak needs besides the cell's position - A = H dT,
+// A^2, 256 A^2 and the Gaussian's reach for cells of 32 R / sub points, nmrfit_math.cuh make_far_peak)
 template <int R>
 __device__ __forceinline__ void prep_item_coef(const double* __restrict__ xs, int k, double h, double w_ulp,
-                                               double* __restrict__ cs, double* __restrict__ coef_out) {
+                                               double* __restrict__ cs, double* __restrict__ coef_out,
+                                               double* __restrict__ farpk, int sub) {
     SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
     if (c.exact) c = null_span_coef();                     // the span loop adds zero; the peak is handled after it
     double* o = cs + k * 8;
     o[0] = c.loc; o[1] = c.kL; o[2] = c.kG; o[3] = c.aL; o[4] = c.aG; o[5] = c.dT; o[6] = c.thr; o[7] = c.c2;
+    const FarPeak f = make_far_peak(c, 0.5 * (double)(32 * R / sub));
+    double* q = farpk + k * 4;
+    q[0] = f.A; q[1] = f.A2; q[2] = f.A2x; q[3] = f.reach;
     if (coef_out) {
         double* g = coef_out + k * 8;
 #pragma unroll
@@ -82,19 +88,20 @@ __device__ __forceinline__ void prep_item_exact_count(const double* __restrict__
 
 // the series of one (cell, peak) pair -> pr[kPairDoubles]; `ic` = the cell's first point; needs cs complete
 template <int R>
-__device__ __forceinline__ void prep_item_pair(const double* __restrict__ cs, const double* __restrict__ sw, double h, int N,
+__device__ __forceinline__ void prep_item_pair(const double* __restrict__ cs, const double* __restrict__ farpk,
+                                               const double* __restrict__ sw, double h, int N,
                                                int sub, long long ic, int k, double* __restrict__ pr) {
     const int cell_pts = 32 * R / sub;
-    const double H = 0.5 * (double)cell_pts;               // half a cell, in points
     double kind = -1.0;                                    // -1: padding cell or exact-path peak (neither near nor far)
     if (ic < N) {
         const double* o = cs + k * 8;
-        SpanCoef c;
-        c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
-        if (!(c.thr < 0.0)) {
+        if (!(o[6] < 0.0)) {
+            const double* q = farpk + k * 4;
+            FarPeak f;
+            f.A = q[0]; f.A2 = q[1]; f.A2x = q[2]; f.reach = q[3];
             const double w_c = fma(0.5 * (double)(cell_pts - 1), h, sw[ic]);
             double v[kFarTerms];
-            kind = (double)far_terms(w_c - c.loc, c, H, v);
+            kind = (double)far_terms_pre(w_c - o[0], o[1], o[2], f, v);
 #pragma unroll
             for (int n = 0; n < kFarTerms; ++n) pr[1 + n] = v[n];
         }
@@ -108,13 +115,12 @@ __device__ __forceinline__ void prep_item_pair(const double* __restrict__ cs, co
 // called by ALL lanes of a warp (`ok` false for lanes without a cell): the union block of a region is combined from
 // its `sub` cells - consecutive lanes - by shuffles; mask_region points at the region's first block, ci = cell in region.
 template <int R>
-__device__ __forceinline__ void prep_item_cell(bool ok, const double* __restrict__ cs, const double* __restrict__ sw, double h,
-                                               int N, int P, int sub, long long ic, int ci,
+__device__ __forceinline__ void prep_item_cell(bool ok, const double* __restrict__ cs, const double* __restrict__ farpk,
+                                               const double* __restrict__ sw, double h, int N, int P, int sub, long long ic, int ci,
                                                const double* __restrict__ pairs_row, double* __restrict__ far_dst,
                                                unsigned* __restrict__ mask_region) {
     const int MW = (P + 31) / 32;
     const int cell_pts = 32 * R / sub;
-    const double H = 0.5 * (double)cell_pts;
     double C[kFarTerms];
 #pragma unroll
     for (int n = 0; n < kFarTerms; ++n) C[n] = 0.0;
@@ -141,11 +147,18 @@ __device__ __forceinline__ void prep_item_cell(bool ok, const double* __restrict
                     }
                 } else {
                     const double* o = cs + k * 8;
-                    SpanCoef c;
-                    c.loc = o[0]; c.kL = o[1]; c.kG = o[2]; c.aL = o[3]; c.aG = o[4]; c.dT = o[5]; c.thr = o[6]; c.c2 = o[7];
-                    if (c.thr < 0.0) continue;             // exact-path peak: neither near nor far
-                    if (far_accumulate(w_c - c.loc, c, H, C)) any_far = 1u;
-                    else m |= 1u << (k & 31);
+                    if (o[6] < 0.0) continue;              // exact-path peak (thr < 0): neither near nor far
+                    const double2 c01 = *reinterpret_cast<const double2*>(o);            // loc, kL
+                    const double2 c23 = *reinterpret_cast<const double2*>(o + 2);        // kG, aL
+                    const double2 f01 = *reinterpret_cast<const double2*>(farpk + k * 4);
+                    const double2 f23 = *reinterpret_cast<const double2*>(farpk + k * 4 + 2);
+                    FarPeak f;
+                    f.A = f01.x; f.A2 = f01.y; f.A2x = f23.x; f.reach = f23.y;
+                    double v[kFarTerms];
+                    const int kind = far_terms_pre(w_c - c01.x, c01.y, c23.x, f, v);
+                    if (kind == kFarNear) { m |= 1u << (k & 31); continue; }
+                    any_far = 1u;
+                    if (kind == kFarSeries) far_add(c23.y, v, C);
                 }
             }
         }
@@ -170,7 +183,8 @@ __device__ __forceinline__ void prep_item_cell(bool ok, const double* __restrict
 
 // All items of ONE particle by the `nthreads` (a multiple of 32) threads of a CTA - what the fused swarm kernel runs
 // per generation.  xs: the particle's D parameters; sw: its spectrum's w plane (N points); cs: shared [P][8] scratch
-// that ends up holding the span coefficients; coef_out: optional second copy of them; part [kPartDoubles];
+// that ends up holding the span coefficients; farpk: shared [P][4] scratch (per-peak far-field constants);
+// coef_out: optional second copy of the coefficients; part [kPartDoubles];
 // far [cells][kFarTerms]; anchor [regions][2]; mask [regions][mask_words_per_region].  Regions [r_lo, r_hi) are filled,
 // at index r - r_lo (default: all NRP slots; the slots of regions past the end of the axis are neutral).  Contains
 // __syncthreads().  `pairs` (optional shared scratch of cells*P*kPairDoubles doubles): the (cell, peak) series are
@@ -182,14 +196,14 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
                                                  double* __restrict__ cs, double* __restrict__ coef_out,
                                                  double* __restrict__ part, double* __restrict__ far,
                                                  double* __restrict__ anchor, unsigned* __restrict__ mask,
-                                                 double* __restrict__ pairs = nullptr, int r_lo = 0, int r_hi = -1,
-                                                 int sub = 1) {
+                                                 double* __restrict__ farpk, double* __restrict__ pairs = nullptr,
+                                                 int r_lo = 0, int r_hi = -1, int sub = 1) {
     if (r_hi < 0) r_hi = NRP;
     const int nr = r_hi - r_lo, nc = nr * sub;
     const int cell_pts = 32 * R / sub;
     const int MWR = mask_words_per_region(P, sub);
     (void)NR;
-    for (int k = tid; k < P; k += nthreads) prep_item_coef<R>(xs, k, h, w_ulp, cs, coef_out);
+    for (int k = tid; k < P; k += nthreads) prep_item_coef<R>(xs, k, h, w_ulp, cs, coef_out, farpk, sub);
     // the threads at the far end of the CTA do the phase tables and the anchors while the first do the peaks
     for (int e = nthreads - 1 - tid; e < kTableItems + nr; e += nthreads) {
         if (e < kTableItems) prep_item_table<R>(xs, e, N, P, part);
@@ -200,7 +214,8 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
     if (pairs) {
         for (int pi = tid; pi < nc * P; pi += nthreads) {  // one (cell, peak) pair per thread, in rounds
             const int cl = pi / P, k = pi - cl * P;
-            prep_item_pair<R>(cs, sw, h, N, sub, ((long long)r_lo * sub + cl) * cell_pts, k, pairs + (size_t)pi * kPairDoubles);
+            prep_item_pair<R>(cs, farpk, sw, h, N, sub, ((long long)r_lo * sub + cl) * cell_pts, k,
+                              pairs + (size_t)pi * kPairDoubles);
         }
         __syncthreads();
     }
@@ -208,7 +223,7 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
         const int cl = base + (tid & 31);
         const bool ok = cl < nc;
         const int rl = cl / sub, ci = cl - rl * sub;
-        prep_item_cell<R>(ok, cs, sw, h, N, P, sub, ((long long)r_lo * sub + cl) * cell_pts, ci,
+        prep_item_cell<R>(ok, cs, farpk, sw, h, N, P, sub, ((long long)r_lo * sub + cl) * cell_pts, ci,
                           pairs ? pairs + (size_t)cl * P * kPairDoubles : nullptr, far + (size_t)cl * kFarTerms,
                           mask + (size_t)rl * MWR);
     }
