@@ -74,7 +74,7 @@ def make_inputs(name):
     return data, weights, np.array(lo), np.array(up), true
 
 
-def workload_config(name, gpus, exchange='nccl'):
+def workload_config(name, gpus, exchange='p2p'):
     wl = WORKLOADS[name]
     if 'B' in wl:
         return {'workload': wl['title'], 'n_peaks': wl['P'], 'n_points': wl['N'], 'particles_per_swarm': wl['S'],
@@ -84,7 +84,8 @@ def workload_config(name, gpus, exchange='nccl'):
     return {'workload': wl['title'], 'n_peaks': wl['P'], 'n_points': wl['N'], 'particles_per_gpu': wl['S'],
             'swarm_total': wl['S'] * gpus,
             'parallelism': 'particles sharded over %d GPU(s), one best-record %s per generation'
-                           % (gpus, 'exchange over peer memory (NVLink stores)' if exchange == 'p2p' else 'all-gather'),
+                           % (gpus, 'exchange over peer memory inside the finish kernel (NVLink stores)' if exchange == 'p2p'
+                              else 'NCCL all-gather'),
             'l2': 'flushed between timed steps (256 MiB fill outside the per-step event brackets)'}
 
 
@@ -283,7 +284,7 @@ class ClockSampler:
 class SwarmRun:
     """One BASELINE workload set up on this rank's GPU: spectra resident, swarm initialised, `step()` = one generation."""
 
-    def __init__(self, name, world, rank, local, exchange='nccl', tune='', particles=None):
+    def __init__(self, name, world, rank, local, exchange='p2p', tune='', particles=None):
         import torch
         import torch.distributed as dist
         from nmrfit_b200 import _cabi, swarm, synth, utils
@@ -319,11 +320,25 @@ class SwarmRun:
         opts.minfunc = -1.0
         self.sharded = world > 1 and not self.batched
         self.p2p = self.sharded and exchange == 'p2p'
+        self.exchange_note = None
         if self.p2p:
-            handle, _ = ctx.peer_export(world, rank)
-            handles = [None] * world
-            dist.all_gather_object(handles, handle)
-            ctx.peer_open(ipc_handles=handles)
+            # map every rank's exchange window (CUDA IPC).  Every rank must end up on the same path: if the mapping
+            # fails anywhere (IPC not permitted on the box) all ranks take the NCCL all-gather instead, and say so
+            ok, err = 1, ''
+            try:
+                handle, _ = ctx.peer_export(world, rank)
+                handles = [None] * world
+                dist.all_gather_object(handles, handle)
+                ctx.peer_open(ipc_handles=handles)
+            except Exception as e:                          # noqa: BLE001 - reported, not swallowed
+                ok, err = 0, str(e)
+                if 'handles' not in locals():
+                    dist.all_gather_object([None] * world, None)
+            flag = torch.tensor([ok], device='cuda')
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if int(flag.item()) == 0:
+                self.p2p = False
+                self.exchange_note = 'peer-memory exchange unavailable (%s): NCCL all-gather used' % (err or 'failed on another rank')
             dist.barrier()
         ctx.pso_begin(self.lo, self.up, opts, stream=self.stream)
         self.rec = None
@@ -433,7 +448,8 @@ def roofline(name, run, res, burst, sustained):
     out = {'bound': 'fp64', 'unit': 'TFLOP/s', 'peak': sustained, 'peak_burst': burst,
            'peak_source': 'DFMA probe (nmrfit_fp64_peak) measured in this run, back-to-back average (burst %.2f); '
                           'MEASURED_PEAKS.json has no FP64 entry' % burst,
-           'kernel': 'objective_uniform_kernel' if uniform else 'objective_kernel',
+           'kernel': ('objective_stream_kernel' if run.ctx.get_variant(run.S)[0] == 1 else 'objective_uniform_kernel')
+                     if uniform else 'objective_kernel',
            'kernel_ms_per_launch': eval_ms, 'prepare_ms_per_launch': prep_ms,
            'kernel_share_of_step': res['eval_ms'] / float(res['step_ms'].sum()),
            'prepare_share_of_step': res['prep_ms'] / float(res['step_ms'].sum()),
@@ -634,13 +650,15 @@ def run_b200(args):
             'warmup': args.warmup, 'ms_per_step': total_ms / args.steps, 'higher_is_better': True,
             'scaling': 'strong' if run.batched else 'weak',
             'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': dict(workload_config(args.workload, world, args.exchange), kernel=tune),
+            'config': dict(workload_config(args.workload, world, 'p2p' if run.p2p or not run.sharded else 'nccl'), kernel=tune),
             'peak_points_per_s': value * run.N * run.P,
             'roofline': rf,
             'e2e': e2e,
             'gpu_launches': res['launches'],
             'clocks': clocks,
         }
+        if run.exchange_note:
+            line['config']['exchange_note'] = run.exchange_note
         if same_main is not None:
             line['sharded_identical_on_all_ranks'] = bool(same_main)
         if flags:
@@ -768,9 +786,10 @@ def main():
     ap.add_argument('--warmup', type=int, default=5)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--workload', default='metric', choices=sorted(WORKLOADS))
-    ap.add_argument('--exchange', default='nccl', choices=['nccl', 'p2p'],
-                    help='particle sharding (N > 1): best-record all-gather over NCCL, or the exchange + commit kernel '
-                         'over peer memory (CUDA IPC windows, NVLink stores)')
+    ap.add_argument('--exchange', default='p2p', choices=['nccl', 'p2p'],
+                    help='particle sharding (N > 1): the best records exchanged over peer memory inside the finish kernel '
+                         '(CUDA IPC windows, NVLink stores: three launches per generation, no collective call; default), '
+                         'or one NCCL all-gather + a commit kernel per generation')
     ap.add_argument('--tune', default='', help='threads,points_per_thread,exp_table_bits,particles_per_cta')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--quick', action='store_true', help='main measurement only (no CPU baseline, no secondary configs / fits)')

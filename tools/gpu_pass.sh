@@ -12,8 +12,11 @@ for f in smoke pytest_gpu bench bench_reference; do tail -n 3 gpurun_out/${TAG}_
 [ -n "$2" ] && exit 0
 timeout 300 python bench.py --steps 20 --warmup 3 --quick > gpurun_out/${TAG}_bench_short.log 2>&1 &&
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches.csv python bench.py --steps 20 --warmup 3 --quick > gpurun_out/${TAG}_ncu_launches.log 2>&1
+# (gpurun merges at most 64 MiB back: the source pages - ~20 MB per report - only for the headline workload)
 for WL in metric c2 c3 c4; do
+  SRC=""; [ "$WL" = metric ] && SRC="--import-source on"
   timeout 300 python bench.py --steps 8 --warmup 3 --quick --workload $WL > gpurun_out/${TAG}_bench_short_$WL.log 2>&1 &&
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:objective_stream_kernel -s 5 -c 1 -o gpurun_out/${TAG}_prof_$WL python bench.py --steps 8 --warmup 3 --quick --workload $WL > gpurun_out/${TAG}_ncu_full_$WL.log 2>&1
+  timeout 900 ncu --set full --clock-control none $SRC -k regex:objective_stream_kernel -s 5 -c 1 -o gpurun_out/${TAG}_prof_$WL python bench.py --steps 8 --warmup 3 --quick --workload $WL > gpurun_out/${TAG}_ncu_full_$WL.log 2>&1
 done
+du -sh gpurun_out
 ls -la gpurun_out/${TAG}_*
