@@ -4,6 +4,7 @@
 #include <cmath>
 #include <atomic>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -93,6 +94,7 @@ struct nmrfit_ctx {
     DevBuf<unsigned> fbarrier;
     DevBuf<int> ferror;                // fused swarm kernel: barrier-timeout flag
     DevBuf<unsigned> mt_state;         // MT19937 key [624] + position, for nmrfit_ctx_mt19937
+    DevBuf<unsigned> mt_words;         // ... and the tempered word stream of one call
     long long mt_elems = 0;            // elements of one random array (n_spectra * swarmsize * D)
     DevBuf<double> fin_scratch;        // finish kernel: per-CTA candidates
     DevBuf<unsigned> fin_tickets;
@@ -204,7 +206,11 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
     t.variant = 0;
     t.stages = 0;
     t.occ = 3;
-    if (uni && c->precision == NMRFIT_FP64 && c->user_tune.variant != 0 && t.tb == 6) {     // (built for the default table)
+    // ... when there is enough work to stream: a small swarm (a single fit's 100-204 particles on a short axis) is a few
+    // dozen CTAs either way, and then one group per CTA finishes sooner than a handful of CTAs walking several groups each
+    const long long particle_tiles = (long long)((c->N + t.threads * t.r - 1) / (t.threads * t.r)) * S * c->B;
+    const bool enough = particle_tiles >= 8192 || c->user_tune.variant == 1;
+    if (uni && c->precision == NMRFIT_FP64 && c->user_tune.variant != 0 && t.tb == 6 && enough) {   // (built for the default table)
         t.variant = 1;
         t.occ = c->user_tune.occ == 3 ? 3 : 2;
         const size_t budget = (t.occ == 2 ? 112 : 74) * 1024;
@@ -473,6 +479,7 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->fbarrier.release();
     c->ferror.release();
     c->mt_state.release();
+    c->mt_words.release();
     c->ftiming.release();
     for (void* p : c->peer_opened) cudaIpcCloseMemHandle(p);
     if (c->peer_win) cudaFree(c->peer_win);
@@ -736,8 +743,9 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
     CK(c->f_stage.reserve(nf));
     // A large particle set of one spectrum goes through in slices on two streams: while slice k is evaluated, slice
     // k + 1's positions are on their way in and slice k - 1's values on their way out (each slice has its own scratch).
-    constexpr int kSlices = 4, kPad = 64;
-    if (c->B == 1 && S >= 4 * 4096 && !c->profiling) {
+    constexpr int kPad = 64;
+    static const int kSlices = [] { const char* e = getenv("NMRFIT_E2E_SLICES"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+    if (c->B == 1 && S >= 4 * 4096 && !c->profiling && kSlices > 1) {
         for (int k = 0; k < 2; ++k)
             if (!c->pipe[k]) CK(cudaStreamCreateWithFlags(&c->pipe[k], cudaStreamNonBlocking));
         const int chunk = ((S + kSlices - 1) / kSlices + 63) & ~63;
@@ -861,12 +869,13 @@ int nmrfit_ctx_mt19937(nmrfit_ctx* c, unsigned* key, int* pos, long long n_array
     CK(c->rnd_a.reserve((size_t)(pairs * nsd)));
     CK(c->rnd_b.reserve((size_t)(pairs * nsd)));
     CK(c->mt_state.reserve(625));
+    CK(c->mt_words.reserve((size_t)(2 * n_arrays * nsd)));
     unsigned host[625];
     std::memcpy(host, key, sizeof(unsigned) * 624);
     host[624] = (unsigned)*pos;
     CK(cudaMemcpyAsync(c->mt_state.ptr, host, sizeof(host), cudaMemcpyHostToDevice, st));
     cudaError_t e = launch_mt19937(c->mt_state.ptr, reinterpret_cast<int*>(c->mt_state.ptr + 624), n_arrays * nsd,
-                                   c->rnd_a.ptr, c->rnd_b.ptr, nsd, st);
+                                   c->mt_words.ptr, c->rnd_a.ptr, c->rnd_b.ptr, nsd, st);
     if (e != cudaSuccess) return fail_cuda(e, "MT19937 launch");
     CK(cudaMemcpyAsync(host, c->mt_state.ptr, sizeof(host), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));

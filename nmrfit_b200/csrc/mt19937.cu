@@ -6,10 +6,9 @@
 // (genrand_res53: (a >> 5) * 2^26 + (b >> 6), over 2^53, from two tempered 32-bit words) and hands back the advanced
 // state, which the host puts back with np.random.set_state - the stream ends where pyswarm would have left it.
 //
-// The state recurrence is sequential from block to block (624 words) but parallel inside a block: word k of the next
-// block needs words k, k + 1, k + 397 of the current one, so a block regenerates in four dependent sweeps
-// ([0, 227), [227, 454), [454, 623), {623}).  One CTA walks the blocks; a C1 fit (100 particles x 22 parameters x
-// 2 x 101 draws) is 1,425 blocks, ~0.1 ms.
+// The recurrence x[n] = f(x[n-624], x[n-623], x[n-227]) is sequential with a lag of 227 words: one CTA advances 227
+// words per step (one __syncthreads each) and writes the tempered words out; a second, fully parallel kernel turns word
+// pairs into doubles.  A C1 fit (100 particles x 22 parameters x 2 x 101 draws = 888,800 words) is ~3,900 steps.
 #include <cuda_runtime.h>
 #include <cstdint>
 #include "nmrfit_internal.h"
@@ -32,72 +31,73 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
     return y;
 }
 
-// key_io [624] (global): the state, updated in place; *pos_io: words of it already consumed (0..624).
-// Doubles q = 0..n-1 of the stream go to out_a[q] - or, when nsd > 0, de-interleaved as pyswarm consumes them
-// (uniform(size=(S, D)) for rp, then again for rg, per generation): q = (2 g + which) nsd + e -> (which ? out_b : out_a)[g nsd + e].
+// Pass 1 (sequential in steps, one CTA): the raw recurrence x[n] = twist(x[n-624], x[n-623], x[n-227]) advances
+// 227 words per step - the lag of the nearest dependence - with ONE __syncthreads per step; every new word is tempered
+// on the spot and written to the word stream.  key_io [624] (global): the state, updated in place; *pos_io: words of it
+// already consumed (0..624); words_out [n_words]: the next n_words tempered 32-bit words of the stream.
+constexpr int kMtLag = kMtN - kMtM;                        // 227
 __global__ void __launch_bounds__(kMtThreads)
-mt19937_kernel(uint32_t* __restrict__ key_io, int* __restrict__ pos_io, long long n, double* __restrict__ out_a,
-               double* __restrict__ out_b, long long nsd) {
-    __shared__ uint32_t key[kMtN];
-    __shared__ uint32_t word[kMtN];                        // tempered words of the current block
+mt19937_words_kernel(uint32_t* __restrict__ key_io, int* __restrict__ pos_io, long long n_words,
+                     uint32_t* __restrict__ words_out) {
+    __shared__ uint32_t ring[1024];                        // x[n] at slot n & 1023 (needs the last 624 + 227 words)
     const int tid = threadIdx.x;
-    for (int k = tid; k < kMtN; k += kMtThreads) key[k] = key_io[k];
     const int pos = *pos_io;
+    // absolute numbering: the given state is x[0..623]; the stream's word t (t = 0, 1, ...) is temper(x[pos + t])
+    for (int k = tid; k < kMtN; k += kMtThreads) ring[k] = key_io[k];
     __syncthreads();
-    const long long n_words = 2 * n;
-    // stream word t = 0, 1, ... is the t-th word drawn from now on; t0 = stream index of word 0 of the current block
-    long long t0 = pos < kMtN ? -(long long)pos : 0;
-    bool twist = pos >= kMtN;                              // the given block is used up: start with a fresh one
-    uint32_t carry = 0;                                    // last word of the previous block (a pair may straddle two)
-    long long last_t0 = t0;
-    while (t0 < n_words) {
-        if (twist) {
-            // regenerate: four sweeps, each reading only words the previous sweeps have finished with
-            for (int k = tid; k < kMtN - kMtM; k += kMtThreads) key[k] = mt_twist(key[k], key[k + 1], key[k + kMtM]);
-            __syncthreads();
-            for (int k = kMtN - kMtM + tid; k < 2 * (kMtN - kMtM); k += kMtThreads)
-                key[k] = mt_twist(key[k], key[k + 1], key[k - (kMtN - kMtM)]);
-            __syncthreads();
-            for (int k = 2 * (kMtN - kMtM) + tid; k < kMtN - 1; k += kMtThreads)
-                key[k] = mt_twist(key[k], key[k + 1], key[k - (kMtN - kMtM)]);
-            __syncthreads();
-            if (tid == 0) key[kMtN - 1] = mt_twist(key[kMtN - 1], key[0], key[kMtM - 1]);
-            __syncthreads();
+    const long long last = (long long)pos + n_words;       // one past the last word needed (absolute)
+    for (long long n = pos + tid; n < (last < kMtN ? last : kMtN); n += kMtThreads)
+        words_out[n - pos] = mt_temper(ring[n]);           // what is left of the given block
+    long long base = kMtN;
+    while (base < last) {
+        const long long n = base + tid;
+        if (tid < kMtLag && n < last + kMtN) {              // (a little past the end, so that a whole final block exists)
+            const uint32_t x = mt_twist(ring[(n - kMtN) & 1023], ring[(n - kMtN + 1) & 1023], ring[(n - kMtLag) & 1023]);
+            ring[n & 1023] = x;
+            if (n < last) words_out[n - pos] = mt_temper(x);
         }
-        twist = true;
-        for (int k = tid; k < kMtN; k += kMtThreads) word[k] = mt_temper(key[k]);
-        __syncthreads();
-        // the doubles whose SECOND word (stream word 2q + 1) lies in this block; the first is here too or is `carry`
-        const long long lo = t0 < 0 ? 0 : t0;                                         // first stream word in use here
-        const long long hi = (t0 + kMtN < n_words ? t0 + kMtN : n_words) - 1;         // last one
-        for (long long q = lo / 2 + tid; 2 * q + 1 <= hi; q += kMtThreads) {
-            const long long ta = 2 * q, tb = 2 * q + 1;
-            const uint32_t a = ta >= t0 ? word[ta - t0] : carry;
-            const uint32_t b = word[tb - t0];
-            const double x = ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
-            if (nsd > 0) {
-                const long long blk = q / nsd, e = q - blk * nsd;
-                ((blk & 1) ? out_b : out_a)[(blk >> 1) * nsd + e] = x;
-            } else {
-                out_a[q] = x;
-            }
-        }
-        __syncthreads();
-        carry = word[kMtN - 1];
-        last_t0 = t0;
-        t0 += kMtN;
+        base += kMtLag;
         __syncthreads();
     }
-    for (int k = tid; k < kMtN; k += kMtThreads) key_io[k] = key[k];
-    if (tid == 0 && n_words > 0) *pos_io = (int)(n_words - last_t0);      // words consumed from the last block touched
+    // the state to hand back: numpy keeps whole blocks, so the block that holds the last word drawn, [b0, b0 + 624).
+    // If that block was only partly generated above, finish it (its words are never drawn here, only stored).
+    const long long b0 = last <= kMtN ? 0 : ((last - 1) / kMtN) * kMtN;
+    long long done = base;                                 // words [0, done) exist... up to last + 624 at most
+    while (done < b0 + kMtN) {
+        const long long n = done + tid;
+        if (tid < kMtLag && n < b0 + kMtN)
+            ring[n & 1023] = mt_twist(ring[(n - kMtN) & 1023], ring[(n - kMtN + 1) & 1023], ring[(n - kMtLag) & 1023]);
+        done += kMtLag;
+        __syncthreads();
+    }
+    for (int k = tid; k < kMtN; k += kMtThreads) key_io[k] = ring[(b0 + k) & 1023];
+    if (tid == 0 && n_words > 0) *pos_io = (int)(last - b0);
+}
+
+// Pass 2 (fully parallel): doubles from word pairs - genrand_res53 - de-interleaved as pyswarm consumes them.
+// Double q uses words (2q, 2q + 1); with nsd > 0, q = (2 g + which) nsd + e -> (which ? out_b : out_a)[g nsd + e].
+__global__ void mt19937_doubles_kernel(const uint32_t* __restrict__ words, long long n, double* __restrict__ out_a,
+                                       double* __restrict__ out_b, long long nsd) {
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    const uint32_t a = words[2 * q], b = words[2 * q + 1];
+    const double x = ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
+    if (nsd > 0) {
+        const long long blk = q / nsd, e = q - blk * nsd;
+        ((blk & 1) ? out_b : out_a)[(blk >> 1) * nsd + e] = x;
+    } else {
+        out_a[q] = x;
+    }
 }
 
 }  // namespace
 
-cudaError_t launch_mt19937(unsigned* key_dev, int* pos_dev, long long n, double* out_a, double* out_b, long long nsd,
-                           cudaStream_t st) {
-    mt19937_kernel<<<1, kMtThreads, 0, st>>>(key_dev, pos_dev, n, out_a, out_b, nsd);
-    count_launches(1);
+cudaError_t launch_mt19937(unsigned* key_dev, int* pos_dev, long long n, unsigned* words_dev, double* out_a, double* out_b,
+                           long long nsd, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    mt19937_words_kernel<<<1, kMtThreads, 0, st>>>(key_dev, pos_dev, 2 * n, words_dev);
+    mt19937_doubles_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(words_dev, n, out_a, out_b, nsd);
+    count_launches(2);
     return cudaGetLastError();
 }
 

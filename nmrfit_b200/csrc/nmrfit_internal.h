@@ -183,8 +183,8 @@ cudaError_t launch_phase_acme(const double* u, const double* v, int B, int N, co
                               cudaStream_t st);
 
 // ---- numpy's legacy MT19937 stream continued on the device (mt19937.cu) --------------------
-cudaError_t launch_mt19937(unsigned* key_dev, int* pos_dev, long long n, double* out_a, double* out_b, long long nsd,
-                           cudaStream_t st);
+cudaError_t launch_mt19937(unsigned* key_dev, int* pos_dev, long long n, unsigned* words_dev, double* out_a, double* out_b,
+                           long long nsd, cudaStream_t st);
 
 // ---- K10 auto peak selection (peaks.cu) ----------------------------------------------
 // front: upsample, smooth, global baseline, maxima (unsorted indices + the upsampled signal there);
