@@ -433,7 +433,7 @@ def load_ncu(name):
     return json.load(open(path)).get(name)
 
 
-def roofline(name, run, res, burst, sustained):
+def roofline(name, run, res, burst, sustained, sm_mhz=None):
     """The evaluation kernel against the FP64 pipe.  `achieved` counts what the hardware EXECUTED: FP64 instructions
     per peak-point from the ncu capture of this kernel on this workload x the peak-points of a launch / the kernel's
     CUDA-event time, two flop per instruction slot (the DFMA convention of the measured peak) - so achieved / peak is
@@ -465,6 +465,19 @@ def roofline(name, run, res, burst, sustained):
             out['achieved_flop_counting_dmul_dadd_as_one'] = flop * pp / (eval_ms * 1e-3) / 1e12
         out['fp64_inst_per_peak_point'] = ncu['fp64_arith_inst_per_peak_point']
         out['algorithmic_speedup'] = canonical / out['achieved']
+        # What actually bounds the kernel: the warp schedulers' issue ports.  An FP64 warp instruction holds its
+        # sub-partition's port for two cycles (64 FP64 lanes per SM) and nothing else issues in its shadow
+        # (tools/probes/issue_probe.cu, profiles/r02b_issue_probe.log: 8 DFMA + M integer ops cost 16 + ~1.25 M cycles),
+        # so the port time of a launch is 2 x FP64 instructions + every other instruction.
+        if ncu.get('warp_inst_per_peak_point') and sm_mhz:
+            total_w = ncu['warp_inst_per_peak_point'] * pp / 32.0
+            fp64_w = inst / 32.0
+            ports = 148 * 4 * sm_mhz * 1e6 * (eval_ms * 1e-3)                 # issue cycles available, all sub-partitions
+            out['issue_port'] = {'frac': (total_w + fp64_w) / ports, 'fp64_share_of_instructions': fp64_w / total_w,
+                                 'fp64_frac_ceiling_at_this_mix': 2 * fp64_w / (total_w + fp64_w), 'sm_mhz': sm_mhz,
+                                 'note': 'port cycles used / available = (all warp instructions + FP64 ones once more) / '
+                                         '(592 sub-partitions x SM clock x kernel time); the ceiling is what roofline.frac '
+                                         'could reach at this instruction mix with the ports 100 % busy'}
         out['traffic'] = ncu.get('dram_bytes_per_launch')
         out['ncu'] = ncu
         out['note'] = ('achieved = FP64 instructions the kernel EXECUTES (ncu: smsp__sass_thread_inst_executed_op_{dfma,dmul,'
@@ -623,7 +636,7 @@ def run_b200(args):
 
     e2e = measure_e2e(run, args.steps, args.warmup)
     burst, sustained = _cabi.fp64_peak(local, iters=4096, repeats=20)
-    rf = roofline(args.workload, run, res, burst, sustained)
+    rf = roofline(args.workload, run, res, burst, sustained, clocks.get('sm_mhz'))
     tune = run.ctx.get_tuning(run.S)
     run.close()
 
