@@ -111,6 +111,8 @@ struct nmrfit_ctx {
     double peer_timeout_ms = 20000.0;  // wall-time bound of a wait for the peers' tokens
     DevBuf<double> wscratch, wbounds;  // batched weights: sweep scratch [B][N], windows + values
     cudaStream_t pipe[2] = {nullptr, nullptr};   // nmrfit_objective_batch_host: slices of a large particle set
+    double* h_f = nullptr;                       // ... and page-locked staging of their values
+    size_t h_f_cap = 0;
     int far_cells = 0;                 // far-field cells per region: 0 = far_cells_per_region(N, R), else 1 | 2 | 4
     int fused_mode = NMRFIT_FUSED_AUTO;
     DevBuf<long long> ftiming;         // optional per-phase cycle counters of the fused kernel
@@ -492,6 +494,7 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->wbounds.release();
     for (int k = 0; k < 2; ++k)
         if (c->pipe[k]) cudaStreamDestroy(c->pipe[k]);
+    if (c->h_f) cudaFreeHost(c->h_f);
     if (c->h_flags) cudaFreeHost(c->h_flags);
     for (cudaEvent_t ev : c->prof_events) cudaEventDestroy(ev);
     delete c;
@@ -748,6 +751,13 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
     if (c->B == 1 && S >= 4 * 4096 && !c->profiling && kSlices > 1) {
         for (int k = 0; k < 2; ++k)
             if (!c->pipe[k]) CK(cudaStreamCreateWithFlags(&c->pipe[k], cudaStreamNonBlocking));
+        if (c->h_f_cap < nf) {
+            if (c->h_f) cudaFreeHost(c->h_f);
+            c->h_f = nullptr;
+            c->h_f_cap = 0;
+            CK(cudaMallocHost(&c->h_f, sizeof(double) * nf));
+            c->h_f_cap = nf;
+        }
         const int chunk = ((S + kSlices - 1) / kSlices + 63) & ~63;
         const size_t total = (size_t)kSlices * (chunk + kPad);
         for (int k = 0, s0 = 0; s0 < S; ++k, s0 += chunk) {
@@ -758,10 +768,13 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
             if (int rc = run_objective(c, c->x_stage.ptr + (size_t)s0 * c->D, ns, fit_im, c->f_stage.ptr + s0, nullptr, ps,
                                        nullptr, nullptr, nullptr, nullptr, (size_t)k * (chunk + kPad), total))
                 return rc;
-            CK(cudaMemcpyAsync(f_host + s0, c->f_stage.ptr + s0, sizeof(double) * ns, cudaMemcpyDeviceToHost, ps));
+            // (into page-locked staging: an "async" copy into the caller's pageable array would block the host until
+            // the slice has been evaluated, and the slices would run one after the other)
+            CK(cudaMemcpyAsync(c->h_f + s0, c->f_stage.ptr + s0, sizeof(double) * ns, cudaMemcpyDeviceToHost, ps));
         }
         CK(cudaStreamSynchronize(c->pipe[0]));
         CK(cudaStreamSynchronize(c->pipe[1]));
+        std::memcpy(f_host, c->h_f, sizeof(double) * nf);
         return NMRFIT_OK;
     }
     cudaStream_t st = 0;
