@@ -747,8 +747,8 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
     // A large particle set of one spectrum goes through in slices on two streams: while slice k is evaluated, slice
     // k + 1's positions are on their way in and slice k - 1's values on their way out (each slice has its own scratch).
     constexpr int kPad = 64;
-    static const int kSlices = [] { const char* e = getenv("NMRFIT_E2E_SLICES"); const int v = e ? atoi(e) : 4; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
-    if (c->B == 1 && S >= 4 * 4096 && !c->profiling && kSlices > 1) {
+    static const int kSlices = [] { const char* e = getenv("NMRFIT_E2E_SLICES"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
+    if (c->B == 1 && S >= 4 * 4096 && !c->profiling && kSlices > 1) {       // (two slices measured best: tools/e2e_probe.py)
         for (int k = 0; k < 2; ++k)
             if (!c->pipe[k]) CK(cudaStreamCreateWithFlags(&c->pipe[k], cudaStreamNonBlocking));
         if (c->h_f_cap < nf) {

@@ -329,8 +329,15 @@ cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaSt
     int G = std::max(1, std::min(16, std::min(a.S, 2 * kPrepThreads / nc)));
     while (G > 1 && G * per_particle > 40 * 1024) --G;     // stay inside the default dynamic shared-memory limit
     // a particle with >= 128 cells fills a CTA of 128 threads on its own (and many small CTAs schedule better)
-    const int pthreads = nc >= 128 ? 128 : kPrepThreads;
+    int pthreads = nc >= 128 ? 128 : kPrepThreads;
     if (nc >= 128) G = 1;
+    // a small swarm (a single fit): as many CTAs as there are particles - the critical path of one CTA, not the
+    // machine's throughput, is what the generation waits for
+    const long long want_ctas = 2 * 148;
+    if ((long long)a.S * B / G < want_ctas) {
+        G = (int)std::max<long long>(1, std::min<long long>(G, (long long)a.S * B / want_ctas));
+        if (G == 1) pthreads = 128;
+    }
     dim3 pgrid((a.S + G - 1) / G, B);
     const size_t bytes = G * per_particle;
     const MoveArgs none{};
