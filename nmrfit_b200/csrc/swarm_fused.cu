@@ -438,10 +438,12 @@ static cudaError_t plan_one(const FusedArgs& a, int D, int particles, int thread
     const int NW = threads / 32, NRP = a.n_vtiles * a.vw, n_super = (NRP + NW - 1) / NW;
     const int per = (n_super + cluster - 1) / cluster;
     const int grid = particles * cluster;
+    // keeping the spectrum resident matters more than the pair-parallel constants pass (whose scratch grows with the
+    // number of far-field cells): resident + pairs, resident, then one supertile at a time with / without pairs
     for (int attempt = 0; attempt < 4; ++attempt) {
-        const int slots = (attempt & 1) ? 1 : per;
-        const bool pairs = attempt < 2;
-        if ((attempt & 1) && per == 1) continue;
+        const int slots = attempt < 2 ? per : 1;
+        const bool pairs = (attempt & 1) == 0;
+        if (attempt >= 2 && per == 1) continue;
         const size_t bytes = (size_t)FusedSmem(a.P, D, threads, r, slots, NRP, per * NW, pairs, a.sub).total * sizeof(double);
         if (bytes > 200 * 1024) continue;
         long long capacity = 0;
