@@ -83,13 +83,13 @@ struct F32Smem {
         wpart = o;  o += sp * nw;
         coef = o;   o += sp * P * 8;
         part = o;   o += sp * kPartDoubles;
-        far = o;    o += sp * nw * kFarTerms;
+        far = o;    o += sp * nw * kFarPoly;
         anchor = o; o += sp * nw * 2;
         mask = o;   o += ((sp * nw * (mw + 1) + 3) / 4) * 2;
         // single-precision copies made once per CTA (a double -> float conversion costs four FP64 issue slots: doing
         // it per thread and particle was 30 conversions per 8 points, now 1.5 + the 8 of the residual)
         coef32 = o; o += sp * P * 4;                       // 8 floats per peak: kL, kG, dT, aL, aG, c2, thr, -
-        far32 = o;  o += (sp * nw * kFarTerms + 1) / 2;
+        far32 = o;  o += (sp * nw * kFarPoly + 1) / 2;
         o = (o + 1) & ~1;
         total = o;
     }
@@ -129,14 +129,14 @@ objective_uniform_f32_kernel(ObjArgs a) {
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t b_coef = SP * P * 8 * 8, b_part = SP * kPartDoubles * 8, b_far = NW * kFarTerms * 8;
+        const uint32_t b_coef = SP * P * 8 * 8, b_part = SP * kPartDoubles * 8, b_far = NW * kFarPoly * 8;
         const uint32_t b_anchor = NW * 2 * 8, b_mask = NW * (MW + 1) * 4;
         mbar_expect_tx(bar, b_coef + b_part + SP * (b_far + b_anchor + b_mask));
         bulk_g2s(smem + L.coef, a.prep_coef + q0 * P * 8, b_coef, bar);
         bulk_g2s(smem + L.part, a.prep_part + q0 * kPartDoubles, b_part, bar);
         for (int sp = 0; sp < SP; ++sp) {
             const size_t rs = (q0 + sp) * NRP + (size_t)tile * NW;
-            bulk_g2s(smem + L.far + sp * NW * kFarTerms, a.prep_far + rs * kFarTerms, b_far, bar);
+            bulk_g2s(smem + L.far + sp * NW * kFarPoly, a.prep_far + rs * kFarPoly, b_far, bar);
             bulk_g2s(smem + L.anchor + sp * NW * 2, a.prep_anchor + rs * 2, b_anchor, bar);
             bulk_g2s(reinterpret_cast<unsigned*>(smem + L.mask) + sp * NW * (MW + 1), a.prep_mask + rs * (MW + 1), b_mask, bar);
         }
@@ -159,7 +159,7 @@ objective_uniform_f32_kernel(ObjArgs a) {
         o[0] = (float)c[1]; o[1] = (float)c[2]; o[2] = (float)c[5]; o[3] = (float)c[3];
         o[4] = (float)c[4]; o[5] = (float)c[7]; o[6] = (float)c[6]; o[7] = 0.f;
     }
-    for (int e = tid; e < SP * NW * kFarTerms; e += THREADS) far32[e] = (float)farc[e];
+    for (int e = tid; e < SP * NW * kFarPoly; e += THREADS) far32[e] = (float)farc[e];
     __syncthreads();
 
     for (int sp = 0; sp < nsp; ++sp) {
@@ -178,19 +178,19 @@ objective_uniform_f32_kernel(ObjArgs a) {
             peak_span_f32<R>(d0 * f0.x, d0 * f0.y, f0.z, f0.w, f1.x, f1.y, f1.z, acc);
         }
         if (mk[MW]) {
-            const float* fc = far32 + (size_t)(sp * NW + warp) * kFarTerms;
-            float C[kFarTerms];
+            const float* fc = far32 + (size_t)(sp * NW + warp) * kFarPoly;
+            float C[kFarPoly];
 #pragma unroll
-            for (int n = 0; n < kFarTerms; n += 4) {
-                const float4 t = *reinterpret_cast<const float4*>(fc + n);
-                C[n] = t.x; C[n + 1] = t.y; C[n + 2] = t.z; C[n + 3] = t.w;
+            for (int n = 0; n < kFarPoly; n += 2) {
+                const float2 t = *reinterpret_cast<const float2*>(fc + n);
+                C[n] = t.x; C[n + 1] = t.y;
             }
 #pragma unroll
             for (int j = 0; j < R; ++j) {
                 const float xi = fmaf((float)j, 1.f / H, xi0);
-                float p = C[kFarTerms - 1];
+                float p = C[kFarPoly - 1];
 #pragma unroll
-                for (int n = kFarTerms - 2; n >= 1; --n) p = fmaf(p, xi, C[n]);
+                for (int n = kFarPoly - 2; n >= 1; --n) p = fmaf(p, xi, C[n]);
                 acc[j] = fmaf(p, xi, acc[j] + C[0]);
             }
         }

@@ -58,7 +58,7 @@ struct StreamSmem {
         int q = 0;
         coef = q;    q += spg * P * 8;
         part = q;    q += spg * kPartDoubles;
-        far = q;     q += spg * nw * sub * kFarTerms;       // per far-field cell (uniform_eval.cuh)
+        far = q;     q += spg * nw * sub * kFarPoly;       // per far-field cell (uniform_eval.cuh)
         anchor = q;  q += spg * nw * 2;
         mask = q;    q += ((spg * nw * mask_words_per_region(P, sub) + 3) / 4) * 2;
         slot = q;
@@ -104,7 +104,7 @@ objective_stream_kernel(ObjArgs a) {
     const size_t pb = (size_t)b * a.S;                     // first particle slot of this spectrum
     const size_t tb_ = ((size_t)b * n_tiles + tile) * a.S; // ... of this (spectrum, tile) in the tile-major arrays
 
-    const uint32_t b_coef = SPG * P * 8 * 8, b_part = SPG * kPartDoubles * 8, b_far = SPG * NW * SUB * kFarTerms * 8;
+    const uint32_t b_coef = SPG * P * 8 * 8, b_part = SPG * kPartDoubles * 8, b_far = SPG * NW * SUB * kFarPoly * 8;
     const int MWR = mask_words_per_region(P, SUB);
     const uint32_t b_anchor = SPG * NW * 2 * 8, b_mask = SPG * NW * MWR * 4;
     // one thread asks the TMA for group g (relative to g_lo) into slot g % ST.  Whole groups are copied (the
@@ -117,7 +117,7 @@ objective_stream_kernel(ObjArgs a) {
         mbar_expect_tx(bar, b_coef + b_part + b_far + b_anchor + b_mask);
         bulk_g2s(dst + L.coef, a.prep_coef + (pb + q0) * P * 8, b_coef, bar);
         bulk_g2s(dst + L.part, a.prep_part + (pb + q0) * kPartDoubles, b_part, bar);
-        bulk_g2s(dst + L.far, a.prep_far + (tb_ + q0) * NW * SUB * kFarTerms, b_far, bar);
+        bulk_g2s(dst + L.far, a.prep_far + (tb_ + q0) * NW * SUB * kFarPoly, b_far, bar);
         bulk_g2s(dst + L.anchor, a.prep_anchor + (tb_ + q0) * NW * 2, b_anchor, bar);
         bulk_g2s(dst + L.mask, a.prep_mask + (tb_ + q0) * NW * MWR, b_mask, bar);
     };
@@ -136,8 +136,9 @@ objective_stream_kernel(ObjArgs a) {
         const int i = tile0 + e;
         const bool ok = i < N;
         const int t = e / R, j = e % R;
-        suv[j * THREADS + t] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
-        swt[j * THREADS + t] = ok ? sw[3 * N + i] : 0.0;    // zero weight: padding contributes nothing
+        const double wgt = ok ? sw[3 * N + i] : 0.0;    // zero weight: padding contributes nothing
+        suv[j * THREADS + t] = stage_point(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0, wgt);
+        swt[j * THREADS + t] = wgt;
     }
     {
         const int i_first = tile0 + tid * R;
@@ -153,7 +154,7 @@ objective_stream_kernel(ObjArgs a) {
     __syncthreads();                                       // the only CTA-wide barrier: tile, table, mbarriers
 
     // strides between consecutive particles of a slot / of the output
-    const int s_coef = P * 8, s_far = NW * SUB * kFarTerms, s_mask = NW * MWR;
+    const int s_coef = P * 8, s_far = NW * SUB * kFarPoly, s_mask = NW * MWR;
     const size_t s_out = (size_t)n_tiles * NW * NSUM;
     int sl = 0;
     uint32_t phase = 0;
@@ -168,7 +169,7 @@ objective_stream_kernel(ObjArgs a) {
         const double w_first = swf[t];
         const double* cf = slot + L.coef;
         const double* pt = slot + L.part;
-        const double* fc = slot + L.far + rw * SUB * kFarTerms;
+        const double* fc = slot + L.far + rw * SUB * kFarPoly;
         const double2* an = reinterpret_cast<const double2*>(slot + L.anchor) + rw;
         const unsigned* mk = reinterpret_cast<const unsigned*>(slot + L.mask) + rw * MWR;
         const double* xs = a.x + (pb + q0) * D;

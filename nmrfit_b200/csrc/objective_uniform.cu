@@ -151,7 +151,7 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
         const RegionDst rd(a, b, s0 + g, NRP);
         const size_t rs = rd.region(rl);
         prep_item_cell<R>(ok, cs + (size_t)g * P * 8, farpk + (size_t)g * P * 4, sw, h, N, P, sub, (long long)cl * cell_pts, ci, nullptr,
-                          a.prep_far + (rs * sub + ci) * kFarTerms, a.prep_mask + rs * MWR);
+                          a.prep_far + (rs * sub + ci) * kFarPoly, a.prep_mask + rs * MWR);
     }
 }
 
@@ -170,7 +170,7 @@ struct UniSmem {
         wpart = o;  o += sp * nw * nsum;                   // nsum = 2: real and imaginary sums of fit_im
         coef = o;   o += sp * P * 8;
         part = o;   o += sp * kPartDoubles;
-        far = o;    o += sp * nw * sub * kFarTerms;       // far-field polynomial per (particle, cell of a warp region)
+        far = o;    o += sp * nw * sub * kFarPoly;       // far-field polynomial per (particle, cell of a warp region)
         anchor = o; o += sp * nw * 2;                     // phase at the first point of each warp region
         mask = o;   o += ((sp * nw * mask_words_per_region(P, sub) + 3) / 4) * 2;
         total = o;
@@ -214,7 +214,7 @@ objective_uniform_kernel(ObjArgs a) {
     if (tid == 0) {
         mbar_init(bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        const uint32_t b_coef = SP * P * 8 * 8, b_part = SP * kPartDoubles * 8, b_far = NW * SUB * kFarTerms * 8;
+        const uint32_t b_coef = SP * P * 8 * 8, b_part = SP * kPartDoubles * 8, b_far = NW * SUB * kFarPoly * 8;
         const int MWR = mask_words_per_region(P, SUB);
         const uint32_t b_anchor = NW * 2 * 8, b_mask = NW * MWR * 4;
         mbar_expect_tx(bar, b_coef + b_part + SP * (b_far + b_anchor + b_mask));
@@ -222,7 +222,7 @@ objective_uniform_kernel(ObjArgs a) {
         bulk_g2s(smem + L.part, a.prep_part + q0 * kPartDoubles, b_part, bar);
         for (int sp = 0; sp < SP; ++sp) {
             const size_t rs = (q0 + sp) * NRP + (size_t)tile * NW;
-            bulk_g2s(smem + L.far + sp * NW * SUB * kFarTerms, a.prep_far + rs * SUB * kFarTerms, b_far, bar);
+            bulk_g2s(smem + L.far + sp * NW * SUB * kFarPoly, a.prep_far + rs * SUB * kFarPoly, b_far, bar);
             bulk_g2s(smem + L.anchor + sp * NW * 2, a.prep_anchor + rs * 2, b_anchor, bar);
             bulk_g2s(reinterpret_cast<unsigned*>(smem + L.mask) + sp * NW * MWR, a.prep_mask + rs * MWR,
                      b_mask, bar);
@@ -234,8 +234,9 @@ objective_uniform_kernel(ObjArgs a) {
         const int i = tile0 + e;
         const bool ok = i < N;
         const int t = e / R, j = e % R;
-        suv[stage_slot_uv(t, j, THREADS)] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
-        swt[stage_slot_wt(t, j, THREADS)] = ok ? sw[3 * N + i] : 0.0;      // zero weight: padding contributes nothing
+        const double wgt = ok ? sw[3 * N + i] : 0.0;      // zero weight: padding contributes nothing
+        suv[stage_slot_uv(t, j, THREADS)] = stage_point(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0, wgt);
+        swt[stage_slot_wt(t, j, THREADS)] = wgt;
     }
     const int i_first = tile0 + tid * R;                   // this thread's first point
     const double w_first = i_first < N ? sw[i_first] : fma((double)i_first, h, sw[0]);
@@ -254,7 +255,7 @@ objective_uniform_kernel(ObjArgs a) {
         double ssi = 0.0;
         const double ss = eval_region<R, TB, KK>(
             coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + warp) * mask_words_per_region(P, SUB),
-            farc + (size_t)(sp * NW + warp) * SUB * kFarTerms, anchor[sp * NW + warp], MW, P, lane, SUB, w_first, xi0, inv_H,
+            farc + (size_t)(sp * NW + warp) * SUB * kFarPoly, anchor[sp * NW + warp], MW, P, lane, SUB, w_first, xi0, inv_H,
             suv, swt, tid, THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
         if (lane == 0) {
             wpart[(sp * NW + warp) * NSUM] = ss;
@@ -306,7 +307,7 @@ void objective_uniform_prep_sizes(int N, int P, const ObjTune& t, int sub, size_
     const size_t nrp = (size_t)objective_tiles(N, t) * (t.threads / 32);
     *coef = (size_t)P * 8;                      // doubles per particle
     *part = kPartDoubles;
-    *far = nrp * sub * kFarTerms;
+    *far = nrp * sub * kFarPoly;
     *anchor = nrp * 2;
     *mask_words = nrp * mask_words_per_region(P, sub);    // 32-bit words per particle
     *pad_particles = kPadParticles;

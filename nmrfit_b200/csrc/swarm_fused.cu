@@ -56,7 +56,7 @@ struct FusedSmem {
         cs = o;     o += P * 8;
         farpk = o;  o += P * 4;
         part = o;   o += kPartDoubles;
-        far = o;    o += NRL * sub * kFarTerms;              // per far-field cell (uniform_eval.cuh)
+        far = o;    o += NRL * sub * kFarPoly;              // per far-field cell (uniform_eval.cuh)
         anchor = o; o += NRL * 2;
         mask = o;   o += ((NRL * mask_words_per_region(P, sub) + 3) / 4) * 2;
         wpart = o;  o += (NRP + 1) & ~1;
@@ -176,8 +176,9 @@ swarm_fused_kernel(FusedArgs a) {
             const int i = base + e;
             const bool ok = i < N;
             const int t = e / R, j = e % R, o = slot * THREADS * R;
-            suv[o + stage_slot_uv(t, j, THREADS)] = make_double2(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0);
-            swt[o + stage_slot_wt(t, j, THREADS)] = ok ? sw[3 * N + i] : 0.0;      // zero weight: padding adds nothing
+            const double wgt = ok ? sw[3 * N + i] : 0.0;      // zero weight: padding adds nothing
+            suv[o + stage_slot_uv(t, j, THREADS)] = stage_point(ok ? sw[N + i] : 0.0, ok ? sw[2 * N + i] : 0.0, wgt);
+            swt[o + stage_slot_wt(t, j, THREADS)] = wgt;
         }
     };
     if (resident)
@@ -226,7 +227,7 @@ swarm_fused_kernel(FusedArgs a) {
                 const double w_first = i_first < N ? __ldg(sw + i_first) : fma((double)i_first, h, __ldg(sw));
                 const double2 ew = *reinterpret_cast<const double2*>(anchor + 2 * rl);
                 const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rl * mask_words_per_region(P, SUB),
-                                                     farc + (size_t)rl * SUB * kFarTerms, ew, MW, P, lane, SUB, w_first, xi0,
+                                                     farc + (size_t)rl * SUB * kFarPoly, ew, MW, P, lane, SUB, w_first, xi0,
                                                      inv_H, suv + slot * THREADS * R, swt + slot * THREADS * R, tid, THREADS,
                                                      tab, xs, sw + i_first, N - i_first, h, w_ulp);
                 if (!CL) {

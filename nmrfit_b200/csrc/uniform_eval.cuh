@@ -176,8 +176,9 @@ __device__ __forceinline__ void prep_item_cell(bool ok, const double* __restrict
         if (ok && ci == 0) mask_region[MW] = fu;
     }
     if (ok) {
+        far_economise(C);                                  // 12 series terms -> kFarPoly stored coefficients
 #pragma unroll
-        for (int n = 0; n < kFarTerms; ++n) far_dst[n] = C[n];
+        for (int n = 0; n < kFarPoly; n += 2) *reinterpret_cast<double2*>(far_dst + n) = make_double2(C[n], C[n + 1]);
     }
 }
 
@@ -185,7 +186,7 @@ __device__ __forceinline__ void prep_item_cell(bool ok, const double* __restrict
 // per generation.  xs: the particle's D parameters; sw: its spectrum's w plane (N points); cs: shared [P][8] scratch
 // that ends up holding the span coefficients; farpk: shared [P][4] scratch (per-peak far-field constants);
 // coef_out: optional second copy of the coefficients; part [kPartDoubles];
-// far [cells][kFarTerms]; anchor [regions][2]; mask [regions][mask_words_per_region].  Regions [r_lo, r_hi) are filled,
+// far [cells][kFarPoly]; anchor [regions][2]; mask [regions][mask_words_per_region].  Regions [r_lo, r_hi) are filled,
 // at index r - r_lo (default: all NRP slots; the slots of regions past the end of the axis are neutral).  Contains
 // __syncthreads().  `pairs` (optional shared scratch of cells*P*kPairDoubles doubles): the (cell, peak) series are
 // computed one pair per thread instead of one cell per thread - same values, same order of accumulation, but P times
@@ -224,7 +225,7 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
         const bool ok = cl < nc;
         const int rl = cl / sub, ci = cl - rl * sub;
         prep_item_cell<R>(ok, cs, farpk, sw, h, N, P, sub, ((long long)r_lo * sub + cl) * cell_pts, ci,
-                          pairs ? pairs + (size_t)cl * P * kPairDoubles : nullptr, far + (size_t)cl * kFarTerms,
+                          pairs ? pairs + (size_t)cl * P * kPairDoubles : nullptr, far + (size_t)cl * kFarPoly,
                           mask + (size_t)rl * MWR);
     }
 }
@@ -236,11 +237,16 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
 // different banks instead of colliding 8-way.  Plain (!SWZ): at column t; the staging stores collide, which a kernel
 // that stages once per CTA and then evaluates hundreds of particles (objective_stream.cu) does not notice, and the
 // evaluation's addresses are one base plus compile-time offsets - no integer work per point.
+// What the evaluation kernels stage per point: the data pre-multiplied by the residual weights - the residual
+// weights * (u cos - v sin - V_fit) then costs one multiply less per (particle, point).
+__device__ __forceinline__ double2 stage_point(double u, double v, double wt) {
+    return make_double2(__dmul_rn(wt, u), __dmul_rn(wt, v));
+}
 __device__ __forceinline__ int stage_slot_uv(int t, int j, int stride) { return j * stride + (t ^ j); }
 __device__ __forceinline__ int stage_slot_wt(int t, int j, int stride) { return j * stride + (t ^ (2 * j)); }
 
 // One warp, one particle, one region: sum over the warp's 32*R points of (weights * (V_data - V_fit))^2, identical
-// in every lane on return.  cf [P][8], pt [kPartDoubles], mk [mask_words_per_region], fc [sub][kFarTerms] (16-byte aligned) and ew
+// in every lane on return.  cf [P][8], pt [kPartDoubles], mk [mask_words_per_region], fc [sub][kFarPoly] (16-byte aligned) and ew
 // are the particle's constants for this region (`sub` far-field cells of 32/sub lanes each; xi0 is the lane's first
 // point's position inside ITS cell and inv_H the step of that coordinate per point); the R points of thread t of the
 // tile sit at stage_slot_uv/wt(t, j, stride) of suv / swt (SWZ) or at j*stride + t (!SWZ); w_first is the abscissa of its
@@ -259,19 +265,21 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
     const int cell = (lane * sub) >> 5;                    // this lane's cell inside the region
     const unsigned* mkc = mk + (sub == 1 ? 0 : 1 + cell) * (MW + 1);   // mk: the union's block (prepare_particle)
     double acc[R];
-    // all far peaks of this lane's cell at once; the accumulators start from it
+    const double py = pt[66];                              // P*yoff: yoff is added once per peak (equations.py:147,195)
+    // all far peaks of this lane's cell at once; the accumulators start from it (and from P*yoff)
     if (mk[MW]) {
-        const double* fcc = fc + cell * kFarTerms;
-        double C[kFarTerms];
+        const double* fcc = fc + cell * kFarPoly;
+        double C[kFarPoly];
 #pragma unroll
-        for (int n = 0; n < kFarTerms; n += 2) {
+        for (int n = 0; n < kFarPoly; n += 2) {
             const double2 t2 = *reinterpret_cast<const double2*>(fcc + n);
             C[n] = t2.x; C[n + 1] = t2.y;
         }
+        C[0] += py;
         far_init<R>(C, xi0, inv_H, acc);
     } else {
 #pragma unroll
-        for (int j = 0; j < R; ++j) acc[j] = 0.0;
+        for (int j = 0; j < R; ++j) acc[j] = py;
     }
     for (int wd = 0; wd < MW; ++wd) {
         const unsigned mine = mkc[wd];                     // peaks near this lane's cell
@@ -298,7 +306,7 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
     }
     // residual against the phase-rotated data; the rotation advances by p1/N per point
     const double2 el = *reinterpret_cast<const double2*>(pt + 2 * lane);
-    const double cd = pt[64], sd = pt[65], py = pt[66];
+    const double cd = pt[64], sd = pt[65];
     double cr = fma(ew.x, el.x, -(ew.y * el.y));
     double ci = fma(ew.y, el.x, ew.x * el.y);
     double ss = 0.0, ssi = 0.0;
@@ -324,11 +332,11 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
     for (int j = 0; j < R; ++j) {
         const double2 uv = SWZ ? suv[stage_slot_uv(t, j, stride)] : puv[j * stride];
         const double wt = SWZ ? swt[stage_slot_wt(t, j, stride)] : pwt[j * stride];
-        const double vd = fma(uv.x, cr, -fma(uv.y, ci, py));     // V_data - P*yoff
-        const double res = wt * (vd - acc[j]);
+        // weights * (V_data - V_fit); the staged data carry the weights: uv = weights * (u, v) (stage_point)
+        const double res = fma(uv.x, cr, -fma(uv.y, ci, wt * acc[j]));
         ss = fma(res, res, ss);
         if (KK) {
-            const double idat = fma(uv.x, ci, uv.y * cr);
+            const double idat = fma(uv.x, ci, uv.y * cr);  // weights * I_data
             // abscissa: w_first + j*h on the uniform axis; the stored value when the peak is too narrow for that
             const double wj = (kexact && j < n_valid) ? sw_first[j] : (j == 0 ? w_first : fma((double)j, h, w_first));
             const double d = wj - kloc;
@@ -336,7 +344,7 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
             const double rq = rcp_pos(fma(tt, tt, 1.0));
             const double daw = dawson(d * kkG, NMRFIT_DAW_TAB, NMRFIT_DAW_TAIL);
             const double ifit = fma(kaL * tt, rq, kaG * daw);
-            const double ri = wt * (idat - ifit);
+            const double ri = fma(-wt, ifit, idat);
             ssi = fma(ri, ri, ssi);
         }
         if (j + 1 < R) {

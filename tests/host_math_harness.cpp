@@ -47,17 +47,19 @@ static void regions(const double* w, int n, double h, const double* x, int P, co
             if (cs[k].exact || !nmrfit::far_accumulate(wc - cs[k].loc, cs[k], H, C)) near.push_back(k);
         }
         near_total += (int)near.size();
+        nmrfit::far_economise(C);                              // 12 series terms -> 10 stored coefficients
+        double Ce[nmrfit::kFarPoly];
+        for (int n2 = 0; n2 < nmrfit::kFarPoly; ++n2) Ce[n2] = C[n2];
         for (int lane = 0; lane < 32; ++lane) {
             const int i0 = r0 + lane * R;
             if (i0 >= n) break;
             double acc[R];
-            for (int j = 0; j < R; ++j) acc[j] = 0.0;
+            const double xi0 = ((double)(lane * R) - 0.5 * (RG - 1)) / H;
+            nmrfit::far_init<R>(Ce, xi0, 1.0 / H, acc);       // the accumulators start from the far field
             for (int k : near) {
                 if (!cs[k].exact) nmrfit::peak_span<R, TB>(w[i0] - cs[k].loc, cs[k], tab, acc);
                 else nmrfit::peak_exact<R, TB>(w + i0, n - i0, w[i0], h, cs[k], tab, acc);
             }
-            const double xi0 = ((double)(lane * R) - 0.5 * (RG - 1)) / H;
-            nmrfit::far_eval<R>(C, xi0, 1.0 / H, acc);
             for (int j = 0; j < R && i0 + j < n; ++j) vfit[i0 + j] = acc[j] + (double)P * x[3];
         }
     }
