@@ -83,13 +83,18 @@ template <> struct ExpPoly<0> {
         return p;
     }
 };
+// The kernels' default table (64 entries, |r| <= ln2/128 = 5.4e-3).  Taylor coefficients of (e^r - 1)/r: the series
+// is cut at r^6/720 < 3.5e-17, and 1/24 and 1/120 are TRUNCATED TO THEIR HIGH WORD (their terms are < 3.5e-11, the
+// 2.4e-7 relative truncation moves the result by < 1e-17): such constants, like 1.0 and 0.5, are 32-bit immediates of
+// the FP64 instructions, whereas a full 64-bit constant costs two extra instructions to materialise wherever it is
+// used - and in these issue-bound kernels an integer instruction costs half an FP64 one.
 template <> struct ExpPoly<6> {
     static NMRFIT_HD double eval(double r) {
-        double p = NMRFIT_EXP_T6_C4;
-        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C3);
-        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C2);
-        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C1);
-        p = NMRFIT_FMA(p, r, NMRFIT_EXP_T6_C0);
+        double p = 0.008333332836627960205078125;          // 1/120, high word only
+        p = NMRFIT_FMA(p, r, 0.0416666567325592041015625); // 1/24, high word only
+        p = NMRFIT_FMA(p, r, 0.16666666666666666);
+        p = NMRFIT_FMA(p, r, 0.5);
+        p = NMRFIT_FMA(p, r, 1.0);
         return p;
     }
 };
@@ -125,7 +130,9 @@ NMRFIT_HD double exp_neg(double x, const double* __restrict__ tab) {
     unsigned hi = (unsigned)nmrfit_hi(x);
     hi = hi < (unsigned)kExpClampHi ? hi : (unsigned)kExpClampHi;
     x = nmrfit_mk((int)hi, nmrfit_lo(x));
-    constexpr double scale = (double)(1 << TB) / kLn2;
+    // (64/ln2 truncated to its high word for the default table: n is only the CHOICE of the table entry - the
+    // reduction r = x - n*step below is exact for whatever n - and |r| grows by < 3e-7 |x| / step, 12 % at x = -700)
+    constexpr double scale = TB == 6 ? 92.33245849609375 : (double)(1 << TB) / kLn2;
     constexpr double step = kLn2 / (double)(1 << TB);
     double t = NMRFIT_FMA(x, scale, kMagic);
     int n = nmrfit_lo(t);

@@ -150,6 +150,7 @@ objective_stream_kernel(ObjArgs a) {
     }
     constexpr double H = 16.0 * R;                         // half a region, in points
     const double xi0 = cell_xi0<R>(lane, SUB);             // first point's position inside its far-field cell
+    const LaneCell lcell = lane_cell(lane, SUB, P);
     const double inv_H = (double)SUB / H;
     __syncthreads();                                       // the only CTA-wide barrier: tile, table, mbarriers
 
@@ -177,7 +178,7 @@ objective_stream_kernel(ObjArgs a) {
         mbar_wait(bars + sl, phase);                       // this fill of the slot has landed
         for (int sp = 0; sp < nsp; ++sp) {
             double ssi = 0.0;
-            const double ss = eval_region<R, TB, KK, false>(cf, pt, mk, fc, *an, MW, P, lane, SUB, w_first, xi0, inv_H, suv,
+            const double ss = eval_region<R, TB, KK, false>(cf, pt, mk, fc, *an, MW, P, lane, lcell, w_first, xi0, inv_H, suv,
                                                             swt, t, THREADS, tab, xs, sw + i_first, N - i_first, h, w_ulp,
                                                             &ssi);
             if (lane == 0) {

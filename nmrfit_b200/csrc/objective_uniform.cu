@@ -245,6 +245,7 @@ objective_uniform_kernel(ObjArgs a) {
         for (int i = tid; i < (1 << TB); i += THREADS) tab[i] = src[i];
     }
     const double xi0 = cell_xi0<R>(lane, SUB);             // first point's position inside its far-field cell
+    const LaneCell lcell = lane_cell(lane, SUB, P);
     const double inv_H = (double)SUB / H;
     __syncthreads();                                       // tile, table and the mbarrier initialisation are visible
     mbar_wait(bar, 0);                                     // the constants have landed
@@ -255,7 +256,7 @@ objective_uniform_kernel(ObjArgs a) {
         double ssi = 0.0;
         const double ss = eval_region<R, TB, KK>(
             coef + (size_t)sp * P * 8, part + sp * kPartDoubles, mask + (size_t)(sp * NW + warp) * mask_words_per_region(P, SUB),
-            farc + (size_t)(sp * NW + warp) * SUB * kFarPoly, anchor[sp * NW + warp], MW, P, lane, SUB, w_first, xi0, inv_H,
+            farc + (size_t)(sp * NW + warp) * SUB * kFarPoly, anchor[sp * NW + warp], MW, P, lane, lcell, w_first, xi0, inv_H,
             suv, swt, tid, THREADS, tab, a.x + (q0 + sp) * D, sw + i_first, N - i_first, h, w_ulp, &ssi);
         if (lane == 0) {
             wpart[(sp * NW + warp) * NSUM] = ss;

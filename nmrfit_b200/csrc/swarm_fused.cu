@@ -148,6 +148,7 @@ swarm_fused_kernel(FusedArgs a) {
     const size_t bs = (size_t)b * S + sl;
     constexpr double H = 16.0 * R;
     const double xi0 = cell_xi0<R>(lane, SUB);
+    const LaneCell lcell = lane_cell(lane, SUB, P);
     const double inv_H = (double)SUB / H;
 
     // ---- load the particle and the swarm's shared state
@@ -227,7 +228,7 @@ swarm_fused_kernel(FusedArgs a) {
                 const double w_first = i_first < N ? __ldg(sw + i_first) : fma((double)i_first, h, __ldg(sw));
                 const double2 ew = *reinterpret_cast<const double2*>(anchor + 2 * rl);
                 const double ss = eval_region<R, TB>(cs, part, mask + (size_t)rl * mask_words_per_region(P, SUB),
-                                                     farc + (size_t)rl * SUB * kFarPoly, ew, MW, P, lane, SUB, w_first, xi0,
+                                                     farc + (size_t)rl * SUB * kFarPoly, ew, MW, P, lane, lcell, w_first, xi0,
                                                      inv_H, suv + slot * THREADS * R, swt + slot * THREADS * R, tid, THREADS,
                                                      tab, xs, sw + i_first, N - i_first, h, w_ulp);
                 if (!CL) {

@@ -247,28 +247,39 @@ __device__ __forceinline__ int stage_slot_wt(int t, int j, int stride) { return 
 
 // One warp, one particle, one region: sum over the warp's 32*R points of (weights * (V_data - V_fit))^2, identical
 // in every lane on return.  cf [P][8], pt [kPartDoubles], mk [mask_words_per_region], fc [sub][kFarPoly] (16-byte aligned) and ew
-// are the particle's constants for this region (`sub` far-field cells of 32/sub lanes each; xi0 is the lane's first
+// are the particle's constants for this region (`sub` far-field cells of 32/sub lanes each, lc = lane_cell(lane, sub, P); xi0 is the lane's first
 // point's position inside ITS cell and inv_H the step of that coordinate per point); the R points of thread t of the
 // tile sit at stage_slot_uv/wt(t, j, stride) of suv / swt (SWZ) or at j*stride + t (!SWZ); w_first is the abscissa of its
 // first point.  The exact path (peaks too narrow for the recurrences) reads the particle's parameters xs and the stored
 // abscissae sw_first[0..n_valid).
 // KK = 1 (fit_im, reference semantics) also returns through *ss_im the same sum for the imaginary parts:
 // I_data = u sin(phi) + v cos(phi) against the last peak's Kramers-Kronig counterpart (closed form, nmrfit_math.cuh).
+// Where a lane's far-field cell keeps its mask block and its polynomial inside the region's constants: loop-invariant,
+// computed once per thread (mk_off == 0 <=> the region is one cell and has no separate union block).
+struct LaneCell { int mk_off, fc_off; };
+__device__ __forceinline__ LaneCell lane_cell(int lane, int sub, int P) {
+    const int cell = (lane * sub) >> 5, MW = (P + 31) / 32;
+    LaneCell lc;
+    lc.mk_off = sub == 1 ? 0 : (1 + cell) * (MW + 1);
+    lc.fc_off = cell * kFarPoly;
+    return lc;
+}
+
 template <int R, int TB, int KK = 0, bool SWZ = true>
 __device__ __forceinline__ double eval_region(const double* __restrict__ cf, const double* __restrict__ pt,
                                               const unsigned* __restrict__ mk, const double* __restrict__ fc,
-                                              const double2 ew, int MW, int P, int lane, int sub, double w_first, double xi0,
+                                              const double2 ew, int MW, int P, int lane, const LaneCell lc, double w_first, double xi0,
                                               double inv_H, const double2* __restrict__ suv, const double* __restrict__ swt,
                                               int t, int stride, const double* __restrict__ tab,
                                               const double* __restrict__ xs, const double* __restrict__ sw_first,
                                               int n_valid, double h, double w_ulp, double* ss_im = nullptr) {
-    const int cell = (lane * sub) >> 5;                    // this lane's cell inside the region
-    const unsigned* mkc = mk + (sub == 1 ? 0 : 1 + cell) * (MW + 1);   // mk: the union's block (prepare_particle)
+    const unsigned* mkc = mk + lc.mk_off;                  // this lane's cell; mk itself: the union's block (prepare_particle)
     double acc[R];
     const double py = pt[66];                              // P*yoff: yoff is added once per peak (equations.py:147,195)
-    // all far peaks of this lane's cell at once; the accumulators start from it (and from P*yoff)
-    if (mk[MW]) {
-        const double* fcc = fc + cell * kFarPoly;
+    // all far peaks of this lane's cell at once; the accumulators start from it (and from P*yoff).  A cell without far
+    // peaks holds zeros: evaluated all the same - rare, and a branch here costs every other cell a dozen instructions.
+    {
+        const double* fcc = fc + lc.fc_off;
         double C[kFarPoly];
 #pragma unroll
         for (int n = 0; n < kFarPoly; n += 2) {
@@ -277,9 +288,6 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
         }
         C[0] += py;
         far_init<R>(C, xi0, inv_H, acc);
-    } else {
-#pragma unroll
-        for (int j = 0; j < R; ++j) acc[j] = py;
     }
     for (int wd = 0; wd < MW; ++wd) {
         const unsigned mine = mkc[wd];                     // peaks near this lane's cell
@@ -294,7 +302,7 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
             c.loc = c01.x; c.kL = c01.y; c.kG = c23.x; c.aL = c23.y;
             c.aG = c45.x; c.dT = c45.y; c.thr = c67.x; c.c2 = c67.y;
             // (in a cell for which the peak is far it is already inside that cell's polynomial)
-            if (sub == 1 || ((mine >> kb) & 1u)) peak_span<R, TB>(w_first - c.loc, c, tab, acc);
+            if (lc.mk_off == 0 || ((mine >> kb) & 1u)) peak_span<R, TB>(w_first - c.loc, c, tab, acc);
         }
     }
     if (pt[67] != 0.0) {                                   // rare: peaks too narrow for the uniform-axis shortcuts
