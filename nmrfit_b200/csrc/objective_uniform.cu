@@ -102,8 +102,9 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     const size_t ps0 = (size_t)b * a.S + s0;
     if (MOVE) {
         const SwarmState& s = mv.s;
+        const float inv_D = 1.0f / (float)D;
         for (int e = tid; e < ng * D; e += nthreads) {
-            const int g = e / D, d = e - g * D;
+            const int g = fast_div(e, D, inv_D), d = e - g * D;
             const size_t idx = (ps0 + g) * D + d;
             double rp, rg;
             if (mv.rp) {
@@ -123,31 +124,41 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
         }
         __syncthreads();
     }
-    // ---- phase 1: per particle P span coefficients + the phase table + NRP anchors
-    const int per = P + kTableItems + NRP;
+    // ---- phase 1: per particle kTableItems + NRP rotation items (one sincos each; packed, so that the warps are
+    // full whatever the shape) from the first thread up, P span coefficients from the last thread down
+    const int per = kTableItems + NRP;
+    const float inv_per = 1.0f / (float)per, inv_P = 1.0f / (float)P;
     for (int e = tid; e < ng * per; e += nthreads) {
-        const int g = e / per, it = e - g * per;
+        const int g = fast_div(e, per, inv_per), it = e - g * per;
         const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
-        if (it < P) {
-            prep_item_coef<R>(xs, it, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8,
-                              farpk + (size_t)g * P * 4, sub);
-        } else if (it < P + kTableItems) {
-            prep_item_table<R>(xs, it - P, N, P, a.prep_part + (ps0 + g) * kPartDoubles);
+        double sn, cn;
+        sincos(prep_item_angle<R>(xs, it, N), &sn, &cn);
+        double* dst;
+        if (it < kTableItems) {
+            dst = a.prep_part + (ps0 + g) * kPartDoubles + 2 * it;
         } else {
-            const int rl = it - P - kTableItems;
             const RegionDst rd(a, b, s0 + g, NRP);
-            prep_item_anchor<R>(xs, rl, N, a.prep_anchor + rd.region(rl) * 2);
+            dst = a.prep_anchor + rd.region(it - kTableItems) * 2;
         }
+        *reinterpret_cast<double2*>(dst) = make_double2(cn, sn);
+    }
+    for (int e = nthreads - 1 - tid; e < ng * P; e += nthreads) {
+        const int g = fast_div(e, P, inv_P), k = e - g * P;
+        const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
+        prep_item_coef<R>(xs, k, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8,
+                          farpk + (size_t)g * P * 4, sub, P, a.prep_part + (ps0 + g) * kPartDoubles);
     }
     __syncthreads();
     // ---- phase 2: the far-field cells of all ng particles, whole warps (prep_item_cell shuffles)
     for (int e = tid; e < ng; e += nthreads)
         prep_item_exact_count(cs + (size_t)e * P * 8, P, a.prep_part + (ps0 + e) * kPartDoubles);
+    const float inv_nc = 1.0f / (float)nc;
+    const int sub_shift = sub == 4 ? 2 : sub == 2 ? 1 : 0;
     for (int base = tid & ~31; base < ng * nc; base += nthreads) {
         const int e = base + (tid & 31);
         const bool ok = e < ng * nc;
-        const int g = ok ? e / nc : 0, cl = ok ? e - g * nc : 0;
-        const int rl = cl / sub, ci = cl - rl * sub;
+        const int g = ok ? fast_div(e, nc, inv_nc) : 0, cl = ok ? e - g * nc : 0;
+        const int rl = cl >> sub_shift, ci = cl & (sub - 1);  // sub is 1, 2 or 4
         const RegionDst rd(a, b, s0 + g, NRP);
         const size_t rs = rd.region(rl);
         prep_item_cell<R>(ok, cs + (size_t)g * P * 8, farpk + (size_t)g * P * 4, sw, h, N, P, sub, (long long)cl * cell_pts, ci, nullptr,

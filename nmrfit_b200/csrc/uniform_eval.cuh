@@ -32,7 +32,7 @@ __host__ __device__ inline int mask_words_per_region(int P, int sub) { return (s
 // kernel (objective_uniform.cu) spreads the items of SEVERAL particles over the threads of a CTA so that no warp idles,
 // the fused swarm kernel (one CTA per particle) those of one.  Same item, same arithmetic, whoever executes it.
 constexpr int kPairDoubles = kFarTerms + 1;                // a (cell, peak) series: kind, then v[n]
-constexpr int kTableItems = 34;                            // phase table: 32 lane factors, the per-point step, P*yoff
+constexpr int kTableItems = 33;                            // phase table: 32 lane factors, the per-point step
 
 // span coefficients of peak k -> cs[k][8] (shared) and optionally a second copy
 // (farpk [P][4], shared: what the far-field classification of this peak needs besides the cell's position - A = H dT,
@@ -40,7 +40,8 @@ constexpr int kTableItems = 34;                            // phase table: 32 la
 template <int R>
 __device__ __forceinline__ void prep_item_coef(const double* __restrict__ xs, int k, double h, double w_ulp,
                                                double* __restrict__ cs, double* __restrict__ coef_out,
-                                               double* __restrict__ farpk, int sub) {
+                                               double* __restrict__ farpk, int sub, int P, double* __restrict__ part) {
+    if (k == 0) part[66] = (double)P * xs[3];              // yoff is added once per peak (equations.py:147,195)
     SpanCoef c = make_span_coef(xs[2], xs[4 + 3 * k], xs[5 + 3 * k], xs[6 + 3 * k], h, w_ulp, R);
     if (c.exact) c = null_span_coef();                     // the span loop adds zero; the peak is handled after it
     double* o = cs + k * 8;
@@ -55,28 +56,27 @@ __device__ __forceinline__ void prep_item_coef(const double* __restrict__ xs, in
     }
 }
 
-// phase table entry e: phi_i = p0 + (p1*i)/N with i = i_r + lane*R + j is anchor(i_r) * e^{i p1 (lane R)/N} *
-// (e^{i p1/N})^j; entries 0..31 are the lanes' factors, 32 the per-point step, 33 holds P*yoff
+// The rotation items of a particle - kTableItems entries of its phase table, then one anchor per region - are all "one
+// angle -> (cos, sin)": item `it` of a particle yields its angle here and the caller takes ONE sincos for whatever
+// mix of items its warp holds (they used to be two call sites: a warp with both paid for both).
+//   phi_i = p0 + (p1*i)/N with i = i_r + lane*R + j is anchor(i_r) * e^{i p1 (lane R)/N} * (e^{i p1/N})^j:
+//   items 0..31 the lanes' factors, 32 the per-point step (-> part[2*it]), 33 + ra the phase at the first point of
+//   region ra (-> the region's anchor; regions past the end of the axis get angle 0: cos 1, sin 0).
 template <int R>
-__device__ __forceinline__ void prep_item_table(const double* __restrict__ xs, int e, int N, int P, double* __restrict__ part) {
-    if (e == 33) {
-        part[66] = (double)P * xs[3];                      // yoff is added once per peak (equations.py:147,195)
-        return;
-    }
-    const double p1 = xs[1];
-    double sn, cn;
-    sincos(e < 32 ? (p1 * (double)(e * R)) / (double)N : p1 / (double)N, &sn, &cn);
-    part[2 * e] = cn;
-    part[2 * e + 1] = sn;
+__device__ __forceinline__ double prep_item_angle(const double* __restrict__ xs, int it, int N) {
+    if (it < 32) return (xs[1] * (double)(it * R)) / (double)N;
+    if (it == 32) return xs[1] / (double)N;
+    const int ra = it - kTableItems;
+    return (long long)ra * 32 * R < N ? xs[0] + (xs[1] * (double)(ra * 32 * R)) / (double)N : 0.0;
 }
 
-// phase at the first point of region ra -> dst[2]
-template <int R>
-__device__ __forceinline__ void prep_item_anchor(const double* __restrict__ xs, int ra, int N, double* __restrict__ dst) {
-    double sn = 0.0, cn = 1.0;
-    if ((long long)ra * 32 * R < N) sincos(xs[0] + (xs[1] * (double)(ra * 32 * R)) / (double)N, &sn, &cn);
-    dst[0] = cn;
-    dst[1] = sn;
+// e / d for 0 <= e < 2^22 with inv = 1.0f / d (exact after one correction step): the prepare pass maps flat item
+// numbers to (particle, item) a few times per thread, and an integer division is ~20 instructions
+__device__ __forceinline__ int fast_div(int e, int d, float inv) {
+    int q = __float2int_rz(__int2float_rn(e) * inv);
+    const int r = e - q * d;
+    q += (r >= d) - (r < 0);
+    return q;
 }
 
 // number of exact-path peaks (thr < 0 marks a nulled peak) -> part[67]; needs the particle's cs complete
@@ -204,11 +204,14 @@ __device__ __forceinline__ void prepare_particle(const double* __restrict__ xs, 
     const int cell_pts = 32 * R / sub;
     const int MWR = mask_words_per_region(P, sub);
     (void)NR;
-    for (int k = tid; k < P; k += nthreads) prep_item_coef<R>(xs, k, h, w_ulp, cs, coef_out, farpk, sub);
-    // the threads at the far end of the CTA do the phase tables and the anchors while the first do the peaks
+    for (int k = tid; k < P; k += nthreads) prep_item_coef<R>(xs, k, h, w_ulp, cs, coef_out, farpk, sub, P, part);
+    // the threads at the far end of the CTA do the phase table and the anchors while the first do the peaks
     for (int e = nthreads - 1 - tid; e < kTableItems + nr; e += nthreads) {
-        if (e < kTableItems) prep_item_table<R>(xs, e, N, P, part);
-        else prep_item_anchor<R>(xs, r_lo + e - kTableItems, N, anchor + 2 * (e - kTableItems));
+        double sn, cn;
+        sincos(prep_item_angle<R>(xs, e < kTableItems ? e : e + r_lo, N), &sn, &cn);
+        double* dst = e < kTableItems ? part + 2 * e : anchor + 2 * (e - kTableItems);
+        dst[0] = cn;
+        dst[1] = sn;
     }
     __syncthreads();
     if (tid == nthreads - 1) prep_item_exact_count(cs, P, part);
