@@ -222,48 +222,61 @@ constexpr int kFinWarps = 8;
 __global__ void __launch_bounds__(kFinWarps * 32)
 swarm_finish_kernel(SwarmState s, const double* __restrict__ partials, int n_tiles, int nsum, int N,
                     double* rec, double* __restrict__ scratch, unsigned* __restrict__ tickets, int commit,
-                    int maxiter, int nw, PeerArgs pa) {
+                    int maxiter, int nw, int L, PeerArgs pa) {
     extern __shared__ __align__(16) double srec[];         // commit == 2: the ranks' records of this spectrum
     const int b = blockIdx.y, blk = blockIdx.x, nblk = gridDim.x;
     if (s.stop[b]) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int i = blk * kFinWarps + warp;                  // this warp's particle
+    // L lanes per particle (a power of two, at least the number of tiles up to a whole warp): a warp takes 32 / L
+    // particles - with a whole warp per particle a two-tile axis left 30 lanes idle and 65,536 particles were 8,192
+    // CTAs, each a chain of dependent memory round trips, plus as many candidates for the last CTA to scan
+    const int ppw = 32 / L, sl = lane & (L - 1), lane0 = lane & ~(L - 1);
+    const int i = (blk * kFinWarps + warp) * ppw + lane / L;     // this lane group's particle
     __shared__ double sf[kFinWarps];
     __shared__ int si[kFinWarps];
     __shared__ int s_last;
     double cf = CUDART_INF;
     int ci = 0x7fffffff;
-    if (i < s.S) {
-        const size_t bs = (size_t)b * s.S + i;
+    {
+        const bool valid = i < s.S;
+        const size_t bs = (size_t)b * s.S + (valid ? i : 0);
         // partial sums per tile (nw == 1) or per region, [n_tiles][nw] (the streamed kernel; nw = 4 or 8 divides 32):
         // the regions of a tile are added first, then the tiles
         const double* p = partials + bs * n_tiles * nw * nsum;
         double sv = 0.0, sim = 0.0;
-        for (int t0 = 0; t0 < n_tiles; t0 += 32) {         // a lane per tile: its regions in order (in parallel over the
-            const int t = t0 + lane;                       // lanes), then the tiles in order - every lane sums all of
+        for (int t0 = 0; t0 < n_tiles; t0 += L) {          // a lane per tile: its regions in order (in parallel over the
+            const int t = t0 + sl;                         // lanes), then the tiles in order - every lane sums all of
             double a0 = 0.0, a1 = 0.0;                     // them, the same sequential order as objective_finalize_kernel
-            if (t < n_tiles) {
+            if (valid && t < n_tiles) {
                 for (int w = 0; w < nw; ++w) {
                     a0 += p[(t * nw + w) * nsum];
                     if (nsum == 2) a1 += p[(t * nw + w) * nsum + 1];
                 }
             }
-            const int cnt = min(32, n_tiles - t0);
+            const int cnt = min(L, n_tiles - t0);
             for (int k = 0; k < cnt; ++k) {
-                sv += __shfl_sync(0xffffffffu, a0, k);
-                if (nsum == 2) sim += __shfl_sync(0xffffffffu, a1, k);
+                sv += __shfl_sync(0xffffffffu, a0, lane0 + k);
+                if (nsum == 2) sim += __shfl_sync(0xffffffffu, a1, lane0 + k);
             }
         }
-        double fx = sqrt(sv / (double)N);
-        if (nsum == 2) fx = (fx + sqrt(sim / (double)N)) / 2.0;
-        double fp = s.fp[bs];
-        if (fx < fp) {
-            fp = fx;
-            for (int d = lane; d < s.D; d += 32) s.p[bs * s.D + d] = s.x[bs * s.D + d];
+        if (valid) {
+            double fx = sqrt(sv / (double)N);
+            if (nsum == 2) fx = (fx + sqrt(sim / (double)N)) / 2.0;
+            double fp = s.fp[bs];
+            if (fx < fp) {
+                fp = fx;
+                for (int d = sl; d < s.D; d += L) s.p[bs * s.D + d] = s.x[bs * s.D + d];
+            }
+            if (sl == 0) { s.fx[bs] = fx; s.fp[bs] = fp; }
+            cf = fp;
+            ci = i;
         }
-        if (lane == 0) { s.fx[bs] = fx; s.fp[bs] = fp; }
-        cf = fp;
-        ci = i;
+    }
+    // the warp's best particle (lowest index wins a tie)
+    for (int o = L; o < 32; o <<= 1) {
+        const double of = __shfl_xor_sync(0xffffffffu, cf, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, ci, o);
+        if (of < cf || (of == cf && oi < ci)) { cf = of; ci = oi; }
     }
     if (lane == 0) { sf[warp] = cf; si[warp] = ci; }
     __syncthreads();
@@ -369,10 +382,13 @@ size_t swarm_finish_scratch_doubles(int B, int S) { return (size_t)B * ((S + kFi
 cudaError_t launch_swarm_finish(const SwarmState& s, const double* partials, int n_tiles, int nsum, int N, double* rec,
                                 double* scratch, unsigned* tickets, int commit, int maxiter, cudaStream_t st, int nw,
                                 const PeerArgs* pa) {
-    dim3 grid((s.S + kFinWarps - 1) / kFinWarps, s.B);
+    int L = 1;                                             // lanes per particle: a power of two >= n_tiles, at most a warp
+    while (L < 32 && L < n_tiles) L <<= 1;
+    const int per_cta = kFinWarps * (32 / L);
+    dim3 grid((s.S + per_cta - 1) / per_cta, s.B);
     const size_t smem = commit == 2 ? (size_t)pa->n_ranks * (s.D + 2) * sizeof(double) : 0;
     swarm_finish_kernel<<<grid, kFinWarps * 32, smem, st>>>(s, partials, n_tiles, nsum, N, rec, scratch, tickets, commit,
-                                                            maxiter, nw, pa ? *pa : PeerArgs{});
+                                                            maxiter, nw, L, pa ? *pa : PeerArgs{});
     count_launches(1);
     return cudaGetLastError();
 }
