@@ -84,7 +84,7 @@ struct RegionDst {
 // are neutral.
 constexpr int kPrepThreads = 256;                          // at most; 128 when a particle alone fills the CTA
 template <int R, bool MOVE>
-__global__ void __launch_bounds__(kPrepThreads)
+__global__ void __launch_bounds__(kPrepThreads, 4)
 objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     const int nthreads = blockDim.x;
     extern __shared__ __align__(16) double sm[];           // cs [G][P][8], farpk [G][P][4], then (MOVE) the moved particles [G][D]
@@ -128,11 +128,12 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     // full whatever the shape) from the first thread up, P span coefficients from the last thread down
     const int per = kTableItems + NRP;
     const float inv_per = 1.0f / (float)per, inv_P = 1.0f / (float)P;
+    const double inv_N = 1.0 / (double)N;
     for (int e = tid; e < ng * per; e += nthreads) {
         const int g = fast_div(e, per, inv_per), it = e - g * per;
         const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
         double sn, cn;
-        sincos(prep_item_angle<R>(xs, it, N), &sn, &cn);
+        sincos(prep_item_angle<R>(xs, it, N, inv_N), &sn, &cn);
         double* dst;
         if (it < kTableItems) {
             dst = a.prep_part + (ps0 + g) * kPartDoubles + 2 * it;
