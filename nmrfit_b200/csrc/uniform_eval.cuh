@@ -262,12 +262,13 @@ __device__ __forceinline__ int stage_slot_wt(int t, int j, int stride) { return 
 // I_data = u sin(phi) + v cos(phi) against the last peak's Kramers-Kronig counterpart (closed form, nmrfit_math.cuh).
 // Where a lane's far-field cell keeps its mask block and its polynomial inside the region's constants: loop-invariant,
 // computed once per thread (mk_off == 0 <=> the region is one cell and has no separate union block).
-struct LaneCell { int mk_off, fc_off; };
+struct LaneCell { int mk_off, fc_off, mirror; };       // mirror: xor mask to the lane holding the mirror-image span
 __device__ __forceinline__ LaneCell lane_cell(int lane, int sub, int P) {
     const int cell = (lane * sub) >> 5, MW = (P + 31) / 32;
     LaneCell lc;
     lc.mk_off = sub == 1 ? 0 : (1 + cell) * (MW + 1);
     lc.fc_off = cell * kFarPoly;
+    lc.mirror = 32 / sub - 1;
     return lc;
 }
 
@@ -293,7 +294,11 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
             C[n] = t2.x; C[n + 1] = t2.y;
         }
         C[0] += py;
-        far_init<R>(C, xi0, inv_H, acc);
+        double mir[R / 2];
+        far_init_half<R>(C, xi0, inv_H, acc, mir);
+        // the last R/2 points: the mirror image, inside the cell, of the first R/2 points of lane ^ (lanes per cell - 1)
+#pragma unroll
+        for (int j = 0; j < R / 2; ++j) acc[R - 1 - j] = __shfl_xor_sync(0xffffffffu, mir[j], lc.mirror);
     }
     for (int wd = 0; wd < MW; ++wd) {
         const unsigned mine = mkc[wd];                     // peaks near this lane's cell
