@@ -227,7 +227,10 @@ ObjTune pick_tune(const nmrfit_ctx* c, int S, bool uni) {
         };
         int stg = c->user_tune.stages > 0 ? c->user_tune.stages : 3;
         int spg = fit_sp(stg);
-        if (c->user_tune.stages == 0 && spg < 4) {         // many peaks: two deeper stages rather than three shallow ones
+        // heavy per-particle constants (many peaks, or four far-field cells per region): two deeper stages rather than
+        // three shallow ones - a group of 7 instead of 5 particles amortises the per-group handshakes (r02ae: -5 % at
+        // 6 peaks x 4,096 points; groups of 7+ gain nothing from the switch)
+        if (c->user_tune.stages == 0 && spg < 6) {
             const int spg2 = fit_sp(2);
             if (spg2 > spg) { stg = 2; spg = spg2; }
         }
@@ -747,8 +750,11 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
     // A large particle set of one spectrum goes through in slices on two streams: while slice k is evaluated, slice
     // k + 1's positions are on their way in and slice k - 1's values on their way out (each slice has its own scratch).
     constexpr int kPad = 64;
-    static const int kSlices = [] { const char* e = getenv("NMRFIT_E2E_SLICES"); const int v = e ? atoi(e) : 2; return v < 1 ? 1 : (v > 16 ? 16 : v); }();
-    if (c->B == 1 && S >= 4 * 4096 && !c->profiling && kSlices > 1) {       // (two slices measured best: tools/e2e_probe.py)
+    // (slices of ~12k particles, two to six of them: 1.24 / 1.15 / 1.13 / 1.12 ms per call with 1 / 2 / 4 / 6 slices
+    // at 65,536 particles of 6 peaks x 4,096 points, tools/e2e_probe.py; NMRFIT_E2E_SLICES overrides)
+    static const int kEnvSlices = [] { const char* e = getenv("NMRFIT_E2E_SLICES"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 16 ? 16 : v); }();
+    const int kSlices = kEnvSlices ? kEnvSlices : std::min(6, std::max(2, S / 12288));
+    if (c->B == 1 && S >= 4 * 4096 && !c->profiling && kSlices > 1) {
         for (int k = 0; k < 2; ++k)
             if (!c->pipe[k]) CK(cudaStreamCreateWithFlags(&c->pipe[k], cudaStreamNonBlocking));
         if (c->h_f_cap < nf) {
