@@ -209,6 +209,22 @@ int nmrfit_pso_run_peers(nmrfit_ctx* ctx, int n_generations, const double* rp_al
                          int* timed_out, void* stream);
 int nmrfit_pso_peer_timeout(nmrfit_ctx* ctx, double milliseconds);
 int nmrfit_pso_peer_error(nmrfit_ctx* ctx, int* timed_out);
+/* The same exchange for a C consumer WITHOUT a collective library: n contexts of ONE process, one per GPU (or several
+ * on one GPU), form a communicator.  This is the library-level counterpart of the reference's `processes=N`
+ * (utils.py:182: pyswarm farms the objective calls of a generation out to a multiprocessing pool) - here the
+ * particles of the swarm are split over the contexts instead.
+ *   init_all: allocates every context's window, enables peer access between their devices and maps every window into
+ *             every context (rank = position in ctxs).  Call before nmrfit_pso_begin; each context then begins its own
+ *             shard (nmrfit_pso_opts.particle_offset = first global particle index of the shard).
+ *   commit:   the initial swarm-best selection over all shards (after every context's nmrfit_pso_begin).
+ *   run:      n_generations sharded generations on every context (three launches per context and generation, queued
+ *             rank by rank so that no rank's host call waits for another), then one synchronisation.  rp_all / rg_all:
+ *             per-context host or device arrays [n_generations][particles of the shard][D], or NULL for the device
+ *             random stream.  n_running: spectra not yet stopped; timed_out: 1 if a rank was lost. */
+int nmrfit_comm_init_all(nmrfit_ctx* const* ctxs, int n);
+int nmrfit_comm_commit(nmrfit_ctx* const* ctxs, int n);
+int nmrfit_comm_run(nmrfit_ctx* const* ctxs, int n, int n_generations, const double* const* rp_all,
+                    const double* const* rg_all, int* n_running, int* timed_out);
 /* Device pointer and length (doubles) of the local best record, [n_spectra][D+2] = (f, global index, x[D]). */
 int nmrfit_pso_record(nmrfit_ctx* ctx, double** rec_dev, int* n_doubles);
 /* Swarm-best update and the minfunc/minstep/maxiter tests.  recs_dev = [n_ranks][n_spectra][D+2]

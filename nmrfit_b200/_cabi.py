@@ -78,6 +78,9 @@ SIGNATURES = {
     'nmrfit_pso_peer_error': (_i, [_vp, c_int_p]),
     'nmrfit_pso_run_peers': (_i, [_vp, _i, _vp, _vp, c_int_p, c_int_p, _vp]),
     'nmrfit_pso_peer_timeout': (_i, [_vp, _d]),
+    'nmrfit_comm_init_all': (_i, [_vp, _i]),
+    'nmrfit_comm_commit': (_i, [_vp, _i]),
+    'nmrfit_comm_run': (_i, [_vp, _i, _i, _vp, _vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
     'nmrfit_pso_record': (_i, [_vp, ctypes.POINTER(_vp), c_int_p]),
     'nmrfit_pso_commit': (_i, [_vp, _vp, _i, _vp]),
     'nmrfit_pso_run': (_i, [_vp, _i, _vp, _vp, c_int_p, _vp]),
@@ -471,6 +474,33 @@ class PhaseScorer:
         score = np.empty((self.B, ph.shape[0]))
         check(lib().nmrfit_phase_acme(self._h, ptr(ph), ph.shape[0], ptr(score)))
         return score
+
+
+class Communicator:
+    """The contexts of ONE process as the ranks of a particle-sharded swarm (nmrfit_comm_*: no collective library; the
+    best records cross between the contexts' windows inside the finish kernel).  ``ctxs[r]`` begins its own shard with
+    ``particle_offset`` = the shard's first global particle index; then ``commit()`` and ``run(n)``."""
+
+    def __init__(self, ctxs):
+        self.ctxs = list(ctxs)
+        self._arr = (ctypes.c_void_p * len(self.ctxs))(*[c._h for c in self.ctxs])
+        check(lib().nmrfit_comm_init_all(self._arr, len(self.ctxs)))
+
+    def commit(self):
+        check(lib().nmrfit_comm_commit(self._arr, len(self.ctxs)))
+
+    def run(self, n_generations, rp_all=None, rg_all=None):
+        """rp_all / rg_all: per-context arrays [n_generations][shard particles][D] (or None: device random numbers).
+        Returns (spectra still running, 1 if a rank was lost)."""
+        n = len(self.ctxs)
+        keep, rp, rg = [], None, None
+        if rp_all is not None:
+            keep = [[c._rand(a, c._swarmsize, n_generations) for c, a in zip(self.ctxs, arrs)] for arrs in (rp_all, rg_all)]
+            rp = (ctypes.c_void_p * n)(*[ptr(a) for a in keep[0]])
+            rg = (ctypes.c_void_p * n)(*[ptr(a) for a in keep[1]])
+        running, lost = ctypes.c_int(0), ctypes.c_int(0)
+        check(lib().nmrfit_comm_run(self._arr, n, int(n_generations), rp, rg, ctypes.byref(running), ctypes.byref(lost)))
+        return running.value, lost.value
 
 
 class PeakPicker:

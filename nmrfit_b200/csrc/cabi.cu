@@ -1035,6 +1035,113 @@ int nmrfit_pso_run_peers(nmrfit_ctx* c, int n_generations, const double* rp_all,
     return NMRFIT_OK;
 }
 
+// ---- the same for the contexts of ONE process (a C consumer with one context per GPU and no NCCL) -------------------
+
+int nmrfit_comm_init_all(nmrfit_ctx* const* ctxs, int n) {
+    if (!ctxs || n < 1 || n > 64) return fail(NMRFIT_ERR_ARG, "ctxs must hold 1..64 contexts");
+    for (int r = 0; r < n; ++r) {
+        if (int rc = check_ctx(ctxs[r])) return rc;
+        if (ctxs[r]->B != ctxs[0]->B || ctxs[r]->D != ctxs[0]->D)
+            return fail(NMRFIT_ERR_ARG, "the contexts of a communicator must agree in spectra and parameters");
+    }
+    // every device stores into every other device's window
+    for (int r = 0; r < n; ++r) {
+        CK(cudaSetDevice(ctxs[r]->device));
+        for (int q = 0; q < n; ++q) {
+            if (ctxs[q]->device == ctxs[r]->device) continue;
+            int can = 0;
+            CK(cudaDeviceCanAccessPeer(&can, ctxs[r]->device, ctxs[q]->device));
+            if (!can) return fail(NMRFIT_ERR_STATE, "the devices of the communicator cannot reach each other's memory");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[q]->device, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) (void)cudaGetLastError();
+            else if (e != cudaSuccess) return fail_cuda(e, "cudaDeviceEnablePeerAccess");
+        }
+    }
+    std::vector<void*> bases(n, nullptr);
+    for (int r = 0; r < n; ++r)
+        if (int rc = nmrfit_pso_peer_export(ctxs[r], n, r, nullptr, &bases[r])) return rc;
+    for (int r = 0; r < n; ++r)
+        if (int rc = nmrfit_pso_peer_open(ctxs[r], nullptr, bases.data())) return rc;
+    return NMRFIT_OK;
+}
+
+namespace {
+int comm_stream(nmrfit_ctx* c, cudaStream_t* st) {
+    CK(cudaSetDevice(c->device));
+    if (!c->pipe[0]) CK(cudaStreamCreateWithFlags(&c->pipe[0], cudaStreamNonBlocking));
+    CK(cudaStreamSynchronize(0));                          // nmrfit_pso_begin and friends ran on the default stream
+    *st = c->pipe[0];
+    return NMRFIT_OK;
+}
+}  // namespace
+
+int nmrfit_comm_commit(nmrfit_ctx* const* ctxs, int n) {
+    if (!ctxs || n < 1) return fail(NMRFIT_ERR_ARG, "ctxs must hold at least one context");
+    for (int r = 0; r < n; ++r) {
+        if (int rc = check_ctx(ctxs[r])) return rc;
+        if (!ctxs[r]->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called on every context");
+    }
+    for (int r = 0; r < n; ++r) {                           // all launched before any is waited for: they wait for each other
+        cudaStream_t st;
+        if (int rc = comm_stream(ctxs[r], &st)) return rc;
+        if (int rc = exchange_commit(ctxs[r], st)) return rc;
+    }
+    for (int r = 0; r < n; ++r) {
+        CK(cudaSetDevice(ctxs[r]->device));
+        CK(cudaStreamSynchronize(ctxs[r]->pipe[0]));
+    }
+    return NMRFIT_OK;
+}
+
+int nmrfit_comm_run(nmrfit_ctx* const* ctxs, int n, int n_generations, const double* const* rp_all,
+                    const double* const* rg_all, int* n_running, int* timed_out) {
+    if (!ctxs || n < 1) return fail(NMRFIT_ERR_ARG, "ctxs must hold at least one context");
+    if ((rp_all == nullptr) != (rg_all == nullptr)) return fail(NMRFIT_ERR_ARG, "rp_all and rg_all must both be given or both be NULL");
+    if (n_generations < 0) return fail(NMRFIT_ERR_ARG, "n_generations must be >= 0");
+    std::vector<const double*> rp_d(n, nullptr), rg_d(n, nullptr);
+    std::vector<cudaStream_t> sts(n);
+    for (int r = 0; r < n; ++r) {
+        nmrfit_ctx* c = ctxs[r];
+        if (int rc = check_ctx(c)) return rc;
+        if (!c->swarm) return fail(NMRFIT_ERR_STATE, "nmrfit_pso_begin has not been called on every context");
+        if (int rc = comm_stream(c, &sts[r])) return rc;
+        const size_t nsd = (size_t)c->sw.B * c->sw.S * c->sw.D;
+        if (rp_all && n_generations > 0) {
+            if (int rc = stage(rp_all[r], nsd * n_generations, c->rnd_a, sts[r], &rp_d[r])) return rc;
+            if (int rc = stage(rg_all[r], nsd * n_generations, c->rnd_b, sts[r], &rg_d[r])) return rc;
+        }
+    }
+    // generation by generation over the contexts: every rank's kernels are queued before the host waits for anything
+    for (int k = 0; k < n_generations; ++k) {
+        for (int r = 0; r < n; ++r) {
+            nmrfit_ctx* c = ctxs[r];
+            CK(cudaSetDevice(c->device));
+            const size_t nsd = (size_t)c->sw.B * c->sw.S * c->sw.D;
+            c->generation += 1;
+            if (int rc = swarm_generation(c, true, rp_d[r] ? rp_d[r] + nsd * k : nullptr, rg_d[r] ? rg_d[r] + nsd * k : nullptr,
+                                          2, sts[r]))
+                return rc;
+        }
+    }
+    int running = 0, lost = 0;
+    for (int r = 0; r < n; ++r) {
+        nmrfit_ctx* c = ctxs[r];
+        CK(cudaSetDevice(c->device));
+        CK(cudaMemcpyAsync(c->h_flags, c->sw.stop, sizeof(int) * c->sw.B, cudaMemcpyDeviceToHost, sts[r]));
+        CK(cudaMemcpyAsync(c->h_flags + c->sw.B, c->peer_err.ptr, sizeof(int), cudaMemcpyDeviceToHost, sts[r]));
+    }
+    for (int r = 0; r < n; ++r) {
+        nmrfit_ctx* c = ctxs[r];
+        CK(cudaSetDevice(c->device));
+        CK(cudaStreamSynchronize(sts[r]));
+        lost |= c->h_flags[c->sw.B];
+        if (r == 0) for (int b = 0; b < c->sw.B; ++b) running += c->h_flags[b] == 0;     // identical on every rank
+    }
+    if (n_running) *n_running = running;
+    if (timed_out) *timed_out = lost;
+    return NMRFIT_OK;
+}
+
 int nmrfit_pso_peer_timeout(nmrfit_ctx* c, double milliseconds) {
     if (int rc = check_ctx(c)) return rc;
     if (!(milliseconds > 0.0)) return fail(NMRFIT_ERR_ARG, "the timeout must be positive");

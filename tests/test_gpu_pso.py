@@ -326,6 +326,57 @@ def test_record_exchange_over_peer_memory_equals_unsharded(ranks):
             c.close()
 
 
+@pytest.mark.parametrize('ranks', [2, 4])
+def test_c_level_communicator_equals_unsharded(ranks):
+    """nmrfit_comm_init_all / _commit / _run: the contexts of one process (one per GPU when the box has that many, else
+    all on this GPU) as the ranks of a particle-sharded swarm, driven through the C ABI alone - no torch.distributed, no
+    NCCL.  Same trajectory, bit for bit, as the unsharded swarm."""
+    import torch
+    g = load_golden('fit_c1_4096x6')
+    S, D, iters = 45, 22, 9
+    rs = np.random.RandomState(4)
+    r_pos, r_vel = rs.rand(S, D), rs.rand(S, D)
+    rp, rg = rs.rand(iters, S, D), rs.rand(iters, S, D)
+    lb, ub = g['lower'], g['upper']
+
+    def opts(cnt, off):
+        return swarm._make_opts(cnt, iters, PSO['omega'], PSO['phip'], PSO['phig'], 1e-8, 1e-8, False, 0, offset=off)
+
+    with _cabi.Context(1, g['w'].size, 6) as ctx:
+        ctx.set_spectrum(0, g['w'], g['u'], g['v'], g['weights'])
+        ctx.pso_begin(lb, ub, opts(S, 0), r_pos, r_vel)
+        ctx.pso_commit()
+        ctx.pso_run(iters, rp, rg)
+        want = ctx.pso_best()
+        want_x = ctx.pso_state()['x'][0]
+
+    n_dev = torch.cuda.device_count()
+    ctxs = [_cabi.Context(1, g['w'].size, 6, device=(r % n_dev) if n_dev >= ranks else 0) for r in range(ranks)]
+    try:
+        shards = [swarm.shard_range(S, r, ranks) for r in range(ranks)]
+        for c in ctxs:
+            c.set_spectrum(0, g['w'], g['u'], g['v'], g['weights'])
+            c.set_fused(_cabi.FUSED_OFF)
+        comm = _cabi.Communicator(ctxs)
+        for r, c in enumerate(ctxs):
+            off, cnt = shards[r]
+            c.pso_begin(lb, ub, opts(cnt, off), r_pos[off:off + cnt], r_vel[off:off + cnt])
+        comm.commit()
+        for k0 in range(0, iters, 4):                      # in chunks, as a caller polling the stop flags would
+            k1 = min(iters, k0 + 4)
+            running, lost = comm.run(k1 - k0,
+                                     [np.ascontiguousarray(rp[k0:k1, off:off + cnt]) for off, cnt in shards],
+                                     [np.ascontiguousarray(rg[k0:k1, off:off + cnt]) for off, cnt in shards])
+            assert lost == 0 and running in (0, 1)
+        for c in ctxs:
+            assert all(np.array_equal(a, b) for a, b in zip(c.pso_best(), want))
+        got_x = np.concatenate([c.pso_state()['x'][0] for c in ctxs])
+        assert np.array_equal(got_x, want_x)
+    finally:
+        for c in ctxs:
+            c.close()
+
+
 @pytest.mark.parametrize('pos0', [624, 0, 1, 7, 311, 622, 623])
 def test_legacy_stream_continued_on_the_device_is_numpys(pos0):
     """csrc/mt19937.cu: given np.random's state the device produces the numbers np.random.rand would, for every
