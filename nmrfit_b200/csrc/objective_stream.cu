@@ -36,8 +36,6 @@ namespace {
 
 template <int TB> struct ExpTabS { static __device__ __forceinline__ const double* src() { return nullptr; } };
 template <> struct ExpTabS<6> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB6; } };
-template <> struct ExpTabS<8> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB8; } };
-template <> struct ExpTabS<10> { static __device__ __forceinline__ const double* src() { return NMRFIT_EXP2_TAB10; } };
 
 // shared-memory carve-up (in doubles); every offset is even (16-byte alignment)
 struct StreamSmem {
@@ -70,7 +68,7 @@ __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.p
 
 // OCC: CTAs of 256 threads per SM the kernel is compiled for (3: 80 registers, 75 KB of shared memory each; 2: up to
 // 128 registers and 113 KB - room for deeper stages when the per-particle constants are large)
-template <int THREADS, int R, int TB, int KK, int OCC>
+template <int THREADS, int R, int TB, int KK, int OCC, int SUB>
 __global__ void __launch_bounds__(THREADS, (R <= 8 ? OCC * 256 : 512) / THREADS)
 objective_stream_kernel(ObjArgs a) {
     constexpr int NSUM = KK ? 2 : 1;
@@ -81,7 +79,6 @@ objective_stream_kernel(ObjArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int P = a.P, N = a.N, D = 4 + 3 * P, SPG = a.sp, ST = a.stages;
     const int n_tiles = a.n_tiles, tile = blockIdx.y, NRP = n_tiles * NW;
-    const int SUB = a.sub;
     const StreamSmem L(SPG, ST, P, THREADS, R, TB, SUB);
     const int MW = L.mw;
     double* tab = smem + L.tab;
@@ -178,7 +175,7 @@ objective_stream_kernel(ObjArgs a) {
         mbar_wait(bars + sl, phase);                       // this fill of the slot has landed
         for (int sp = 0; sp < nsp; ++sp) {
             double ssi = 0.0;
-            const double ss = eval_region<R, TB, KK, false>(cf, pt, mk, fc, *an, MW, P, lane, lcell, w_first, xi0, inv_H, suv,
+            const double ss = eval_region<R, TB, KK, false, SUB>(cf, pt, mk, fc, *an, MW, P, lane, lcell, w_first, xi0, inv_H, suv,
                                                             swt, t, THREADS, tab, xs, sw + i_first, N - i_first, h, w_ulp,
                                                             &ssi);
             if (lane == 0) {
@@ -206,23 +203,35 @@ objective_stream_kernel(ObjArgs a) {
     (void)NRP;
 }
 
-template <int THREADS, int R, int TB, int KK, int OCC>
-cudaError_t launch_occ(const ObjArgs& a, int B, cudaStream_t st) {
+template <int THREADS, int R, int TB, int KK, int OCC, int SUB>
+cudaError_t launch_sub(const ObjArgs& a, int B, cudaStream_t st) {
     static bool attr_set[NMRFIT_MAX_DEVICES] = {};
     StreamSmem L(a.sp, a.stages, a.P, THREADS, R, TB, a.sub);
     const size_t bytes = (size_t)L.total * sizeof(double);
     int dev = 0;
     cudaGetDevice(&dev);
     if (!attr_set[dev % NMRFIT_MAX_DEVICES]) {
-        cudaError_t e = cudaFuncSetAttribute(objective_stream_kernel<THREADS, R, TB, KK, OCC>,
+        cudaError_t e = cudaFuncSetAttribute(objective_stream_kernel<THREADS, R, TB, KK, OCC, SUB>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) return e;
         attr_set[dev % NMRFIT_MAX_DEVICES] = true;
     }
     const int n_groups = (a.S + a.sp - 1) / a.sp;
     dim3 grid((n_groups + a.gpc - 1) / a.gpc, a.n_tiles, B);
-    objective_stream_kernel<THREADS, R, TB, KK, OCC><<<grid, THREADS, bytes, st>>>(a);
+    objective_stream_kernel<THREADS, R, TB, KK, OCC, SUB><<<grid, THREADS, bytes, st>>>(a);
     return cudaGetLastError();
+}
+
+// far-field cells per region as a compile-time constant: the lane's cell, the mirror lane and the cell coordinate's
+// step fold into immediates instead of being recomputed per particle (the kernel runs at its register limit)
+template <int THREADS, int R, int TB, int KK, int OCC>
+cudaError_t launch_occ(const ObjArgs& a, int B, cudaStream_t st) {
+    switch (a.sub) {
+        case 1: return launch_sub<THREADS, R, TB, KK, OCC, 1>(a, B, st);
+        case 2: return launch_sub<THREADS, R, TB, KK, OCC, 2>(a, B, st);
+        case 4: return launch_sub<THREADS, R, TB, KK, OCC, 4>(a, B, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 template <int THREADS, int R, int TB, int KK>
@@ -233,10 +242,8 @@ cudaError_t launch_one(const ObjArgs& a, int B, cudaStream_t st) {
 template <int THREADS, int R>
 cudaError_t launch_tb(const ObjArgs& a, int tb, int B, cudaStream_t st) {
     switch (tb) {
-        case 0: return a.kk ? launch_one<THREADS, R, 0, 1>(a, B, st) : launch_one<THREADS, R, 0, 0>(a, B, st);
+        // (built for the default exp table only: the launcher routes every other table to the one-group kernel)
         case 6: return a.kk ? launch_one<THREADS, R, 6, 1>(a, B, st) : launch_one<THREADS, R, 6, 0>(a, B, st);
-        case 8: return a.kk ? launch_one<THREADS, R, 8, 1>(a, B, st) : launch_one<THREADS, R, 8, 0>(a, B, st);
-        case 10: return a.kk ? launch_one<THREADS, R, 10, 1>(a, B, st) : launch_one<THREADS, R, 10, 0>(a, B, st);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -258,6 +258,7 @@ __device__ __forceinline__ int stage_slot_wt(int t, int j, int stride) { return 
 // tile sit at stage_slot_uv/wt(t, j, stride) of suv / swt (SWZ) or at j*stride + t (!SWZ); w_first is the abscissa of its
 // first point.  The exact path (peaks too narrow for the recurrences) reads the particle's parameters xs and the stored
 // abscissae sw_first[0..n_valid).
+// SUBT: the number of cells when the caller knows it at compile time (0: take everything from lc).
 // KK = 1 (fit_im, reference semantics) also returns through *ss_im the same sum for the imaginary parts:
 // I_data = u sin(phi) + v cos(phi) against the last peak's Kramers-Kronig counterpart (closed form, nmrfit_math.cuh).
 // Where a lane's far-field cell keeps its mask block and its polynomial inside the region's constants: loop-invariant,
@@ -272,7 +273,7 @@ __device__ __forceinline__ LaneCell lane_cell(int lane, int sub, int P) {
     return lc;
 }
 
-template <int R, int TB, int KK = 0, bool SWZ = true>
+template <int R, int TB, int KK = 0, bool SWZ = true, int SUBT = 0>
 __device__ __forceinline__ double eval_region(const double* __restrict__ cf, const double* __restrict__ pt,
                                               const unsigned* __restrict__ mk, const double* __restrict__ fc,
                                               const double2 ew, int MW, int P, int lane, const LaneCell lc, double w_first, double xi0,
@@ -298,7 +299,7 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
         far_init_half<R>(C, xi0, inv_H, acc, mir);
         // the last R/2 points: the mirror image, inside the cell, of the first R/2 points of lane ^ (lanes per cell - 1)
 #pragma unroll
-        for (int j = 0; j < R / 2; ++j) acc[R - 1 - j] = __shfl_xor_sync(0xffffffffu, mir[j], lc.mirror);
+        for (int j = 0; j < R / 2; ++j) acc[R - 1 - j] = __shfl_xor_sync(0xffffffffu, mir[j], SUBT ? 32 / SUBT - 1 : lc.mirror);
     }
     for (int wd = 0; wd < MW; ++wd) {
         const unsigned mine = mkc[wd];                     // peaks near this lane's cell
@@ -313,7 +314,7 @@ __device__ __forceinline__ double eval_region(const double* __restrict__ cf, con
             c.loc = c01.x; c.kL = c01.y; c.kG = c23.x; c.aL = c23.y;
             c.aG = c45.x; c.dT = c45.y; c.thr = c67.x; c.c2 = c67.y;
             // (in a cell for which the peak is far it is already inside that cell's polynomial)
-            if (lc.mk_off == 0 || ((mine >> kb) & 1u)) peak_span<R, TB>(w_first - c.loc, c, tab, acc);
+            if ((SUBT ? SUBT == 1 : lc.mk_off == 0) || ((mine >> kb) & 1u)) peak_span<R, TB>(w_first - c.loc, c, tab, acc);
         }
     }
     if (pt[67] != 0.0) {                                   // rare: peaks too narrow for the uniform-axis shortcuts

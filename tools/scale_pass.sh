@@ -4,7 +4,7 @@
 TAG=${1:-r02}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/${TAG}_gpus.txt 2>&1
-timeout 900 python -m pytest tests/test_gpu_multi.py -m gpu -q --timeout=800 > gpurun_out/${TAG}_pytest_multi.log 2>&1; tail -3 gpurun_out/${TAG}_pytest_multi.log
+timeout 900 python -m pytest tests/test_gpu_multi.py tests/test_gpu_pso.py -m gpu -q --timeout=800 -k "multi or communicator or nccl or sharded" > gpurun_out/${TAG}_pytest_multi.log 2>&1; tail -3 gpurun_out/${TAG}_pytest_multi.log
 PORT=29700
 for N in ${2:-8}; do
   for EX in p2p nccl; do
