@@ -268,7 +268,7 @@ int check_ctx(const nmrfit_ctx* c) {
 
 int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double* f_dev, const int* frozen,
                   cudaStream_t st, const MoveArgs* mv = nullptr, int* tiles_out = nullptr, int* nsum_out = nullptr,
-                  int* nw_out = nullptr, size_t slot0 = 0, size_t slots_total = 0) {
+                  int* nw_out = nullptr, size_t slot0 = 0, size_t slots_total = 0, const double* x_in = nullptr) {
     // slot0 / slots_total (one spectrum only): this launch is one slice of a larger particle set evaluated in pieces on
     // several streams (nmrfit_objective_batch_host); it owns the scratch of particle slots [slot0, slot0 + S + pad)
     for (int b = 0; b < c->B; ++b)
@@ -305,6 +305,7 @@ int run_objective(nmrfit_ctx* c, const double* x_dev, int S, int fit_im, double*
     }
     a.spec = c->spec.ptr;
     a.x = x_dev;
+    a.x_in = x_in;                                         // (two-pass FP64 path only: the caller checks)
     a.partials = c->partials.ptr + slot0 * part_per;
     a.frozen = frozen;
     a.grid_h = c->grid_h.ptr;
@@ -749,11 +750,23 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
     CK(c->f_stage.reserve(nf));
     // A large particle set of one spectrum goes through in slices on two streams: while slice k is evaluated, slice
     // k + 1's positions are on their way in and slice k - 1's values on their way out (each slice has its own scratch).
+    // Page-locked host positions (cudaHostAlloc / cudaHostRegister: mapped into the device under unified addressing) are
+    // read by the prepare pass ITSELF, each element crossing PCIe once while other CTAs compute - no staging copy in
+    // front of the kernels (NMRFIT_E2E_ZEROCOPY=0 turns this off).  Pageable arrays take the copies below.
+    static const bool kZeroCopy = [] { const char* e = getenv("NMRFIT_E2E_ZEROCOPY"); return !(e && atoi(e) == 0); }();
+    const double* x_map = nullptr;                         // the caller's array as the device sees it, or null
+    if (kZeroCopy && use_uniform(c, fit_im) && c->precision == NMRFIT_FP64) {
+        cudaPointerAttributes at{};
+        const cudaError_t pe = cudaPointerGetAttributes(&at, x_host);
+        if (pe != cudaSuccess) (void)cudaGetLastError();
+        if (pe == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) x_map = (const double*)at.devicePointer;
+    }
     constexpr int kPad = 64;
     // (slices of ~12k particles, two to six of them: 1.24 / 1.15 / 1.13 / 1.12 ms per call with 1 / 2 / 4 / 6 slices
     // at 65,536 particles of 6 peaks x 4,096 points, tools/e2e_probe.py; NMRFIT_E2E_SLICES overrides)
     static const int kEnvSlices = [] { const char* e = getenv("NMRFIT_E2E_SLICES"); const int v = e ? atoi(e) : 0; return v < 0 ? 0 : (v > 16 ? 16 : v); }();
-    const int kSlices = kEnvSlices ? kEnvSlices : std::min(6, std::max(2, S / 12288));
+    // (in-place reads are not sliced: 1.048 / 1.084 / 1.105 ms with 1 / 2 / 3 slices - and 1.136 ms for the best copy path)
+    const int kSlices = kEnvSlices ? kEnvSlices : x_map ? 1 : std::min(6, std::max(2, S / 12288));
     if (c->B == 1 && S >= 4 * 4096 && !c->profiling && kSlices > 1) {
         for (int k = 0; k < 2; ++k)
             if (!c->pipe[k]) CK(cudaStreamCreateWithFlags(&c->pipe[k], cudaStreamNonBlocking));
@@ -769,10 +782,12 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
         for (int k = 0, s0 = 0; s0 < S; ++k, s0 += chunk) {
             const int ns = std::min(chunk, S - s0);
             cudaStream_t ps = c->pipe[k & 1];
-            CK(cudaMemcpyAsync(c->x_stage.ptr + (size_t)s0 * c->D, x_host + (size_t)s0 * c->D, sizeof(double) * ns * c->D,
-                               cudaMemcpyHostToDevice, ps));
+            if (!x_map)
+                CK(cudaMemcpyAsync(c->x_stage.ptr + (size_t)s0 * c->D, x_host + (size_t)s0 * c->D, sizeof(double) * ns * c->D,
+                                   cudaMemcpyHostToDevice, ps));
             if (int rc = run_objective(c, c->x_stage.ptr + (size_t)s0 * c->D, ns, fit_im, c->f_stage.ptr + s0, nullptr, ps,
-                                       nullptr, nullptr, nullptr, nullptr, (size_t)k * (chunk + kPad), total))
+                                       nullptr, nullptr, nullptr, nullptr, (size_t)k * (chunk + kPad), total,
+                                       x_map ? x_map + (size_t)s0 * c->D : nullptr))
                 return rc;
             // (into page-locked staging: an "async" copy into the caller's pageable array would block the host until
             // the slice has been evaluated, and the slices would run one after the other)
@@ -784,8 +799,10 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
         return NMRFIT_OK;
     }
     cudaStream_t st = 0;
-    CK(cudaMemcpyAsync(c->x_stage.ptr, x_host, nx * sizeof(double), cudaMemcpyHostToDevice, st));
-    if (int rc = run_objective(c, c->x_stage.ptr, S, fit_im, c->f_stage.ptr, nullptr, st)) return rc;
+    if (!x_map) CK(cudaMemcpyAsync(c->x_stage.ptr, x_host, nx * sizeof(double), cudaMemcpyHostToDevice, st));
+    if (int rc = run_objective(c, c->x_stage.ptr, S, fit_im, c->f_stage.ptr, nullptr, st, nullptr, nullptr, nullptr, nullptr, 0, 0,
+                               x_map))
+        return rc;
     CK(cudaMemcpyAsync(f_host, c->f_stage.ptr, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return NMRFIT_OK;

@@ -14,6 +14,8 @@ void count_launches(int n);   // bookkeeping for nmrfit_launch_count()
 struct ObjArgs {
     const double* spec;     // [B][4][N]: w, u, v, weights
     const double* x;        // [B][S][D] particle positions, D = 4 + 3P
+    const double* x_in;     // null, or where the prepare pass READS the positions instead (page-locked host memory mapped
+                            // into the device: it copies them to x on the way, each element crossing PCIe once)
     double* partials;       // [B][S][n_tiles][nsum]
     const int* frozen;      // [B] or null: spectra whose swarm has stopped are skipped
     const double* grid_h;   // [B][2] axis spacing h and ulp scale 2^-52*max|w| (uniform-axis kernel only)

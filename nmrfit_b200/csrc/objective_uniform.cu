@@ -87,7 +87,7 @@ template <int R, bool MOVE>
 __global__ void __launch_bounds__(kPrepThreads, 4)
 objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     const int nthreads = blockDim.x;
-    extern __shared__ __align__(16) double sm[];           // cs [G][P][8], farpk [G][P][4], then (MOVE) the moved particles [G][D]
+    extern __shared__ __align__(16) double sm[];           // cs [G][P][8], farpk [G][P][4], the (moved) particles [G][D]
     const int b = blockIdx.y, s0 = blockIdx.x * G, tid = threadIdx.x;
     if (MOVE ? mv.s.stop[b] != 0 : (a.frozen && a.frozen[b])) return;
     const int P = a.P, N = a.N, D = 4 + 3 * P, sub = a.sub;
@@ -123,6 +123,18 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
             xsm[e] = x;
         }
         __syncthreads();
+    } else {
+        // the positions of the CTA's particles, once, into shared memory (every item below reads them from there).  With
+        // x_in they come straight from the caller's page-locked host array - the host-to-device copy happens inside this
+        // kernel, overlapped with the other CTAs' arithmetic - and are left in a.x for the evaluation kernel.
+        const double* src = (a.x_in ? a.x_in : a.x) + ps0 * D;
+        double* keep = a.x_in ? const_cast<double*>(a.x) + ps0 * D : nullptr;
+        for (int e = tid; e < ng * D; e += nthreads) {
+            const double v = src[e];
+            xsm[e] = v;
+            if (keep) keep[e] = v;
+        }
+        __syncthreads();
     }
     // ---- phase 1: per particle kTableItems + NRP rotation items (one sincos each; packed, so that the warps are
     // full whatever the shape) from the first thread up, P span coefficients from the last thread down
@@ -131,7 +143,7 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     const double inv_N = 1.0 / (double)N;
     for (int e = tid; e < ng * per; e += nthreads) {
         const int g = fast_div(e, per, inv_per), it = e - g * per;
-        const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
+        const double* xs = xsm + (size_t)g * D;
         double sn, cn;
         sincos(prep_item_angle<R>(xs, it, N, inv_N), &sn, &cn);
         double* dst;
@@ -145,7 +157,7 @@ objective_prepare_kernel(ObjArgs a, MoveArgs mv, int G) {
     }
     for (int e = nthreads - 1 - tid; e < ng * P; e += nthreads) {
         const int g = fast_div(e, P, inv_P), k = e - g * P;
-        const double* xs = MOVE ? xsm + (size_t)g * D : a.x + (ps0 + g) * D;
+        const double* xs = xsm + (size_t)g * D;
         prep_item_coef<R>(xs, k, h, w_ulp, cs + (size_t)g * P * 8, a.prep_coef + (ps0 + g) * P * 8,
                           farpk + (size_t)g * P * 4, sub, P, a.prep_part + (ps0 + g) * kPartDoubles);
     }
@@ -339,7 +351,7 @@ cudaError_t launch_objective_prepare(ObjArgs& a, const ObjTune& t, int B, cudaSt
     if (a.sub < 1) a.sub = 1;
     // particles per CTA: about two rounds of far-field cells for its 256 threads
     const int nc = a.n_tiles * a.nw * a.sub;
-    const size_t per_particle = (size_t)(a.P * 12 + (mv ? 4 + 3 * a.P : 0)) * sizeof(double);
+    const size_t per_particle = (size_t)(a.P * 12 + 4 + 3 * a.P) * sizeof(double);
     int G = std::max(1, std::min(16, std::min(a.S, 2 * kPrepThreads / nc)));
     while (G > 1 && G * per_particle > 40 * 1024) --G;     // stay inside the default dynamic shared-memory limit
     // a particle with >= 128 cells fills a CTA of 128 threads on its own (and many small CTAs schedule better)

@@ -193,3 +193,26 @@ def test_unchanged_spectrum_is_not_resent_but_a_changed_one_is():
     wts[10:20] *= 3.0                                      # in place
     e = equations.objective_batch(xs, data.w, u2, data.v, wts)
     assert relerr(e, orc.objective_swarm(xs, data.w, u2, data.v, wts)) < 1e-11
+
+
+@pytest.mark.parametrize('case', ['c1_4096x6', 'ragged_1000x6', 'p24_1536'])
+def test_page_locked_positions_are_read_in_place(case):
+    """Positions in page-locked host memory are read by the prepare pass itself (no staging copy, each element crosses
+    PCIe once); pageable arrays go through the copy path.  Same values either way, bit for bit - also with fit_im, whose
+    evaluation re-reads the device copy the prepare pass leaves behind - and the golden tolerance holds."""
+    import torch
+    g = load_golden('objective_' + case)
+    xs = np.ascontiguousarray(g['xs'])
+    pinned = torch.empty(xs.shape, dtype=torch.float64).pin_memory().numpy()
+    pinned[:] = xs
+    for fit_im in (False, True):
+        a = equations.objective_batch(xs, g['w'], g['u'], g['v'], g['weights'], fit_im=fit_im)
+        b = equations.objective_batch(pinned, g['w'], g['u'], g['v'], g['weights'], fit_im=fit_im)
+        assert np.array_equal(a, b), fit_im
+    assert relerr(equations.objective_batch(pinned, g['w'], g['u'], g['v'], g['weights']), g['f']) < TOL
+    # a long particle list (the sliced copy path for pageable memory) against the in-place path
+    big = np.ascontiguousarray(np.tile(xs, (20000 // xs.shape[0] + 1, 1))[:20000])
+    big_pinned = torch.empty(big.shape, dtype=torch.float64).pin_memory().numpy()
+    big_pinned[:] = big
+    assert np.array_equal(equations.objective_batch(big, g['w'], g['u'], g['v'], g['weights']),
+                          equations.objective_batch(big_pinned, g['w'], g['u'], g['v'], g['weights']))
