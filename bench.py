@@ -513,7 +513,8 @@ def measure_e2e(run, steps, warmup):
             xs[bb] = synth.particles(run.lo[bb], run.up[bb], S, seed=7 + run.rank * B + bb)
         call = lambda: run.ctx.objective_host(xs)
         api = ('nmrfit_b200._cabi.Context.objective_host(xs[B][S][D]) with host arrays; the %d spectra are resident in '
-               'the context (uploaded once per fit)' % B)
+               'the context (uploaded once per fit); the positions sit in page-locked host memory and cross PCIe once per '
+               'step, read in place by the prepare kernel' % B)
         h2d, d2h = B * S * D * 8, B * S * 8
     else:
         xs = torch.empty((S, D), dtype=torch.float64).pin_memory().numpy()
@@ -522,7 +523,9 @@ def measure_e2e(run, steps, warmup):
         call = lambda: equations.objective_batch(xs, d.w, d.u, d.v, wts)
         api = ('nmrfit_b200.equations.objective_batch(xs, w, u, v, weights) with host arrays; every call hands over '
                'the spectrum too (the reference\'s calling convention) - the library compares it with its host '
-               'copy and re-sends it only when it changed, so the per-step H2D traffic is the positions')
+               'copy and re-sends it only when it changed, so the per-step H2D traffic is the positions.  The positions '
+               'sit in page-locked host memory; the library\'s prepare kernel reads them from there itself (every element '
+               'crosses PCIe once per step, inside the timed region) and the values are copied back')
         h2d, d2h = S * D * 8, S * 8
     for _ in range(max(3, warmup)):
         call()
