@@ -1,7 +1,9 @@
 /* Plain-C consumer of libnmrfit_b200.so: no Python, no torch.  Builds a synthetic two-peak spectrum, evaluates
  * the objective for a few parameter vectors on the GPU, checks them against a straightforward C restatement of
  * equations.objective (equations.py:152-212, real-only), then runs a small swarm through nmrfit_pso_* and prints
- * the fitted parameters.
+ * the fitted parameters - once on one context and once sharded over TWO contexts of this process through
+ * nmrfit_comm_* (the library-level counterpart of the reference's processes=N; both contexts sit on GPU 0 here, a
+ * multi-GPU consumer creates one per device), which must give the identical result.
  *
  *   gcc -std=c99 -O2 -Iinclude examples/c_abi_demo.c -o c_abi_demo -ldl -lm
  *   ./c_abi_demo nmrfit_b200/csrc/libnmrfit_b200.so
@@ -55,6 +57,11 @@ int main(int argc, char** argv) {
     int (*p_nmrfit_pso_run)(nmrfit_ctx*, int, const double*, const double*, int*, void*);
     int (*p_nmrfit_pso_get_best)(nmrfit_ctx*, double*, double*, int*, int*);
     const char* (*p_nmrfit_last_error)(void);
+    int (*p_nmrfit_comm_init_all)(nmrfit_ctx* const*, int);
+    int (*p_nmrfit_comm_commit)(nmrfit_ctx* const*, int);
+    int (*p_nmrfit_comm_run)(nmrfit_ctx* const*, int, int, const double* const*, const double* const*, int*, int*);
+    int (*p_nmrfit_ctx_set_fused)(nmrfit_ctx*, int);
+    LOAD(nmrfit_comm_init_all); LOAD(nmrfit_comm_commit); LOAD(nmrfit_comm_run); LOAD(nmrfit_ctx_set_fused);
     LOAD(nmrfit_ctx_create); LOAD(nmrfit_ctx_destroy); LOAD(nmrfit_ctx_set_spectrum); LOAD(nmrfit_objective_batch_host);
     LOAD(nmrfit_pso_begin); LOAD(nmrfit_pso_commit); LOAD(nmrfit_pso_run); LOAD(nmrfit_pso_get_best); LOAD(nmrfit_last_error);
 
@@ -106,7 +113,43 @@ int main(int argc, char** argv) {
     printf("swarm: f %.3e -> %.3e in %d generations (stop %d); width0 %.5f loc0 %.5f area0 %.5f\n", f0, f1, gens, stop,
            x1[4], x1[5], x1[6]);
     p_nmrfit_ctx_destroy(ctx);
+
+    /* the same swarm, particles split 40 + 24 over two contexts (device random numbers are keyed by the global particle
+     * index, so the split does not change the trajectory); reference run: per-step kernels on one context */
+    double xa[ND], fa, xb[ND], fb, xr[ND], fr;
+    int lost = 0, same = 1;
+    {
+        nmrfit_ctx* one = NULL;
+        if (p_nmrfit_ctx_create(&one, 0, 1, NPTS, NPEAKS, NMRFIT_FP64) || p_nmrfit_ctx_set_spectrum(one, 0, w, u, v, wt) ||
+            p_nmrfit_ctx_set_fused(one, NMRFIT_FUSED_OFF) || p_nmrfit_pso_begin(one, lb, ub, &o, NULL, NULL, NULL) ||
+            p_nmrfit_pso_commit(one, NULL, 1, NULL) || p_nmrfit_pso_run(one, 60, NULL, NULL, &running, NULL) ||
+            p_nmrfit_pso_get_best(one, xr, &fr, NULL, NULL)) { fprintf(stderr, "%s\n", p_nmrfit_last_error()); return 3; }
+        p_nmrfit_ctx_destroy(one);
+    }
+    nmrfit_ctx* pair[2] = {NULL, NULL};
+    const int count[2] = {40, 24};
+    for (int r = 0; r < 2; ++r)
+        if (p_nmrfit_ctx_create(&pair[r], 0, 1, NPTS, NPEAKS, NMRFIT_FP64) || p_nmrfit_ctx_set_spectrum(pair[r], 0, w, u, v, wt) ||
+            p_nmrfit_ctx_set_fused(pair[r], NMRFIT_FUSED_OFF)) { fprintf(stderr, "%s\n", p_nmrfit_last_error()); return 3; }
+    if (p_nmrfit_comm_init_all(pair, 2)) { fprintf(stderr, "%s\n", p_nmrfit_last_error()); return 3; }
+    for (int r = 0; r < 2; ++r) {
+        nmrfit_pso_opts os = o;
+        os.swarmsize = count[r];
+        os.particle_offset = r ? count[0] : 0;
+        if (p_nmrfit_pso_begin(pair[r], lb, ub, &os, NULL, NULL, NULL)) { fprintf(stderr, "%s\n", p_nmrfit_last_error()); return 3; }
+    }
+    if (p_nmrfit_comm_commit(pair, 2) || p_nmrfit_comm_run(pair, 2, 60, NULL, NULL, &running, &lost) ||
+        p_nmrfit_pso_get_best(pair[0], xa, &fa, NULL, NULL) || p_nmrfit_pso_get_best(pair[1], xb, &fb, NULL, NULL)) {
+        fprintf(stderr, "%s\n", p_nmrfit_last_error());
+        return 3;
+    }
+    for (int d = 0; d < ND; ++d) same = same && xa[d] == xb[d] && xa[d] == xr[d];
+    same = same && fa == fb && fa == fr && !lost;
+    printf("communicator: f %.15e on both contexts, one context %.15e: %s\n", fa, fr, same ? "identical" : "DIFFERENT");
+    p_nmrfit_ctx_destroy(pair[0]);
+    p_nmrfit_ctx_destroy(pair[1]);
     dlclose(lib);
+    if (!same) { fprintf(stderr, "the sharded swarm differs from the unsharded one\n"); return 1; }
     if (!(worst < 1e-11)) { fprintf(stderr, "parity %.3e exceeds 1e-11\n", worst); return 1; }
     if (!(f1 < f0)) { fprintf(stderr, "swarm did not improve\n"); return 1; }
     return 0;

@@ -76,6 +76,26 @@ int h_region_fit(const double* w, int n, double h, const double* x, int P, int R
     return near;
 }
 
+// the 12-term far-field polynomial at x[0..n) by Horner (`full`) and after far_economise, by the even/odd form the
+// kernels evaluate (`econ`: far_init on one point at a time)
+void h_far_poly(const double* C12, const double* x, int n, double* full, double* econ) {
+    double C[nmrfit::kFarTerms], Ce[nmrfit::kFarPoly];
+    for (int k = 0; k < nmrfit::kFarTerms; ++k) C[k] = C12[k];
+    for (int i = 0; i < n; ++i) {
+        double p = C[nmrfit::kFarTerms - 1];
+        for (int k = nmrfit::kFarTerms - 2; k >= 0; --k) p = std::fma(p, x[i], C[k]);
+        full[i] = p;
+    }
+    nmrfit::far_economise(C);
+    for (int k = 0; k < nmrfit::kFarPoly; ++k) Ce[k] = C[k];
+    for (int i = 0; i + 1 < n; i += 2) {
+        double acc[2];
+        nmrfit::far_init<2>(Ce, x[i], x[i + 1] - x[i], acc);
+        econ[i] = acc[0];
+        econ[i + 1] = acc[1];
+    }
+}
+
 void h_exp_neg(int tb, const double* x, int n, double* out) {
     for (int i = 0; i < n; ++i) {
         switch (tb) {

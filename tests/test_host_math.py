@@ -198,6 +198,29 @@ def test_far_field_extremes(hm):
             assert np.abs(got - want).max() < 2e-12 * np.abs(want).max(), R
 
 
+def test_far_polynomial_economisation(hm):
+    """far_economise: the 12-term series of a far-field cell folded into 10 coefficients (Chebyshev, the T11 and T10 parts
+    dropped) and evaluated as even + odd parts.  With coefficients decaying like the series' own (|C_n| <= |u|^n,
+    |u| <= 1/16) the result stays within 2e-15 of C_0's scale of the 12-term Horner value everywhere on the cell."""
+    rng = np.random.default_rng(3)
+    x = np.ascontiguousarray(np.concatenate([np.linspace(-1, 1, 1001), [-1.0, 1.0, 0.0]])[:1002])
+    worst = 0.0
+    for rep in range(200):
+        rho = rng.uniform(0.01, 1 / 16)
+        C = rng.uniform(-1, 1, 12) * rho ** np.arange(12)
+        C[0] = rng.choice([-1.0, 1.0])
+        full, econ = np.empty_like(x), np.empty_like(x)
+        hm.h_far_poly(P(np.ascontiguousarray(C)), P(x), x.size, P(full), P(econ))
+        assert np.abs(full - np.polyval(C[::-1], x)).max() < 1e-15
+        worst = max(worst, np.abs(econ - full).max())
+    assert worst < 2e-15, worst
+    # and the bound is about the decay: a polynomial that does NOT decay loses digits, as it must
+    C = np.ones(12)
+    full, econ = np.empty_like(x), np.empty_like(x)
+    hm.h_far_poly(P(C), P(x), x.size, P(full), P(econ))
+    assert 1e-4 < np.abs(econ - full).max() < 4e-3          # |C11|/1024 + |C10|/512 = 2.9e-3
+
+
 def test_stepsize_sum_reproduces_numpys_pairwise_order(hm):
     """pyswarm: stepsize = np.sqrt(np.sum((g - p_min)**2)).  The device commit sums the rounded squares in numpy's
     pairwise order (eight interleaved accumulators up to 128 elements, halves rounded to multiples of 8 beyond), so the
