@@ -186,6 +186,14 @@ int nmrfit_pso_step(nmrfit_ctx* ctx, const double* rp, const double* rg, void* s
 int nmrfit_ctx_mt19937_shape(nmrfit_ctx* ctx, long long elements_per_array);
 int nmrfit_ctx_mt19937(nmrfit_ctx* ctx, unsigned* key, int* pos, long long n_arrays, double** a_dev, double** b_dev,
                        void* stream);
+/* The same in two halves on a stream of the context's own: `begin` queues the generation (state: key [624], pos) and
+ * returns at once; `end` waits for it and returns the advanced state (key_out / pos_out nullable: a draw that turns out
+ * not to be needed is simply dropped).  Meanwhile the caller runs the swarm on the arrays of the previous begin - the
+ * sequential recurrence hides behind the fit's kernels.  Two sets of arrays are used in turn: the pointers of one begin
+ * stay valid until the begin after the next. */
+int nmrfit_ctx_mt19937_begin(nmrfit_ctx* ctx, const unsigned* key, int pos, long long n_arrays, double** a_dev,
+                             double** b_dev);
+int nmrfit_ctx_mt19937_end(nmrfit_ctx* ctx, unsigned* key_out, int* pos_out);
 
 /* ---- particle sharding without a collective call: the record exchange over peer memory (NVLink stores) -----------
  * Each rank's context owns a window of records and generation tokens; every rank maps every window (CUDA IPC between

@@ -78,6 +78,8 @@ SIGNATURES = {
     'nmrfit_pso_peer_error': (_i, [_vp, c_int_p]),
     'nmrfit_pso_run_peers': (_i, [_vp, _i, _vp, _vp, c_int_p, c_int_p, _vp]),
     'nmrfit_pso_peer_timeout': (_i, [_vp, _d]),
+    'nmrfit_ctx_mt19937_begin': (_i, [_vp, _vp, _i, ctypes.c_longlong, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
+    'nmrfit_ctx_mt19937_end': (_i, [_vp, _vp, ctypes.POINTER(_i)]),
     'nmrfit_comm_init_all': (_i, [_vp, _i]),
     'nmrfit_comm_commit': (_i, [_vp, _i]),
     'nmrfit_comm_run': (_i, [_vp, _i, _i, _vp, _vp, ctypes.POINTER(_i), ctypes.POINTER(_i)]),
@@ -353,6 +355,31 @@ class Context:
                                        ctypes.byref(b), ptr(stream)))
         np.random.set_state((kind, key, p.value, has_gauss, cached))
         return a.value, b.value
+
+    def legacy_uniform_pairs_begin(self, n_pairs, elements):
+        """``legacy_uniform_pairs`` in two halves: queue the generation of the next ``2 * n_pairs`` arrays from
+        np.random's CURRENT state and return at once (the state is not advanced yet); ``legacy_uniform_pairs_end``
+        waits, advances np.random and returns the two device addresses."""
+        kind, key, pos, has_gauss, cached = np.random.get_state()
+        if kind != 'MT19937':
+            raise RuntimeError('numpy legacy generator is not MT19937')
+        key = np.ascontiguousarray(key, dtype=np.uint32)
+        a, b = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib().nmrfit_ctx_mt19937_shape(self._h, int(elements)))
+        check(lib().nmrfit_ctx_mt19937_begin(self._h, ptr(key), int(pos), 2 * int(n_pairs), ctypes.byref(a), ctypes.byref(b)))
+        return (a.value, b.value, kind, has_gauss, cached)
+
+    def legacy_uniform_pairs_end(self, pending, advance=True):
+        """Wait for a ``legacy_uniform_pairs_begin``; ``advance=False`` drops the draw (np.random keeps its state)."""
+        a, b, kind, has_gauss, cached = pending
+        if not advance:
+            check(lib().nmrfit_ctx_mt19937_end(self._h, None, None))
+            return None
+        key = np.empty(624, dtype=np.uint32)
+        p = ctypes.c_int(0)
+        check(lib().nmrfit_ctx_mt19937_end(self._h, ptr(key), ctypes.byref(p)))
+        np.random.set_state((kind, key, p.value, has_gauss, cached))
+        return a, b
 
     # -- record exchange over peer memory
     def peer_export(self, n_ranks, rank):

@@ -96,6 +96,11 @@ struct nmrfit_ctx {
     DevBuf<unsigned> mt_state;         // MT19937 key [624] + position, for nmrfit_ctx_mt19937
     DevBuf<unsigned> mt_words;         // ... and the tempered word stream of one call
     long long mt_elems = 0;            // elements of one random array (n_spectra * swarmsize * D)
+    DevBuf<double> mt_a[2], mt_b[2];   // nmrfit_ctx_mt19937_begin / _end: two sets of arrays, used in turn
+    DevBuf<unsigned> mt_state2, mt_words2;
+    cudaStream_t mt_stream = nullptr;
+    unsigned* mt_host = nullptr;       // page-locked [2][625]: state in, state out
+    int mt_flip = 0, mt_pending = 0;
     DevBuf<double> fin_scratch;        // finish kernel: per-CTA candidates
     DevBuf<unsigned> fin_tickets;
     // record exchange over peer memory (particle sharding without a collective call)
@@ -485,6 +490,11 @@ void nmrfit_ctx_destroy(nmrfit_ctx* c) {
     c->fbarrier.release();
     c->ferror.release();
     c->mt_state.release();
+    for (int k = 0; k < 2; ++k) { c->mt_a[k].release(); c->mt_b[k].release(); }
+    c->mt_state2.release();
+    c->mt_words2.release();
+    if (c->mt_stream) cudaStreamDestroy(c->mt_stream);
+    if (c->mt_host) cudaFreeHost(c->mt_host);
     c->mt_words.release();
     c->ftiming.release();
     for (void* p : c->peer_opened) cudaIpcCloseMemHandle(p);
@@ -919,6 +929,53 @@ int nmrfit_ctx_mt19937(nmrfit_ctx* c, unsigned* key, int* pos, long long n_array
     *pos = (int)host[624];
     *a_dev = c->rnd_a.ptr;
     *b_dev = c->rnd_b.ptr;
+    return NMRFIT_OK;
+}
+
+// The same in two halves, on a stream of the context's own: `begin` queues the generation and returns at once, `end`
+// waits for it and hands back the advanced state.  Between the two the caller runs the swarm on the PREVIOUS set of
+// arrays - the sequential recurrence (one CTA, ~0.2 us per 227 words) hides behind the fit's kernels.  Two sets of
+// arrays are used in turn: the pointers of one `begin` stay valid until the `begin` after the next.
+int nmrfit_ctx_mt19937_begin(nmrfit_ctx* c, const unsigned* key, int pos, long long n_arrays, double** a_dev, double** b_dev) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!key || !a_dev || !b_dev) return fail(NMRFIT_ERR_ARG, "NULL argument");
+    if (pos < 0 || pos > 624) return fail(NMRFIT_ERR_ARG, "MT19937 position must be 0..624");
+    if (n_arrays < 2 || (n_arrays & 1)) return fail(NMRFIT_ERR_ARG, "n_arrays must be even: arrays come in (first, second) pairs");
+    if (c->mt_elems == 0) return fail(NMRFIT_ERR_STATE, "call nmrfit_ctx_mt19937_shape first");
+    if (c->mt_pending) return fail(NMRFIT_ERR_STATE, "nmrfit_ctx_mt19937_end has not been called for the previous begin");
+    CK(cudaSetDevice(c->device));
+    if (!c->mt_stream) CK(cudaStreamCreateWithFlags(&c->mt_stream, cudaStreamNonBlocking));
+    if (!c->mt_host) CK(cudaMallocHost(&c->mt_host, sizeof(unsigned) * 2 * 625));
+    const long long nsd = c->mt_elems, pairs = n_arrays / 2;
+    const int k = c->mt_flip;
+    // (growing a buffer frees and allocates: an implicit device synchronisation, first calls only)
+    CK(c->mt_a[k].reserve((size_t)(pairs * nsd)));
+    CK(c->mt_b[k].reserve((size_t)(pairs * nsd)));
+    CK(c->mt_state2.reserve(625));
+    CK(c->mt_words2.reserve((size_t)(2 * n_arrays * nsd)));
+    std::memcpy(c->mt_host, key, sizeof(unsigned) * 624);
+    c->mt_host[624] = (unsigned)pos;
+    cudaStream_t st = c->mt_stream;
+    CK(cudaMemcpyAsync(c->mt_state2.ptr, c->mt_host, sizeof(unsigned) * 625, cudaMemcpyHostToDevice, st));
+    cudaError_t e = launch_mt19937(c->mt_state2.ptr, reinterpret_cast<int*>(c->mt_state2.ptr + 624), n_arrays * nsd,
+                                   c->mt_words2.ptr, c->mt_a[k].ptr, c->mt_b[k].ptr, nsd, st);
+    if (e != cudaSuccess) return fail_cuda(e, "MT19937 launch");
+    CK(cudaMemcpyAsync(c->mt_host + 625, c->mt_state2.ptr, sizeof(unsigned) * 625, cudaMemcpyDeviceToHost, st));
+    *a_dev = c->mt_a[k].ptr;
+    *b_dev = c->mt_b[k].ptr;
+    c->mt_flip ^= 1;
+    c->mt_pending = 1;
+    return NMRFIT_OK;
+}
+
+int nmrfit_ctx_mt19937_end(nmrfit_ctx* c, unsigned* key_out, int* pos_out) {
+    if (int rc = check_ctx(c)) return rc;
+    if (!c->mt_pending) return fail(NMRFIT_ERR_STATE, "no nmrfit_ctx_mt19937_begin is pending");
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->mt_stream));
+    c->mt_pending = 0;
+    if (key_out) std::memcpy(key_out, c->mt_host + 625, sizeof(unsigned) * 624);
+    if (pos_out) *pos_out = (int)c->mt_host[625 + 624];
     return NMRFIT_OK;
 }
 

@@ -17,7 +17,7 @@ namespace nmrfit {
 
 namespace {
 
-constexpr int kMtN = 624, kMtM = 397, kMtThreads = 256;
+constexpr int kMtN = 624, kMtM = 397, kMtThreads = 128;
 
 __device__ __forceinline__ uint32_t mt_twist(uint32_t cur, uint32_t next, uint32_t far) {
     const uint32_t y = (cur & 0x80000000u) | (next & 0x7fffffffu);
@@ -32,10 +32,12 @@ __device__ __forceinline__ uint32_t mt_temper(uint32_t y) {
 }
 
 // Pass 1 (sequential in steps, one CTA): the raw recurrence x[n] = twist(x[n-624], x[n-623], x[n-227]) advances
-// 227 words per step - the lag of the nearest dependence - with ONE __syncthreads per step; every new word is tempered
-// on the spot and written to the word stream.  key_io [624] (global): the state, updated in place; *pos_io: words of it
-// already consumed (0..624); words_out [n_words]: the next n_words tempered 32-bit words of the stream.
+// 227 words per step - the lag of the nearest dependence - with ONE __syncthreads per step; every new word goes to the
+// word stream as it is (the second pass tempers).  key_io [624] (global): the state, updated in place; *pos_io: words of it
+// already consumed (0..624); words_out [n_words]: the next n_words 32-bit words of the stream, UNTEMPERED.
 constexpr int kMtLag = kMtN - kMtM;                        // 227
+// (128 threads, two words each: the step is a chain of shared-memory round trips and a barrier - four warps keep the
+// barrier cheap and give every thread two independent words to overlap the latencies; 32-bit ring arithmetic.)
 __global__ void __launch_bounds__(kMtThreads)
 mt19937_words_kernel(uint32_t* __restrict__ key_io, int* __restrict__ pos_io, long long n_words,
                      uint32_t* __restrict__ words_out) {
@@ -46,28 +48,50 @@ mt19937_words_kernel(uint32_t* __restrict__ key_io, int* __restrict__ pos_io, lo
     for (int k = tid; k < kMtN; k += kMtThreads) ring[k] = key_io[k];
     __syncthreads();
     const long long last = (long long)pos + n_words;       // one past the last word needed (absolute)
+    // The UNTEMPERED words go out (the parallel second pass tempers them): every instruction saved here is saved ~4,000
+    // times in a row on one warp scheduler - the kernel is a single chain of dependent steps.
     for (long long n = pos + tid; n < (last < kMtN ? last : kMtN); n += kMtThreads)
-        words_out[n - pos] = mt_temper(ring[n]);           // what is left of the given block
-    long long base = kMtN;
-    while (base < last) {
-        const long long n = base + tid;
-        if (tid < kMtLag && n < last + kMtN) {              // (a little past the end, so that a whole final block exists)
-            const uint32_t x = mt_twist(ring[(n - kMtN) & 1023], ring[(n - kMtN + 1) & 1023], ring[(n - kMtLag) & 1023]);
-            ring[n & 1023] = x;
-            if (n < last) words_out[n - pos] = mt_temper(x);
+        words_out[n - pos] = ring[n];                      // what is left of the given block
+    // the state to hand back: numpy keeps whole blocks, so the block that holds the last word drawn, [b0, b0 + 624);
+    // the recurrence runs to its end (words past `last` are stored in the ring, not written out)
+    const long long b0 = last <= kMtN ? 0 : ((last - 1) / kMtN) * kMtN;
+    const long long end = b0 + kMtN;
+    const bool second = tid + kMtThreads < kMtLag;         // this thread's second word of a step exists
+    // steps [0, full): every word of the step exists and is written out; the last few steps are checked word by word
+    const long long n_steps = (end - kMtN + kMtLag - 1) / kMtLag;
+    const long long full_ll = last > kMtN ? (last - kMtN) / kMtLag : 0;
+    const int steps = (int)n_steps, full = (int)(full_ll < n_steps ? full_ll : n_steps);
+    unsigned r0 = (unsigned)tid;                           // (n - 624) & 1023 of this thread's first word: n starts at 624 + tid
+    uint32_t* o0 = words_out + (kMtN - pos) + tid;         // where the first word of the current step goes
+    for (int st = 0; st < full; ++st) {
+        const unsigned r1 = (r0 + kMtThreads) & 1023u;
+        const uint32_t x0 = mt_twist(ring[r0], ring[(r0 + 1) & 1023u], ring[(r0 + kMtM) & 1023u]);
+        uint32_t x1 = 0;
+        if (second) x1 = mt_twist(ring[r1], ring[(r1 + 1) & 1023u], ring[(r1 + kMtM) & 1023u]);
+        // (slots read in a step - 624 + 227 consecutive ones - and slots written never coincide modulo 1,024)
+        ring[(r0 + kMtN) & 1023u] = x0;
+        o0[0] = x0;
+        if (second) {
+            ring[(r1 + kMtN) & 1023u] = x1;
+            o0[kMtThreads] = x1;
         }
-        base += kMtLag;
+        r0 = (r0 + kMtLag) & 1023u;
+        o0 += kMtLag;
         __syncthreads();
     }
-    // the state to hand back: numpy keeps whole blocks, so the block that holds the last word drawn, [b0, b0 + 624).
-    // If that block was only partly generated above, finish it (its words are never drawn here, only stored).
-    const long long b0 = last <= kMtN ? 0 : ((last - 1) / kMtN) * kMtN;
-    long long done = base;                                 // words [0, done) exist... up to last + 624 at most
-    while (done < b0 + kMtN) {
-        const long long n = done + tid;
-        if (tid < kMtLag && n < b0 + kMtN)
-            ring[n & 1023] = mt_twist(ring[(n - kMtN) & 1023], ring[(n - kMtN + 1) & 1023], ring[(n - kMtLag) & 1023]);
-        done += kMtLag;
+    for (int st = full; st < steps; ++st) {
+        const long long n0 = kMtN + (long long)st * kMtLag + tid, n1 = n0 + kMtThreads;
+        const bool do0 = n0 < end, do1 = second && n1 < end;
+        const unsigned r1 = (r0 + kMtThreads) & 1023u;
+        uint32_t x0 = 0, x1 = 0;
+        if (do0) x0 = mt_twist(ring[r0], ring[(r0 + 1) & 1023u], ring[(r0 + kMtM) & 1023u]);
+        if (do1) x1 = mt_twist(ring[r1], ring[(r1 + 1) & 1023u], ring[(r1 + kMtM) & 1023u]);
+        if (do0) ring[(r0 + kMtN) & 1023u] = x0;
+        if (do1) ring[(r1 + kMtN) & 1023u] = x1;
+        if (do0 && n0 < last) o0[0] = x0;
+        if (do1 && n1 < last) o0[kMtThreads] = x1;
+        r0 = (r0 + kMtLag) & 1023u;
+        o0 += kMtLag;
         __syncthreads();
     }
     for (int k = tid; k < kMtN; k += kMtThreads) key_io[k] = ring[(b0 + k) & 1023];
@@ -80,7 +104,7 @@ __global__ void mt19937_doubles_kernel(const uint32_t* __restrict__ words, long 
                                        double* __restrict__ out_b, long long nsd) {
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= n) return;
-    const uint32_t a = words[2 * q], b = words[2 * q + 1];
+    const uint32_t a = mt_temper(words[2 * q]), b = mt_temper(words[2 * q + 1]);     // (pass 1 writes raw words)
     const double x = ((double)(a >> 5) * 67108864.0 + (double)(b >> 6)) / 9007199254740992.0;
     if (nsd > 0) {
         const long long blk = q / nsd, e = q - blk * nsd;

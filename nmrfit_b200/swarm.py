@@ -107,8 +107,21 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
         ctx.set_fused(_fused_mode(fused))
         ctx.set_spectrum(0, w, u, v, weights)
         opts = _make_opts(S, maxiter, omega, phip, phig, minstep, minfunc, fit_im, seed)
+        # the generations go through in chunks: the stop flag is polled less and less often; with host numbers an early
+        # stop rewinds the stream and redraws what was used, so the chunks stay moderate there
+        sizes, c, left = [], (max(1, int(chunk)) if trace is None else 1), maxiter
+        while left > 0:
+            sizes.append(min(c, left))
+            left -= sizes[-1]
+            if trace is None:
+                c = min(2 * c, 256 if not host else 64)
+        first = None
         if on_device:
-            r_pos, r_vel = ctx.legacy_uniform_pairs(1, S * D)
+            # one draw for the initial positions / velocities AND the first chunk's (rp, rg): pair 0, then pairs 1..n
+            state0 = np.random.get_state()
+            n0 = sizes[0] if sizes else 0
+            r_pos, r_vel = ctx.legacy_uniform_pairs_end(ctx.legacy_uniform_pairs_begin(1 + n0, S * D))
+            first = (r_pos + 8 * S * D, r_vel + 8 * S * D)
         else:
             r_pos = np.random.rand(S, D) if host else None
             r_vel = np.random.rand(S, D) if host else None
@@ -118,37 +131,50 @@ def pso_single(w, u, v, weights, lower, upper, fit_im=False, swarmsize=100, maxi
             x, f, it, stop = ctx.pso_best()
             trace.append((0, x[0].copy(), float(f[0])))
         done = 0
-        chunk = max(1, int(chunk)) if trace is None else 1
-        while done < maxiter:
-            n = min(chunk, maxiter - done)
-            if trace is None:
-                # poll the stop flag less and less often; with host numbers an early stop rewinds the stream and
-                # redraws what was used, so the chunks stay moderate there
-                chunk = min(2 * chunk, 256 if not host else 64)
-            if host:
-                state = np.random.get_state()
-                rp, rg = ctx.legacy_uniform_pairs(n, S * D) if on_device else _draw_generations(np.random, n, S, D)
-            else:
-                rp = rg = None
-            running = ctx.pso_run(n, rp, rg)
-            if trace is not None:
-                x, f, it, stop = ctx.pso_best()
-                trace.append((int(it[0]), x[0].copy(), float(f[0])))
-            if running == 0:
+        # rng='host': the legacy stream continues on the device, one chunk AHEAD of the swarm - while chunk k runs, the
+        # numbers of chunk k + 1 are generated on a stream of their own (legacy_uniform_pairs_begin / _end)
+        pending = ctx.legacy_uniform_pairs_begin(sizes[1], S * D) if on_device and len(sizes) > 1 else None
+        try:
+            for k, n in enumerate(sizes):
+                extra = 0                                   # pairs drawn together with this chunk's (the initial pair)
                 if host:
-                    # leave the legacy stream where pyswarm would have: it stops drawing
-                    # at the generation that tripped the test
+                    if on_device and k == 0:
+                        state, extra = state0, 1
+                        rp, rg = first
+                    elif on_device:
+                        state = np.random.get_state()
+                        rp, rg = ctx.legacy_uniform_pairs_end(pending)          # np.random: now after chunk k
+                        pending = (ctx.legacy_uniform_pairs_begin(sizes[k + 1], S * D) if k + 1 < len(sizes) else None)
+                    else:
+                        state = np.random.get_state()
+                        rp, rg = _draw_generations(np.random, n, S, D)
+                else:
+                    rp = rg = None
+                running = ctx.pso_run(n, rp, rg)
+                if trace is not None:
                     x, f, it, stop = ctx.pso_best()
-                    used = int(it[0]) - done
-                    if used < n:
-                        np.random.set_state(state)
-                        if used > 0:
-                            if on_device:
-                                ctx.legacy_uniform_pairs(used, S * D)
-                            else:
-                                _draw_generations(np.random, used, S, D)
-                break
-            done += n
+                    trace.append((int(it[0]), x[0].copy(), float(f[0])))
+                if running == 0:
+                    if host:
+                        # leave the legacy stream where pyswarm would have: it stops drawing
+                        # at the generation that tripped the test
+                        if pending is not None:
+                            ctx.legacy_uniform_pairs_end(pending, advance=False)    # drawn ahead, not needed
+                            pending = None
+                        x, f, it, stop = ctx.pso_best()
+                        used = int(it[0]) - done
+                        if used < n:
+                            np.random.set_state(state)
+                            if used + extra > 0:
+                                if on_device:
+                                    ctx.legacy_uniform_pairs(used + extra, S * D)
+                                else:
+                                    _draw_generations(np.random, used, S, D)
+                    break
+                done += n
+        finally:
+            if pending is not None:
+                ctx.legacy_uniform_pairs_end(pending, advance=False)
         x, f, it, stop = ctx.pso_best()
     info = dict(generations=int(it[0]), stop=int(stop[0]), evaluations=S * (int(it[0]) + 1))
     if not quiet:
