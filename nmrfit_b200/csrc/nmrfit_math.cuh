@@ -152,7 +152,8 @@ NMRFIT_HD double exp_neg(double x, const double* __restrict__ tab) {
 
 // Dawson's integral F(s) = exp(-s^2) * int_0^s exp(t^2) dt, any real s (odd).
 // Piecewise degree-12 polynomials on |s| < 8 (table read through the read-only
-// path: lanes sit in different intervals), asymptotic form beyond.
+// path: lanes sit in different intervals), asymptotic form beyond: F = G(1/s^2)/(2 s) with G of degree 8 up to
+// |s| = 32 and of degree 4 beyond (each to < 1e-16 relative).
 NMRFIT_HD double dawson(double s, const double* __restrict__ core, const double* __restrict__ tail) {
     double as = s < 0 ? -s : s;
     double res;
@@ -167,10 +168,20 @@ NMRFIT_HD double dawson(double s, const double* __restrict__ core, const double*
         res = p;
     } else {
         double inv = rcp_pos(as);                          // as >= 8: MUFU seed + cubic correction, no IEEE division
-        double y = inv * inv - NMRFIT_DAW_TAIL_MID;
-        double p = tail[NMRFIT_DAW_TAIL_DEG];
+        double y2 = inv * inv, p;
+        if (as >= NMRFIT_DAW_FAR_SMIN) {
+            // far tail, a shorter polynomial: most points of a wide window are > 32 units of s from a narrow peak, and
+            // neighbouring points fall on the same side of the split (generate_result is bound by these FMAs)
+            const double y = y2 - NMRFIT_DAW_FAR_MID;
+            p = NMRFIT_DAW_FAR[NMRFIT_DAW_FAR_DEG];
 #pragma unroll
-        for (int i = NMRFIT_DAW_TAIL_DEG - 1; i >= 0; --i) p = NMRFIT_FMA(p, y, tail[i]);
+            for (int i = NMRFIT_DAW_FAR_DEG - 1; i >= 0; --i) p = NMRFIT_FMA(p, y, NMRFIT_DAW_FAR[i]);
+        } else {
+            const double y = y2 - NMRFIT_DAW_TAIL_MID;
+            p = tail[NMRFIT_DAW_TAIL_DEG];
+#pragma unroll
+            for (int i = NMRFIT_DAW_TAIL_DEG - 1; i >= 0; --i) p = NMRFIT_FMA(p, y, tail[i]);
+        }
         res = 0.5 * inv * p;
     }
     return s < 0 ? -res : res;
