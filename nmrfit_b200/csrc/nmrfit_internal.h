@@ -22,7 +22,7 @@ struct ObjArgs {
     // uniform-axis kernel: per-particle constants written by its prepare pass (see objective_uniform.cu)
     double* prep_coef;      // [B][S][P][8]
     double* prep_part;      // [B][S][68]
-    double* prep_far;       // [B][S][n_tiles*nw][12]   regions in tile-major order
+    double* prep_far;       // [B][S][n_tiles*nw][sub][kFarPoly = 10]   (tile-major for the streamed kernel)
     double* prep_anchor;    // [B][S][n_tiles*nw][2]
     unsigned* prep_mask;    // [B][S][n_tiles*nw][ceil(P/32)+1]
     int n_tiles, nw;        // point tiles, warps (= regions) per tile (filled by the launcher)

@@ -7,16 +7,20 @@
 //     two-multiply recurrence and only its two anchors need an exponential; beyond 6.5 units of s it
 //     is skipped (< 4.5e-19 of its height);
 //   * Lorentzian reciprocals are taken four at a time from one reciprocal of the product;
-//   * Lorentzians of peaks FAR from a warp's region of 32*R points are not evaluated peak by peak at
-//     all: their Taylor series about the region's centre are summed into ONE degree-11 polynomial per
-//     (particle, region), 12 FMAs per point for all far peaks together; only the peaks near the region
-//     (1.5 of 12 on average at BASELINE config 2, 2.2 of 24 at config 4) are evaluated individually.
+//   * Lorentzians of peaks FAR from a far-field cell (a warp's region of 32*R points, or half / a quarter of it
+//     on short axes: far_cells_per_region) are not evaluated peak by peak at all: their Taylor series about the
+//     cell's centre are summed into ONE polynomial per (particle, cell) - 12 terms, economised to degree 9 and
+//     evaluated by even / odd parts with the cell's mirror lane supplying half of a thread's points, ~7 FP64
+//     instructions per point for all far peaks together; only the peaks near the cell (1.5 of 12 on average at
+//     BASELINE config 2, 2.2 of 24 at config 4) are evaluated individually.
 //
 // Two passes per swarm generation:
-//   objective_prepare_kernel   one CTA per particle: span coefficients of its peaks, phase tables, and
-//                              per region the near-peak mask, the far-field polynomial and the phase
-//                              anchor -> a few KB per particle in global memory;
-//   objective_uniform_kernel   grid (particle groups, point tiles, spectra).  A CTA owns THREADS*R
+//   objective_prepare_kernel   a CTA takes a few particles: span coefficients of their peaks, phase tables, and
+//                              per region the near-peak masks, the far-field polynomials and the phase
+//                              anchor -> a few KB per particle in global memory (with the swarm's move folded in
+//                              when a swarm runs; positions in page-locked host memory are read in place);
+//   objective_stream_kernel    (objective_stream.cu) the evaluation for all but small particle sets;
+//   objective_uniform_kernel   the one-group-per-CTA evaluation: grid (particle groups, point tiles, spectra).  A CTA owns THREADS*R
 //                              consecutive points (one region of 32*R per warp) and SP particles.  Its
 //                              per-particle constants arrive by TMA bulk copies (cp.async.bulk completing
 //                              on an mbarrier) issued by one thread while all threads stage the tile's
