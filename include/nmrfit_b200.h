@@ -147,6 +147,13 @@ int nmrfit_ctx_profile_read_split(nmrfit_ctx* ctx, double* prepare_ms, double* e
 int nmrfit_objective_batch(nmrfit_ctx* ctx, const double* x_dev, int n_particles, int fit_im, double* f_dev,
                            void* stream);
 int nmrfit_objective_batch_host(nmrfit_ctx* ctx, const double* x_host, int n_particles, int fit_im, double* f_host);
+/* equations.objective(x, w, u, v, weights) as the reference calls it - the spectrum comes along with every call - for a
+ * context of ONE spectrum: set_spectrum + objective_batch_host in one.  An unchanged spectrum is not sent again; with
+ * page-locked positions the kernels are launched before the arrays are compared with the context's host copy (the
+ * comparison overlaps the evaluation; a spectrum that did change is uploaded and the evaluation repeated). */
+int nmrfit_objective_spectrum_host(nmrfit_ctx* ctx, const double* w, const double* u, const double* v,
+                                   const double* weights, const double* x_host, int n_particles, int fit_im,
+                                   double* f_host);
 
 /* ---- swarm: pyswarm.pso as called at utils.py:176-182, state resident on the device -----------
  * Generation g (g = 0 is the initial swarm) is   begin|advance -> [exchange records] -> commit.

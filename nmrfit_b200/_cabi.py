@@ -78,6 +78,7 @@ SIGNATURES = {
     'nmrfit_pso_peer_error': (_i, [_vp, c_int_p]),
     'nmrfit_pso_run_peers': (_i, [_vp, _i, _vp, _vp, c_int_p, c_int_p, _vp]),
     'nmrfit_pso_peer_timeout': (_i, [_vp, _d]),
+    'nmrfit_objective_spectrum_host': (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     'nmrfit_ctx_mt19937_begin': (_i, [_vp, _vp, _i, ctypes.c_longlong, ctypes.POINTER(_vp), ctypes.POINTER(_vp)]),
     'nmrfit_ctx_mt19937_end': (_i, [_vp, _vp, ctypes.POINTER(_i)]),
     'nmrfit_comm_init_all': (_i, [_vp, _i]),
@@ -302,6 +303,20 @@ class Context:
         f = np.empty((self.B, x.shape[1]), dtype=np.float64)
         check(lib().nmrfit_objective_batch_host(self._h, ptr(x), x.shape[1], int(fit_im), ptr(f)))
         return f[0] if squeeze else f
+
+    def objective_with_spectrum(self, x, w, u, v, weights, fit_im=REAL_ONLY):
+        """``set_spectrum(0, ...)`` + ``objective_host(x)`` in one call (contexts of one spectrum): x [S, D] -> f [S].
+        With page-locked ``x`` the comparison of the spectrum with the context's copy overlaps the evaluation."""
+        x = as_f64(x)
+        if x.ndim != 2 or x.shape[1] != self.D:
+            raise ValueError('x must have shape [S, %d], got %s' % (self.D, x.shape))
+        arrs = [as_f64(a) for a in (w, u, v, weights)]
+        for a in arrs:
+            if a.shape != (self.N,):
+                raise ValueError('spectrum arrays must have shape (%d,), got %s' % (self.N, a.shape))
+        f = np.empty(x.shape[0], dtype=np.float64)
+        check(lib().nmrfit_objective_spectrum_host(self._h, *[ptr(a) for a in arrs], ptr(x), x.shape[0], int(fit_im), ptr(f)))
+        return f
 
     def objective_device(self, x_dev, n_particles, f_dev, fit_im=REAL_ONLY, stream=None):
         """Asynchronous: x_dev/f_dev are device pointers (ints) or torch CUDA tensors."""

@@ -750,6 +750,18 @@ int nmrfit_objective_batch(nmrfit_ctx* c, const double* x_dev, int S, int fit_im
     return run_objective(c, x_dev, S, fit_im, f_dev, nullptr, (cudaStream_t)stream);
 }
 
+namespace {
+// Page-locked host positions as the device sees them (null: pageable memory, or a path without the prepare pass)
+const double* mapped_positions(const nmrfit_ctx* c, const double* x_host, int fit_im) {
+    static const bool kZeroCopy = [] { const char* e = getenv("NMRFIT_E2E_ZEROCOPY"); return !(e && atoi(e) == 0); }();
+    if (!kZeroCopy || !use_uniform(c, fit_im) || c->precision != NMRFIT_FP64) return nullptr;
+    cudaPointerAttributes at{};
+    const cudaError_t pe = cudaPointerGetAttributes(&at, x_host);
+    if (pe != cudaSuccess) (void)cudaGetLastError();
+    return (pe == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) ? (const double*)at.devicePointer : nullptr;
+}
+}  // namespace
+
 int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int fit_im, double* f_host) {
     if (int rc = check_ctx(c)) return rc;
     if (!x_host || !f_host) return fail(NMRFIT_ERR_ARG, "x_host and f_host must be non-NULL");
@@ -763,14 +775,7 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
     // Page-locked host positions (cudaHostAlloc / cudaHostRegister: mapped into the device under unified addressing) are
     // read by the prepare pass ITSELF, each element crossing PCIe once while other CTAs compute - no staging copy in
     // front of the kernels (NMRFIT_E2E_ZEROCOPY=0 turns this off).  Pageable arrays take the copies below.
-    static const bool kZeroCopy = [] { const char* e = getenv("NMRFIT_E2E_ZEROCOPY"); return !(e && atoi(e) == 0); }();
-    const double* x_map = nullptr;                         // the caller's array as the device sees it, or null
-    if (kZeroCopy && use_uniform(c, fit_im) && c->precision == NMRFIT_FP64) {
-        cudaPointerAttributes at{};
-        const cudaError_t pe = cudaPointerGetAttributes(&at, x_host);
-        if (pe != cudaSuccess) (void)cudaGetLastError();
-        if (pe == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer) x_map = (const double*)at.devicePointer;
-    }
+    const double* x_map = mapped_positions(c, x_host, fit_im);     // the caller's array as the device sees it, or null
     constexpr int kPad = 64;
     // (slices of ~12k particles, two to six of them: 1.24 / 1.15 / 1.13 / 1.12 ms per call with 1 / 2 / 4 / 6 slices
     // at 65,536 particles of 6 peaks x 4,096 points, tools/e2e_probe.py; NMRFIT_E2E_SLICES overrides)
@@ -814,6 +819,45 @@ int nmrfit_objective_batch_host(nmrfit_ctx* c, const double* x_host, int S, int 
                                x_map))
         return rc;
     CK(cudaMemcpyAsync(f_host, c->f_stage.ptr, nf * sizeof(double), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return NMRFIT_OK;
+}
+
+// equations.objective's own calling convention - the spectrum comes along with every call - for one spectrum:
+// nmrfit_ctx_set_spectrum + nmrfit_objective_batch_host in one.  When the context already holds a spectrum and the
+// positions are page-locked, the kernels are launched FIRST, on the spectrum the device has, and the four arrays are
+// compared with the host copy while they run (1 MB at 32,768 points: ~60 us that used to sit in front of every call);
+// a spectrum that did change is uploaded and the evaluation repeated.
+int nmrfit_objective_spectrum_host(nmrfit_ctx* c, const double* w, const double* u, const double* v, const double* weights,
+                                   const double* x_host, int S, int fit_im, double* f_host) {
+    if (int rc = check_ctx(c)) return rc;
+    if (c->B != 1) return fail(NMRFIT_ERR_ARG, "nmrfit_objective_spectrum_host is for contexts of one spectrum");
+    if (!w || !u || !v || !weights || !x_host || !f_host) return fail(NMRFIT_ERR_ARG, "NULL argument");
+    if (S < 1) return fail(NMRFIT_ERR_ARG, "n_particles must be >= 1");
+    CK(cudaSetDevice(c->device));
+    const size_t N = (size_t)c->N;
+    const bool have = c->spec_set[0] && !c->shadow.empty() && c->shadow[0].size() == 4 * N && !is_device_pointer(w) &&
+                      !is_device_pointer(u) && !is_device_pointer(v) && !is_device_pointer(weights);
+    const double* x_map = have && !c->profiling ? mapped_positions(c, x_host, fit_im) : nullptr;
+    if (!x_map) {
+        if (int rc = nmrfit_ctx_set_spectrum(c, 0, w, u, v, weights)) return rc;
+        return nmrfit_objective_batch_host(c, x_host, S, fit_im, f_host);
+    }
+    CK(c->x_stage.reserve((size_t)S * c->D));
+    CK(c->f_stage.reserve((size_t)S));
+    cudaStream_t st = 0;
+    if (int rc = run_objective(c, c->x_stage.ptr, S, fit_im, c->f_stage.ptr, nullptr, st, nullptr, nullptr, nullptr, nullptr, 0, 0,
+                               x_map))
+        return rc;
+    const double* src[4] = {w, u, v, weights};
+    bool same = true;
+    for (int k = 0; same && k < 4; ++k) same = std::memcmp(c->shadow[0].data() + (size_t)k * N, src[k], sizeof(double) * N) == 0;
+    if (!same) {
+        CK(cudaStreamSynchronize(st));                     // the speculative evaluation is dropped
+        if (int rc = nmrfit_ctx_set_spectrum(c, 0, w, u, v, weights)) return rc;
+        return nmrfit_objective_batch_host(c, x_host, S, fit_im, f_host);
+    }
+    CK(cudaMemcpyAsync(f_host, c->f_stage.ptr, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     return NMRFIT_OK;
 }

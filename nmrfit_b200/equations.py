@@ -83,8 +83,7 @@ def objective_batch(xs, w, u, v, weights, fit_im=False, precision=_cabi.FP64):
         raise ValueError('xs must be [n_particles, 4 + 3*n_peaks]')
     w = _cabi.as_f64(w)
     ctx = _context(w.size, (xs.shape[1] - 4) // 3, precision)
-    ctx.set_spectrum(0, w, u, v, weights)
-    return ctx.objective_host(xs, _fit_im_mode(fit_im))
+    return ctx.objective_with_spectrum(xs, w, u, v, weights, _fit_im_mode(fit_im))
 
 
 def objective(x, w, u, v, weights, fit_im=False):

@@ -216,3 +216,15 @@ def test_page_locked_positions_are_read_in_place(case):
     big_pinned[:] = big
     assert np.array_equal(equations.objective_batch(big, g['w'], g['u'], g['v'], g['weights']),
                           equations.objective_batch(big_pinned, g['w'], g['u'], g['v'], g['weights']))
+    # with page-locked positions the kernels start BEFORE the spectrum is compared with the context's copy: a spectrum
+    # modified in place must still be noticed (the speculative evaluation is dropped and repeated)
+    a = equations.objective_batch(pinned, g['w'], g['u'], g['v'], g['weights'])
+    u2 = g['u'].copy()
+    b = equations.objective_batch(pinned, g['w'], u2, g['v'], g['weights'])
+    assert np.array_equal(a, b)
+    u2[u2.size // 2] += 0.25
+    c = equations.objective_batch(pinned, g['w'], u2, g['v'], g['weights'])
+    assert not np.array_equal(a, c)
+    assert relerr(c, orc.objective_swarm(xs, g['w'], u2, g['v'], g['weights'])) < TOL
+    u2[u2.size // 2] -= 0.25
+    assert np.array_equal(a, equations.objective_batch(pinned, g['w'], u2, g['v'], g['weights']))
